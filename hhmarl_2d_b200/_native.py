@@ -1,0 +1,114 @@
+"""ctypes binding of libhhmarl_b200.so (C ABI: include/hhmarl_b200.h).
+
+The library is the product: there is NO Python/CPU fallback.  If the shared object is missing
+or cannot be loaded this module raises -- it never silently routes around the CUDA path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libhhmarl_b200.so")
+SOURCES = ["hh_api.cu"]
+HEADERS = ["hh_env.cuh", "hh_state.cuh", "hh_geodesic.cuh", os.path.join("..", "..", "include", "hhmarl_b200.h")]
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
+              "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared"]
+
+I32 = ctypes.c_int32
+U64 = ctypes.c_uint64
+D = ctypes.c_double
+VP = ctypes.c_void_p
+
+
+class HHConfig(ctypes.Structure):
+    _fields_ = [("level", I32), ("agent_mode", I32), ("horizon", I32), ("esc_dist_rew", I32),
+                ("friendly_kill", I32), ("friendly_punish", I32), ("autoreset", I32), ("reserved", I32),
+                ("map_size", D), ("rew_scale", D), ("glob_frac", D), ("seed", U64), ("arena_base", U64)]
+
+
+_F64_4 = ("lat", "lon", "heading", "speed", "new_heading", "new_speed")
+_I32_4 = ("cannon_remain", "cannon_burst", "cannon_max", "missile_remain", "rocket_max", "missile_wait",
+          "alive", "has_missile", "opp_to_attack")
+_F64_2 = ("r_lat", "r_lon", "r_heading", "r_new_heading")
+_I32_2 = ("r_alive", "r_age", "r_target", "r_id")
+_I32_1 = ("steps", "alive_agents", "alive_opps", "escaping", "escaping_time", "next_unit_id", "policy_set",
+          "opp_mode", "error")
+_U64_1 = ("draws_g", "draws_c")
+STATE_FIELDS = ([(n, "f8", 4) for n in _F64_4] + [(n, "i4", 4) for n in _I32_4] + [(n, "f8", 2) for n in _F64_2]
+                + [(n, "i4", 2) for n in _I32_2] + [(n, "i4", 1) for n in _I32_1] + [(n, "u8", 1) for n in _U64_1])
+
+
+class HHStateView(ctypes.Structure):
+    _fields_ = [(n, VP) for n, _, _ in STATE_FIELDS]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA library for sm_100a with nvcc (cross-compiles without a GPU)."""
+    if force or needs_build():
+        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+        subprocess.run(cmd, cwd=CSRC, check=True)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). hhmarl_2d_b200 has no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    P = ctypes.POINTER
+    L.hh_create.argtypes = [P(HHConfig), I32, I32, P(VP)]
+    L.hh_create.restype = ctypes.c_int
+    L.hh_destroy.argtypes = [VP]
+    L.hh_destroy.restype = None
+    L.hh_n_arenas.argtypes = [VP]
+    L.hh_n_arenas.restype = I32
+    L.hh_obs_dim.argtypes = [VP, I32]
+    L.hh_obs_dim.restype = I32
+    L.hh_reset.argtypes = [VP, VP, VP, VP, VP]
+    L.hh_reset.restype = ctypes.c_int
+    L.hh_step.argtypes = [VP, VP, VP, VP, VP, VP, VP]
+    L.hh_step.restype = ctypes.c_int
+    L.hh_reset_host.argtypes = [VP, VP, VP, VP]
+    L.hh_reset_host.restype = ctypes.c_int
+    L.hh_step_host.argtypes = [VP, VP, VP, VP, VP, VP]
+    L.hh_step_host.restype = ctypes.c_int
+    L.hh_get_state.argtypes = [VP, P(HHStateView)]
+    L.hh_get_state.restype = ctypes.c_int
+    L.hh_set_state.argtypes = [VP, P(HHStateView)]
+    L.hh_set_state.restype = ctypes.c_int
+    L.hh_launch_count.argtypes = [VP]
+    L.hh_launch_count.restype = U64
+    L.hh_last_error.restype = ctypes.c_char_p
+    L.hh_version.restype = ctypes.c_char_p
+    _lib = L
+    return L
+
+
+EXPORTS = ["hh_create", "hh_destroy", "hh_n_arenas", "hh_obs_dim", "hh_reset", "hh_step", "hh_reset_host",
+           "hh_step_host", "hh_get_state", "hh_set_state", "hh_launch_count", "hh_last_error", "hh_version"]
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().hh_last_error().decode()
+        if rc == -1:
+            raise ValueError(f"{what}: {msg}")
+        raise RuntimeError(f"{what}: {msg} (code {rc})")

@@ -1,0 +1,163 @@
+"""VecLowLevelEnv -- N independent 2-vs-2 low-level arenas advanced in lock-step by one fused
+sm_100a kernel per step (hhmarl_2d_b200/csrc/hh_api.cu) through the C ABI
+(include/hhmarl_b200.h).  Mirrors envs/env_hetero.py::LowLevelEnv (reset / step /
+observation_space / action_space) with a leading arena axis.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _native as nat
+from .config import make_args
+from .spaces import Box, Dict, MultiDiscrete
+
+ACTION_NVEC_AC1 = (13, 9, 2, 2)  # env_hetero.py:38
+ACTION_NVEC_AC2 = (13, 9, 2)     # env_hetero.py:39
+
+
+class VecLowLevelEnv:
+    """Batched twin of the reference's LowLevelEnv.
+
+    Parameters
+    ----------
+    n_arenas : number of independent 2-vs-2 arenas.
+    args     : namespace with the reference's `args` fields (see hhmarl_2d_b200.make_args).
+    device   : CUDA device index.
+    seed     : Philox key; arena k uses counter-based streams keyed by (seed, arena_base + k), so
+               results do not depend on how arenas are sharded over GPUs.
+    autoreset: reset finished arenas inside the step launch (sampler semantics); the returned obs
+               of such an arena is the first observation of its next episode.
+    """
+
+    def __init__(self, n_arenas: int, args=None, device: int = 0, seed: int = 0, arena_base: int = 0,
+                 autoreset: bool = True):
+        self.args = args if args is not None else make_args()
+        a = self.args
+        if a.num_agents != 2 or a.num_opps != 2:
+            raise ValueError("VecLowLevelEnv implements the 2-vs-2 low-level scenario")
+        self.n_arenas = int(n_arenas)
+        self.device_index = int(device)
+        cfg = nat.HHConfig(level=a.level, agent_mode=0 if a.agent_mode == "fight" else 1, horizon=a.horizon,
+                           esc_dist_rew=int(bool(a.esc_dist_rew)), friendly_kill=int(bool(a.friendly_kill)),
+                           friendly_punish=int(bool(a.friendly_punish)), autoreset=int(bool(autoreset)),
+                           reserved=0, map_size=float(a.map_size), rew_scale=float(a.rew_scale),
+                           glob_frac=float(a.glob_frac), seed=int(seed), arena_base=int(arena_base))
+        self._cfg = cfg
+        self._h = nat.VP()
+        nat.check(nat.lib().hh_create(ctypes.byref(cfg), self.n_arenas, self.device_index, ctypes.byref(self._h)),
+                  "hh_create")
+        self.obs_dim = (nat.lib().hh_obs_dim(self._h, 1), nat.lib().hh_obs_dim(self._h, 2))
+        # reference spaces (env_hetero.py:29-44) for agents 1, 2
+        self.observation_space = Dict({1: Box(0.0, 1.0, (self.obs_dim[0],), np.float32),
+                                       2: Box(0.0, 1.0, (self.obs_dim[1],), np.float32)})
+        self.action_space = Dict({1: MultiDiscrete(ACTION_NVEC_AC1), 2: MultiDiscrete(ACTION_NVEC_AC2)})
+        self._agent_ids = {1, 2}
+        self._torch = None
+        self._bufs = None
+
+    # ------------------------------------------------------------------ device (torch) API
+    def _ensure_torch(self):
+        if self._bufs is None:
+            import torch
+            self._torch = torch
+            dev = torch.device("cuda", self.device_index)
+            n = self.n_arenas
+            self._bufs = dict(obs1=torch.empty((n, self.obs_dim[0]), dtype=torch.float32, device=dev),
+                              obs2=torch.empty((n, self.obs_dim[1]), dtype=torch.float32, device=dev),
+                              rew=torch.empty((n, 2), dtype=torch.float32, device=dev),
+                              done=torch.empty((n,), dtype=torch.uint8, device=dev))
+        return self._bufs
+
+    def _stream(self):
+        return self._torch.cuda.current_stream(self.device_index).cuda_stream
+
+    def reset(self, mask=None, out=None):
+        """Reset all arenas (or those with mask != 0). Returns (obs1 [N,d1], obs2 [N,d2]) CUDA tensors."""
+        b = out if out is not None else self._ensure_torch()
+        self._ensure_torch()
+        mptr = None
+        if mask is not None:
+            assert mask.is_cuda and mask.dtype == self._torch.uint8 and mask.numel() == self.n_arenas
+            mptr = mask.data_ptr()
+        nat.check(nat.lib().hh_reset(self._h, mptr, b["obs1"].data_ptr(), b["obs2"].data_ptr(), self._stream()),
+                  "hh_reset")
+        return b["obs1"], b["obs2"]
+
+    def step(self, actions, out=None):
+        """actions: int32 CUDA tensor [N, 2, 4]. Returns (obs1, obs2, rew [N,2], done [N] u8).
+
+        The returned tensors are the env's own output buffers (overwritten by the next call)
+        unless `out` (a dict with the same keys) is given.  Enqueued on the current torch stream;
+        no host synchronisation."""
+        b = out if out is not None else self._ensure_torch()
+        self._ensure_torch()
+        t = self._torch
+        if not (actions.is_cuda and actions.dtype == t.int32 and actions.is_contiguous()
+                and actions.numel() == self.n_arenas * 8):
+            raise ValueError("actions must be a contiguous int32 CUDA tensor of shape [N, 2, 4]")
+        nat.check(nat.lib().hh_step(self._h, actions.data_ptr(), b["obs1"].data_ptr(), b["obs2"].data_ptr(),
+                                    b["rew"].data_ptr(), b["done"].data_ptr(), self._stream()), "hh_step")
+        return b["obs1"], b["obs2"], b["rew"], b["done"]
+
+    # ------------------------------------------------------------------ host (numpy) API
+    def reset_host(self, mask: np.ndarray | None = None):
+        o1 = np.empty((self.n_arenas, self.obs_dim[0]), np.float32)
+        o2 = np.empty((self.n_arenas, self.obs_dim[1]), np.float32)
+        mp = None
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, np.uint8)
+            mp = mask.ctypes.data
+        nat.check(nat.lib().hh_reset_host(self._h, mp, o1.ctypes.data, o2.ctypes.data), "hh_reset_host")
+        return o1, o2
+
+    def step_host(self, actions: np.ndarray, out=None):
+        """actions: int32 [N, 2, 4] host array -> (obs1, obs2, rew, done) host arrays.
+        Host->device and device->host copies happen inside the call."""
+        a = np.ascontiguousarray(actions, np.int32)
+        if a.size != self.n_arenas * 8:
+            raise ValueError("actions must have shape [N, 2, 4]")
+        if out is None:
+            out = (np.empty((self.n_arenas, self.obs_dim[0]), np.float32),
+                   np.empty((self.n_arenas, self.obs_dim[1]), np.float32),
+                   np.empty((self.n_arenas, 2), np.float32), np.empty((self.n_arenas,), np.uint8))
+        o1, o2, r, d = out
+        nat.check(nat.lib().hh_step_host(self._h, a.ctypes.data, o1.ctypes.data, o2.ctypes.data, r.ctypes.data,
+                                         d.ctypes.data), "hh_step_host")
+        return o1, o2, r, d
+
+    # ------------------------------------------------------------------ state access
+    def _alloc_view(self):
+        n = self.n_arenas
+        arrays = {name: np.zeros(n * per, dtype=np.dtype(dt)) for name, dt, per in nat.STATE_FIELDS}
+        view = nat.HHStateView(**{k: v.ctypes.data for k, v in arrays.items()})
+        return arrays, view
+
+    def get_state(self) -> dict:
+        arrays, view = self._alloc_view()
+        nat.check(nat.lib().hh_get_state(self._h, ctypes.byref(view)), "hh_get_state")
+        n = self.n_arenas
+        return {name: arrays[name].reshape(n, per) if per > 1 else arrays[name]
+                for name, _, per in nat.STATE_FIELDS}
+
+    def set_state(self, state: dict):
+        arrays, view = self._alloc_view()
+        for name, dt, per in nat.STATE_FIELDS:
+            arrays[name][:] = np.asarray(state[name], dtype=np.dtype(dt)).reshape(-1)
+        nat.check(nat.lib().hh_set_state(self._h, ctypes.byref(view)), "hh_set_state")
+
+    @property
+    def launch_count(self) -> int:
+        return int(nat.lib().hh_launch_count(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            nat.lib().hh_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,104 @@
+/*
+ * include/hhmarl_b200.h -- C ABI of the B200-native hhmarl_2D hot path.
+ *
+ * The reference (IDSIA/hhmarl_2D) is pure Python and has no FFI; the interface this library
+ * replaces is the RLlib MultiAgentEnv surface of envs/env_hetero.py + envs/env_base.py:
+ *
+ *   hh_create      <- LowLevelEnv.__init__(env_config)            env_hetero.py:20-51
+ *   hh_reset       <- LowLevelEnv.reset()                         env_hetero.py:53-60, env_base.py:62-77
+ *   hh_step        <- HHMARLBaseEnv.step(action_dict)             env_base.py:79-109
+ *                     (LowLevelEnv._take_action env_hetero.py:105-186, CmanoSimulator.do_tick
+ *                      cmano_simulator.py:138-157, _get_rewards env_hetero.py:188-225,
+ *                      lowlevel_state env_hetero.py:65-103) for N arenas in lock-step
+ *   hh_step_host / hh_reset_host  same, host buffers in / out (the call an RLlib-style CPU
+ *                     driver makes; copies are part of the call)
+ *   hh_get_state / hh_set_state   (no reference counterpart: test / checkpoint access to the
+ *                     struct-of-arrays arena state, incl. RNG counters)
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a
+ * negative error code and records a message retrievable with hh_last_error(); no C++
+ * exception crosses the boundary.  A handle is single-owner and stream-ordered: hh_step
+ * enqueues on `stream` (a cudaStream_t passed as void*, NULL = default stream) and never
+ * synchronises.  All *_dev pointers are device pointers owned by the caller.
+ *
+ * Shapes (N = n_arenas, row-major):
+ *   actions  int32 [N][2][4]   agent 1: MultiDiscrete[13,9,2,2]; agent 2: [13,9,2] (4th ignored)
+ *   obs1     f32   [N][hh_obs_dim(env,1)]   26 (fight) / 30 (escape)
+ *   obs2     f32   [N][hh_obs_dim(env,2)]   24 (fight) / 29 (escape)
+ *   rew      f32   [N][2]      0 for an agent that has no entry in the reference's reward dict
+ *   done     u8    [N]         terminateds["__all__"] (== truncateds["__all__"], env_base.py:89-90)
+ */
+#ifndef HHMARL_B200_H
+#define HHMARL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hh_env hh_env;
+
+/* The `args` fields the env reads (config.py:14-56). */
+typedef struct {
+  int32_t level;           /* 1..3 scripted opponents (4, 5: frozen-policy opponents, see hh_step_begin) */
+  int32_t agent_mode;      /* 0 = "fight", 1 = "escape" */
+  int32_t horizon;         /* config.py:95 {1:150, 2:200, 3:300, 4:350, 5:400} */
+  int32_t esc_dist_rew;    /* bool */
+  int32_t friendly_kill;   /* bool */
+  int32_t friendly_punish; /* bool */
+  int32_t autoreset;       /* 1: an arena whose step returns done is reset inside the same launch and
+                              obs are the first observation of the new episode (what RLlib's sampler
+                              does after a terminal step); 0: caller resets (reference semantics) */
+  int32_t reserved;
+  double map_size;         /* 0.3 */
+  double rew_scale;        /* 1 */
+  double glob_frac;        /* 0 */
+  uint64_t seed;           /* Philox key */
+  uint64_t arena_base;     /* global id of local arena 0: results are invariant to how arenas are
+                              partitioned over GPUs */
+} hh_config;
+
+/* Host-side, caller-allocated view of the complete state of all arenas (unpacked). */
+typedef struct {
+  double *lat, *lon, *heading, *speed, *new_heading, *new_speed;           /* [N*4] */
+  int32_t *cannon_remain, *cannon_burst, *cannon_max;                      /* [N*4] */
+  int32_t *missile_remain, *rocket_max, *missile_wait, *alive, *has_missile; /* [N*4] */
+  int32_t *opp_to_attack;                                                  /* [N*4] 0 = None */
+  double *r_lat, *r_lon, *r_heading, *r_new_heading;                       /* [N*2] slot = shooter id 1 / 3 */
+  int32_t *r_alive, *r_age, *r_target, *r_id;                              /* [N*2] */
+  int32_t *steps, *alive_agents, *alive_opps, *escaping, *escaping_time;   /* [N] */
+  int32_t *next_unit_id, *policy_set, *opp_mode, *error;                   /* [N] */
+  uint64_t *draws_g, *draws_c;                                             /* [N] */
+} hh_state_view;
+
+int hh_create(const hh_config* cfg, int32_t n_arenas, int32_t device, hh_env** out);
+void hh_destroy(hh_env* env);
+
+int32_t hh_n_arenas(const hh_env* env);
+int32_t hh_obs_dim(const hh_env* env, int32_t agent_id /* 1 or 2 */);
+
+/* mask_dev: u8[N] (non-zero = reset that arena) or NULL = all. obs pointers may be NULL. */
+int hh_reset(hh_env* env, const uint8_t* mask_dev, float* obs1_dev, float* obs2_dev, void* stream);
+int hh_step(hh_env* env, const int32_t* actions_dev, float* obs1_dev, float* obs2_dev, float* rew_dev,
+            uint8_t* done_dev, void* stream);
+
+/* Host-buffer variants: H2D of the actions, the launch, D2H of obs/rew/done and a stream
+ * synchronise all happen inside the call (pinned staging owned by the handle). */
+int hh_reset_host(hh_env* env, const uint8_t* mask_host, float* obs1_host, float* obs2_host);
+int hh_step_host(hh_env* env, const int32_t* actions_host, float* obs1_host, float* obs2_host,
+                 float* rew_host, uint8_t* done_host);
+
+int hh_get_state(hh_env* env, hh_state_view* out_host);
+int hh_set_state(hh_env* env, const hh_state_view* in_host);
+
+/* Number of kernels this library has launched on behalf of `env` since creation. */
+uint64_t hh_launch_count(const hh_env* env);
+
+const char* hh_last_error(void);
+const char* hh_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

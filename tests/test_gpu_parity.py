@@ -1,0 +1,194 @@
+"""GPU parity tests proper: the fused CUDA step (through the C ABI, include/hhmarl_b200.h)
+against (a) the committed golden trajectories of the reference's unmodified LowLevelEnv and
+(b) the C oracle on fresh seeds, plus size-independent properties at the BASELINE size.
+
+Bar (BASELINE.json north_star): bit-exact hit/kill bookkeeping (alive flags and counters, ammo,
+missile bookkeeping, RNG draw counts, done, reward-dict membership), <= 1e-5 relative on float
+dynamics / observations / rewards (atol 1e-6 for values that are ~0)."""
+import numpy as np
+import pytest
+
+import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 1e-6
+INT_FIELDS = ("cannon_remain", "cannon_burst", "cannon_max", "missile_remain", "rocket_max", "missile_wait",
+              "alive", "has_missile", "opp_to_attack")
+F64_FIELDS = ("lat", "lon", "heading", "speed", "new_heading", "new_speed")
+
+
+def _vec(n, level, mode, seed, arena_base=0, autoreset=True, **kw):
+    from hhmarl_2d_b200 import VecLowLevelEnv, make_args
+    return VecLowLevelEnv(n, make_args(level=level, agent_mode=mode, **kw), device=0, seed=seed,
+                          arena_base=arena_base, autoreset=autoreset)
+
+
+def _close(a, b, what):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    err = np.abs(a - b) - (ATOL + RTOL * np.abs(b))
+    assert (err <= 0).all(), f"{what}: max excess {err.max():.3e} at {np.unravel_index(err.argmax(), err.shape)}"
+
+
+@pytest.mark.parametrize("path", gu.golden_files(), ids=lambda p: p.split("lowlevel_")[-1][:-4])
+def test_cuda_replays_reference_golden(path):
+    g, seed, arena, level, mode, kw = gu.load(path)
+    env = _vec(1, level, mode, seed, arena_base=arena, autoreset=False, **kw)
+    o1, o2 = env.reset_host()
+    ep = 0
+    _close(o1[0], g["reset_obs1"][0], "reset obs1")
+    _close(o2[0], g["reset_obs2"][0], "reset obs2")
+    prev_alive = np.ones(2, bool)
+    worst = 0.0
+    for t in range(len(g["done"])):
+        act = g["actions"][t].astype(np.int32)[None]
+        o1, o2, rew, done = env.step_host(act)
+        st = env.get_state()
+        assert int(st["error"][0]) == 0
+        assert bool(done[0]) == bool(g["done"][t]), t
+        sc = [int(st[k][0]) for k in ("steps", "alive_agents", "alive_opps", "escaping", "escaping_time",
+                                      "next_unit_id", "draws_g", "draws_c")]
+        assert sc == [int(x) for x in g["scalars"][t]], (t, sc, g["scalars"][t])
+        for k in INT_FIELDS:
+            assert (st[k][0] == g[k][t]).all(), (t, k, st[k][0], g[k][t])
+        alive = g["alive"][t].astype(bool)
+        for k in F64_FIELDS:
+            _close(st[k][0], g[k][t], f"t={t} {k}")
+            worst = max(worst, np.abs(st[k][0] - g[k][t]).max())
+        # rockets: golden indexes by shooter id 1..4, CUDA by slot (shooters 1 and 3)
+        for slot, shooter in enumerate((0, 2)):
+            if g["has_missile"][t][shooter] and g["r_alive"][t][shooter]:
+                assert st["r_alive"][0][slot] == 1 and st["r_target"][0][slot] == g["r_target"][t][shooter]
+                assert st["r_age"][0][slot] == g["r_age"][t][shooter] and st["r_id"][0][slot] == g["r_id"][t][shooter]
+                for a, b in (("r_lat", "r_lat"), ("r_lon", "r_lon"), ("r_heading", "r_heading"),
+                             ("r_new_heading", "r_new_heading")):
+                    _close(st[a][0][slot], g[b][t][shooter], f"t={t} {a}")
+        _close(o1[0], g["obs1"][t], f"t={t} obs1")
+        _close(o2[0], g["obs2"][t], f"t={t} obs2")
+        _close(rew[0] * prev_alive, g["rew"][t], f"t={t} rew")
+        assert (prev_alive.astype(np.uint8) == g["present"][t]).all()
+        prev_alive = alive[:2]
+        if done[0]:
+            ep += 1
+            o1, o2 = env.reset_host()
+            _close(o1[0], g["reset_obs1"][ep], "reset obs1")
+            _close(o2[0], g["reset_obs2"][ep], "reset obs2")
+            prev_alive = np.ones(2, bool)
+    assert ep == len(g["reset_obs1"]) - 1
+    print(f"max abs state diff vs reference golden: {worst:.3e}")
+
+
+@pytest.mark.parametrize("level,mode,kw", [
+    (1, "fight", {}), (2, "fight", {}), (3, "fight", {}), (3, "escape", {"esc_dist_rew": True}),
+    (3, "fight", {"glob_frac": 0.25, "friendly_punish": True, "rew_scale": 2}), (2, "fight", {"friendly_kill": False}),
+])
+def test_cuda_matches_oracle_many_arenas(level, mode, kw):
+    """256 arenas x 350 lock-step ticks with device-side auto-reset against 256 scalar C oracles."""
+    import torch
+    import oracle as orc
+    n, T, seed, base = 256, 350, 99173 + level, 1000
+    env = _vec(n, level, mode, seed, arena_base=base, autoreset=True, **kw)
+    oracles = [orc.OracleEnv(orc.make_args(level=level, agent_mode=mode, **kw), seed, base + k) for k in range(n)]
+    o1, o2 = env.reset()
+    ref1 = np.stack([o.reset() for o in oracles])  # [n, 2] object pairs
+    r1 = np.stack([p[0] for p in ref1]); r2 = np.stack([p[1] for p in ref1])
+    _close(o1.cpu().numpy(), r1, "reset obs1"); _close(o2.cpu().numpy(), r2, "reset obs2")
+    rng = np.random.default_rng(level)
+    n_done = n_kills = 0
+    for t in range(T):
+        act = np.stack([rng.integers(0, 13, (n, 2)), rng.integers(0, 9, (n, 2)), rng.integers(0, 2, (n, 2)),
+                        rng.integers(0, 2, (n, 2))], axis=-1).astype(np.int32)
+        g1, g2, grew, gdone = env.step(torch.from_numpy(act).cuda())
+        g1, g2, grew, gdone = g1.cpu().numpy(), g2.cpu().numpy(), grew.cpu().numpy(), gdone.cpu().numpy()
+        e1 = np.empty_like(g1); e2 = np.empty_like(g2); erew = np.empty_like(grew, dtype=np.float64)
+        edone = np.empty(n, np.uint8)
+        for k, o in enumerate(oracles):
+            a1, a2, r, pres, d = o.step(act[k])
+            edone[k] = d
+            erew[k] = r
+            if d:
+                a1, a2 = o.reset()
+            e1[k], e2[k] = a1, a2
+        assert (gdone == edone).all(), f"t={t} done mismatch at {np.nonzero(gdone != edone)[0][:8]}"
+        _close(grew, erew, f"t={t} rew")
+        _close(g1, e1, f"t={t} obs1")
+        _close(g2, e2, f"t={t} obs2")
+        n_done += int(edone.sum())
+        if t % 50 == 49 or t == T - 1:
+            st = env.get_state()
+            os_ = [o.state() for o in oracles]
+            for fld in F64_FIELDS:
+                _close(st[fld], np.array([list(getattr(s, fld)[:4]) for s in os_]), f"t={t} {fld}")
+            for fld in ("missile_remain", "missile_wait", "alive", "has_missile", "opp_to_attack"):
+                assert (st[fld] == np.array([list(getattr(s, fld)[:4]) for s in os_])).all(), (t, fld)
+            for fld, ofld in (("cannon_remain", "cannon_remain"), ("cannon_burst", "cannon_burst")):
+                assert (st[fld] == np.array([list(getattr(s, ofld)[:4]) for s in os_])).all(), (t, fld)
+            for fld, ofld in (("steps", "steps"), ("alive_agents", "alive_agents"), ("alive_opps", "alive_opps"),
+                              ("escaping", "escaping"), ("escaping_time", "escaping_time"),
+                              ("next_unit_id", "next_unit_id"), ("draws_g", "draws_g"), ("draws_c", "draws_c")):
+                assert (st[fld] == np.array([getattr(s, ofld) for s in os_])).all(), (t, fld)
+            assert (st["error"] == 0).all()
+            n_kills += int((st["alive"] == 0).sum())
+    assert n_done > n and n_kills > 0   # several episodes per arena slot were exercised
+
+
+def test_full_size_properties():
+    """BASELINE size (8192 arenas, L3): determinism, range, partition invariance, ragged N."""
+    import torch
+    n, T = 8192, 40
+    torch.manual_seed(0)
+    acts = torch.stack([torch.randint(0, 13, (T, n, 2)), torch.randint(0, 9, (T, n, 2)),
+                        torch.randint(0, 2, (T, n, 2)), torch.randint(0, 2, (T, n, 2))], dim=-1).to(torch.int32).cuda()
+
+    def run(n_arenas, base, sl):
+        env = _vec(n_arenas, 3, "fight", 5, arena_base=base)
+        outs = [torch.cat([x.clone() for x in env.reset()], dim=1)]
+        for t in range(T):
+            o1, o2, r, d = env.step(acts[t, sl].contiguous())
+            outs.append(torch.cat([o1, o2, r, d.float()[:, None]], dim=1).clone())
+        return outs, env.get_state()
+
+    full, st = run(n, 0, slice(0, n))
+    again, _ = run(n, 0, slice(0, n))
+    for a, b in zip(full, again):
+        assert torch.equal(a, b)                                   # bitwise deterministic
+    for o in full:
+        assert torch.isfinite(o).all()
+        assert (o[:, :50] >= 0).all() and (o[:, :50] <= 1).all()   # Box(0, 1) observation space
+    # sharding invariance + ragged (non multiple of 32) arena counts: arenas [1000, 1000+777)
+    part, _ = run(777, 1000, slice(1000, 1777))
+    for a, b in zip(full, part):
+        assert torch.equal(a[1000:1777], b)
+    assert (st["error"] == 0).all()
+    assert ((st["alive"].sum(1) >= 0) & (st["steps"] <= 300)).all()
+
+
+def test_lowlevel_env_dict_api_matches_oracle():
+    """The reference-shaped single-arena facade (reset/step with dicts) against the oracle."""
+    import oracle as orc
+    from hhmarl_2d_b200 import LowLevelEnv, make_args
+    args = make_args(level=3)
+    env = LowLevelEnv({"args": args, "seed": 31, "arena_id": 4})
+    oe = orc.OracleEnv(orc.make_args(level=3), 31, 4)
+    obs, info = env.reset()
+    e1, e2 = oe.reset()
+    assert info == {} and set(obs) == {1, 2}
+    _close(obs[1], e1, "obs1"); _close(obs[2], e2, "obs2")
+    rng = np.random.default_rng(0)
+    for t in range(300):
+        a = {1: rng.integers(0, [13, 9, 2, 2]), 2: rng.integers(0, [13, 9, 2])}
+        obs, rew, term, trunc, info = env.step(a)
+        act = np.zeros((2, 4), np.int32); act[0] = a[1]; act[1, :3] = a[2]
+        e1, e2, r, pres, d = oe.step(act)
+        assert term is trunc and term["__all__"] == d and info == {}
+        assert set(rew) == {i + 1 for i in range(2) if pres[i]}
+        for i in rew:
+            assert abs(rew[i] - r[i - 1]) <= ATOL + RTOL * abs(r[i - 1])
+        _close(obs[1], e1, "obs1"); _close(obs[2], e2, "obs2")
+        assert obs[1].dtype == np.float32 and obs[1].shape == (26,) and obs[2].shape == (24,)
+        if d:
+            obs, _ = env.reset(); e1, e2 = oe.reset()
+            _close(obs[1], e1, "obs1")
+    with pytest.raises(ValueError):
+        env.step({1: np.array([13, 0, 0, 0]), 2: np.array([0, 0, 0])})
