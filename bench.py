@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the B200-native hhmarl_2D hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (one rank per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the reference path on the host cores
+
+Workload (BASELINE.json configs[1]): 8 192 arenas of the 2-vs-2 level-3 (scripted-opponent) fight
+scenario per GPU, all arenas advanced one tick per "step" by ONE fused kernel launch (action
+decode -> scripted opponents -> tick -> rewards -> auto-reset -> observations).  Actions are
+uniform MultiDiscrete samples, pre-generated on the device (`value`) or supplied from host
+memory each step (`e2e`, through the C ABI's host entry point hh_step_host: H2D of actions and
+D2H of observations/rewards/done inside the timed region).
+
+  value     whole-job env-steps/s, inputs resident in HBM, per-step CUDA events, L2 flushed
+            between steps, max over ranks
+  e2e       same metric through hh_step_host (host buffers)
+  roofline  algorithmic bytes of one launch / its CUDA-event duration vs the measured HBM peak
+  cpu_baseline  the C oracle (port of the reference algorithm) on this box's host cores,
+            bounded sample
+The reference itself is Python + ray and cannot travel to the GPU box (no ray, no
+geographiclib, no /root/reference there); `--impl reference` therefore times the oracle port
+(oracle/hhmarl_oracle.c) with every host thread it can use, as the task's tier rules prescribe.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "env-steps/sec"
+UNIT = "env-steps/s"
+ALGO_BYTES_PER_ENV_STEP = 840          # SURVEY.md section 8(d), levels 1-3
+FALLBACK_HBM_GBS = 6650.0              # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--arenas", type=int, default=8192, help="arenas per GPU")
+    ap.add_argument("--level", type=int, default=3)
+    ap.add_argument("--cpu-sample-steps", type=int, default=400_000, help="env-steps per host thread")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------ CPU legs
+def cpu_oracle_throughput(level: int, steps_per_thread: int, threads: int):
+    """env-steps/s of the C oracle, one arena per host thread (the reference's one-env-per-rollout-
+    worker layout, train_hetero.py:212), uniformly random actions, auto-reset."""
+    from concurrent.futures import ThreadPoolExecutor
+    import oracle as orc
+    envs = [orc.OracleEnv(orc.make_args(level=level), 0, k) for k in range(threads)]
+    for e in envs:
+        e.run_random(1000, 7)  # warm caches / page in
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:   # ctypes releases the GIL inside the C call
+        list(ex.map(lambda e: e.run_random(steps_per_thread, 1), envs))
+    dt = time.perf_counter() - t0
+    return threads * steps_per_thread / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = max(20_000, args.cpu_sample_steps // 8)
+    for _ in range(args.warmup):
+        cpu_oracle_throughput(args.level, per_step // 10, cores)
+    t_total, n_total = 0.0, 0
+    for _ in range(args.steps):
+        v, dt = cpu_oracle_throughput(args.level, per_step, cores)
+        t_total += dt
+        n_total += cores * per_step
+    value = n_total / t_total
+    sample = f"{cores} host threads x {per_step} env-steps of the L{args.level} scenario per bench step, random actions"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(args, cores_note=True),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(args, cores_note=False):
+    return {"workload": f"{args.arenas} arenas/GPU, 2-vs-2 level-{args.level} scripted-opponent fight, "
+                        f"horizon {({1: 150, 2: 200, 3: 300}).get(args.level)}, uniform random MultiDiscrete actions, "
+                        "auto-reset",
+            "arenas_per_gpu": args.arenas, "level": args.level, "agent_mode": "fight",
+            "cache": "L2 flushed (256 MiB write) between timed steps"}
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.samples = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.perf_counter(), line.strip()))
+
+    def summary(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        rows = [s for (t, s) in self.samples if t0 <= t <= t1] or [s for (_, s) in self.samples]
+        sm, mx, reasons = [], None, set()
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except Exception:  # noqa: BLE001
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(rows)}
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from hhmarl_2d_b200 import VecLowLevelEnv, make_args
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    n, K, W = args.arenas, args.steps, args.warmup
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        v, dt = cpu_oracle_throughput(args.level, args.cpu_sample_steps, cores)
+        cpu_base = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": f"C oracle, {cores} host threads x {args.cpu_sample_steps} env-steps (L{args.level}, "
+                              f"random actions, auto-reset), {dt:.1f} s wall"}
+
+    env = VecLowLevelEnv(n, make_args(level=args.level), device=local, seed=0, arena_base=rank * n, autoreset=True)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    n_act = 16  # distinct action tensors cycled through
+    acts = torch.stack([torch.randint(0, 13, (n_act, n, 2), device=dev, generator=g),
+                        torch.randint(0, 9, (n_act, n, 2), device=dev, generator=g),
+                        torch.randint(0, 2, (n_act, n, 2), device=dev, generator=g),
+                        torch.randint(0, 2, (n_act, n, 2), device=dev, generator=g)], dim=-1).to(torch.int32).contiguous()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    env.reset()
+    launches0 = env.launch_count
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput: per-step CUDA events, L2 flush between steps
+    for w in range(W):
+        flush.fill_(w & 0xFF)
+        env.step(acts[w % n_act])
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    t0 = time.perf_counter()
+    launches_before = env.launch_count
+    for k in range(K):
+        flush.fill_(k & 0xFF)          # evict the arena state from L2 (outside the event bracket)
+        ev0[k].record()
+        env.step(acts[k % n_act])
+        ev1[k].record()
+    barrier()
+    t1 = time.perf_counter()
+    gpu_launches = env.launch_count - launches_before
+    clocks = sampler.summary(t0, t1) if sampler else None
+    step_ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
+    total_ms = float(sum(step_ms))
+    tot = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    total_ms = float(tot.item())
+    value = world * n * K / (total_ms * 1e-3)
+
+    # ---- back-to-back (no flush; state stays in L2), one event pair around K launches
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(K):
+        env.step(acts[k % n_act])
+    e1.record()
+    barrier()
+    b2b_ms = e0.elapsed_time(e1)
+
+    # ---- end to end through the host entry point of the C ABI
+    acts_host = acts.cpu().numpy()
+    outs = None
+    for w in range(max(3, W // 4)):
+        outs = env.step_host(acts_host[w % n_act], out=outs)
+    barrier()
+    th0 = time.perf_counter()
+    for k in range(K):
+        outs = env.step_host(acts_host[k % n_act], out=outs)
+    torch.cuda.synchronize()
+    th1 = time.perf_counter()
+    e2e_t = torch.tensor([th1 - th0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * K / float(e2e_t.item())
+    d1, d2 = env.obs_dim
+    h2d, d2h = n * 8 * 4, n * ((d1 + d2 + 2) * 4 + 1)
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+        if os.path.exists(peaks_path):
+            try:
+                peak = float(json.load(open(peaks_path))["hbm_gbs"])
+                peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+            except Exception:  # noqa: BLE001
+                pass
+        kern_ms = total_ms / K                      # one kernel per step: event bracket == the launch
+        achieved = ALGO_BYTES_PER_ENV_STEP * n / (kern_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:  # noqa: BLE001
+                pass
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": workload_config(args),
+                "agent_steps_per_s": 2 * value,
+                "back_to_back": {"value": world * n * K / (b2b_ms * 1e-3), "unit": UNIT,
+                                 "note": "no L2 flush, K launches under one event pair (rank 0)"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "api": "hh_step_host (C ABI, host buffers; copies + sync inside the call)"},
+                "gpu_launches": int(gpu_launches),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * n,
+                             "kernel": "hh::step_kernel<3,0>", "kernel_ms": kern_ms,
+                             "note": "FP64-issue/latency bound, not DRAM bound: see DESIGN.md section 4"},
+                "clocks": clocks}
+        if cpu_base is not None:
+            line["cpu_baseline"] = cpu_base
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

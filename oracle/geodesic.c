@@ -29,7 +29,7 @@ typedef struct {
 } geod_t;
 
 static geod_t G;
-static int g_last_numit = 0;
+static __thread int g_last_numit = 0;
 
 static double sq(double x) { return x * x; }
 

@@ -91,7 +91,7 @@ def test_cuda_matches_oracle_many_arenas(level, mode, kw):
     env = _vec(n, level, mode, seed, arena_base=base, autoreset=True, **kw)
     oracles = [orc.OracleEnv(orc.make_args(level=level, agent_mode=mode, **kw), seed, base + k) for k in range(n)]
     o1, o2 = env.reset()
-    ref1 = np.stack([o.reset() for o in oracles])  # [n, 2] object pairs
+    ref1 = [o.reset() for o in oracles]
     r1 = np.stack([p[0] for p in ref1]); r2 = np.stack([p[1] for p in ref1])
     _close(o1.cpu().numpy(), r1, "reset obs1"); _close(o2.cpu().numpy(), r2, "reset obs2")
     rng = np.random.default_rng(level)
