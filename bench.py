@@ -71,11 +71,24 @@ def cpu_oracle_throughput(level: int, steps_per_thread: int, threads: int):
     return threads * steps_per_thread / dt, dt
 
 
+def best_thread_count(level: int):
+    """Host boxes may expose more logical CPUs than the cgroup lets us use: probe a few thread
+    counts on a small sample and keep the fastest."""
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cands = sorted({c for c in (4, 8, 16, 32, 64, 96, 128, 192, avail) if c <= avail} | {avail})
+    best, best_v = cands[0], 0.0
+    for c in cands:
+        v, _ = cpu_oracle_throughput(level, 15_000, c)
+        if v > best_v * 1.03:
+            best, best_v = c, v
+    return best
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = best_thread_count(args.level)
     per_step = max(20_000, args.cpu_sample_steps // 8)
     for _ in range(args.warmup):
         cpu_oracle_throughput(args.level, per_step // 10, cores)
@@ -85,7 +98,8 @@ def run_reference(args):
         t_total += dt
         n_total += cores * per_step
     value = n_total / t_total
-    sample = f"{cores} host threads x {per_step} env-steps of the L{args.level} scenario per bench step, random actions"
+    sample = (f"{cores} host threads (best of a thread-count probe; box reports {os.cpu_count()} logical CPUs) x "
+              f"{per_step} env-steps of the L{args.level} scenario per bench step, random actions")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -106,45 +120,55 @@ def workload_config(args, cores_note=False):
 
 # ------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Polls NVML (SM clock, max SM clock, power, throttle reasons) every ~5 ms on a thread."""
+    BITS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+            "hw_power_brake": 0x80}
 
     def __init__(self, index: int):
-        self.samples = []
-        self.proc = None
+        self.samples, self.ok, self._stop = [], False, False
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+            self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
-        except Exception:  # noqa: BLE001
-            self.proc = None
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.samples.append((time.perf_counter(), line.strip()))
+    def _poll(self):
+        nv = self.nv
+        while not self._stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.samples.append((time.perf_counter(), sm, rs, pw))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.004)
 
     def summary(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        rows = [s for (t, s) in self.samples if t0 <= t <= t1] or [s for (_, s) in self.samples]
-        sm, mx, reasons = [], None, set()
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "")]}
+        self._stop = True
+        rows = [r for r in self.samples if t0 <= r[0] <= t1]
+        scope = "timed region"
+        if not rows:
+            rows, scope = self.samples, "whole run (timed region shorter than the sampling period)"
+        sm = sorted(r[1] for r in rows)
+        reasons = set()
         for r in rows:
-            f = [x.strip() for x in r.split(",")]
-            try:
-                sm.append(float(f[0]))
-                mx = float(f[1])
-            except Exception:  # noqa: BLE001
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if val.lower().startswith("active"):
+            for name, bit in self.BITS.items():
+                if r[2] & bit:
                     reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(rows)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_sm, "reasons": sorted(reasons),
+                "samples": len(rows), "scope": scope, "power_w_max": max((r[3] for r in rows), default=None)}
 
 
 # ------------------------------------------------------------------------------------ GPU arm
@@ -165,12 +189,14 @@ def run_b200(args):
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        cores = best_thread_count(args.level)
         v, dt = cpu_oracle_throughput(args.level, args.cpu_sample_steps, cores)
         cpu_base = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                    "sample": f"C oracle, {cores} host threads x {args.cpu_sample_steps} env-steps (L{args.level}, "
+                    "sample": f"C oracle, {cores} host threads (best of a thread-count probe; box reports "
+                              f"{os.cpu_count()} logical CPUs) x {args.cpu_sample_steps} env-steps (L{args.level}, "
                               f"random actions, auto-reset), {dt:.1f} s wall"}
 
+    sampler = ClockSampler(local) if rank == 0 else None
     env = VecLowLevelEnv(n, make_args(level=args.level), device=local, seed=0, arena_base=rank * n, autoreset=True)
     g = torch.Generator(device=dev)
     g.manual_seed(1234 + rank)
@@ -194,7 +220,6 @@ def run_b200(args):
         env.step(acts[w % n_act])
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     t0 = time.perf_counter()
     launches_before = env.launch_count
