@@ -1,12 +1,14 @@
 // hh_api.cu -- fused step / reset kernels and the C ABI declared in include/hhmarl_b200.h.
 //
-// Kernel shape: one thread per arena, 32-thread CTAs (one warp) so that the 256 warps of the
-// N = 8192 headline configuration spread over all 148 SMs; the arena's 320 B of state are read
-// with 16-byte coalesced loads into registers, advanced through
+// Kernel shape: a QUAD of lanes per arena (lane = aircraft, hh_quad.cuh), 8 arenas per warp,
+// one-warp CTAs so that the 1024 warps of the N = 8192 headline configuration spread evenly
+// over the 148 SMs (6.9 warps / SM).  Each lane reads its own aircraft's slice of the 320 B
+// struct-of-arrays arena state with coalesced 8-byte loads, the quad advances the arena through
 //   action decode -> scripted opponents -> tick (kinematics, cannon, rockets; WGS84 FP64) ->
 //   rewards / out-of-bounds / termination -> (auto-reset) -> observations
-// and written back once.  Observations are staged through shared memory so that the [N][26]
-// and [N][24] float rows leave the SM as contiguous 16-byte stores.
+// exchanging cross-unit data with warp shuffles, and writes the state back once.  Observations
+// are staged through shared memory so that the [N][26] and [N][24] float rows leave the SM as
+// contiguous 16-byte stores.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -17,11 +19,12 @@
 #include <vector>
 
 #include "../../include/hhmarl_b200.h"
-#include "hh_env.cuh"
+#include "hh_quad.cuh"
 
 namespace hh {
 
-constexpr int kThreads = 32;
+constexpr int kThreads = 32;                 // one warp per CTA = 8 arenas
+constexpr int kArenasPerCta = kThreads / 4;
 
 template <int MODE>
 struct ObsDims {
@@ -30,30 +33,25 @@ struct ObsDims {
 };
 
 // contiguous, coalesced copy of `n_floats` staged floats (16-byte aligned on both sides)
-__device__ __forceinline__ void flush_rows(float* __restrict__ dst, const float* __restrict__ src, int n_floats,
-                                           int lane) {
+__device__ __forceinline__ void flush_rows(float* __restrict__ dst, const float* __restrict__ src, int n_floats) {
   const int n4 = n_floats >> 2;
   const float4* s4 = reinterpret_cast<const float4*>(src);
   float4* d4 = reinterpret_cast<float4*>(dst);
-  for (int k = lane; k < n4; k += kThreads) d4[k] = s4[k];
-  for (int k = (n4 << 2) + lane; k < n_floats; k += kThreads) dst[k] = src[k];
+  for (int k = threadIdx.x; k < n4; k += kThreads) d4[k] = s4[k];
+  for (int k = (n4 << 2) + threadIdx.x; k < n_floats; k += kThreads) dst[k] = src[k];
 }
 
+// agents' observations (lanes 0 and 1 of each quad) -> shared staging -> contiguous rows in HBM
 template <int MODE>
-__device__ __forceinline__ void write_agent_obs(Arena& A, const Geom& g, float* obs1, float* obs2, float* s1,
-                                                float* s2, int arena0, int n_valid, bool valid) {
+__device__ __forceinline__ void write_agent_obs(Lane& L, const Geom& g, int u, float* obs1, float* obs2, float* s1,
+                                                float* s2, int arena0, int n_valid) {
   constexpr int D1 = ObsDims<MODE>::D1, D2 = ObsDims<MODE>::D2;
-  const int lane = threadIdx.x;
-  if (valid) {
-    HVec hv[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) hv[u] = heading_vec(A.hdg[u]);
-    unit_observation<0, MODE>(A, g, hv, s1 + lane * D1);
-    unit_observation<1, MODE>(A, g, hv, s2 + lane * D2);
-  }
+  const int al = threadIdx.x >> 2;
+  const World W = gather_world(L, u);
+  if (u < 2) L.ota = unit_observation(L, W, g, u, MODE, u == 0 ? s1 + al * D1 : s2 + al * D2);
   __syncwarp();
-  if (obs1) flush_rows(obs1 + (size_t)arena0 * D1, s1, n_valid * D1, lane);
-  if (obs2) flush_rows(obs2 + (size_t)arena0 * D2, s2, n_valid * D2, lane);
+  if (obs1) flush_rows(obs1 + (size_t)arena0 * D1, s1, n_valid * D1);
+  if (obs2) flush_rows(obs2 + (size_t)arena0 * D2, s2, n_valid * D2);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -63,61 +61,354 @@ template <int LEVEL, int MODE>
 __global__ void __launch_bounds__(kThreads)
 step_kernel(StatePtrs S, Params P, const int32_t* __restrict__ actions, float* __restrict__ obs1,
             float* __restrict__ obs2, float* __restrict__ rew_out, uint8_t* __restrict__ done_out) {
-  __shared__ __align__(16) float s1[kThreads * ObsDims<MODE>::D1];
-  __shared__ __align__(16) float s2[kThreads * ObsDims<MODE>::D2];
-  const int arena0 = blockIdx.x * kThreads;
-  const int a = arena0 + threadIdx.x;
-  const bool valid = a < P.n_arenas;
-  const int n_valid = min(kThreads, P.n_arenas - arena0);
+  __shared__ __align__(16) float s1[kArenasPerCta * ObsDims<MODE>::D1];
+  __shared__ __align__(16) float s2[kArenasPerCta * ObsDims<MODE>::D2];
+  const int u = threadIdx.x & 3;
+  const int arena0 = blockIdx.x * kArenasPerCta;
+  const int a_raw = arena0 + (threadIdx.x >> 2);
+  const bool valid = a_raw < P.n_arenas;
+  const int a = valid ? a_raw : P.n_arenas - 1;  // tail lanes shadow the last arena, never store
+  const int n_valid = min(kArenasPerCta, P.n_arenas - arena0);
   const Geom g = make_geom(P.map_size);
-  Arena A;
-  if (valid) {
-    load_arena(S, a, A);
-    const Rng rng{P.seed_lo, P.seed_hi, P.arena_base + (uint32_t)a};
-    const int4* ap = reinterpret_cast<const int4*>(actions) + 2 * (size_t)a;
-    const int4 act0 = ap[0], act1 = ap[1];
+  const Rng rng{P.seed_lo, P.seed_hi, P.arena_base + (uint32_t)a};
+  Lane L;
+  load_lane(S, a, u, L);
+  int4 act = make_int4(6, 0, 0, 0);
+  if (u < 2) act = reinterpret_cast<const int4*>(actions)[(size_t)a * 2 + u];
 
-    // ---- LowLevelEnv._take_action, env_hetero.py:105-186
-    A.steps += 1;
-    double rew[2] = {0.0, 0.0};
-    double opp_focus[2] = {0.0, 0.0};
-    const bool present[2] = {A.alive[0], A.alive[1]};
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      if (A.alive[i]) {
-        const int t = A.ota[i];
-        if (t != 0 && pick4(A.alive, t - 1)) {  // opp_stats[i][0], env_hetero.py:169-170
-          double lat_t = pick4(A.lat, t - 1), lon_t = pick4(A.lon, t - 1);
-          opp_focus[i] = focus_norm_from_deg(
-              focus_deg(heading_vec(pick4(A.hdg, t - 1)), lat_t, lon_t, A.lat[i], A.lon[i]));
-        }
-        take_base_action<MODE>(A, rng, i, t, i == 0 ? act0 : act1, rew[i]);
-      }
-    }
-#pragma unroll
-    for (int i = 2; i < 4; ++i) {
-      if (A.alive[i]) {
-        if (LEVEL == 1) opp_missile_rule(A, rng, g, i);
-        else if (LEVEL == 2) opp_level2(A, rng, g, i);
-        else opp_level3(A, rng, g, i);
-      }
-    }
+  // ===================================================== LowLevelEnv._take_action, env_hetero.py:105-186
+  L.steps += 1;
+  const bool present = L.alive;       // agents: has an entry in the reward dict (env_hetero.py:168)
+  double rew = 0.0;
 
-    // ---- CmanoSimulator.do_tick + _get_rewards
-    Kills K;
+  // ---- pre-tick geometry, one relation per lane, all four in parallel:
+  //   agents   : opp_stats[i][0] = focus_norm(opp_to_attack -> self)      (env_hetero.py:169-170)
+  //   opponents: nearest agent, and for level 3 sign / focus(self -> agent) (env_hetero.py:251-260)
+  double lat4[4], lon4[4], hdg4[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { K.killer[j] = 0; K.by_rocket[j] = false; }
-    do_tick(A, rng, P, K);
-    assemble_rewards<MODE>(A, P, g, K, opp_focus, present, rew);
-
-    // ---- HHMARLBaseEnv.step, env_base.py:89-90
-    const bool done = A.alive_ag <= 0 || A.alive_op <= 0 || A.steps >= P.horizon;
-    if (rew_out) reinterpret_cast<float2*>(rew_out)[a] = make_float2((float)rew[0], (float)rew[1]);
-    if (done_out) done_out[a] = done ? 1 : 0;
-    if (done && P.autoreset) reset_arena(A, rng, P);
+  for (int j = 0; j < 4; ++j) {
+    lat4[j] = qshfl(L.lat, j);
+    lon4[j] = qshfl(L.lon, j);
+    hdg4[j] = qshfl(L.hdg, j);
   }
-  write_agent_obs<MODE>(A, g, obs1, obs2, s1, s2, arena0, n_valid, valid);
-  if (valid) store_arena(S, a, A);
+  const int alive_pre = quad_ballot(L.alive);
+  double near_dn = 0.0;
+  int near_t = -1;
+  if (u >= 2 && L.alive) near_t = nearest_enemy(g, u, L.lat, L.lon, lat4, lon4, alive_pre, near_dn);
+  // relation "from X towards Y"
+  int rel_x = -1, rel_y = -1;
+  if (u < 2) {
+    if (L.alive && L.ota != 0 && ((alive_pre >> (L.ota - 1)) & 1)) { rel_x = L.ota - 1; rel_y = u; }
+  } else if (LEVEL == 3 && near_t >= 0) {
+    rel_x = u;
+    rel_y = near_t;
+  }
+  double rel_focus = 0.0;
+  int rel_sign = 1;
+  if (rel_x >= 0) {
+    const double xlat = pick4d(lat4[0], lat4[1], lat4[2], lat4[3], rel_x);
+    const double xlon = pick4d(lon4[0], lon4[1], lon4[2], lon4[3], rel_x);
+    const double ylat = pick4d(lat4[0], lat4[1], lat4[2], lat4[3], rel_y);
+    const double ylon = pick4d(lon4[0], lon4[1], lon4[2], lon4[3], rel_y);
+    const double xh = pick4d(hdg4[0], hdg4[1], hdg4[2], hdg4[3], rel_x);
+    rel_focus = focus_deg(heading_vec(xh), xlat, xlon, ylat, ylon);
+    if (u >= 2) rel_sign = correct_angle_sign(xlat, xlon, xh, ylat, ylon);
+  }
+  const double opp_focus = u < 2 ? focus_norm_from_deg(rel_focus) : 0.0;  // 0 when no opp_stats entry
+
+  // ---- agents: _take_base_action (env_base.py:214-238), lanes 0 and 1 in parallel
+  bool want_missile = false;
+  int tgt = -1;
+  if (u < 2 && L.alive) {
+    set_heading(L, pymod(L.hdg + (double)((act.x - 6) * 15), 360.0));
+    set_speed(L, u, 100.0 + ((max_speed(u) - 100.0) / 8.0) * (double)act.y);
+    if (act.z != 0 && L.crem > 0) {
+      fire_cannon(L, u);
+      if (MODE == 1 && L.crem < 90) rew -= 0.1;
+    }
+    want_missile = is_ac1(u) && act.w != 0 && L.ota != 0 && L.mrem > 0 && !L.hasm && L.mwait == 0;
+    tgt = L.ota - 1;
+  }
+  // missile_wait = randint(7, 17) is drawn iff the launch is attempted (env_base.py:228-230)
+  const int agent_draws = quad_ballot(want_missile) & 1;
+  int new_wait = 0;
+  if (u == 0 && want_missile) new_wait = randint_from(7, 17, g_random_at(rng, L.dg));
+  L.dg += agent_draws;
+
+  // ---- scripted opponents, id order, shared escape state (env_hetero.py:118-158)
+#pragma unroll 1
+  for (int k = 2; k < 4; ++k) {
+    const bool k_alive = (alive_pre >> k) & 1;
+    const bool k_hasm = qshfl((int)L.hasm, k) != 0;
+    const int k_mwait = qshfl(L.mwait, k);
+    const int k_near = qshfl(near_t, k);
+    const double k_dn = qshfl(near_dn, k);
+    const double k_focus = qshfl(rel_focus, k);
+    const int k_sign = qshfl(rel_sign, k);
+    const double k_lat = qshfl(L.lat, k), k_lon = qshfl(L.lon, k), k_hdg = qshfl(L.hdg, k);
+    const OppDecision d = scripted_opponent<LEVEL>(L, rng, g, k, k_alive, k_hasm, k_mwait, k_lat, k_lon, k_hdg,
+                                                   k_near, k_dn, k_focus, k_sign);
+    if (u == k && k_alive) {
+      if (d.set_hs) {
+        set_heading(L, d.heading);
+        set_speed(L, u, d.speed);
+      }
+      if (d.fire) fire_cannon(L, u);
+      want_missile = d.want_missile;
+      tgt = d.tgt;
+    }
+  }
+
+  // ---- launches (Rafale.fire_missile, ac1.py:72-79): shooters 0 and 2 in parallel, ids in id order
+  const int tq = tgt < 0 ? 0 : tgt;
+  const double tlat = pick4d(lat4[0], lat4[1], lat4[2], lat4[3], tq);
+  const double tlon = pick4d(lon4[0], lon4[1], lon4[2], lon4[3], tq);
+  const bool launched = try_launch(L, want_missile, tlat, tlon, tq);
+  const int launch_m = quad_ballot(launched);
+  if (launched) L.rid = L.next_id + __popc(launch_m & ((1 << u) - 1));
+  L.next_id += __popc(launch_m);
+  if (want_missile) {
+    if (u < 2) {
+      L.mwait = new_wait;
+      if (MODE == 1 && L.mrem < 3) rew -= 0.1;
+    } else {
+      L.mwait = LEVEL == 3 ? 10 : 5;
+    }
+  }
+  if (u < 2 && L.alive && L.mwait > 0 && !L.hasm) L.mwait -= 1;  // env_base.py:235-236
+
+  // ===================================================== CmanoSimulator.do_tick, cmano_simulator.py:138-157
+  const int alive0 = alive_pre;                  // snapshot: nothing dies in the action phase
+  const bool upd = L.alive;
+  const bool rocket0 = L.ralive;                 // snapshot includes rockets launched this step
+  const double max_deg = is_ac1(u) ? 5.0 : 3.5, max_kn = is_ac1(u) ? 35.0 : 28.0;
+  if (upd) {                                     // ac1.py:82-99
+    if (L.hdg != L.nhdg) {
+      const double delta = signed_heading_diff(L.hdg, L.nhdg);
+      L.hdg = fabs(delta) <= max_deg ? L.nhdg : pymod(L.hdg + (delta >= 0.0 ? max_deg : -max_deg), 360.0);
+    }
+    if (L.spd != L.nspd) {
+      const double delta = L.nspd - L.spd;
+      L.spd = fabs(delta) <= max_kn ? L.nspd : L.spd + (delta >= 0.0 ? max_kn : -max_kn);
+    }
+  }
+  const bool firing = upd && L.burst > 0;        // ac1.py:101-104
+  if (firing) {
+    L.burst -= 1;
+    L.crem = L.crem > 0 ? L.crem - 1 : 0;
+  }
+  // every unit's move (Unit.update, cmano_simulator.py:65-72) depends only on itself
+  double nlat = L.lat, nlon = L.lon;
+  if (upd && L.spd > 0.0) {
+    const double2 p = geo::direct(L.lat, L.lon, L.hdg, L.spd * kKnotsToMs * 1.0);
+    nlat = p.x;
+    nlon = p.y;
+  }
+  // cannon geometry: shooter u sees lower ids at their NEW position, higher ids at the OLD one,
+  // itself at its old position with its new heading (ac1.py:105-115, A.3 of SURVEY.md)
+  int in_range = 0;
+  {
+    const double range = is_ac1(u) ? 2.0 : 4.5, half_w = (is_ac1(u) ? 10.0 : 7.0) / 2.0;
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      const double jl_new = qshfl(nlat, j), jo_new = qshfl(nlon, j);
+      const double jl_old = qshfl(L.lat, j), jo_old = qshfl(L.lon, j);   // L.lat/lon are still pre-tick here
+      const double jl = j < u ? jl_new : jl_old;
+      const double jo = j < u ? jo_new : jo_old;
+      const bool group_ok = P.friendly_kill || ((u < 2) != (j < 2));
+      if (firing && j != u && ((alive0 >> j) & 1) && group_ok)
+        if (unit_in_cannon_range(L.lat, L.lon, L.hdg, jl, jo, range, half_w)) in_range |= 1 << j;
+    }
+  }
+  // kill resolution in (shooter, target) id order; C-stream draws only for live in-range targets
+  int alive_m = alive0;
+  unsigned killer_pack = 0;  // 4 bits per victim: killer id (0 = none)
+  int by_rocket_m = 0;
+  {
+    const unsigned inr_pack = (unsigned)qshfl(in_range, 0) | ((unsigned)qshfl(in_range, 1) << 4) |
+                              ((unsigned)qshfl(in_range, 2) << 8) | ((unsigned)qshfl(in_range, 3) << 12);
+    if (inr_pack != 0) {
+#pragma unroll 1
+      for (int k = 0; k < 4; ++k) {
+        const unsigned row = (inr_pack >> (4 * k)) & 0xFu;
+        if (row == 0) continue;
+        const double p_hit = (k & 1) ? 0.9 / (3.0 / 1.0) : 0.75 / (5.0 / 1.0);
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+          if (((row >> j) & 1) && ((alive_m >> j) & 1)) {
+            if (c_random_at(rng, L.dc++) < p_hit) {
+              alive_m &= ~(1 << j);
+              killer_pack |= (unsigned)(k + 1) << (4 * j);
+            }
+          }
+        }
+      }
+    }
+  }
+  // missile heading noise (ac1.py:117-128): G draws in shooter id order
+  {
+    const bool noise = upd && is_ac1(u) && L.hasm && rocket0;
+    if (upd && is_ac1(u) && L.hasm && !rocket0) L.hasm = false;
+    const int noise_m = quad_ballot(noise);
+    if (noise) {
+      const double f = uniform_from(0.95, 1.05, g_random_at(rng, L.dg + (u == 2 ? (noise_m & 1) : 0)));
+      L.rnhdg = clip(__dmul_rn(L.rhdg, f), 0.0, 359.0);
+    }
+    L.dg += __popc(noise_m);
+  }
+  if (upd) {
+    L.lat = nlat;
+    L.lon = nlon;
+  }
+  // rockets (rocket_unit.py:37-73), after every aircraft, in launch (id) order
+  {
+    const int t = L.rtgt > 0 ? L.rtgt - 1 : 0;
+    const double t_lat = qshfl(L.lat, t), t_lon = qshfl(L.lon, t);     // targets have already moved
+    const double f_lat = qshfl(L.lat, 1), f_lon = qshfl(L.lon, 1);     // "friendly" is always id 2 (A.6.5)
+    bool hit_t = false, hit_f = false;
+    if (rocket0) {
+      hit_t = within_1km(L.rlat, L.rlon, t_lat, t_lon);
+      if (P.friendly_kill && ((alive_m >> 1) & 1)) hit_f = within_1km(L.rlat, L.rlon, f_lat, f_lon);
+    }
+    const int live_m = quad_ballot(rocket0), hit_t_m = quad_ballot(hit_t), hit_f_m = quad_ballot(hit_f);
+    const int rid0 = qshfl(L.rid, 0), rid2 = qshfl(L.rid, 2);
+    const int tg0 = qshfl(t, 0), tg2 = qshfl(t, 2);
+    int exploded_m = 0;
+    if (live_m != 0) {
+      const int first = ((live_m & 5) == 5) ? (rid0 < rid2 ? 0 : 2) : ((live_m & 1) ? 0 : 2);
+#pragma unroll 1
+      for (int n = 0; n < 2; ++n) {
+        const int s = n == 0 ? first : 2 - first;
+        if (!((live_m >> s) & 1)) continue;
+        const int tt = s == 0 ? tg0 : tg2;
+        if (((hit_t_m >> s) & 1) && ((alive_m >> tt) & 1)) {
+          alive_m &= ~(1 << tt);
+          killer_pack |= (unsigned)(s + 1) << (4 * tt);
+          by_rocket_m |= 1 << tt;
+          exploded_m |= 1 << s;
+        } else if (((hit_f_m >> s) & 1) && ((alive_m >> 1) & 1)) {
+          alive_m &= ~2;
+          killer_pack |= (unsigned)(s + 1) << 4;
+          by_rocket_m |= 2;
+          exploded_m |= 1 << s;
+        }
+      }
+    }
+    if (rocket0) {
+      if ((exploded_m >> u) & 1) {
+        L.ralive = false;
+      } else if (L.rage > 10) {
+        L.ralive = false;
+      } else {
+        if (L.rhdg != L.rnhdg) {
+          const double delta = signed_heading_diff(L.rhdg, L.rnhdg);
+          L.rhdg = fabs(delta) <= 10.0 ? L.rnhdg : L.rhdg + (delta >= 0.0 ? 10.0 : -10.0);
+        }
+        const double2 p = geo::direct(L.rlat, L.rlon, L.rhdg, rocket_speed(L.rage) * kKnotsToMs * 1.0);
+        L.rlat = p.x;
+        L.rlon = p.y;
+        L.rage += 1;
+      }
+    }
+  }
+  L.alive = (alive_m >> u) & 1;
+
+  // ===================================================== _get_rewards / _combat_rewards
+  // (env_hetero.py:188-225, env_base.py:240-310), evaluated identically in the four lanes
+  {
+    const double s = P.rew_scale;
+    const int oob_m = quad_ballot(L.alive && !in_boundary(g, L.lat, L.lon));
+    if ((oob_m >> u) & 1) L.alive = false;
+    alive_m &= ~oob_m;
+    double rews0 = 0.0, rews1 = 0.0;
+    int destroyed_m = oob_m & 3;
+    if (oob_m & 1) rews0 += -5.0 * s;
+    if (oob_m & 2) rews1 += -5.0 * s;
+    L.alive_ag -= __popc(oob_m & 3);
+    L.alive_op -= __popc(oob_m & 12);
+    const double of0 = qshfl(opp_focus, 0), of1 = qshfl(opp_focus, 1);
+    const int cr0 = qshfl(L.crem, 0), cr1 = qshfl(L.crem, 1), cm0 = qshfl(L.cmax, 0), cm1 = qshfl(L.cmax, 1);
+    const int mr0 = qshfl(L.mrem, 0), rm0 = qshfl(L.rmax, 0);
+    if (killer_pack != 0) {   // quad-uniform but warp-divergent: no shuffles inside
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = (killer_pack >> (4 * j)) & 0xF;
+        if (k == 0) continue;
+        double add0 = 0.0, add1 = 0.0;
+        if (k <= 2) {
+          if (j >= 2) {
+            if (MODE == 0) {
+              double r;
+              if ((by_rocket_m >> j) & 1)
+                r = (1.0 + 0.5 * ((double)mr0 / (double)rm0)) * s;       // only agent 1 carries missiles
+              else
+                r = ((0.5 + 0.5 * ((double)(k == 1 ? cr0 : cr1) / (double)(k == 1 ? cm0 : cm1))) +
+                     (0.5 + 0.5 * (k == 1 ? of0 : of1))) * s;
+              if (k == 1) add0 = r; else add1 = r;
+            }
+            L.alive_op -= 1;
+          } else {
+            if (k == 1) add0 = -2.0 * s; else add1 = -2.0 * s;
+            if (P.friendly_punish) {
+              if (j == 0) add0 += -2.0 * s; else add1 += -2.0 * s;
+              destroyed_m |= 1 << j;
+            }
+            L.alive_ag -= 1;
+          }
+        } else {
+          if (j < 2) {
+            if (j == 0) add0 = -2.0 * s; else add1 = -2.0 * s;
+            destroyed_m |= 1 << j;
+            L.alive_ag -= 1;
+          } else {
+            L.alive_op -= 1;
+          }
+        }
+        rews0 += add0;
+        rews1 += add1;
+      }
+    }
+    if (MODE == 1 && P.esc_dist_rew) {           // env_hetero.py:198-214 (per agent lane)
+      const double l2 = qshfl(L.lat, 2), o2 = qshfl(L.lon, 2), l3 = qshfl(L.lat, 3), o3 = qshfl(L.lon, 3);
+      double mine = 0.0;
+      if (u < 2 && L.alive) {
+        const double d2 = dist_raw(L.lat, L.lon, l2, o2), d3 = dist_raw(L.lat, L.lon, l3, o3);
+        const bool has2 = (alive_m >> 2) & 1, has3 = (alive_m >> 3) & 1;
+        const bool swap = has2 && has3 && (g.inv_diag * d3) < (g.inv_diag * d2);
+        const double first = has2 ? (swap ? d3 : d2) : d3, second = swap ? d2 : d3;
+        const int n = (int)has2 + (int)has3;
+        for (int j = 1; j <= n; ++j) {
+          const double od = j == 1 ? first : second;
+          if (od < 0.06) {
+            mine += -0.02 / j;
+            if (L.spd < 200.0) mine += -0.02 / j;
+          } else if (od > 0.13) {
+            mine += 0.02 / j;
+            if (L.spd > 500.0) mine += 0.02 / j;
+          }
+        }
+      }
+      rews0 += qshfl(mine, 0);
+      rews1 += qshfl(mine, 1);
+    }
+    if (u < 2 && present && (L.alive || ((destroyed_m >> u) & 1))) {
+      const double own = u == 0 ? rews0 : rews1, other = u == 0 ? rews1 : rews0;
+      rew += (P.glob_frac > 0.0 && MODE == 0) ? own + P.glob_frac * other : own;
+    }
+  }
+
+  // ===================================================== HHMARLBaseEnv.step, env_base.py:89-90
+  const bool done = L.alive_ag <= 0 || L.alive_op <= 0 || L.steps >= P.horizon;
+  {
+    const double r1 = qshfl(rew, 1);
+    if (valid && u == 0) {
+      if (rew_out) reinterpret_cast<float2*>(rew_out)[a] = make_float2((float)rew, (float)r1);
+      if (done_out) done_out[a] = done ? 1 : 0;
+    }
+  }
+  if (done && P.autoreset) reset_lane(L, rng, P, u);
+  write_agent_obs<MODE>(L, g, u, obs1, obs2, s1, s2, arena0, n_valid);
+  store_lane(S, a, u, L, valid);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -127,28 +418,28 @@ template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 reset_kernel(StatePtrs S, Params P, const uint8_t* __restrict__ mask, int first_time, float* __restrict__ obs1,
              float* __restrict__ obs2) {
-  __shared__ __align__(16) float s1[kThreads * ObsDims<MODE>::D1];
-  __shared__ __align__(16) float s2[kThreads * ObsDims<MODE>::D2];
-  const int arena0 = blockIdx.x * kThreads;
-  const int a = arena0 + threadIdx.x;
-  const bool valid = a < P.n_arenas;
-  const int n_valid = min(kThreads, P.n_arenas - arena0);
+  __shared__ __align__(16) float s1[kArenasPerCta * ObsDims<MODE>::D1];
+  __shared__ __align__(16) float s2[kArenasPerCta * ObsDims<MODE>::D2];
+  const int u = threadIdx.x & 3;
+  const int arena0 = blockIdx.x * kArenasPerCta;
+  const int a_raw = arena0 + (threadIdx.x >> 2);
+  const bool valid = a_raw < P.n_arenas;
+  const int a = valid ? a_raw : P.n_arenas - 1;
+  const int n_valid = min(kArenasPerCta, P.n_arenas - arena0);
   const Geom g = make_geom(P.map_size);
-  Arena A;
-  if (valid) {
-    const Rng rng{P.seed_lo, P.seed_hi, P.arena_base + (uint32_t)a};
-    if (first_time) {
-      A.dg = 0;
-      A.dc = 0;
-      A.err = 0;
-      reset_arena(A, rng, P);
-    } else {
-      load_arena(S, a, A);
-      if (!mask || mask[a]) reset_arena(A, rng, P);
-    }
+  const Rng rng{P.seed_lo, P.seed_hi, P.arena_base + (uint32_t)a};
+  Lane L;
+  if (first_time) {
+    L.dg = 0;
+    L.dc = 0;
+    L.err = 0;
+    reset_lane(L, rng, P, u);
+  } else {
+    load_lane(S, a, u, L);
+    if (!mask || mask[a]) reset_lane(L, rng, P, u);
   }
-  write_agent_obs<MODE>(A, g, obs1, obs2, s1, s2, arena0, n_valid, valid);
-  if (valid) store_arena(S, a, A);
+  write_agent_obs<MODE>(L, g, u, obs1, obs2, s1, s2, arena0, n_valid);
+  store_lane(S, a, u, L, valid);
 }
 
 }  // namespace hh
@@ -295,7 +586,7 @@ extern "C" uint64_t hh_launch_count(const hh_env* e) { return e ? e->launches : 
 extern "C" int hh_reset(hh_env* e, const uint8_t* mask_dev, float* obs1, float* obs2, void* stream) {
   if (!e) return fail(-1, "hh_reset: null env");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int blocks = (e->n + kThreads - 1) / kThreads;
+  const int blocks = (e->n + kArenasPerCta - 1) / kArenasPerCta;
   const int first = e->initialised ? 0 : 1;
   if (e->cfg.agent_mode == 0)
     reset_kernel<0><<<blocks, kThreads, 0, st>>>(e->S, e->P, mask_dev, first, obs1, obs2);
@@ -310,7 +601,7 @@ extern "C" int hh_reset(hh_env* e, const uint8_t* mask_dev, float* obs1, float* 
 template <int LEVEL>
 static void launch_step(hh_env* e, const int32_t* actions, float* obs1, float* obs2, float* rew, uint8_t* done,
                         cudaStream_t st) {
-  const int blocks = (e->n + kThreads - 1) / kThreads;
+  const int blocks = (e->n + kArenasPerCta - 1) / kArenasPerCta;
   if (e->cfg.agent_mode == 0)
     step_kernel<LEVEL, 0><<<blocks, kThreads, 0, st>>>(e->S, e->P, actions, obs1, obs2, rew, done);
   else
