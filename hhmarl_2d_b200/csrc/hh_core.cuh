@@ -80,7 +80,7 @@ __device__ __forceinline__ double c_random_at(const Rng& r, unsigned int idx) {
 
 // ------------------------------------------------------------------------------------- scalar helpers
 __device__ __forceinline__ double pymod(double x, double m) {  // CPython float %, m > 0
-  double r = fmod(x, m);
+  double r = m::fmod_(x, m);
   if (r != 0.0 && r < 0.0) r += m;
   return r;
 }
@@ -133,7 +133,7 @@ struct HVec {
 __device__ __forceinline__ HVec heading_vec(double heading) {
   HVec h;
   double th = pymod(90.0 - heading, 360.0) * (geo::kPi / 180.0);
-  sincos(th, &h.s, &h.c);
+  m::sincos_(th, &h.s, &h.c);
   h.n = sqrt(h.c * h.c + h.s * h.s);
   return h;
 }
@@ -141,7 +141,7 @@ __device__ __forceinline__ HVec heading_vec(double heading) {
 __device__ __forceinline__ double focus_deg(const HVec& ha, double lat_a, double lon_a, double lat_b, double lon_b) {
   double v0 = lon_b - lon_a, v1 = lat_b - lat_a;
   double x = clip((ha.c * v0 + ha.s * v1) / (ha.n * sqrt(v0 * v0 + v1 * v1) + 1e-10), -1.0, 1.0);
-  return acos(x) * (180.0 / geo::kPi);
+  return m::acos_(x) * (180.0 / geo::kPi);
 }
 __device__ __forceinline__ double focus_norm_from_deg(double deg) { return clip(deg / 180.0, 0.0, 1.0); }
 // env_base.py:441-446
@@ -149,11 +149,11 @@ __device__ __forceinline__ double aspect_from_deg(double deg) { return clip((180
 // env_base.py:448-456
 __device__ __forceinline__ double hdiff_norm(const HVec& a, const HVec& b) {
   double x = clip((a.c * b.c + a.s * b.s) / (a.n * b.n + 1e-10), -1.0, 1.0);
-  return clip((acos(x) * (180.0 / geo::kPi)) / 180.0, 0.0, 1.0);
+  return clip((m::acos_(x) * (180.0 / geo::kPi)) / 180.0, 0.0, 1.0);
 }
 // env_base.py:434-439
 __device__ __forceinline__ double dist_raw(double lat_a, double lon_a, double lat_b, double lon_b) {
-  return hypot(lon_b - lon_a, lat_b - lat_a);
+  return m::hypot_(lon_b - lon_a, lat_b - lat_a);
 }
 __device__ __forceinline__ double hdg_feature(double heading) {
   return clip(pymod(heading, 359.0) / 359.0, 0.0, 1.0);
@@ -170,7 +170,7 @@ __device__ __forceinline__ bool angle_in_radar_range(double heading, double angl
 __device__ __forceinline__ int correct_angle_sign(double lat_o, double lon_o, double hdg_o, double lat_a,
                                                   double lon_a) {
   double s, c;
-  sincos(pymod(hdg_o, 360.0) * (geo::kPi / 180.0), &s, &c);
+  m::sincos_(pymod(hdg_o, 360.0) * (geo::kPi / 180.0), &s, &c);
   double x1 = lon_o + rint(s * 1000.0) / 1000.0;  // round(sin, 3)
   double y1 = lat_o + rint(c * 1000.0) / 1000.0;
   double val = (x1 - lon_o) * (lat_a - lat_o) - (lon_a - lon_o) * (y1 - lat_o);
@@ -180,7 +180,7 @@ __device__ __forceinline__ int correct_angle_sign(double lat_o, double lon_o, do
 // ------------------------------------------------------------------------------------- range tests
 // The reference decides cannon hits and rocket proximity from the WGS84 geodesic distance
 // (units_distance_km, cmano_simulator.py:167-169).  On the ellipsoid the metric satisfies
-//   ds >= 109.6 km/deg * hypot(dlat, dlon)   for |lat| <= 10 deg
+//   ds >= 109.6 km/deg * m::hypot_(dlat, dlon)   for |lat| <= 10 deg
 // (meridional arc >= 110.574 km/deg everywhere, parallel arc >= 111.320*cos(10 deg) = 109.63 km/deg),
 // so a pair whose flat separation already exceeds range / 109.6 deg is out of range with
 // certainty and the ~2.5 k-instruction inverse solve is skipped; everything closer goes through
@@ -190,7 +190,7 @@ constexpr double kKmPerDegLower = 109.6;
 // ac1.py:135-142 / ac2.py:109-116
 __device__ __forceinline__ bool unit_in_cannon_range(double lat_s, double lon_s, double hdg_s, double lat_t,
                                                      double lon_t, double range_km, double half_width) {
-  double h = hypot(lon_t - lon_s, lat_t - lat_s);
+  double h = m::hypot_(lon_t - lon_s, lat_t - lat_s);
   if (h * kKmPerDegLower >= range_km) return false;
   double2 inv = geo::inverse(lat_s, lon_s, lat_t, lon_t);
   if (inv.x / 1000.0 < range_km) {
@@ -201,7 +201,7 @@ __device__ __forceinline__ bool unit_in_cannon_range(double lat_s, double lon_s,
 }
 // rocket_unit.py:39,49: units_distance_km(self, x) < 1
 __device__ __forceinline__ bool within_1km(double lat_r, double lon_r, double lat_t, double lon_t) {
-  double h = hypot(lon_t - lon_r, lat_t - lat_r);
+  double h = m::hypot_(lon_t - lon_r, lat_t - lat_r);
   if (h * kKmPerDegLower >= 1.0) return false;
   return geo::inverse(lat_r, lon_r, lat_t, lon_t).x / 1000.0 < 1.0;
 }

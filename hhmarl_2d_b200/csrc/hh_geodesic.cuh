@@ -17,6 +17,20 @@
 #include <math.h>
 
 namespace hh {
+
+// libdevice's FP64 sincos/atan2/acos/hypot/fmod expand to 60-250 instructions at EVERY call site.
+// The step kernel has ~80 such sites; inlined it is ~200 KB of SASS streamed once per warp and the
+// profile (profiles/r1b_*) shows instruction fetch as the top stall.  One shared copy of each keeps
+// the hot math inside the 32 KB L1.5 instruction cache; the call costs ~10 cycles.
+namespace m {
+__device__ __noinline__ void sincos_(double x, double* s, double* c) { ::sincos(x, s, c); }
+__device__ __noinline__ void sincospi_(double x, double* s, double* c) { ::sincospi(x, s, c); }
+__device__ __noinline__ double atan2_(double y, double x) { return ::atan2(y, x); }
+__device__ __noinline__ double acos_(double x) { return ::acos(x); }
+__device__ __noinline__ double hypot_(double x, double y) { return ::hypot(x, y); }
+__device__ __noinline__ double fmod_(double x, double y) { return ::fmod(x, y); }
+}  // namespace m
+
 namespace geo {
 
 constexpr double kA = 6378137.0;
@@ -77,7 +91,7 @@ constexpr double kEtol2 = 3.6424611488788524e-08;  // 0.1*tol2/sqrt(max(.001,|f|
 __device__ __forceinline__ double sq(double x) { return x * x; }
 
 __device__ __forceinline__ void norm2(double& s, double& c) {
-  double r = 1.0 / hypot(s, c);
+  double r = 1.0 / m::hypot_(s, c);
   s *= r;
   c *= r;
 }
@@ -101,7 +115,7 @@ __device__ __forceinline__ void sincosd(double x, double& sx, double& cx) {
   double q = rint(x / 90.0);
   double r = fma(-90.0, q, x);
   double s, c;
-  sincospi(r * (1.0 / 180.0), &s, &c);
+  m::sincospi_(r * (1.0 / 180.0), &s, &c);
   int iq = (int)q & 3;
   double ss = (iq & 1) ? c : s;
   double cc = (iq & 1) ? s : c;
@@ -123,7 +137,7 @@ __device__ __forceinline__ double atan2d(double y, double x) {
     x = -x;
     ++q;
   }
-  double ang = atan2(y, x) * (180.0 / kPi);
+  double ang = m::atan2_(y, x) * (180.0 / kPi);
   if (q == 1) ang = copysign(180.0, y) - ang;
   else if (q == 2) ang = 90.0 - ang;
   else if (q == 3) ang = -90.0 + ang;
@@ -254,7 +268,7 @@ __device__ __noinline__ double2 direct(double lat1, double lon1, double azi1, do
   norm2(sbet1, cbet1);
   cbet1 = fmax(kTiny, cbet1);
   double salp0 = salp1 * cbet1;
-  double calp0 = hypot(calp1, salp1 * sbet1);
+  double calp0 = m::hypot_(calp1, salp1 * sbet1);
   double ssig1 = sbet1, somg1 = salp0 * sbet1;
   double csig1 = (sbet1 != 0.0 || calp1 != 0.0) ? cbet1 * calp1 : 1.0;
   double comg1 = csig1;
@@ -265,7 +279,7 @@ __device__ __noinline__ double2 direct(double lat1, double lon1, double azi1, do
   double A1m1 = A1m1f(eps);
   double B11 = S6(ssig1, csig1, C1f(eps));
   double s, c;
-  sincos(B11, &s, &c);
+  m::sincos_(B11, &s, &c);
   double stau1 = ssig1 * c + csig1 * s;
   double ctau1 = csig1 * c - ssig1 * s;
   C5 c3 = C3f(eps);
@@ -273,18 +287,18 @@ __device__ __noinline__ double2 direct(double lat1, double lon1, double azi1, do
   double B31 = S5(ssig1, csig1, c3);
 
   double tau12 = s12 / (kB * (1.0 + A1m1));
-  sincos(tau12, &s, &c);
+  m::sincos_(tau12, &s, &c);
   double B12 = -S6(stau1 * c + ctau1 * s, ctau1 * c - stau1 * s, C1pf(eps));
   double sig12 = tau12 - (B12 - B11);
   double ssig12, csig12;
-  sincos(sig12, &ssig12, &csig12);
+  m::sincos_(sig12, &ssig12, &csig12);
   double ssig2 = ssig1 * csig12 + csig1 * ssig12;
   double csig2 = csig1 * csig12 - ssig1 * ssig12;
   double sbet2 = calp0 * ssig2;
-  double cbet2 = hypot(salp0, calp0 * csig2);
+  double cbet2 = m::hypot_(salp0, calp0 * csig2);
   if (cbet2 == 0.0) cbet2 = csig2 = kTiny;
   double somg2 = salp0 * ssig2, comg2 = csig2;
-  double omg12 = atan2(somg2 * comg1 - comg2 * somg1, comg2 * comg1 + somg2 * somg1);
+  double omg12 = m::atan2_(somg2 * comg1 - comg2 * somg1, comg2 * comg1 + somg2 * somg1);
   double lam12 = omg12 + A3c * (sig12 + (S5(ssig2, csig2, c3) - B31));
   double lon12 = lam12 * (180.0 / kPi);
   double2 out;
@@ -324,7 +338,7 @@ __device__ __forceinline__ void lambda12(double sbet1, double cbet1, double dn1,
                                          double slam120, double clam120, bool diffp, Lam12Out& o) {
   if (sbet1 == 0.0 && calp1 == 0.0) calp1 = -kTiny;
   double salp0 = salp1 * cbet1;
-  double calp0 = hypot(calp1, salp1 * sbet1);
+  double calp0 = m::hypot_(calp1, salp1 * sbet1);
   double ssig1 = sbet1, somg1 = salp0 * sbet1;
   double csig1 = calp1 * cbet1, comg1 = csig1;
   norm2(ssig1, csig1);
@@ -338,10 +352,10 @@ __device__ __forceinline__ void lambda12(double sbet1, double cbet1, double dn1,
   double ssig2 = sbet2, somg2 = salp0 * sbet2;
   double csig2 = calp2 * cbet2, comg2 = csig2;
   norm2(ssig2, csig2);
-  double sig12 = atan2(fmax(0.0, csig1 * ssig2 - ssig1 * csig2) + 0.0, csig1 * csig2 + ssig1 * ssig2);
+  double sig12 = m::atan2_(fmax(0.0, csig1 * ssig2 - ssig1 * csig2) + 0.0, csig1 * csig2 + ssig1 * ssig2);
   double somg12 = fmax(0.0, comg1 * somg2 - somg1 * comg2) + 0.0;
   double comg12 = comg1 * comg2 + somg1 * somg2;
-  double eta = atan2(somg12 * clam120 - comg12 * slam120, comg12 * clam120 + somg12 * slam120);
+  double eta = m::atan2_(somg12 * clam120 - comg12 * slam120, comg12 * clam120 + somg12 * slam120);
   double k2 = sq(calp0) * kEp2;
   double eps = k2 / (2.0 * (1.0 + sqrt(1.0 + k2)) + k2);
   C5 c3 = C3f(eps);
@@ -394,7 +408,7 @@ __device__ __noinline__ double2 inverse(double lat1, double lon1, double lat2, d
     double q = rint(lon12 / 90.0);
     double r = ang_round(fma(-90.0, q, lon12) + lon12s);
     double s, c;
-    sincospi(r * (1.0 / 180.0), &s, &c);
+    m::sincospi_(r * (1.0 / 180.0), &s, &c);
     int iq = (int)q & 3;
     double ss = (iq & 1) ? c : s;
     double cc = (iq & 1) ? s : c;
@@ -442,7 +456,7 @@ __device__ __noinline__ double2 inverse(double lat1, double lon1, double lat2, d
     calp2 = 1.0;
     salp2 = 0.0;
     double ssig1 = sbet1, csig1 = calp1 * cbet1, ssig2 = sbet2, csig2 = calp2 * cbet2;
-    double sig12 = atan2(fmax(0.0, csig1 * ssig2 - ssig1 * csig2) + 0.0, csig1 * csig2 + ssig1 * ssig2);
+    double sig12 = m::atan2_(fmax(0.0, csig1 * ssig2 - ssig1 * csig2) + 0.0, csig1 * csig2 + ssig1 * ssig2);
     // Lengths(n, ...) for s12b (m12b is only used for the sig12 >= 1 test, never true here)
     double A1 = 1.0 + A1m1f(kN);
     C6 ca = C1f(kN);
@@ -460,7 +474,7 @@ __device__ __noinline__ double2 inverse(double lat1, double lon1, double lat2, d
       sbetm2 /= sbetm2 + sq(cbet1 + cbet2);
       dnm = sqrt(1.0 + kEp2 * sbetm2);
       double omg12 = lam12 / (kF1 * dnm);
-      sincos(omg12, &somg12, &comg12);
+      m::sincos_(omg12, &somg12, &comg12);
     } else {
       somg12 = slam12;
       comg12 = clam12;
@@ -468,14 +482,14 @@ __device__ __noinline__ double2 inverse(double lat1, double lon1, double lat2, d
     salp1 = cbet2 * somg12;
     calp1 = comg12 >= 0.0 ? sbet12 + cbet2 * sbet1 * sq(somg12) / (1.0 + comg12)
                           : sbet12a - cbet2 * sbet1 * sq(somg12) / (1.0 - comg12);
-    double ssig12 = hypot(salp1, calp1);
+    double ssig12 = m::hypot_(salp1, calp1);
     double csig12 = sbet1 * sbet2 + cbet1 * cbet2 * comg12;
     double sig12 = -1.0;
     if (shortline && ssig12 < kEtol2) {
       salp2 = cbet1 * somg12;
       calp2 = sbet12 - cbet1 * sbet2 * (comg12 >= 0.0 ? sq(somg12) / (1.0 + comg12) : 1.0 - comg12);
       norm2(salp2, calp2);
-      sig12 = atan2(ssig12, csig12);
+      sig12 = m::atan2_(ssig12, csig12);
     }
     if (!(salp1 <= 0.0)) {
       norm2(salp1, calp1);
@@ -505,7 +519,7 @@ __device__ __noinline__ double2 inverse(double lat1, double lon1, double lat2, d
           double dalp1 = -vv / dv;
           if (fabs(dalp1) < kPi) {
             double sd, cd;
-            sincos(dalp1, &sd, &cd);
+            m::sincos_(dalp1, &sd, &cd);
             double nsalp1 = salp1 * cd + calp1 * sd;
             if (nsalp1 > 0.0) {
               calp1 = calp1 * cd - salp1 * sd;
