@@ -442,6 +442,21 @@ reset_kernel(StatePtrs S, Params P, const uint8_t* __restrict__ mask, int first_
   store_lane(S, a, u, L, valid);
 }
 
+// ------------------------------------------------------------------------------------------
+// test access to the device geodesics (hh_debug_geodesic)
+// ------------------------------------------------------------------------------------------
+__global__ void geodesic_debug_kernel(int mode, int n, const double* __restrict__ in, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double a = in[i], b = in[n + i], c = in[2 * n + i], d = in[3 * n + i];
+  double2 r;
+  if (mode == 0) r = geo::direct(a, b, c, d);
+  else if (mode == 1) r = geo::inverse(a, b, c, d);
+  else r = geo::inverse_local(a, b, c, d);
+  out[i] = r.x;
+  out[n + i] = r.y;
+}
+
 }  // namespace hh
 
 // ============================================================================================
@@ -490,6 +505,20 @@ static int obs_dim(const hh_config& c, int agent) {
 
 extern "C" const char* hh_last_error(void) { return g_last_error.c_str(); }
 extern "C" const char* hh_version(void) { return "hhmarl_2d_b200 0.1 (sm_100a)"; }
+
+extern "C" int hh_debug_geodesic(int32_t mode, int32_t n, const double* in_host, double* out_host) {
+  if (mode < 0 || mode > 2 || n <= 0 || !in_host || !out_host) return fail(-1, "hh_debug_geodesic: bad argument");
+  double *d_in = nullptr, *d_out = nullptr;
+  HH_CUDA(cudaMalloc(&d_in, sizeof(double) * 4 * n));
+  HH_CUDA(cudaMalloc(&d_out, sizeof(double) * 2 * n));
+  HH_CUDA(cudaMemcpy(d_in, in_host, sizeof(double) * 4 * n, cudaMemcpyHostToDevice));
+  geodesic_debug_kernel<<<(n + 127) / 128, 128>>>(mode, n, d_in, d_out);
+  HH_CUDA(cudaGetLastError());
+  HH_CUDA(cudaMemcpy(out_host, d_out, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost));
+  cudaFree(d_in);
+  cudaFree(d_out);
+  return 0;
+}
 
 extern "C" int hh_create(const hh_config* cfg, int32_t n_arenas, int32_t device, hh_env** out) {
   if (!cfg || !out) return fail(-1, "hh_create: null argument");

@@ -153,7 +153,8 @@ __device__ __forceinline__ double hdiff_norm(const HVec& a, const HVec& b) {
 }
 // env_base.py:434-439
 __device__ __forceinline__ double dist_raw(double lat_a, double lon_a, double lat_b, double lon_b) {
-  return m::hypot_(lon_b - lon_a, lat_b - lat_a);
+  const double dx = lon_b - lon_a, dy = lat_b - lat_a;  // math.hypot of two O(0.1) numbers
+  return sqrt(dx * dx + dy * dy);
 }
 __device__ __forceinline__ double hdg_feature(double heading) {
   return clip(pymod(heading, 359.0) / 359.0, 0.0, 1.0);
@@ -180,30 +181,57 @@ __device__ __forceinline__ int correct_angle_sign(double lat_o, double lon_o, do
 // ------------------------------------------------------------------------------------- range tests
 // The reference decides cannon hits and rocket proximity from the WGS84 geodesic distance
 // (units_distance_km, cmano_simulator.py:167-169).  On the ellipsoid the metric satisfies
-//   ds >= 109.6 km/deg * m::hypot_(dlat, dlon)   for |lat| <= 10 deg
+//   ds >= 109.6 km/deg * hypot(dlat, dlon)   for |lat| <= 10 deg
 // (meridional arc >= 110.574 km/deg everywhere, parallel arc >= 111.320*cos(10 deg) = 109.63 km/deg),
 // so a pair whose flat separation already exceeds range / 109.6 deg is out of range with
 // certainty and the ~2.5 k-instruction inverse solve is skipped; everything closer goes through
 // the exact solve.  The Boolean outcome is therefore identical to the reference's.
 constexpr double kKmPerDegLower = 109.6;
 
+// Decision margins for the local solution (see geo::inverse_local): inside them the exact solver
+// decides, outside them the local solution provably agrees with it.
+constexpr double kMarginDistM = 1e-3;     // 1 mm  (local error <= 4 um up to 7 km)
+constexpr double kMarginAziDeg = 1e-5;    //       (local error <= 2e-8 deg up to 7 km)
+constexpr double kMarginAziFarDeg = 1e-3; //       (local error <= 2e-6 deg up to 80 km)
+
 // ac1.py:135-142 / ac2.py:109-116
 __device__ __forceinline__ bool unit_in_cannon_range(double lat_s, double lon_s, double hdg_s, double lat_t,
                                                      double lon_t, double range_km, double half_width) {
-  double h = m::hypot_(lon_t - lon_s, lat_t - lat_s);
-  if (h * kKmPerDegLower >= range_km) return false;
-  double2 inv = geo::inverse(lat_s, lon_s, lat_t, lon_t);
+  const double dx = lon_t - lon_s, dy = lat_t - lat_s;
+  if (sqrt(dx * dx + dy * dy) * kKmPerDegLower >= range_km) return false;
+  const double range_m = range_km * 1000.0;
+  double2 inv = geo::inverse_local(lat_s, lon_s, lat_t, lon_t);
+  bool ambiguous = fabs(inv.x - range_m) < kMarginDistM;
+  if (!ambiguous) {
+    if (inv.x >= range_m) return false;
+    const double delta = fabs(signed_heading_diff(hdg_s, normalize_angle(inv.y)));
+    if (fabs(delta - half_width) >= kMarginAziDeg) return delta <= half_width;
+  }
+  inv = geo::inverse(lat_s, lon_s, lat_t, lon_t);  // razor-thin shell around a threshold: exact
   if (inv.x / 1000.0 < range_km) {
-    double delta = fabs(signed_heading_diff(hdg_s, normalize_angle(inv.y)));
+    const double delta = fabs(signed_heading_diff(hdg_s, normalize_angle(inv.y)));
     return delta <= half_width;
   }
   return false;
 }
 // rocket_unit.py:39,49: units_distance_km(self, x) < 1
 __device__ __forceinline__ bool within_1km(double lat_r, double lon_r, double lat_t, double lon_t) {
-  double h = m::hypot_(lon_t - lon_r, lat_t - lat_r);
-  if (h * kKmPerDegLower >= 1.0) return false;
+  const double dx = lon_t - lon_r, dy = lat_t - lat_r;
+  if (sqrt(dx * dx + dy * dy) * kKmPerDegLower >= 1.0) return false;
+  const double s = geo::inverse_local(lat_r, lon_r, lat_t, lon_t).x;
+  if (fabs(s - 1000.0) >= kMarginDistM) return s < 1000.0;
   return geo::inverse(lat_r, lon_r, lat_t, lon_t).x / 1000.0 < 1.0;
+}
+// Rafale.fire_missile's launch gate (ac1.py:75-76): distance <= 111 km and the skewed radar cone
+__device__ __forceinline__ bool launch_gate(double lat_s, double lon_s, double hdg_s, double lat_t, double lon_t) {
+  double2 inv = geo::inverse_local(lat_s, lon_s, lat_t, lon_t);
+  const double c = normalize_angle(hdg_s + 60.0);  // sum_angles(heading, 120/2), ac1.py:145
+  if (inv.x < 100000.0) {                           // certainly <= 111 km
+    const double delta = fabs(signed_heading_diff(c, normalize_angle(inv.y)));
+    if (fabs(delta - 61.0) >= kMarginAziFarDeg) return delta < 61.0;   // int(delta) <= 60
+  }
+  inv = geo::inverse(lat_s, lon_s, lat_t, lon_t);
+  return inv.x / 1000.0 <= 111.0 && angle_in_radar_range(hdg_s, normalize_angle(inv.y));
 }
 
 }  // namespace hh

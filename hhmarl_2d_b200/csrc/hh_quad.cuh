@@ -187,8 +187,7 @@ __device__ __forceinline__ int nearest_enemy(const Geom& g, int u, double lat, d
 __device__ __forceinline__ bool try_launch(Lane& L, bool want, double tlat, double tlon, int tgt_index) {
   bool launched = false;
   if (want && !L.hasm && L.mrem > 0) {
-    double2 inv = geo::inverse(L.lat, L.lon, tlat, tlon);
-    if (inv.x / 1000.0 <= 111.0 && angle_in_radar_range(L.hdg, normalize_angle(inv.y))) {
+    if (launch_gate(L.lat, L.lon, L.hdg, tlat, tlon)) {
       L.rlat = L.lat;
       L.rlon = L.lon;
       L.rhdg = L.hdg;

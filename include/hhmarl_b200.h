@@ -95,6 +95,13 @@ int hh_set_state(hh_env* env, const hh_state_view* in_host);
 /* Number of kernels this library has launched on behalf of `env` since creation. */
 uint64_t hh_launch_count(const hh_env* env);
 
+/* Test access to the device WGS84 solvers (replacing geographiclib's Geodesic.WGS84 as used at
+ * warsim/utils/geodesics.py:12-24).  in_host: f64[4][n], out_host: f64[2][n].
+ *   mode 0: direct  (lat1, lon1, azi1 [deg], s12 [m]) -> (lat2, lon2)
+ *   mode 1: inverse (lat1, lon1, lat2, lon2)          -> (s12 [m], azi1 [deg])   exact series
+ *   mode 2: inverse, local closed form used for threshold decisions (same outputs) */
+int hh_debug_geodesic(int32_t mode, int32_t n, const double* in_host, double* out_host);
+
 const char* hh_last_error(void);
 const char* hh_version(void);
 
