@@ -86,6 +86,10 @@ def lib() -> ctypes.CDLL:
     L.hh_reset.restype = ctypes.c_int
     L.hh_step.argtypes = [VP, VP, VP, VP, VP, VP, VP]
     L.hh_step.restype = ctypes.c_int
+    L.hh_step_begin.argtypes = [VP, VP, VP, VP, VP, VP]
+    L.hh_step_begin.restype = ctypes.c_int
+    L.hh_step_finish.argtypes = [VP, VP, VP, VP, VP, VP, VP]
+    L.hh_step_finish.restype = ctypes.c_int
     L.hh_reset_host.argtypes = [VP, VP, VP, VP]
     L.hh_reset_host.restype = ctypes.c_int
     L.hh_step_host.argtypes = [VP, VP, VP, VP, VP, VP]
@@ -104,7 +108,7 @@ def lib() -> ctypes.CDLL:
     return L
 
 
-EXPORTS = ["hh_create", "hh_destroy", "hh_n_arenas", "hh_obs_dim", "hh_reset", "hh_step", "hh_reset_host",
+EXPORTS = ["hh_create", "hh_destroy", "hh_n_arenas", "hh_obs_dim", "hh_reset", "hh_step", "hh_step_begin", "hh_step_finish", "hh_reset_host",
            "hh_step_host", "hh_get_state", "hh_set_state", "hh_launch_count", "hh_debug_geodesic", "hh_last_error", "hh_version"]
 
 

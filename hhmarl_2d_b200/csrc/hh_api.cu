@@ -55,130 +55,91 @@ __device__ __forceinline__ void write_agent_obs(Lane& L, const Geom& g, int u, f
 }
 
 // ------------------------------------------------------------------------------------------
-// step: levels 1-3 (scripted opponents) in one launch
+// step phases (shared by the fused level 1-3 kernel and the split level 4-5 kernels)
 // ------------------------------------------------------------------------------------------
-template <int LEVEL, int MODE>
-__global__ void __launch_bounds__(kThreads)
-step_kernel(StatePtrs S, Params P, const int32_t* __restrict__ actions, float* __restrict__ obs1,
-            float* __restrict__ obs2, float* __restrict__ rew_out, uint8_t* __restrict__ done_out) {
-  __shared__ __align__(16) float s1[kArenasPerCta * ObsDims<MODE>::D1];
-  __shared__ __align__(16) float s2[kArenasPerCta * ObsDims<MODE>::D2];
-  const int u = threadIdx.x & 3;
-  const int arena0 = blockIdx.x * kArenasPerCta;
-  const int a_raw = arena0 + (threadIdx.x >> 2);
-  const bool valid = a_raw < P.n_arenas;
-  const int a = valid ? a_raw : P.n_arenas - 1;  // tail lanes shadow the last arena, never store
-  const int n_valid = min(kArenasPerCta, P.n_arenas - arena0);
-  const Geom g = make_geom(P.map_size);
-  const Rng rng{P.seed_lo, P.seed_hi, P.arena_base + (uint32_t)a};
-  Lane L;
-  load_lane(S, a, u, L);
-  int4 act = make_int4(6, 0, 0, 0);
-  if (u < 2) act = reinterpret_cast<const int4*>(actions)[(size_t)a * 2 + u];
-
-  // ===================================================== LowLevelEnv._take_action, env_hetero.py:105-186
-  L.steps += 1;
-  const bool present = L.alive;       // agents: has an entry in the reward dict (env_hetero.py:168)
-  double rew = 0.0;
-
-  // ---- pre-tick geometry, one relation per lane, all four in parallel:
-  //   agents   : opp_stats[i][0] = focus_norm(opp_to_attack -> self)      (env_hetero.py:169-170)
-  //   opponents: nearest agent, and for level 3 sign / focus(self -> agent) (env_hetero.py:251-260)
+struct PreTick {  // pre-tick view of the four aircraft, identical in the four lanes
   double lat4[4], lon4[4], hdg4[4];
+  int alive_m;
+};
+__device__ __forceinline__ PreTick gather_pre(const Lane& L) {
+  PreTick p;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    lat4[j] = qshfl(L.lat, j);
-    lon4[j] = qshfl(L.lon, j);
-    hdg4[j] = qshfl(L.hdg, j);
+    p.lat4[j] = qshfl(L.lat, j);
+    p.lon4[j] = qshfl(L.lon, j);
+    p.hdg4[j] = qshfl(L.hdg, j);
   }
-  const int alive_pre = quad_ballot(L.alive);
-  double near_dn = 0.0;
-  int near_t = -1;
-  if (u >= 2 && L.alive) near_t = nearest_enemy(g, u, L.lat, L.lon, lat4, lon4, alive_pre, near_dn);
-  // relation "from X towards Y"
+  p.alive_m = quad_ballot(L.alive);
+  return p;
+}
+#define HH_P(field, i) pick4d(p.field[0], p.field[1], p.field[2], p.field[3], (i))
+
+// One flat-plane relation per lane, all four lanes in parallel:
+//   agents   : opp_stats[i][0] = focus(opp_to_attack -> self)              (env_hetero.py:169-170)
+//   opponents: nearest agent; with WITH_L3 also sign / focus(self -> agent) (env_hetero.py:251-260)
+template <bool WITH_L3>
+__device__ __forceinline__ void pre_tick_relations(const Lane& L, int u, const Geom& g, const PreTick& p, int& near_t,
+                                                   double& near_dn, double& rel_focus, int& rel_sign) {
+  near_dn = 0.0;
+  near_t = -1;
+  if (u >= 2 && L.alive) near_t = nearest_enemy(g, u, L.lat, L.lon, p.lat4, p.lon4, p.alive_m, near_dn);
   int rel_x = -1, rel_y = -1;
   if (u < 2) {
-    if (L.alive && L.ota != 0 && ((alive_pre >> (L.ota - 1)) & 1)) { rel_x = L.ota - 1; rel_y = u; }
-  } else if (LEVEL == 3 && near_t >= 0) {
+    if (L.alive && L.ota != 0 && ((p.alive_m >> (L.ota - 1)) & 1)) { rel_x = L.ota - 1; rel_y = u; }
+  } else if (WITH_L3 && near_t >= 0) {
     rel_x = u;
     rel_y = near_t;
   }
-  double rel_focus = 0.0;
-  int rel_sign = 1;
+  rel_focus = 0.0;
+  rel_sign = 1;
   if (rel_x >= 0) {
-    const double xlat = pick4d(lat4[0], lat4[1], lat4[2], lat4[3], rel_x);
-    const double xlon = pick4d(lon4[0], lon4[1], lon4[2], lon4[3], rel_x);
-    const double ylat = pick4d(lat4[0], lat4[1], lat4[2], lat4[3], rel_y);
-    const double ylon = pick4d(lon4[0], lon4[1], lon4[2], lon4[3], rel_y);
-    const double xh = pick4d(hdg4[0], hdg4[1], hdg4[2], hdg4[3], rel_x);
+    const double xlat = HH_P(lat4, rel_x), xlon = HH_P(lon4, rel_x), xh = HH_P(hdg4, rel_x);
+    const double ylat = HH_P(lat4, rel_y), ylon = HH_P(lon4, rel_y);
     rel_focus = focus_deg(heading_vec(xh), xlat, xlon, ylat, ylon);
     if (u >= 2) rel_sign = correct_angle_sign(xlat, xlon, xh, ylat, ylon);
   }
-  const double opp_focus = u < 2 ? focus_norm_from_deg(rel_focus) : 0.0;  // 0 when no opp_stats entry
+}
 
-  // ---- agents: _take_base_action (env_base.py:214-238), lanes 0 and 1 in parallel
-  bool want_missile = false;
-  int tgt = -1;
-  if (u < 2 && L.alive) {
+// _take_base_action (env_base.py:214-238) up to the launch decision, for the lanes with mine == true
+// (agents, or frozen-policy opponents at levels 4/5).  Also draws missile_wait = randint(7, 17), which the
+// reference consumes iff the launch is attempted (env_base.py:228-230); only an AC1 lane can attempt.
+template <int MODE>
+__device__ __forceinline__ void base_action(Lane& L, const Rng& rng, int u, bool mine, const int4 act, double& rew,
+                                            bool& want_missile, int& tgt, int& new_wait) {
+  want_missile = false;
+  tgt = -1;
+  new_wait = 0;
+  if (mine) {
     set_heading(L, pymod(L.hdg + (double)((act.x - 6) * 15), 360.0));
     set_speed(L, u, 100.0 + ((max_speed(u) - 100.0) / 8.0) * (double)act.y);
     if (act.z != 0 && L.crem > 0) {
       fire_cannon(L, u);
-      if (MODE == 1 && L.crem < 90) rew -= 0.1;
+      if (MODE == 1 && u < 2 && L.crem < 90) rew -= 0.1;
     }
     want_missile = is_ac1(u) && act.w != 0 && L.ota != 0 && L.mrem > 0 && !L.hasm && L.mwait == 0;
     tgt = L.ota - 1;
   }
-  // missile_wait = randint(7, 17) is drawn iff the launch is attempted (env_base.py:228-230)
-  const int agent_draws = quad_ballot(want_missile) & 1;
-  int new_wait = 0;
-  if (u == 0 && want_missile) new_wait = randint_from(7, 17, g_random_at(rng, L.dg));
-  L.dg += agent_draws;
+  const int draws = __popc(quad_ballot(want_missile));   // 0 or 1: lanes 0/1 or lanes 2/3 act, one AC1 among them
+  if (want_missile) new_wait = randint_from(7, 17, g_random_at(rng, L.dg));
+  L.dg += draws;
+}
 
-  // ---- scripted opponents, id order, shared escape state (env_hetero.py:118-158)
-#pragma unroll 1
-  for (int k = 2; k < 4; ++k) {
-    const bool k_alive = (alive_pre >> k) & 1;
-    const bool k_hasm = qshfl((int)L.hasm, k) != 0;
-    const int k_mwait = qshfl(L.mwait, k);
-    const int k_near = qshfl(near_t, k);
-    const double k_dn = qshfl(near_dn, k);
-    const double k_focus = qshfl(rel_focus, k);
-    const int k_sign = qshfl(rel_sign, k);
-    const double k_lat = qshfl(L.lat, k), k_lon = qshfl(L.lon, k), k_hdg = qshfl(L.hdg, k);
-    const OppDecision d = scripted_opponent<LEVEL>(L, rng, g, k, k_alive, k_hasm, k_mwait, k_lat, k_lon, k_hdg,
-                                                   k_near, k_dn, k_focus, k_sign);
-    if (u == k && k_alive) {
-      if (d.set_hs) {
-        set_heading(L, d.heading);
-        set_speed(L, u, d.speed);
-      }
-      if (d.fire) fire_cannon(L, u);
-      want_missile = d.want_missile;
-      tgt = d.tgt;
-    }
-  }
-
-  // ---- launches (Rafale.fire_missile, ac1.py:72-79): shooters 0 and 2 in parallel, ids in id order
+// Rafale.fire_missile (ac1.py:72-79) for every lane that wants to launch; rocket ids in shooter id order
+__device__ __forceinline__ void launch_phase(Lane& L, int u, const PreTick& p, bool want_missile, int tgt) {
   const int tq = tgt < 0 ? 0 : tgt;
-  const double tlat = pick4d(lat4[0], lat4[1], lat4[2], lat4[3], tq);
-  const double tlon = pick4d(lon4[0], lon4[1], lon4[2], lon4[3], tq);
-  const bool launched = try_launch(L, want_missile, tlat, tlon, tq);
+  const bool launched = try_launch(L, want_missile, HH_P(lat4, tq), HH_P(lon4, tq), tq);
   const int launch_m = quad_ballot(launched);
   if (launched) L.rid = L.next_id + __popc(launch_m & ((1 << u) - 1));
   L.next_id += __popc(launch_m);
-  if (want_missile) {
-    if (u < 2) {
-      L.mwait = new_wait;
-      if (MODE == 1 && L.mrem < 3) rew -= 0.1;
-    } else {
-      L.mwait = LEVEL == 3 ? 10 : 5;
-    }
-  }
-  if (u < 2 && L.alive && L.mwait > 0 && !L.hasm) L.mwait -= 1;  // env_base.py:235-236
+}
 
-  // ===================================================== CmanoSimulator.do_tick, cmano_simulator.py:138-157
-  const int alive0 = alive_pre;                  // snapshot: nothing dies in the action phase
+// CmanoSimulator.do_tick (cmano_simulator.py:138-157) + _get_rewards/_combat_rewards (env_hetero.py:188-225,
+// env_base.py:240-310).  `rew` enters with the action-phase penalties and leaves with the step reward of
+// the calling agent lane.  Returns done (env_base.py:89-90).
+template <int MODE>
+__device__ __forceinline__ bool tick_and_rewards(Lane& L, const Rng& rng, const Geom& g, const Params& P, int u,
+                                                 const PreTick& p, double opp_focus, bool present, double& rew) {
+  const int alive0 = p.alive_m;                  // snapshot: nothing dies in the action phase
   const bool upd = L.alive;
   const bool rocket0 = L.ralive;                 // snapshot includes rockets launched this step
   const double max_deg = is_ac1(u) ? 5.0 : 3.5, max_kn = is_ac1(u) ? 35.0 : 28.0;
@@ -200,9 +161,9 @@ step_kernel(StatePtrs S, Params P, const int32_t* __restrict__ actions, float* _
   // every unit's move (Unit.update, cmano_simulator.py:65-72) depends only on itself
   double nlat = L.lat, nlon = L.lon;
   if (upd && L.spd > 0.0) {
-    const double2 p = geo::direct(L.lat, L.lon, L.hdg, L.spd * kKnotsToMs * 1.0);
-    nlat = p.x;
-    nlon = p.y;
+    const double2 q = geo::direct(L.lat, L.lon, L.hdg, L.spd * kKnotsToMs * 1.0);
+    nlat = q.x;
+    nlon = q.y;
   }
   // cannon geometry: shooter u sees lower ids at their NEW position, higher ids at the OLD one,
   // itself at its old position with its new heading (ac1.py:105-115, A.3 of SURVEY.md)
@@ -304,17 +265,16 @@ step_kernel(StatePtrs S, Params P, const int32_t* __restrict__ actions, float* _
           const double delta = signed_heading_diff(L.rhdg, L.rnhdg);
           L.rhdg = fabs(delta) <= 10.0 ? L.rnhdg : L.rhdg + (delta >= 0.0 ? 10.0 : -10.0);
         }
-        const double2 p = geo::direct(L.rlat, L.rlon, L.rhdg, rocket_speed(L.rage) * kKnotsToMs * 1.0);
-        L.rlat = p.x;
-        L.rlon = p.y;
+        const double2 q = geo::direct(L.rlat, L.rlon, L.rhdg, rocket_speed(L.rage) * kKnotsToMs * 1.0);
+        L.rlat = q.x;
+        L.rlon = q.y;
         L.rage += 1;
       }
     }
   }
   L.alive = (alive_m >> u) & 1;
 
-  // ===================================================== _get_rewards / _combat_rewards
-  // (env_hetero.py:188-225, env_base.py:240-310), evaluated identically in the four lanes
+  // ---- rewards, evaluated identically in the four lanes
   {
     const double s = P.rew_scale;
     const int oob_m = quad_ballot(L.alive && !in_boundary(g, L.lat, L.lon));
@@ -396,19 +356,178 @@ step_kernel(StatePtrs S, Params P, const int32_t* __restrict__ actions, float* _
       rew += (P.glob_frac > 0.0 && MODE == 0) ? own + P.glob_frac * other : own;
     }
   }
+  return L.alive_ag <= 0 || L.alive_op <= 0 || L.steps >= P.horizon;   // env_base.py:89-90
+}
 
-  // ===================================================== HHMARLBaseEnv.step, env_base.py:89-90
-  const bool done = L.alive_ag <= 0 || L.alive_op <= 0 || L.steps >= P.horizon;
-  {
-    const double r1 = qshfl(rew, 1);
-    if (valid && u == 0) {
-      if (rew_out) reinterpret_cast<float2*>(rew_out)[a] = make_float2((float)rew, (float)r1);
-      if (done_out) done_out[a] = done ? 1 : 0;
-    }
+// terminal bookkeeping shared by the fused and the finishing kernel
+template <int MODE>
+__device__ __forceinline__ void finish_step(Lane& L, const Rng& rng, const Geom& g, const Params& P, const StatePtrs& S,
+                                            int a, int u, bool valid, bool done, double rew, float* obs1, float* obs2,
+                                            float* rew_out, uint8_t* done_out, float* s1, float* s2, int arena0,
+                                            int n_valid) {
+  const double r1 = qshfl(rew, 1);
+  if (valid && u == 0) {
+    if (rew_out) reinterpret_cast<float2*>(rew_out)[a] = make_float2((float)rew, (float)r1);
+    if (done_out) done_out[a] = done ? 1 : 0;
   }
   if (done && P.autoreset) reset_lane(L, rng, P, u);
   write_agent_obs<MODE>(L, g, u, obs1, obs2, s1, s2, arena0, n_valid);
   store_lane(S, a, u, L, valid);
+}
+
+#define HH_KERNEL_PROLOGUE                                                                        \
+  const int u = threadIdx.x & 3;                                                                  \
+  const int arena0 = blockIdx.x * kArenasPerCta;                                                  \
+  const int a_raw = arena0 + (threadIdx.x >> 2);                                                  \
+  const bool valid = a_raw < P.n_arenas;                                                          \
+  const int a = valid ? a_raw : P.n_arenas - 1; /* tail lanes shadow the last arena, never store */ \
+  const int n_valid = min(kArenasPerCta, P.n_arenas - arena0);                                    \
+  const Geom g = make_geom(P.map_size);                                                           \
+  const Rng rng{P.seed_lo, P.seed_hi, P.arena_base + (uint32_t)a};                                \
+  Lane L;                                                                                         \
+  load_lane(S, a, u, L);
+
+// ------------------------------------------------------------------------------------------
+// step, levels 1-3 (scripted opponents): one launch
+// ------------------------------------------------------------------------------------------
+template <int LEVEL, int MODE>
+__global__ void __launch_bounds__(kThreads)
+step_kernel(StatePtrs S, Params P, const int32_t* __restrict__ actions, float* __restrict__ obs1,
+            float* __restrict__ obs2, float* __restrict__ rew_out, uint8_t* __restrict__ done_out) {
+  __shared__ __align__(16) float s1[kArenasPerCta * ObsDims<MODE>::D1];
+  __shared__ __align__(16) float s2[kArenasPerCta * ObsDims<MODE>::D2];
+  HH_KERNEL_PROLOGUE
+  int4 act = make_int4(6, 0, 0, 0);
+  if (u < 2) act = reinterpret_cast<const int4*>(actions)[(size_t)a * 2 + u];
+
+  // LowLevelEnv._take_action, env_hetero.py:105-186
+  L.steps += 1;
+  const bool present = L.alive;       // agents: has an entry in the reward dict (env_hetero.py:168)
+  double rew = 0.0;
+  const PreTick p = gather_pre(L);
+  int near_t, rel_sign;
+  double near_dn, rel_focus;
+  pre_tick_relations<LEVEL == 3>(L, u, g, p, near_t, near_dn, rel_focus, rel_sign);
+  const double opp_focus = u < 2 ? focus_norm_from_deg(rel_focus) : 0.0;  // 0 when no opp_stats entry
+
+  bool want_missile;
+  int tgt, new_wait;
+  base_action<MODE>(L, rng, u, u < 2 && L.alive, act, rew, want_missile, tgt, new_wait);
+
+  // scripted opponents, id order, shared escape state (env_hetero.py:118-158)
+#pragma unroll 1
+  for (int k = 2; k < 4; ++k) {
+    const bool k_alive = (p.alive_m >> k) & 1;
+    const bool k_hasm = qshfl((int)L.hasm, k) != 0;
+    const int k_mwait = qshfl(L.mwait, k);
+    const int k_near = qshfl(near_t, k);
+    const double k_dn = qshfl(near_dn, k);
+    const double k_focus = qshfl(rel_focus, k);
+    const int k_sign = qshfl(rel_sign, k);
+    const double k_lat = qshfl(L.lat, k), k_lon = qshfl(L.lon, k), k_hdg = qshfl(L.hdg, k);
+    const OppDecision d = scripted_opponent<LEVEL>(L, rng, g, k, k_alive, k_hasm, k_mwait, k_lat, k_lon, k_hdg,
+                                                   k_near, k_dn, k_focus, k_sign);
+    if (u == k && k_alive) {
+      if (d.set_hs) {
+        set_heading(L, d.heading);
+        set_speed(L, u, d.speed);
+      }
+      if (d.fire) fire_cannon(L, u);
+      want_missile = d.want_missile;
+      tgt = d.tgt;
+    }
+  }
+  launch_phase(L, u, p, want_missile, tgt);
+  if (want_missile) {
+    if (u < 2) {
+      L.mwait = new_wait;
+      if (MODE == 1 && L.mrem < 3) rew -= 0.1;
+    } else {
+      L.mwait = LEVEL == 3 ? 10 : 5;   // env_hetero.py:123,136,158 (never decremented: SURVEY A.6.1)
+    }
+  }
+  if (u < 2 && L.alive && L.mwait > 0 && !L.hasm) L.mwait -= 1;  // env_base.py:235-236
+
+  const bool done = tick_and_rewards<MODE>(L, rng, g, P, u, p, opp_focus, present, rew);
+  finish_step<MODE>(L, rng, g, P, S, a, u, valid, done, rew, obs1, obs2, rew_out, done_out, s1, s2, arena0, n_valid);
+}
+
+// ------------------------------------------------------------------------------------------
+// step, levels 4-5 (frozen-policy opponents, env_base.py:349-398): the opponent's observation is
+// needed mid-step -- after the agents' fire decisions, before the tick -- so the step is split:
+//   step_begin_kernel : agents' _take_base_action, then lowlevel_state(opp_mode) of both opponents
+//   (batched opponent networks, outside this library)
+//   step_finish_kernel: opponents' _take_base_action with the per-head argmax, tick, rewards, obs
+// ------------------------------------------------------------------------------------------
+constexpr int kOppD3 = OBS_ESC_AC1, kOppD4 = OBS_ESC_AC2;   // row strides of the opponent-obs buffers (max over modes)
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+step_begin_kernel(StatePtrs S, Params P, const int32_t* __restrict__ actions, float* __restrict__ opp_obs3,
+                  float* __restrict__ opp_obs4, uint8_t* __restrict__ pset_out, float* __restrict__ rew_pre) {
+  __shared__ __align__(16) float s3[kArenasPerCta * kOppD3];
+  __shared__ __align__(16) float s4[kArenasPerCta * kOppD4];
+  HH_KERNEL_PROLOGUE
+  int4 act = make_int4(6, 0, 0, 0);
+  if (u < 2) act = reinterpret_cast<const int4*>(actions)[(size_t)a * 2 + u];
+  L.steps += 1;
+  double rew = 0.0;
+  const PreTick p = gather_pre(L);
+  bool want_missile;
+  int tgt, new_wait;
+  base_action<MODE>(L, rng, u, u < 2 && L.alive, act, rew, want_missile, tgt, new_wait);
+  launch_phase(L, u, p, want_missile, tgt);
+  if (want_missile) {
+    L.mwait = new_wait;
+    if (MODE == 1 && L.mrem < 3) rew -= 0.1;
+  }
+  if (u < 2 && L.alive && L.mwait > 0 && !L.hasm) L.mwait -= 1;
+  {
+    const double r1 = qshfl(rew, 1);
+    if (valid && u == 0 && rew_pre) reinterpret_cast<float2*>(rew_pre)[a] = make_float2((float)rew, (float)r1);
+    if (valid && u == 0 && pset_out) pset_out[a] = (uint8_t)L.pset;   // k of env_hetero.py:57 (0 below level 5)
+  }
+  // _policy_actions -> lowlevel_state(policy_type, opp id): the opponents already see this step's bursts / launches
+  const World W = gather_world(L, u);
+  const int al = threadIdx.x >> 2;
+  if (u >= 2) {
+    float* row = u == 2 ? s3 + al * kOppD3 : s4 + al * kOppD4;
+    const int len = obs_len(u, L.opp_mode), stride = u == 2 ? kOppD3 : kOppD4;
+    L.ota = unit_observation(L, W, g, u, L.opp_mode, row);
+    for (int k = len; k < stride; ++k) row[k] = 0.0f;
+  }
+  __syncwarp();
+  if (opp_obs3) flush_rows(opp_obs3 + (size_t)arena0 * kOppD3, s3, n_valid * kOppD3);
+  if (opp_obs4) flush_rows(opp_obs4 + (size_t)arena0 * kOppD4, s4, n_valid * kOppD4);
+  store_lane(S, a, u, L, valid);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+step_finish_kernel(StatePtrs S, Params P, const int32_t* __restrict__ opp_actions, const float* __restrict__ rew_pre,
+                   float* __restrict__ obs1, float* __restrict__ obs2, float* __restrict__ rew_out,
+                   uint8_t* __restrict__ done_out) {
+  __shared__ __align__(16) float s1[kArenasPerCta * ObsDims<MODE>::D1];
+  __shared__ __align__(16) float s2[kArenasPerCta * ObsDims<MODE>::D2];
+  HH_KERNEL_PROLOGUE
+  int4 act = make_int4(6, 0, 0, 0);
+  if (u >= 2) act = reinterpret_cast<const int4*>(opp_actions)[(size_t)a * 2 + (u - 2)];
+  const bool present = L.alive;
+  double rew = 0.0;
+  if (u < 2 && rew_pre) rew = (double)rew_pre[(size_t)a * 2 + u];
+  const PreTick p = gather_pre(L);
+  int near_t, rel_sign;
+  double near_dn, rel_focus;
+  pre_tick_relations<false>(L, u, g, p, near_t, near_dn, rel_focus, rel_sign);   // positions are still pre-tick
+  const double opp_focus = u < 2 ? focus_norm_from_deg(rel_focus) : 0.0;
+  bool want_missile;
+  int tgt, new_wait;
+  base_action<MODE>(L, rng, u, u >= 2 && L.alive, act, rew, want_missile, tgt, new_wait);
+  launch_phase(L, u, p, want_missile, tgt);
+  if (want_missile) L.mwait = new_wait;
+  if (u >= 2 && L.alive && L.mwait > 0 && !L.hasm) L.mwait -= 1;
+  const bool done = tick_and_rewards<MODE>(L, rng, g, P, u, p, opp_focus, present, rew);
+  finish_step<MODE>(L, rng, g, P, S, a, u, valid, done, rew, obs1, obs2, rew_out, done_out, s1, s2, arena0, n_valid);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -486,6 +605,8 @@ struct hh_env {
   size_t slab_bytes = 0;
   Params P{};
   bool initialised = false;
+  bool mid_step = false;
+  float* rew_pre = nullptr;
   uint64_t launches = 0;
   // host-variant staging
   cudaStream_t hstream = nullptr;
@@ -523,8 +644,7 @@ extern "C" int hh_debug_geodesic(int32_t mode, int32_t n, const double* in_host,
 extern "C" int hh_create(const hh_config* cfg, int32_t n_arenas, int32_t device, hh_env** out) {
   if (!cfg || !out) return fail(-1, "hh_create: null argument");
   if (n_arenas <= 0) return fail(-1, "hh_create: n_arenas must be positive");
-  if (cfg->level < 1 || cfg->level > 3)
-    return fail(-1, "hh_create: level must be 1..3 for the fused scripted-opponent kernel");
+  if (cfg->level < 1 || cfg->level > 5) return fail(-1, "hh_create: level must be 1..5");
   if (cfg->agent_mode != 0 && cfg->agent_mode != 1) return fail(-1, "hh_create: agent_mode must be 0 or 1");
   if (!(cfg->map_size > 0)) return fail(-1, "hh_create: map_size must be positive");
   if (cfg->horizon <= 0 || cfg->horizon > 65535) return fail(-1, "hh_create: horizon out of range");
@@ -600,6 +720,7 @@ extern "C" void hh_destroy(hh_env* e) {
   if (e->d_rew) cudaFree(e->d_rew);
   if (e->d_done) cudaFree(e->d_done);
   if (e->d_mask) cudaFree(e->d_mask);
+  if (e->rew_pre) cudaFree(e->rew_pre);
   if (e->pinned) cudaFreeHost(e->pinned);
   if (e->hstream) cudaStreamDestroy(e->hstream);
   delete e;
@@ -642,6 +763,8 @@ extern "C" int hh_step(hh_env* e, const int32_t* actions_dev, float* obs1, float
   if (!e) return fail(-1, "hh_step: null env");
   if (!e->initialised) return fail(-4, "hh_step: call hh_reset first");
   if (!actions_dev) return fail(-1, "hh_step: null actions");
+  if (e->cfg.level >= 4)
+    return fail(-5, "hh_step: levels 4/5 have frozen-policy opponents: use hh_step_begin / hh_step_finish");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (e->cfg.level) {
     case 1: launch_step<1>(e, actions_dev, obs1, obs2, rew, done, st); break;
@@ -650,6 +773,44 @@ extern "C" int hh_step(hh_env* e, const int32_t* actions_dev, float* obs1, float
   }
   HH_CUDA(cudaGetLastError());
   e->launches += 1;
+  return 0;
+}
+
+extern "C" int hh_step_begin(hh_env* e, const int32_t* actions_dev, float* opp_obs3_dev, float* opp_obs4_dev,
+                             uint8_t* policy_set_dev, void* stream) {
+  if (!e) return fail(-1, "hh_step_begin: null env");
+  if (!e->initialised) return fail(-4, "hh_step_begin: call hh_reset first");
+  if (e->cfg.level < 4) return fail(-5, "hh_step_begin: only levels 4/5 split the step");
+  if (!actions_dev || !opp_obs3_dev || !opp_obs4_dev) return fail(-1, "hh_step_begin: null argument");
+  if (!e->rew_pre) HH_CUDA(cudaMalloc(&e->rew_pre, sizeof(float) * 2 * (size_t)e->n));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = (e->n + kArenasPerCta - 1) / kArenasPerCta;
+  if (e->cfg.agent_mode == 0)
+    step_begin_kernel<0><<<blocks, kThreads, 0, st>>>(e->S, e->P, actions_dev, opp_obs3_dev, opp_obs4_dev, policy_set_dev,
+                                                      e->rew_pre);
+  else
+    step_begin_kernel<1><<<blocks, kThreads, 0, st>>>(e->S, e->P, actions_dev, opp_obs3_dev, opp_obs4_dev, policy_set_dev,
+                                                      e->rew_pre);
+  HH_CUDA(cudaGetLastError());
+  e->launches += 1;
+  e->mid_step = true;
+  return 0;
+}
+
+extern "C" int hh_step_finish(hh_env* e, const int32_t* opp_actions_dev, float* obs1, float* obs2, float* rew,
+                              uint8_t* done, void* stream) {
+  if (!e) return fail(-1, "hh_step_finish: null env");
+  if (!e->mid_step) return fail(-4, "hh_step_finish: call hh_step_begin first");
+  if (!opp_actions_dev) return fail(-1, "hh_step_finish: null opponent actions");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = (e->n + kArenasPerCta - 1) / kArenasPerCta;
+  if (e->cfg.agent_mode == 0)
+    step_finish_kernel<0><<<blocks, kThreads, 0, st>>>(e->S, e->P, opp_actions_dev, e->rew_pre, obs1, obs2, rew, done);
+  else
+    step_finish_kernel<1><<<blocks, kThreads, 0, st>>>(e->S, e->P, opp_actions_dev, e->rew_pre, obs1, obs2, rew, done);
+  HH_CUDA(cudaGetLastError());
+  e->launches += 1;
+  e->mid_step = false;
   return 0;
 }
 

@@ -32,7 +32,7 @@ class VecLowLevelEnv:
     """
 
     def __init__(self, n_arenas: int, args=None, device: int = 0, seed: int = 0, arena_base: int = 0,
-                 autoreset: bool = True):
+                 autoreset: bool = True, opponent_policies=None):
         self.args = args if args is not None else make_args()
         a = self.args
         if a.num_agents != 2 or a.num_opps != 2:
@@ -56,6 +56,9 @@ class VecLowLevelEnv:
         self._agent_ids = {1, 2}
         self._torch = None
         self._bufs = None
+        self._opp = None
+        self._opp_policies_arg = opponent_policies
+        self.level = int(a.level)
 
     # ------------------------------------------------------------------ device (torch) API
     def _ensure_torch(self):
@@ -97,9 +100,38 @@ class VecLowLevelEnv:
         if not (actions.is_cuda and actions.dtype == t.int32 and actions.is_contiguous()
                 and actions.numel() == self.n_arenas * 8):
             raise ValueError("actions must be a contiguous int32 CUDA tensor of shape [N, 2, 4]")
+        if self.level >= 4:
+            opp_actions = self.opponent_actions(actions)
+            nat.check(nat.lib().hh_step_finish(self._h, opp_actions.data_ptr(), b["obs1"].data_ptr(),
+                                               b["obs2"].data_ptr(), b["rew"].data_ptr(), b["done"].data_ptr(),
+                                               self._stream()), "hh_step_finish")
+            return b["obs1"], b["obs2"], b["rew"], b["done"]
         nat.check(nat.lib().hh_step(self._h, actions.data_ptr(), b["obs1"].data_ptr(), b["obs2"].data_ptr(),
                                     b["rew"].data_ptr(), b["done"].data_ptr(), self._stream()), "hh_step")
         return b["obs1"], b["obs2"], b["rew"], b["done"]
+
+    # ------------------------------------------------------------------ levels 4/5: frozen-policy opponents
+    def _ensure_opponents(self):
+        if self._opp is None:
+            from .opponents import OpponentPolicies
+            t = self._torch
+            dev = t.device("cuda", self.device_index)
+            n = self.n_arenas
+            self._opp = OpponentPolicies(self.level, self.args.agent_mode, self._opp_policies_arg, seed=0, device=dev)
+            self._opp_bufs = dict(obs3=t.empty((n, 30), dtype=t.float32, device=dev),
+                                  obs4=t.empty((n, 29), dtype=t.float32, device=dev),
+                                  pset=t.empty((n,), dtype=t.uint8, device=dev))
+        return self._opp
+
+    def opponent_actions(self, actions):
+        """First half of a level-4/5 step (hh_step_begin) + the batched opponent networks.
+        Returns the opponents' int32 [N,2,4] actions; leaves the env mid-step until hh_step_finish."""
+        opp = self._ensure_opponents()
+        ob = self._opp_bufs
+        nat.check(nat.lib().hh_step_begin(self._h, actions.data_ptr(), ob["obs3"].data_ptr(), ob["obs4"].data_ptr(),
+                                          ob["pset"].data_ptr(), self._stream()), "hh_step_begin")
+        self.last_opp_actions = opp.act(ob["obs3"], ob["obs4"], ob["pset"]).contiguous()
+        return self.last_opp_actions
 
     # ------------------------------------------------------------------ host (numpy) API
     def reset_host(self, mask: np.ndarray | None = None):
@@ -118,6 +150,10 @@ class VecLowLevelEnv:
         a = np.ascontiguousarray(actions, np.int32)
         if a.size != self.n_arenas * 8:
             raise ValueError("actions must have shape [N, 2, 4]")
+        if self.level >= 4:   # the opponent networks run on the device: go through the tensor API
+            t = self._ensure_torch() and self._torch
+            o1, o2, r, d = self.step(t.from_numpy(a.reshape(self.n_arenas, 2, 4)).cuda(self.device_index))
+            return o1.cpu().numpy(), o2.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy()
         if out is None:
             out = (np.empty((self.n_arenas, self.obs_dim[0]), np.float32),
                    np.empty((self.n_arenas, self.obs_dim[1]), np.float32),

