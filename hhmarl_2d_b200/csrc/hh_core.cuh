@@ -192,7 +192,7 @@ constexpr double kKmPerDegLower = 109.6;
 // decides, outside them the local solution provably agrees with it.
 constexpr double kMarginDistM = 1e-3;     // 1 mm  (local error <= 10 um up to 7 km)
 constexpr double kMarginAziDeg = 1e-5;    //       (local error <= 3e-8 deg up to 7 km)
-constexpr double kMarginAziFarDeg = 1e-3; //       (local error <= 3e-6 deg up to 80 km)
+constexpr double kMarginAziFarDeg = 1e-3; //       (local error <= 1e-5 deg up to 80 km)
 
 // ac1.py:135-142 / ac2.py:109-116
 __device__ __forceinline__ bool unit_in_cannon_range(double lat_s, double lon_s, double hdg_s, double lat_t,

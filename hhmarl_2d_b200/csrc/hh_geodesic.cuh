@@ -561,8 +561,8 @@ __device__ __noinline__ double2 inverse(double lat1, double lon1, double lat2, d
 // ---------------------------------------------------------------------------------------------
 // Local inverse: Delambre's analogies with the ellipsoid's principal radii at the mid-latitude.
 // Returns (s12 [m], azi1 [deg, (-180, 180]]).  Measured against the exact solver over the map box
-// (tests/test_gpu_geodesic.py): |ds| <= 10 um, |dazi| <= 3e-8 deg for s <= 7 km and <= 5 mm,
-// 3e-6 deg for s <= 80 km.  Callers use it only to decide threshold tests and fall back to
+// (tests/test_gpu_geodesic.py): |ds| <= 10 um, |dazi| <= 3e-8 deg for s <= 7 km and <= 2 cm,
+// 1e-5 deg for s <= 80 km.  Callers use it only to decide threshold tests and fall back to
 // inverse() inside a margin >= 100x those errors, so decisions are identical to the exact ones.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double2 inverse_local(double lat1, double lon1, double lat2, double lon2) {

@@ -35,6 +35,5 @@ def test_shared_layer_and_parameter_names():
     for n in ("inp1._model.0.weight", "att_act.in_proj_weight", "att_val.out_proj.bias", "shared_layer._model.0.weight",
               "v3._model.0.bias", "val_out._model.0.weight"):
         assert n in names
-    assert sum(p.numel() for p in p1.parameters()) == 423_852 + 0 or True
     a = M.deterministic_actions(torch.randn(5, 26), 1)
     assert a.shape == (5, 4) and (a[:, 0] < 13).all() and (a[:, 3] < 2).all()
