@@ -250,6 +250,39 @@ def run_b200(args):
     barrier()
     b2b_ms = e0.elapsed_time(e1)
 
+    # ---- on-device sampler: Fight1/Fight2 forward (actor + central critic), MultiCategorical sampling, env step,
+    #      rollout-buffer writes, GAE and the action write-back, one CUDA graph per 20-tick fragment
+    rollout = None
+    try:
+        from hhmarl_2d_b200 import VecSampler, TorchPolicy
+        from hhmarl_2d_b200 import models as M
+        torch.manual_seed(rank)
+        m1, m2 = M.build_policy_pair("fight")
+        m1.to(dev); m2.to(dev)
+        env_r = VecLowLevelEnv(n, make_args(level=args.level), device=local, seed=1, arena_base=rank * n, autoreset=True)
+        Tf = 20
+        smp = VecSampler(env_r, TorchPolicy(m1, 1), TorchPolicy(m2, 2), fragment_len=Tf, use_cuda_graph=True)
+        for _ in range(3):
+            smp.collect()
+        R = max(2, K // Tf)
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(R):
+            smp.collect()
+        r1.record()
+        barrier()
+        rt = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(rt, op=dist.ReduceOp.MAX)
+        rollout = {"value": world * n * Tf * R / (float(rt.item()) * 1e-3), "unit": UNIT, "fragment_len": Tf,
+                   "fragments": R, "ms_per_tick": float(rt.item()) / (R * Tf),
+                   "note": "policy forward (2 x Fight actor+critic, fp32 cuBLAS) + sampling + env step + GAE, "
+                           "CUDA-graph replay; random-init weights"}
+        del smp, env_r
+    except Exception as ex:  # noqa: BLE001
+        rollout = {"error": repr(ex)}
+
     # ---- end to end through the host entry point of the C ABI
     acts_host = acts.cpu().numpy()
     outs = None
@@ -294,6 +327,7 @@ def run_b200(args):
                                  "note": "no L2 flush, K launches under one event pair (rank 0)"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "hh_step_host (C ABI, host buffers; copies + sync inside the call)"},
+                "rollout": rollout,
                 "gpu_launches": int(gpu_launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

@@ -9,4 +9,19 @@ from .config import make_args, HORIZON_BY_LEVEL  # noqa: F401
 from .vec_env import VecLowLevelEnv  # noqa: F401
 from .env_hetero import LowLevelEnv  # noqa: F401
 
-__all__ = ["VecLowLevelEnv", "LowLevelEnv", "make_args", "HORIZON_BY_LEVEL"]
+
+def __getattr__(name):   # torch-dependent pieces are imported lazily
+    if name in ("VecSampler", "TorchPolicy"):
+        from . import sampler
+        return getattr(sampler, name)
+    if name == "PPOLearner":
+        from .ppo import PPOLearner
+        return PPOLearner
+    if name == "OpponentPolicies":
+        from .opponents import OpponentPolicies
+        return OpponentPolicies
+    raise AttributeError(name)
+
+
+__all__ = ["VecLowLevelEnv", "LowLevelEnv", "make_args", "HORIZON_BY_LEVEL", "VecSampler", "TorchPolicy", "PPOLearner",
+           "OpponentPolicies"]

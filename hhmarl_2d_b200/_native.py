@@ -100,6 +100,8 @@ def lib() -> ctypes.CDLL:
     L.hh_set_state.restype = ctypes.c_int
     L.hh_launch_count.argtypes = [VP]
     L.hh_launch_count.restype = U64
+    L.hh_gae.argtypes = [I32, I32, VP, VP, VP, VP, ctypes.c_float, ctypes.c_float, VP, VP, VP]
+    L.hh_gae.restype = ctypes.c_int
     L.hh_debug_geodesic.argtypes = [I32, I32, VP, VP]
     L.hh_debug_geodesic.restype = ctypes.c_int
     L.hh_last_error.restype = ctypes.c_char_p
@@ -109,7 +111,7 @@ def lib() -> ctypes.CDLL:
 
 
 EXPORTS = ["hh_create", "hh_destroy", "hh_n_arenas", "hh_obs_dim", "hh_reset", "hh_step", "hh_step_begin", "hh_step_finish", "hh_reset_host",
-           "hh_step_host", "hh_get_state", "hh_set_state", "hh_launch_count", "hh_debug_geodesic", "hh_last_error", "hh_version"]
+           "hh_step_host", "hh_get_state", "hh_set_state", "hh_launch_count", "hh_gae", "hh_debug_geodesic", "hh_last_error", "hh_version"]
 
 
 def check(rc: int, what: str):

@@ -562,6 +562,29 @@ reset_kernel(StatePtrs S, Params P, const uint8_t* __restrict__ mask, int first_
 }
 
 // ------------------------------------------------------------------------------------------
+// generalised advantage estimation over a rollout fragment [T][N][2] (RLlib postprocessing,
+// compute_advantages with use_gae=True): one thread per (arena, agent), backward scan over t;
+// consecutive threads touch consecutive addresses in every [t] slab.
+// ------------------------------------------------------------------------------------------
+__global__ void gae_kernel(int T, int n_pairs, const float* __restrict__ rew, const float* __restrict__ vf,
+                           const float* __restrict__ last_vf, const uint8_t* __restrict__ done, float gamma,
+                           float lam, float* __restrict__ adv, float* __restrict__ vtarg) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // i = arena * 2 + agent
+  if (i >= n_pairs) return;
+  const int arena = i >> 1, n_arenas = n_pairs >> 1;
+  float next_v = last_vf[i], gae = 0.0f;
+  for (int t = T - 1; t >= 0; --t) {
+    const size_t k = (size_t)t * n_pairs + i;
+    const float nonterminal = done[(size_t)t * n_arenas + arena] ? 0.0f : 1.0f;   // terminated == truncated here
+    const float delta = rew[k] + gamma * next_v * nonterminal - vf[k];
+    gae = delta + gamma * lam * nonterminal * gae;
+    adv[k] = gae;
+    vtarg[k] = gae + vf[k];
+    next_v = vf[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // test access to the device geodesics (hh_debug_geodesic)
 // ------------------------------------------------------------------------------------------
 __global__ void geodesic_debug_kernel(int mode, int n, const double* __restrict__ in, double* __restrict__ out) {
@@ -626,6 +649,17 @@ static int obs_dim(const hh_config& c, int agent) {
 
 extern "C" const char* hh_last_error(void) { return g_last_error.c_str(); }
 extern "C" const char* hh_version(void) { return "hhmarl_2d_b200 0.1 (sm_100a)"; }
+
+extern "C" int hh_gae(int32_t T, int32_t n_arenas, const float* rew_dev, const float* vf_dev, const float* last_vf_dev,
+                      const uint8_t* done_dev, float gamma, float lam, float* adv_dev, float* vtarg_dev, void* stream) {
+  if (T <= 0 || n_arenas <= 0 || !rew_dev || !vf_dev || !last_vf_dev || !done_dev || !adv_dev || !vtarg_dev)
+    return fail(-1, "hh_gae: bad argument");
+  const int n_pairs = n_arenas * 2;
+  gae_kernel<<<(n_pairs + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(T, n_pairs, rew_dev, vf_dev, last_vf_dev,
+                                                                                 done_dev, gamma, lam, adv_dev, vtarg_dev);
+  HH_CUDA(cudaGetLastError());
+  return 0;
+}
 
 extern "C" int hh_debug_geodesic(int32_t mode, int32_t n, const double* in_host, double* out_host) {
   if (mode < 0 || mode > 2 || n <= 0 || !in_host || !out_host) return fail(-1, "hh_debug_geodesic: bad argument");

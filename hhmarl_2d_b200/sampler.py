@@ -1,0 +1,171 @@
+"""On-device sampler: policy forward -> MultiCategorical sampling -> fused env step, for all arenas in
+lock-step, without touching the host.  Replaces RLlib's RolloutWorker loop:
+
+  central_critic_observer (train_hetero.py:162-181)  -> flat [act_1_own | act_2 | obs_1_own | obs_2], actions 0
+  Policy.compute_actions -> Fight1/Fight2.forward     -> logits, vf_preds (critic sees ZERO actions here, A.6.15)
+  env.step(action_dict)                              -> VecLowLevelEnv.step (one kernel launch)
+  CustomCallback.on_postprocess_trajectory (:120-160) -> real, scaled actions written into the first 7 columns
+  RLlib GAE postprocessing                           -> hh_gae kernel
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _native as nat
+from . import models as M
+
+ACT_SCALE = torch.tensor([12.0, 8.0, 1.0, 1.0])  # train_hetero.py:143-146: a0/12, a1/8, a2, a3
+
+
+def multicategorical_sample(logits: torch.Tensor, splits, explore: bool = True):
+    """Per-head categorical sample (Gumbel-max) or argmax; returns (actions int64 [B,H], logp [B])."""
+    acts, logp, o = [], 0.0, 0
+    for n in splits:
+        seg = logits[:, o:o + n]
+        lsm = torch.log_softmax(seg, dim=-1)
+        if explore:
+            g = -torch.log(-torch.log(torch.rand_like(seg).clamp_(1e-20, 1.0 - 1e-7)))
+            a = torch.argmax(seg + g, dim=-1)
+        else:
+            a = torch.argmax(seg, dim=-1)
+        acts.append(a)
+        logp = logp + lsm.gather(1, a[:, None])[:, 0]
+        o += n
+    return torch.stack(acts, dim=1), logp
+
+
+def multicategorical_logp_entropy_kl(logits, actions, splits, old_logits=None):
+    """log-prob of `actions`, entropy and (optionally) KL(old || new), summed over the heads."""
+    logp = ent = kl = 0.0
+    o = 0
+    for h, n in enumerate(splits):
+        lsm = torch.log_softmax(logits[:, o:o + n], dim=-1)
+        p = lsm.exp()
+        logp = logp + lsm.gather(1, actions[:, h:h + 1].long())[:, 0]
+        ent = ent - (p * lsm).sum(-1)
+        if old_logits is not None:
+            lo = torch.log_softmax(old_logits[:, o:o + n], dim=-1)
+            kl = kl + (lo.exp() * (lo - lsm)).sum(-1)
+        o += n
+    return logp, ent, kl
+
+
+class TorchPolicy:
+    """Minimal mirror of RLlib's Policy for one aircraft type: `compute_actions(obs_batch, ...)` takes the
+    flattened central observation and returns (actions, state_out, extra_fetches) with the RLlib keys."""
+
+    def __init__(self, model: torch.nn.Module, ac_type: int):
+        self.model, self.ac_type = model, ac_type
+        self.splits = M.ACTION_SPLITS[ac_type]
+
+    @torch.no_grad()
+    def compute_actions(self, obs_batch, state_batches=None, prev_action_batch=None, prev_reward_batch=None,
+                        explore=True, **kw):
+        logits, vf = self.model.forward_flat(obs_batch)
+        actions, logp = multicategorical_sample(logits, self.splits, explore)
+        return actions, [], {"action_logp": logp, "action_dist_inputs": logits, "vf_preds": vf}
+
+    def compute_single_action(self, obs, explore=False, **kw):
+        a, s, x = self.compute_actions(obs[None], explore=explore)
+        return a[0], s, {k: v[0] for k, v in x.items()}
+
+
+class VecSampler:
+    """Collects rollout fragments of T lock-step ticks from a VecLowLevelEnv with two policies
+    (ac1_policy for agent 1, ac2_policy for agent 2; policy_mapping_fn of train_hetero.py:240)."""
+
+    def __init__(self, env, policy1: TorchPolicy, policy2: TorchPolicy, fragment_len: int = 64,
+                 gamma: float = 0.99, lam: float = 0.95, use_cuda_graph: bool = True):
+        self.env, self.p1, self.p2, self.T = env, policy1, policy2, fragment_len
+        self.gamma, self.lam = gamma, lam
+        n, T = env.n_arenas, fragment_len
+        d1, d2 = env.obs_dim
+        dev = torch.device("cuda", env.device_index)
+        self.dev = dev
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.buf = dict(
+            flat1=torch.zeros((T, n, 7 + d1 + d2), **f32), flat2=torch.zeros((T, n, 7 + d1 + d2), **f32),
+            actions=torch.zeros((T, n, 2, 4), dtype=torch.int32, device=dev),
+            logp=torch.zeros((T, n, 2), **f32), vf=torch.zeros((T, n, 2), **f32),
+            logits1=torch.zeros((T, n, sum(policy1.splits)), **f32),
+            logits2=torch.zeros((T, n, sum(policy2.splits)), **f32),
+            rew=torch.zeros((T, n, 2), **f32), done=torch.zeros((T, n), dtype=torch.uint8, device=dev),
+            adv=torch.zeros((T, n, 2), **f32), vtarg=torch.zeros((T, n, 2), **f32),
+            last_vf=torch.zeros((n, 2), **f32))
+        self.cur1 = torch.zeros((n, 7 + d1 + d2), **f32)   # [act_1_own(4) | act_2(3) | obs_1_own | obs_2], actions 0
+        self.cur2 = torch.zeros((n, 7 + d1 + d2), **f32)   # [act_1_own(3) | act_2(4) | obs_1_own | obs_2]
+        self.d1, self.d2 = d1, d2
+        self.scale = ACT_SCALE.to(dev)
+        self.use_graph = use_cuda_graph
+        self._graph = None
+        self._started = False
+
+    # central_critic_observer, train_hetero.py:162-181
+    def _set_obs(self, obs1, obs2):
+        d1, d2 = self.d1, self.d2
+        self.cur1[:, 7:7 + d1] = obs1
+        self.cur1[:, 7 + d1:] = obs2
+        self.cur2[:, 7:7 + d2] = obs2
+        self.cur2[:, 7 + d2:] = obs1
+
+    def _tick(self, t):
+        b = self.buf
+        a1, _, x1 = self.p1.compute_actions(self.cur1)
+        a2, _, x2 = self.p2.compute_actions(self.cur2)
+        b["flat1"][t] = self.cur1
+        b["flat2"][t] = self.cur2
+        act = b["actions"][t]
+        act[:, 0, :] = a1.to(torch.int32)
+        act[:, 1, :3] = a2.to(torch.int32)
+        b["logp"][t, :, 0], b["logp"][t, :, 1] = x1["action_logp"], x2["action_logp"]
+        b["vf"][t, :, 0], b["vf"][t, :, 1] = x1["vf_preds"], x2["vf_preds"]
+        b["logits1"][t], b["logits2"][t] = x1["action_dist_inputs"], x2["action_dist_inputs"]
+        obs1, obs2, rew, done = self.env.step(act)
+        b["rew"][t] = rew
+        b["done"][t] = done
+        self._set_obs(obs1, obs2)
+
+    def _fragment(self):
+        for t in range(self.T):
+            self._tick(t)
+        b = self.buf
+        _, v1 = self.p1.model.forward_flat(self.cur1)
+        _, v2 = self.p2.model.forward_flat(self.cur2)
+        b["last_vf"][:, 0], b["last_vf"][:, 1] = v1, v2
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        nat.check(nat.lib().hh_gae(self.T, self.env.n_arenas, b["rew"].data_ptr(), b["vf"].data_ptr(),
+                                   b["last_vf"].data_ptr(), b["done"].data_ptr(), self.gamma, self.lam,
+                                   b["adv"].data_ptr(), b["vtarg"].data_ptr(), st), "hh_gae")
+        # CustomCallback.on_postprocess_trajectory (train_hetero.py:120-160): the critic's action columns get
+        # the real actions, scaled; VF_PREDS / advantages above were computed with zeros
+        a = b["actions"].to(torch.float32)
+        own1, own2 = a[:, :, 0, :] / self.scale, a[:, :, 1, :3] / self.scale[:3]
+        b["flat1"][:, :, 0:4], b["flat1"][:, :, 4:7] = own1, own2
+        b["flat2"][:, :, 0:3], b["flat2"][:, :, 3:7] = own2, own1
+
+    @torch.no_grad()
+    def collect(self):
+        """One rollout fragment: dict of [T, N, ...] CUDA tensors (the sampler's own buffers)."""
+        if not self._started:
+            obs1, obs2 = self.env.reset()
+            self._set_obs(obs1, obs2)
+            self._started = True
+        if not self.use_graph:
+            self._fragment()
+            return self.buf
+        if self._graph is None:
+            s = torch.cuda.Stream(self.dev)
+            s.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(s):
+                self._fragment()                 # warm-up (allocations, cuBLAS handles) outside capture
+            torch.cuda.current_stream(self.dev).wait_stream(s)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._fragment()
+            return self.buf                       # the captured region ran once during capture-free warm-up
+        self._graph.replay()
+        return self.buf
+
+    @property
+    def env_steps_per_fragment(self):
+        return self.T * self.env.n_arenas

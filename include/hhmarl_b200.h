@@ -108,6 +108,13 @@ int hh_set_state(hh_env* env, const hh_state_view* in_host);
 /* Number of kernels this library has launched on behalf of `env` since creation. */
 uint64_t hh_launch_count(const hh_env* env);
 
+/* Generalised advantage estimation over a rollout fragment (what RLlib's postprocessing does per episode
+ * before on_postprocess_trajectory, train_hetero.py:120-160; gamma 0.99, lambda 0.95 at :216).
+ *   rew, vf: f32[T][N][2]; last_vf: f32[N][2] (value of the observation after the fragment);
+ *   done: u8[T][N] (episode ended at that step: no bootstrap across it); adv, vtarg: f32[T][N][2] out. */
+int hh_gae(int32_t T, int32_t n_arenas, const float* rew_dev, const float* vf_dev, const float* last_vf_dev,
+           const uint8_t* done_dev, float gamma, float lam, float* adv_dev, float* vtarg_dev, void* stream);
+
 /* Test access to the device WGS84 solvers (replacing geographiclib's Geodesic.WGS84 as used at
  * warsim/utils/geodesics.py:12-24).  in_host: f64[4][n], out_host: f64[2][n].
  *   mode 0: direct  (lat1, lon1, azi1 [deg], s12 [m]) -> (lat2, lon2)

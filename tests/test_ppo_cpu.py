@@ -1,0 +1,91 @@
+"""Host-side logic of the learner / sampler that does not need a GPU: the sequence re-ordering used for
+RLlib-style max_seq_len chunks, the MultiCategorical helpers, a CPU PPO update, and the 2-rank gloo
+gradient exchange (world_size 2, as the multi-GPU path uses NCCL)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from hhmarl_2d_b200 import models as M
+from hhmarl_2d_b200.ppo import PPOLearner, _seq_major
+from hhmarl_2d_b200.sampler import multicategorical_logp_entropy_kl, multicategorical_sample
+
+
+def _fake_batch(T, N, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.rand(*s, generator=g)
+    acts = torch.stack([torch.randint(0, 13, (T, N, 2), generator=g), torch.randint(0, 9, (T, N, 2), generator=g),
+                        torch.randint(0, 2, (T, N, 2), generator=g), torch.randint(0, 2, (T, N, 2), generator=g)], -1).int()
+    return dict(flat1=r(T, N, 57), flat2=r(T, N, 57), actions=acts, logits1=r(T, N, 26), logits2=r(T, N, 24),
+                logp=-r(T, N, 2) - 3, vf=r(T, N, 2), rew=r(T, N, 2), adv=r(T, N, 2) - 0.5, vtarg=r(T, N, 2),
+                done=torch.zeros(T, N, dtype=torch.uint8))
+
+
+def test_seq_major_keeps_sequences_contiguous():
+    T, N, L = 40, 3, 20
+    x = torch.arange(T)[:, None].repeat(1, N) * 100 + torch.arange(N)[None, :]        # value = t*100 + n
+    y = _seq_major(x, L).reshape(T // L, N, L)
+    for c in range(T // L):
+        for n in range(N):
+            assert (y[c, n] == torch.arange(c * L, (c + 1) * L) * 100 + n).all()
+
+
+def test_multicategorical_helpers():
+    torch.manual_seed(0)
+    logits = torch.randn(4096, 26)
+    a, logp = multicategorical_sample(logits, (13, 9, 2, 2))
+    lp2, ent, kl = multicategorical_logp_entropy_kl(logits, a, (13, 9, 2, 2), logits)
+    assert torch.allclose(logp, lp2, atol=1e-6) and kl.abs().max() < 1e-6 and (ent > 0).all()
+    a_det, _ = multicategorical_sample(logits, (13, 9, 2, 2), explore=False)
+    assert (a_det == M.deterministic_actions(logits, 1)).all()
+    # sampling frequencies follow softmax (first head of the first row repeated)
+    rep = logits[:1].repeat(20000, 1)
+    s, _ = multicategorical_sample(rep, (13, 9, 2, 2))
+    freq = torch.bincount(s[:, 0], minlength=13).float() / 20000
+    assert (freq - torch.softmax(logits[0, :13], 0)).abs().max() < 0.02
+
+
+def test_ppo_update_runs_and_improves_surrogate_on_cpu():
+    torch.manual_seed(0)
+    m1, m2 = M.build_policy_pair("fight")
+    learner = PPOLearner(m1, m2, num_sgd_iter=2, sgd_minibatch_size=80, lr=1e-3)
+    batch = _fake_batch(20, 16)
+    with torch.no_grad():       # make old logits / logp consistent with the current policies
+        for i, (m, k) in enumerate(((m1, "1"), (m2, "2"))):
+            lg, vf = m.forward_flat(batch["flat" + k].reshape(-1, 57))
+            batch["logits" + k] = lg.reshape(20, 16, -1)
+            n = 4 if i == 0 else 3
+            lp, _, _ = multicategorical_logp_entropy_kl(lg, batch["actions"][:, :, i, :n].reshape(-1, n), learner.splits[i])
+            batch["logp"][:, :, i] = lp.reshape(20, 16)
+    w0 = m1.shared_layer._model[0].weight.clone()
+    st = learner.update(batch)
+    assert st["minibatches"] == 2 * (16 // 4) and np.isfinite(st["loss"])
+    assert not torch.equal(w0, m1.shared_layer._model[0].weight)          # the shared layer trains
+    assert m1.shared_layer is m2.shared_layer
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    m1, m2 = M.build_policy_pair("fight")
+    learner = PPOLearner(m1, m2, num_sgd_iter=1, sgd_minibatch_size=80)
+    batch = _fake_batch(20, 8, seed=rank)                                  # different shards per rank
+    learner.update(batch)
+    q.put((rank, float(sum(p.sum() for p in learner.params))))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_keeps_two_ranks_in_sync():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = dict(q.get(timeout=120) for _ in range(2))
+    [p.join(60) for p in procs]
+    assert abs(res[0] - res[1]) < 1e-4 * max(1.0, abs(res[0]))             # identical weights after the update
