@@ -11,7 +11,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libhhmarl_b200.so")
+LIB_PATH = os.environ.get("HH_LIB_PATH") or os.path.join(CSRC, "libhhmarl_b200.so")
 SOURCES = ["hh_api.cu"]
 HEADERS = ["hh_quad.cuh", "hh_core.cuh", "hh_geodesic.cuh", os.path.join("..", "..", "include", "hhmarl_b200.h")]
 

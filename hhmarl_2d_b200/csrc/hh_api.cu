@@ -23,7 +23,13 @@
 
 namespace hh {
 
-constexpr int kThreads = 32;                 // one warp per CTA = 8 arenas
+#ifndef HH_CTA_THREADS
+#define HH_CTA_THREADS 32
+#endif
+constexpr int kThreads = HH_CTA_THREADS;     // warps per CTA x 32; 8 arenas per warp
+__device__ __forceinline__ void cta_sync() {
+  if (kThreads == 32) __syncwarp(); else __syncthreads();
+}
 constexpr int kArenasPerCta = kThreads / 4;
 
 template <int MODE>
@@ -49,7 +55,7 @@ __device__ __forceinline__ void write_agent_obs(Lane& L, const Geom& g, int u, f
   const int al = threadIdx.x >> 2;
   const World W = gather_world(L, u);
   if (u < 2) L.ota = unit_observation(L, W, g, u, MODE, u == 0 ? s1 + al * D1 : s2 + al * D2);
-  __syncwarp();
+  cta_sync();
   if (obs1) flush_rows(obs1 + (size_t)arena0 * D1, s1, n_valid * D1);
   if (obs2) flush_rows(obs2 + (size_t)arena0 * D2, s2, n_valid * D2);
 }
@@ -496,7 +502,7 @@ step_begin_kernel(StatePtrs S, Params P, const int32_t* __restrict__ actions, fl
     L.ota = unit_observation(L, W, g, u, L.opp_mode, row);
     for (int k = len; k < stride; ++k) row[k] = 0.0f;
   }
-  __syncwarp();
+  cta_sync();
   if (opp_obs3) flush_rows(opp_obs3 + (size_t)arena0 * kOppD3, s3, n_valid * kOppD3);
   if (opp_obs4) flush_rows(opp_obs4 + (size_t)arena0 * kOppD4, s4, n_valid * kOppD4);
   store_lane(S, a, u, L, valid);

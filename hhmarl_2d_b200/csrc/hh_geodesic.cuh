@@ -565,11 +565,26 @@ __device__ __noinline__ double2 inverse(double lat1, double lon1, double lat2, d
 // 1e-5 deg for s <= 80 km.  Callers use it only to decide threshold tests and fall back to
 // inverse() inside a margin >= 100x those errors, so decisions are identical to the exact ones.
 // ---------------------------------------------------------------------------------------------
+// sin/cos of the map-centre latitude (5.25 deg: the env's box is lat 5 .. 5+map_size, env_base.py:43);
+// mid-latitudes inside the box are within 0.3 deg of it, so a degree-7 expansion is exact to 1e-17.
+constexpr double kPhi0 = 5.25 * kDeg;
+constexpr double kSinPhi0 = 0.09150161866340238;   // sin(5.25 deg)
+constexpr double kCosPhi0 = 0.9958049275746618;   // cos(5.25 deg)
+
 __device__ __forceinline__ double2 inverse_local(double lat1, double lon1, double lat2, double lon2) {
   const double phim = 0.5 * (lat1 + lat2) * kDeg;
   const double hp = 0.5 * (lat2 - lat1) * kDeg, hl = 0.5 * (lon2 - lon1) * kDeg;
   double sm, cm;
-  m::sincos_(phim, &sm, &cm);
+  const double dl = phim - kPhi0;
+  if (fabs(dl) < 0.02) {   // |dl| < 1.15 deg: always true inside the map box
+    const double d2 = dl * dl;
+    const double sd = dl * (1.0 + d2 * (-1.0 / 6.0 + d2 * (1.0 / 120.0 - d2 * (1.0 / 5040.0))));
+    const double cd = 1.0 + d2 * (-0.5 + d2 * (1.0 / 24.0 - d2 * (1.0 / 720.0)));
+    sm = kSinPhi0 * cd + kCosPhi0 * sd;
+    cm = kCosPhi0 * cd - kSinPhi0 * sd;
+  } else {
+    m::sincos_(phim, &sm, &cm);
+  }
   const double W2 = 1.0 - kE2 * sm * sm;
   const double iW = 1.0 / sqrt(W2);
   const double N = kA * iW, M = kA * (1.0 - kE2) * iW * iW * iW;

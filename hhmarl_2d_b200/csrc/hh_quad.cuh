@@ -51,7 +51,7 @@ struct Lane {
 
 __device__ __forceinline__ int quad_ballot(bool p) {
   unsigned b = __ballot_sync(kFull, p);
-  return (int)((b >> (threadIdx.x & 28)) & 0xFu);
+  return (int)((b >> (threadIdx.x & 28 & 31)) & 0xFu);
 }
 template <typename T>
 __device__ __forceinline__ T qshfl(T v, int src) {
