@@ -94,6 +94,8 @@ def lib() -> ctypes.CDLL:
     L.hh_reset_host.restype = ctypes.c_int
     L.hh_step_host.argtypes = [VP, VP, VP, VP, VP, VP]
     L.hh_step_host.restype = ctypes.c_int
+    L.hh_host_buffers.argtypes = [VP] + [P(VP)] * 5
+    L.hh_host_buffers.restype = ctypes.c_int
     L.hh_get_state.argtypes = [VP, P(HHStateView)]
     L.hh_get_state.restype = ctypes.c_int
     L.hh_set_state.argtypes = [VP, P(HHStateView)]
@@ -111,7 +113,7 @@ def lib() -> ctypes.CDLL:
 
 
 EXPORTS = ["hh_create", "hh_destroy", "hh_n_arenas", "hh_obs_dim", "hh_reset", "hh_step", "hh_step_begin", "hh_step_finish", "hh_reset_host",
-           "hh_step_host", "hh_get_state", "hh_set_state", "hh_launch_count", "hh_gae", "hh_debug_geodesic", "hh_last_error", "hh_version"]
+           "hh_step_host", "hh_host_buffers", "hh_get_state", "hh_set_state", "hh_launch_count", "hh_gae", "hh_debug_geodesic", "hh_last_error", "hh_version"]
 
 
 def check(rc: int, what: str):

@@ -639,6 +639,7 @@ struct hh_env {
   uint64_t launches = 0;
   // host-variant staging
   cudaStream_t hstream = nullptr;
+  void* d_slab = nullptr;
   int32_t* d_actions = nullptr;
   float *d_obs1 = nullptr, *d_obs2 = nullptr, *d_rew = nullptr;
   uint8_t *d_done = nullptr, *d_mask = nullptr;
@@ -754,12 +755,7 @@ extern "C" void hh_destroy(hh_env* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->slab) cudaFree(e->slab);
-  if (e->d_actions) cudaFree(e->d_actions);
-  if (e->d_obs1) cudaFree(e->d_obs1);
-  if (e->d_obs2) cudaFree(e->d_obs2);
-  if (e->d_rew) cudaFree(e->d_rew);
-  if (e->d_done) cudaFree(e->d_done);
-  if (e->d_mask) cudaFree(e->d_mask);
+  if (e->d_slab) cudaFree(e->d_slab);
   if (e->rew_pre) cudaFree(e->rew_pre);
   if (e->pinned) cudaFreeHost(e->pinned);
   if (e->hstream) cudaStreamDestroy(e->hstream);
@@ -855,20 +851,64 @@ extern "C" int hh_step_finish(hh_env* e, const int32_t* opp_actions_dev, float* 
 }
 
 // ------------------------------------------------------------------------------------------ host variants
+// One pinned host slab and one device slab with the same layout:
+//   [ actions i32 N*8 | obs1 f32 N*d1 | obs2 f32 N*d2 | rew f32 N*2 | done u8 N | mask u8 N ]
+// so a host step is ONE H2D (actions), the launch, ONE D2H (obs1..done) and one stream sync.  Callers that
+// use the slab's own regions (hh_host_buffers) skip the host-side memcpys as well.
+namespace {
+struct HostLayout {
+  size_t o_act, o_obs1, o_obs2, o_rew, o_done, o_mask, total, out_bytes;
+};
+HostLayout host_layout(const hh_env* e);
+}  // namespace
+
 static int ensure_staging(hh_env* e) {
   if (e->hstream) return 0;
-  const size_t N = (size_t)e->n;
-  const int d1 = obs_dim(e->cfg, 1), d2 = obs_dim(e->cfg, 2);
+  const HostLayout h = host_layout(e);
   HH_CUDA(cudaSetDevice(e->device));
   HH_CUDA(cudaStreamCreateWithFlags(&e->hstream, cudaStreamNonBlocking));
-  HH_CUDA(cudaMalloc(&e->d_actions, N * 8 * sizeof(int32_t)));
-  HH_CUDA(cudaMalloc(&e->d_obs1, N * d1 * sizeof(float)));
-  HH_CUDA(cudaMalloc(&e->d_obs2, N * d2 * sizeof(float)));
-  HH_CUDA(cudaMalloc(&e->d_rew, N * 2 * sizeof(float)));
-  HH_CUDA(cudaMalloc(&e->d_done, N));
-  HH_CUDA(cudaMalloc(&e->d_mask, N));
-  e->pinned_bytes = N * (8 * sizeof(int32_t) + (d1 + d2 + 2) * sizeof(float) + 2);
-  HH_CUDA(cudaMallocHost(&e->pinned, e->pinned_bytes));
+  HH_CUDA(cudaMalloc(&e->d_slab, h.total));
+  HH_CUDA(cudaMallocHost(&e->pinned, h.total));
+  memset(e->pinned, 0, h.total);
+  e->pinned_bytes = h.total;
+  char* d = static_cast<char*>(e->d_slab);
+  e->d_actions = reinterpret_cast<int32_t*>(d + h.o_act);
+  e->d_obs1 = reinterpret_cast<float*>(d + h.o_obs1);
+  e->d_obs2 = reinterpret_cast<float*>(d + h.o_obs2);
+  e->d_rew = reinterpret_cast<float*>(d + h.o_rew);
+  e->d_done = reinterpret_cast<uint8_t*>(d + h.o_done);
+  e->d_mask = reinterpret_cast<uint8_t*>(d + h.o_mask);
+  return 0;
+}
+
+namespace {
+HostLayout host_layout(const hh_env* e) {
+  const size_t N = (size_t)e->n;
+  const int d1 = obs_dim(e->cfg, 1), d2 = obs_dim(e->cfg, 2);
+  HostLayout h;
+  h.o_act = 0;
+  h.o_obs1 = align_up(N * 8 * sizeof(int32_t), 256);
+  h.o_obs2 = h.o_obs1 + N * d1 * sizeof(float);           // obs1..done are contiguous: one D2H
+  h.o_rew = h.o_obs2 + N * d2 * sizeof(float);
+  h.o_done = h.o_rew + N * 2 * sizeof(float);
+  h.out_bytes = h.o_done + N - h.o_obs1;
+  h.o_mask = align_up(h.o_done + N, 256);
+  h.total = align_up(h.o_mask + N, 256);
+  return h;
+}
+}  // namespace
+
+extern "C" int hh_host_buffers(hh_env* e, int32_t** actions, float** obs1, float** obs2, float** rew, uint8_t** done) {
+  if (!e) return fail(-1, "hh_host_buffers: null env");
+  int rc = ensure_staging(e);
+  if (rc) return rc;
+  const HostLayout h = host_layout(e);
+  char* p = static_cast<char*>(e->pinned);
+  if (actions) *actions = reinterpret_cast<int32_t*>(p + h.o_act);
+  if (obs1) *obs1 = reinterpret_cast<float*>(p + h.o_obs1);
+  if (obs2) *obs2 = reinterpret_cast<float*>(p + h.o_obs2);
+  if (rew) *rew = reinterpret_cast<float*>(p + h.o_rew);
+  if (done) *done = reinterpret_cast<uint8_t*>(p + h.o_done);
   return 0;
 }
 
@@ -878,12 +918,18 @@ extern "C" int hh_reset_host(hh_env* e, const uint8_t* mask_host, float* obs1_ho
   if (rc) return rc;
   const size_t N = (size_t)e->n;
   const int d1 = obs_dim(e->cfg, 1), d2 = obs_dim(e->cfg, 2);
-  if (mask_host) HH_CUDA(cudaMemcpyAsync(e->d_mask, mask_host, N, cudaMemcpyHostToDevice, e->hstream));
+  const HostLayout h = host_layout(e);
+  char* pin = static_cast<char*>(e->pinned);
+  if (mask_host) {
+    memcpy(pin + h.o_mask, mask_host, N);
+    HH_CUDA(cudaMemcpyAsync(e->d_mask, pin + h.o_mask, N, cudaMemcpyHostToDevice, e->hstream));
+  }
   rc = hh_reset(e, mask_host ? e->d_mask : nullptr, e->d_obs1, e->d_obs2, e->hstream);
   if (rc) return rc;
-  if (obs1_host) HH_CUDA(cudaMemcpyAsync(obs1_host, e->d_obs1, N * d1 * sizeof(float), cudaMemcpyDeviceToHost, e->hstream));
-  if (obs2_host) HH_CUDA(cudaMemcpyAsync(obs2_host, e->d_obs2, N * d2 * sizeof(float), cudaMemcpyDeviceToHost, e->hstream));
+  HH_CUDA(cudaMemcpyAsync(pin + h.o_obs1, e->d_obs1, N * (d1 + d2) * sizeof(float), cudaMemcpyDeviceToHost, e->hstream));
   HH_CUDA(cudaStreamSynchronize(e->hstream));
+  if (obs1_host && obs1_host != reinterpret_cast<float*>(pin + h.o_obs1)) memcpy(obs1_host, pin + h.o_obs1, N * d1 * sizeof(float));
+  if (obs2_host && obs2_host != reinterpret_cast<float*>(pin + h.o_obs2)) memcpy(obs2_host, pin + h.o_obs2, N * d2 * sizeof(float));
   return 0;
 }
 
@@ -895,28 +941,18 @@ extern "C" int hh_step_host(hh_env* e, const int32_t* actions_host, float* obs1_
   if (rc) return rc;
   const size_t N = (size_t)e->n;
   const int d1 = obs_dim(e->cfg, 1), d2 = obs_dim(e->cfg, 2);
-  // pageable caller buffers are bounced through the handle's pinned slab so that the copies
-  // are true async DMA; pinned caller buffers (cudaHostRegister'ed / torch pin_memory) would
-  // also work directly.
+  const HostLayout h = host_layout(e);
   char* pin = static_cast<char*>(e->pinned);
-  int32_t* p_act = reinterpret_cast<int32_t*>(pin);
-  float* p_obs1 = reinterpret_cast<float*>(pin + N * 8 * sizeof(int32_t));
-  float* p_obs2 = p_obs1 + N * d1;
-  float* p_rew = p_obs2 + N * d2;
-  uint8_t* p_done = reinterpret_cast<uint8_t*>(p_rew + N * 2);
-  memcpy(p_act, actions_host, N * 8 * sizeof(int32_t));
-  HH_CUDA(cudaMemcpyAsync(e->d_actions, p_act, N * 8 * sizeof(int32_t), cudaMemcpyHostToDevice, e->hstream));
+  if (reinterpret_cast<const char*>(actions_host) != pin + h.o_act) memcpy(pin + h.o_act, actions_host, N * 8 * sizeof(int32_t));
+  HH_CUDA(cudaMemcpyAsync(e->d_actions, pin + h.o_act, N * 8 * sizeof(int32_t), cudaMemcpyHostToDevice, e->hstream));
   rc = hh_step(e, e->d_actions, e->d_obs1, e->d_obs2, e->d_rew, e->d_done, e->hstream);
   if (rc) return rc;
-  if (obs1_host) HH_CUDA(cudaMemcpyAsync(p_obs1, e->d_obs1, N * d1 * sizeof(float), cudaMemcpyDeviceToHost, e->hstream));
-  if (obs2_host) HH_CUDA(cudaMemcpyAsync(p_obs2, e->d_obs2, N * d2 * sizeof(float), cudaMemcpyDeviceToHost, e->hstream));
-  if (rew_host) HH_CUDA(cudaMemcpyAsync(p_rew, e->d_rew, N * 2 * sizeof(float), cudaMemcpyDeviceToHost, e->hstream));
-  if (done_host) HH_CUDA(cudaMemcpyAsync(p_done, e->d_done, N, cudaMemcpyDeviceToHost, e->hstream));
+  HH_CUDA(cudaMemcpyAsync(pin + h.o_obs1, e->d_obs1, h.out_bytes, cudaMemcpyDeviceToHost, e->hstream));
   HH_CUDA(cudaStreamSynchronize(e->hstream));
-  if (obs1_host) memcpy(obs1_host, p_obs1, N * d1 * sizeof(float));
-  if (obs2_host) memcpy(obs2_host, p_obs2, N * d2 * sizeof(float));
-  if (rew_host) memcpy(rew_host, p_rew, N * 2 * sizeof(float));
-  if (done_host) memcpy(done_host, p_done, N);
+  if (obs1_host && reinterpret_cast<char*>(obs1_host) != pin + h.o_obs1) memcpy(obs1_host, pin + h.o_obs1, N * d1 * sizeof(float));
+  if (obs2_host && reinterpret_cast<char*>(obs2_host) != pin + h.o_obs2) memcpy(obs2_host, pin + h.o_obs2, N * d2 * sizeof(float));
+  if (rew_host && reinterpret_cast<char*>(rew_host) != pin + h.o_rew) memcpy(rew_host, pin + h.o_rew, N * 2 * sizeof(float));
+  if (done_host && reinterpret_cast<char*>(done_host) != pin + h.o_done) memcpy(done_host, pin + h.o_done, N);
   return 0;
 }
 

@@ -144,6 +144,21 @@ class VecLowLevelEnv:
         nat.check(nat.lib().hh_reset_host(self._h, mp, o1.ctypes.data, o2.ctypes.data), "hh_reset_host")
         return o1, o2
 
+    def host_buffers(self):
+        """(actions i32 [N,2,4], obs1, obs2, rew f32, done u8) numpy views of the handle's pinned slab: write the
+        actions in place and call `step_host(actions, out=(obs1, obs2, rew, done))` for a zero-copy host step."""
+        ptrs = [nat.VP() for _ in range(5)]
+        nat.check(nat.lib().hh_host_buffers(self._h, *[ctypes.byref(p) for p in ptrs]), "hh_host_buffers")
+        n, (d1, d2) = self.n_arenas, self.obs_dim
+
+        def view(p, ctype, shape):
+            cnt = int(np.prod(shape))
+            return np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctype)), shape=(cnt,)).reshape(shape)
+
+        return (view(ptrs[0], ctypes.c_int32, (n, 2, 4)), view(ptrs[1], ctypes.c_float, (n, d1)),
+                view(ptrs[2], ctypes.c_float, (n, d2)), view(ptrs[3], ctypes.c_float, (n, 2)),
+                view(ptrs[4], ctypes.c_uint8, (n,)))
+
     def step_host(self, actions: np.ndarray, out=None):
         """actions: int32 [N, 2, 4] host array -> (obs1, obs2, rew, done) host arrays.
         Host->device and device->host copies happen inside the call."""

@@ -102,6 +102,11 @@ int hh_reset_host(hh_env* env, const uint8_t* mask_host, float* obs1_host, float
 int hh_step_host(hh_env* env, const int32_t* actions_host, float* obs1_host, float* obs2_host,
                  float* rew_host, uint8_t* done_host);
 
+/* Pointers into the handle's own PINNED host slab (valid until hh_destroy): filling `actions` in place and
+ * passing exactly these pointers to hh_step_host / hh_reset_host makes the call zero-copy on the host side
+ * (one H2D of the actions, one D2H of obs1|obs2|rew|done, one stream synchronise). */
+int hh_host_buffers(hh_env* env, int32_t** actions, float** obs1, float** obs2, float** rew, uint8_t** done);
+
 int hh_get_state(hh_env* env, hh_state_view* out_host);
 int hh_set_state(hh_env* env, const hh_state_view* in_host);
 

@@ -278,3 +278,28 @@ def test_frozen_policy_levels_match_oracle(level, mode):
     assert n_done > n // 2 and n_calls > 1000
     if level == 5 and mode == "fight":
         assert psets == {3, 4, 5}
+
+
+def test_pinned_host_buffers_zero_copy_path_matches_device_path():
+    import torch
+    n = 1000
+    a = _vec(n, 3, "fight", 9)
+    b = _vec(n, 3, "fight", 9)
+    act_pin, o1, o2, r, d = a.host_buffers()
+    ro1, ro2 = a.reset_host()
+    bo1, bo2 = b.reset()
+    assert np.array_equal(ro1, bo1.cpu().numpy()) and np.array_equal(ro2, bo2.cpu().numpy())
+    rng = np.random.default_rng(5)
+    for t in range(30):
+        act = np.stack([rng.integers(0, 13, (n, 2)), rng.integers(0, 9, (n, 2)), rng.integers(0, 2, (n, 2)),
+                        rng.integers(0, 2, (n, 2))], axis=-1).astype(np.int32)
+        act_pin[...] = act
+        x1, x2, xr, xd = a.step_host(act_pin, out=(o1, o2, r, d))
+        assert x1 is o1 and xd is d                                  # results live in the pinned slab itself
+        y1, y2, yr, yd = b.step(torch.from_numpy(act).cuda())
+        assert np.array_equal(o1, y1.cpu().numpy()) and np.array_equal(o2, y2.cpu().numpy())
+        assert np.array_equal(r, yr.cpu().numpy()) and np.array_equal(d, yd.cpu().numpy())
+        # pageable arrays still work (staged through the slab)
+    z1, z2, zr, zd = a.step_host(act)
+    w1, w2, wr, wd = b.step(torch.from_numpy(act).cuda())
+    assert np.array_equal(z1, w1.cpu().numpy()) and np.array_equal(zd, wd.cpu().numpy())
