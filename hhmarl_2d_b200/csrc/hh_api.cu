@@ -888,9 +888,9 @@ HostLayout host_layout(const hh_env* e) {
   HostLayout h;
   h.o_act = 0;
   h.o_obs1 = align_up(N * 8 * sizeof(int32_t), 256);
-  h.o_obs2 = h.o_obs1 + N * d1 * sizeof(float);           // obs1..done are contiguous: one D2H
-  h.o_rew = h.o_obs2 + N * d2 * sizeof(float);
-  h.o_done = h.o_rew + N * 2 * sizeof(float);
+  h.o_obs2 = align_up(h.o_obs1 + N * d1 * sizeof(float), 256);   // obs1..done travel in ONE D2H (regions 256-B
+  h.o_rew = align_up(h.o_obs2 + N * d2 * sizeof(float), 256);    // aligned: the kernels store rows as float4)
+  h.o_done = align_up(h.o_rew + N * 2 * sizeof(float), 256);
   h.out_bytes = h.o_done + N - h.o_obs1;
   h.o_mask = align_up(h.o_done + N, 256);
   h.total = align_up(h.o_mask + N, 256);
@@ -926,7 +926,8 @@ extern "C" int hh_reset_host(hh_env* e, const uint8_t* mask_host, float* obs1_ho
   }
   rc = hh_reset(e, mask_host ? e->d_mask : nullptr, e->d_obs1, e->d_obs2, e->hstream);
   if (rc) return rc;
-  HH_CUDA(cudaMemcpyAsync(pin + h.o_obs1, e->d_obs1, N * (d1 + d2) * sizeof(float), cudaMemcpyDeviceToHost, e->hstream));
+  HH_CUDA(cudaMemcpyAsync(pin + h.o_obs1, e->d_obs1, h.o_obs2 + N * d2 * sizeof(float) - h.o_obs1, cudaMemcpyDeviceToHost,
+                          e->hstream));
   HH_CUDA(cudaStreamSynchronize(e->hstream));
   if (obs1_host && obs1_host != reinterpret_cast<float*>(pin + h.o_obs1)) memcpy(obs1_host, pin + h.o_obs1, N * d1 * sizeof(float));
   if (obs2_host && obs2_host != reinterpret_cast<float*>(pin + h.o_obs2)) memcpy(obs2_host, pin + h.o_obs2, N * d2 * sizeof(float));
