@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--level", type=int, default=3)
     ap.add_argument("--cpu-sample-steps", type=int, default=400_000, help="env-steps per host thread")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-rollout", action="store_true")
     return ap.parse_args()
 
 
@@ -254,6 +255,8 @@ def run_b200(args):
     #      rollout-buffer writes, GAE and the action write-back, one CUDA graph per 20-tick fragment
     rollout = None
     try:
+        if args.no_rollout:
+            raise RuntimeError("skipped (--no-rollout)")
         from hhmarl_2d_b200 import VecSampler, TorchPolicy
         from hhmarl_2d_b200 import models as M
         torch.manual_seed(rank)

@@ -1,8 +1,9 @@
 // hh_api.cu -- fused step / reset kernels and the C ABI declared in include/hhmarl_b200.h.
 //
 // Kernel shape: a QUAD of lanes per arena (lane = aircraft, hh_quad.cuh), 8 arenas per warp,
-// one-warp CTAs so that the 1024 warps of the N = 8192 headline configuration spread evenly
-// over the 148 SMs (6.9 warps / SM).  Each lane reads its own aircraft's slice of the 320 B
+// 4-warp CTAs (32 arenas) whose warps are re-aligned with a barrier at every phase boundary so that
+// they stream the ~160 KB of step code through the instruction caches together (N = 8192 -> 256 CTAs,
+// 6.9 warps / SM).  Each lane reads its own aircraft's slice of the 320 B
 // struct-of-arrays arena state with coalesced 8-byte loads, the quad advances the arena through
 //   action decode -> scripted opponents -> tick (kinematics, cannon, rockets; WGS84 FP64) ->
 //   rewards / out-of-bounds / termination -> (auto-reset) -> observations
@@ -24,11 +25,21 @@
 namespace hh {
 
 #ifndef HH_CTA_THREADS
-#define HH_CTA_THREADS 32
+#define HH_CTA_THREADS 128
+#endif
+#ifndef HH_NO_PHASE_SYNC
+#define HH_PHASE_SYNC 1
 #endif
 constexpr int kThreads = HH_CTA_THREADS;     // warps per CTA x 32; 8 arenas per warp
 __device__ __forceinline__ void cta_sync() {
   if (kThreads == 32) __syncwarp(); else __syncthreads();
+}
+// Re-aligns the warps of a CTA at phase boundaries: the step is ~10 k instructions of straight-line code per
+// warp; warps that drift apart each stream their own copy through the instruction caches (profiles/README.md).
+__device__ __forceinline__ void phase_sync() {
+#ifdef HH_PHASE_SYNC
+  if (kThreads > 32) __syncthreads();
+#endif
 }
 constexpr int kArenasPerCta = kThreads / 4;
 
@@ -165,6 +176,7 @@ __device__ __forceinline__ bool tick_and_rewards(Lane& L, const Rng& rng, const 
     L.crem = L.crem > 0 ? L.crem - 1 : 0;
   }
   // every unit's move (Unit.update, cmano_simulator.py:65-72) depends only on itself
+  phase_sync();
   double nlat = L.lat, nlon = L.lon;
   if (upd && L.spd > 0.0) {
     const double2 q = geo::direct(L.lat, L.lon, L.hdg, L.spd * kKnotsToMs * 1.0);
@@ -173,6 +185,7 @@ __device__ __forceinline__ bool tick_and_rewards(Lane& L, const Rng& rng, const 
   }
   // cannon geometry: shooter u sees lower ids at their NEW position, higher ids at the OLD one,
   // itself at its old position with its new heading (ac1.py:105-115, A.3 of SURVEY.md)
+  phase_sync();
   int in_range = 0;
   {
     const double range = is_ac1(u) ? 2.0 : 4.5, half_w = (is_ac1(u) ? 10.0 : 7.0) / 2.0;
@@ -228,6 +241,7 @@ __device__ __forceinline__ bool tick_and_rewards(Lane& L, const Rng& rng, const 
     L.lon = nlon;
   }
   // rockets (rocket_unit.py:37-73), after every aircraft, in launch (id) order
+  phase_sync();
   {
     const int t = L.rtgt > 0 ? L.rtgt - 1 : 0;
     const double t_lat = qshfl(L.lat, t), t_lon = qshfl(L.lon, t);     // targets have already moved
@@ -281,6 +295,7 @@ __device__ __forceinline__ bool tick_and_rewards(Lane& L, const Rng& rng, const 
   L.alive = (alive_m >> u) & 1;
 
   // ---- rewards, evaluated identically in the four lanes
+  phase_sync();
   {
     const double s = P.rew_scale;
     const int oob_m = quad_ballot(L.alive && !in_boundary(g, L.lat, L.lon));
@@ -377,6 +392,7 @@ __device__ __forceinline__ void finish_step(Lane& L, const Rng& rng, const Geom&
     if (done_out) done_out[a] = done ? 1 : 0;
   }
   if (done && P.autoreset) reset_lane(L, rng, P, u);
+  phase_sync();
   write_agent_obs<MODE>(L, g, u, obs1, obs2, s1, s2, arena0, n_valid);
   store_lane(S, a, u, L, valid);
 }
@@ -415,6 +431,7 @@ step_kernel(StatePtrs S, Params P, const int32_t* __restrict__ actions, float* _
   double near_dn, rel_focus;
   pre_tick_relations<LEVEL == 3>(L, u, g, p, near_t, near_dn, rel_focus, rel_sign);
   const double opp_focus = u < 2 ? focus_norm_from_deg(rel_focus) : 0.0;  // 0 when no opp_stats entry
+  phase_sync();
 
   bool want_missile;
   int tgt, new_wait;
@@ -442,8 +459,10 @@ step_kernel(StatePtrs S, Params P, const int32_t* __restrict__ actions, float* _
       want_missile = d.want_missile;
       tgt = d.tgt;
     }
+    phase_sync();
   }
   launch_phase(L, u, p, want_missile, tgt);
+  phase_sync();
   if (want_missile) {
     if (u < 2) {
       L.mwait = new_wait;
