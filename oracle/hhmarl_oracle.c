@@ -79,6 +79,10 @@ struct orc_env {
   orc_policy_fn policy_fn;
   void* policy_user;
   int error; /* set where the reference would raise */
+  /* HighLevelEnv (env_hier.py): opp_to_attack[i] is a LIST [[id, d_norm, d_raw], ...]; commander actions */
+  struct { int id; double d_norm, d_raw; } ota_list[ORC_MAX_AC + 1][ORC_MAX_AC];
+  int ota_n[ORC_MAX_AC + 1];
+  int commander_actions[ORC_MAX_AC + 1]; /* -1 = None */
 };
 
 /* ------------------------------------------------------------------ small helpers */
@@ -592,25 +596,30 @@ static void state(orc_env_t* e, float* obs1, float* obs2) {
 
 /* ------------------------------------------------------------------ actions */
 /* env_base.py:214-238 (mode "LowLevel") */
-static void take_base_action(orc_env_t* e, unit_t* unit, int unit_id, int opp_id,
-                             const int32_t* act, double* rewards) {
+static void take_base_action_mode(orc_env_t* e, int highlevel, unit_t* unit, int unit_id, int opp_id,
+                                  const int32_t* act, double* rewards) {
   set_heading(e, unit, pymod(unit->heading + (act[0] - 6) * 15, 360));
   set_speed(e, unit, 100 + ((unit->max_speed - 100) / 8) * act[1]);
   if (act[2] != 0 && unit->cannon_remain_secs > 0) {
     fire_cannon(unit);
-    if (unit_id <= e->args.num_agents)
+    if (!highlevel && unit_id <= e->args.num_agents)
       if (e->args.agent_mode == 1 && unit->cannon_remain_secs < 90) rewards[unit_id] -= 0.1;
   }
   if (unit->ac_type == 1 && act[3] != 0) {
     if (opp_id && unit->missile_remain > 0 && !unit->actual_missile && e->missile_wait[unit_id] == 0) {
       fire_missile(e, unit, U(e, opp_id));
-      e->missile_wait[unit_id] = orc_rng_randint(&e->rng_g, 7, 17);
-      if (unit_id <= e->args.num_agents)
+      e->missile_wait[unit_id] = highlevel ? orc_rng_randint(&e->rng_g, 8, 12) : orc_rng_randint(&e->rng_g, 7, 17);
+      if (!highlevel && unit_id <= e->args.num_agents)
         if (e->args.agent_mode == 1 && unit->missile_remain < 3) rewards[unit_id] -= 0.1;
     }
   }
   if (e->missile_wait[unit_id] > 0 && !unit->actual_missile)
     e->missile_wait[unit_id] = e->missile_wait[unit_id] - 1;
+}
+
+static void take_base_action(orc_env_t* e, unit_t* unit, int unit_id, int opp_id, const int32_t* act,
+                             double* rewards) {
+  take_base_action_mode(e, 0, unit, unit_id, opp_id, act, rewards);
 }
 
 /* env_hetero.py:118-123 */
@@ -964,6 +973,338 @@ static void reset_scenario(orc_env_t* e) {
         e->alive_opps += 1;
     }
   }
+}
+
+
+/* ================================================================== HighLevelEnv (envs/env_hier.py) */
+/* opp_ac_values(mode="HighLevel"), env_base.py:185-212: 10 values */
+static int opp_ac_values_hl(orc_env_t* e, int opp_id, int agent_id, double dist, double* st) {
+  const unit_t* unit = U(e, opp_id);
+  int n = 0;
+  relative_position(e, unit->lat, unit->lon, &st[0], &st[1]);
+  n = 2;
+  st[n++] = clip(unit->speed / unit->max_speed, 0, 1);
+  st[n++] = hdg_feature(unit);
+  st[n++] = heading_diff(e, opp_id, agent_id);
+  st[n++] = focus_angle(e, agent_id, opp_id, 1);
+  st[n++] = focus_angle(e, opp_id, agent_id, 1);
+  st[n++] = aspect_angle(e, agent_id, opp_id);
+  st[n++] = aspect_angle(e, opp_id, agent_id);
+  st[n++] = dist;
+  return n;
+}
+
+/* HighLevelEnv.state, env_hier.py:49-98 */
+static void hier_state(orc_env_t* e, float* obs) {
+  int ag, k, na = e->args.num_agents;
+  for (ag = 1; ag <= e->total_num; ++ag) {
+    e->ota_n[ag] = 0;
+    if (ag <= na) {
+      float* out = obs + (size_t)(ag - 1) * ORC_OBS_HL;
+      for (k = 0; k < ORC_OBS_HL; ++k) out[k] = 0.0f;
+      if (unit_exists(e, ag)) {
+        near_t opps[ORC_MAX_AC], fri[ORC_MAX_AC];
+        int n_opps = nearby_object(e, ag, 0, opps);
+        if (n_opps) {
+          double st[64];
+          const unit_t* unit = U(e, ag);
+          int n = 0, filled = 0, n_fri, ffilled = 0;
+          relative_position(e, unit->lat, unit->lon, &st[0], &st[1]);
+          n = 2;
+          st[n++] = clip(unit->speed / unit->max_speed, 0, 1);
+          st[n++] = hdg_feature(unit);
+          for (k = 0; k < n_opps; ++k) {
+            filled += opp_ac_values_hl(e, opps[k].id, ag, opps[k].d_norm, st + n + filled);
+            e->ota_list[ag][e->ota_n[ag]].id = opps[k].id;
+            e->ota_list[ag][e->ota_n[ag]].d_norm = opps[k].d_norm;
+            e->ota_list[ag][e->ota_n[ag]].d_raw = opps[k].d_raw;
+            e->ota_n[ag] += 1;
+            if (filled == 20) break;
+          }
+          for (; filled < 20; ++filled) st[n + filled] = 0;
+          n += 20;
+          n_fri = nearby_object(e, ag, 1, fri);
+          for (k = 0; k < n_fri; ++k) {
+            ffilled += friendly_ac_values(e, ag, fri[k].id, st + n + ffilled);
+            if (ffilled == 10) break;
+          }
+          for (; ffilled < 10; ++ffilled) st[n + ffilled] = 0;
+          n += 10;
+          if (n != ORC_OBS_HL) e->error |= 16;
+          for (k = 0; k < ORC_OBS_HL; ++k) out[k] = (float)st[k];
+        }
+      }
+    } else if (unit_exists(e, ag)) {
+      near_t opps[ORC_MAX_AC];
+      int n_opps = nearby_object(e, ag, 0, opps);
+      for (k = 0; k < n_opps; ++k) {
+        e->ota_list[ag][k].id = opps[k].id;
+        e->ota_list[ag][k].d_norm = opps[k].d_norm;
+        e->ota_list[ag][k].d_raw = opps[k].d_raw;
+      }
+      e->ota_n[ag] = n_opps;
+    }
+  }
+}
+
+/* python list indexing l[idx] with negative wrap; returns -1 when out of range (IndexError) */
+static int py_index(int n, int idx) {
+  if (idx < 0) idx += n;
+  return (idx >= 0 && idx < n) ? idx : -1;
+}
+
+/* HighLevelEnv.lowlevel_state, env_hier.py:100-112 */
+static int hier_lowlevel_state(orc_env_t* e, int mode, int agent_id, float* out) {
+  double st[64];
+  near_t fri[ORC_MAX_AC], opps[ORC_MAX_AC];
+  unit_t* unit = U(e, agent_id);
+  int n_fri = nearby_object(e, agent_id, 1, fri), k, n, len;
+  int fri_id = n_fri ? fri[0].id : 0;
+  int ca = e->commander_actions[agent_id];
+  for (k = 0; k < e->ota_n[agent_id]; ++k) {
+    opps[k].id = e->ota_list[agent_id][k].id;
+    opps[k].d_norm = e->ota_list[agent_id][k].d_norm;
+    opps[k].d_raw = e->ota_list[agent_id][k].d_raw;
+  }
+  if (mode == 0) {
+    int idx = py_index(e->ota_n[agent_id], ca - 1);
+    if (idx < 0) { e->error |= 128; idx = 0; }
+    n = fight_state_values(e, agent_id, &opps[idx], fri_id, st);
+    len = unit->ac_type == 1 ? OBS_AC1 : OBS_AC2;
+  } else {
+    n = esc_state_values(e, agent_id, opps, e->ota_n[agent_id], fri_id, st);
+    len = unit->ac_type == 1 ? OBS_ESC_AC1 : OBS_ESC_AC2;
+  }
+  if (n != len) e->error |= 16;
+  for (k = 0; k < len; ++k) out[k] = (float)st[k];
+  return len;
+}
+
+/* HighLevelEnv._action_assess, env_hier.py:142-190 */
+static void hier_action_assess(orc_env_t* e, double* rewards) {
+  int i, na = e->args.num_agents;
+  for (i = 1; i <= e->total_num; ++i) {
+    if (unit_exists(e, i)) {
+      if (i <= na) {
+        rewards[i] = 0;
+        if (e->commander_actions[i] > 0) {
+          int idx = py_index(e->ota_n[i], e->commander_actions[i] - 1);
+          int opp_id = 0;
+          if (idx >= 0) {
+            opp_id = e->ota_list[i][idx].id;
+          } else {
+            e->commander_actions[i] = 1;
+          }
+          if (!opp_id) rewards[i] = -0.1;
+          if (e->args.hier_action_assess && opp_id) {
+            if (distance(e, i, opp_id, 0) < 0.1 && focus_angle(e, i, opp_id, 0) < 15 && focus_angle(e, opp_id, i, 0) > 40)
+              rewards[i] = 0.1;
+            else
+              rewards[i] = 0;
+          }
+        } else if (e->args.hier_action_assess) {
+          if (e->ota_n[i] > 0) {
+            int cl_opp = e->ota_list[i][0].id;
+            if (distance(e, cl_opp, i, 0) < 0.1 && focus_angle(e, cl_opp, i, 0) < 15 && focus_angle(e, i, cl_opp, 0) > 40)
+              rewards[i] = 0.1;
+          } else {
+            e->error |= 128; /* IndexError in the reference */
+          }
+        }
+      } else {
+        /* Fraction(ratio, 100).limit_denominator().as_integer_ratio() */
+        int p = e->args.hier_opp_fight_ratio, q = 100, a = p, b = q, ag_id;
+        while (b) { int t = a % b; a = b; b = t; }
+        if (a > 0) { p /= a; q /= a; }
+        if (orc_rng_choice2(&e->rng_g, (double)(q - p), (double)p)) {
+          int possible = e->ota_n[i];
+          if (possible > 1 && orc_rng_choice2(&e->rng_g, 1.0, 3.0))
+            ag_id = orc_rng_randint(&e->rng_g, 2, possible);
+          else
+            ag_id = 1;
+        } else {
+          ag_id = 0;
+        }
+        e->commander_actions[i] = ag_id;
+      }
+    } else {
+      if (i <= na) rewards[i] = 0;
+      e->commander_actions[i] = -1;
+    }
+  }
+}
+
+/* HighLevelEnv._surrounding_event, env_hier.py:192-208 */
+static int hier_surrounding_event(orc_env_t* e) {
+  int i, j, event = 0, na = e->args.num_agents;
+  for (i = 1; i <= na; ++i) {
+    for (j = na + 1; j <= e->total_num; ++j) {
+      if (unit_exists(e, i) && unit_exists(e, j)) {
+        event = 0;
+        if (distance(e, i, j, 0) < 0.1)
+          if (focus_angle(e, i, j, 0) < 15 || focus_angle(e, j, i, 0) < 15) event = 1;
+      }
+      if (event) break;
+    }
+    if (event) break;
+  }
+  return event;
+}
+
+/* _combat_rewards(mode="HighLevel") (env_base.py:240-310) + HighLevelEnv._get_rewards (env_hier.py:210-224) */
+static int hier_get_rewards(orc_env_t* e, double* rewards, const event_t* events, int n_events) {
+  double s = e->args.rew_scale, rews[ORC_MAX_AC + 1];
+  int destroyed[ORC_MAX_AC + 1], kill_event = 0, i, k, na = e->args.num_agents;
+  memset(rews, 0, sizeof rews);
+  memset(destroyed, 0, sizeof destroyed);
+  for (i = 1; i <= e->total_num; ++i) {
+    if (unit_exists(e, i)) {
+      unit_t* u = U(e, i);
+      if (!in_boundary(e, u->lat, u->lon)) {
+        remove_unit(e, i);
+        kill_event = 1;
+        if (i <= na) {
+          rews[i] += -2 * s;
+          destroyed[i] = 1;
+          e->alive_agents -= 1;
+        } else {
+          e->alive_opps -= 1;
+        }
+      }
+    }
+  }
+  for (k = 0; k < n_events; ++k) {
+    const event_t* ev = &events[k];
+    if (ev->killer <= na) {
+      if (ev->destroyed >= na + 1 && ev->destroyed <= e->total_num) {
+        rews[ev->killer] += 1; /* constant, unscaled (env_base.py:285) */
+        e->alive_opps -= 1;
+      } else if (ev->destroyed <= na) {
+        e->alive_agents -= 1;
+      }
+    } else if (ev->killer >= na + 1 && ev->killer <= e->total_num) {
+      if (ev->destroyed <= na) {
+        rews[ev->destroyed] += -1 * s;
+        destroyed[ev->destroyed] = 1;
+        e->alive_agents -= 1;
+      } else if (ev->destroyed >= na + 1 && ev->destroyed <= e->total_num) {
+        e->alive_opps -= 1;
+      }
+    }
+    kill_event = 1;
+  }
+  for (i = 1; i <= na; ++i) {
+    if (unit_exists(e, i) || destroyed[i]) {
+      if (e->args.glob_frac > 0) {
+        double others = 0;
+        int j;
+        for (j = 1; j <= na; ++j)
+          if (j != i) others += rews[j];
+        rewards[i] += rews[i] + e->args.glob_frac * others;
+      } else {
+        rewards[i] += rews[i];
+      }
+    }
+  }
+  return kill_event;
+}
+
+/* HighLevelEnv._sample_state (env_hier.py:226-250) + _reset_scenario(mode="HighLevel") (env_base.py:551-585) */
+static void hier_reset_scenario(orc_env_t* e) {
+  int r = orc_rng_randint(&e->rng_g, 1, 2);
+  int group, i;
+  for (group = 0; group < 2; ++group) {
+    int count = group == 0 ? e->args.num_agents : e->args.num_opps;
+    for (i = 0; i < count; ++i) {
+      double x, y, step = 0.4 / count;
+      int a, ac, west = (group == 0) == (r == 1);
+      unit_t u;
+      x = west ? orc_rng_uniform(&e->rng_g, 7.07, 7.22) : orc_rng_uniform(&e->rng_g, 7.28, 7.43);
+      y = orc_rng_uniform(&e->rng_g, 5.07 + i * step, 5.12 + i * step);
+      a = orc_rng_randint(&e->rng_g, 0, 359);
+      ac = i <= 1 ? i + 1 : orc_rng_randint(&e->rng_g, 1, 2);
+      memset(&u, 0, sizeof u);
+      u.kind = ac == 1 ? KIND_AC1 : KIND_AC2;
+      u.lat = y;
+      u.lon = x;
+      u.heading = a;
+      u.speed = (e->args.level <= 2 && group == 1) ? 0 : 100; /* args.level keeps its default 1 in train_hier.py */
+      u.new_heading = u.heading;
+      u.new_speed = u.speed;
+      u.max_speed = ac == 1 ? 900 : 600;
+      u.cannon_remain_secs = u.cannon_max = 300; /* env_base.py:575-578 */
+      u.missile_remain = u.rocket_max = ac == 1 ? 8 : 0;
+      u.friendly_check = e->args.friendly_kill;
+      u.group = group;
+      u.ac_type = ac;
+      add_unit(e, &u);
+      if (group == 0)
+        e->alive_agents += 1;
+      else
+        e->alive_opps += 1;
+    }
+  }
+}
+
+void orc_hier_reset(orc_env_t* e, float* obs) {
+  int i;
+  e->steps = 0;
+  e->alive_agents = 0;
+  e->alive_opps = 0;
+  e->hardcoded_opps_escaping = 0;
+  e->opps_escaping_time = 0;
+  for (i = 0; i <= ORC_MAX_AC; ++i) {
+    e->missile_wait[i] = 0;
+    e->opp_to_attack[i] = 0;
+    e->ota_n[i] = 0;
+    e->commander_actions[i] = -1;
+  }
+  memset(e->units, 0, sizeof e->units);
+  e->next_unit_id = 1;
+  e->utc_time = 0;
+  hier_reset_scenario(e);
+  hier_state(e, obs);
+}
+
+/* HHMARLBaseEnv.step + HighLevelEnv._take_action, env_base.py:79-109, env_hier.py:114-140 */
+int orc_hier_step(orc_env_t* e, const int32_t* commander_actions, float* obs, double* rew, int32_t* info) {
+  double rewards[ORC_MAX_AC + 1];
+  event_t events[ORC_MAX_UNITS];
+  int s = 0, kill_event = 0, situation_event = 0, i, na = e->args.num_agents;
+  const int n_sub_steps = 15, min_sub_steps = 10;
+  memset(rewards, 0, sizeof rewards);
+  for (i = 1; i <= e->total_num; ++i) e->commander_actions[i] = i <= na ? commander_actions[i - 1] : -1;
+  hier_action_assess(e, rewards);
+  if (info)
+    for (i = 1; i <= e->total_num; ++i) info[i] = e->commander_actions[i];
+  while (s <= n_sub_steps && !kill_event && !situation_event) {
+    int n_events;
+    for (i = 1; i <= e->total_num; ++i) {
+      if (unit_exists(e, i)) {
+        unit_t* u = U(e, i);
+        float pobs[64];
+        int32_t act[4] = {0, 0, 0, 0};
+        int mode = e->commander_actions[i] == 0 ? 1 : 0;
+        int len = hier_lowlevel_state(e, mode, i, pobs);
+        int idx = py_index(e->ota_n[i], e->commander_actions[i] - 1);
+        if (e->policy_fn)
+          e->policy_fn(e->policy_user, i, u->ac_type, mode, 0, pobs, len, act);
+        else
+          e->error |= 32;
+        if (idx < 0) { e->error |= 128; idx = 0; }
+        take_base_action_mode(e, 1, u, i, e->ota_list[i][idx].id, act, rewards);
+      }
+    }
+    n_events = do_tick(e, events);
+    kill_event = hier_get_rewards(e, rewards, events, n_events);
+    if (s > min_sub_steps) situation_event = hier_surrounding_event(e);
+    s += 1;
+    e->steps += 1;
+  }
+  if (info) info[0] = s;
+  for (i = 1; i <= na; ++i) rew[i - 1] = rewards[i];
+  hier_state(e, obs);
+  return e->alive_agents <= 0 || e->alive_opps <= 0 || e->steps >= e->args.horizon;
 }
 
 /* ------------------------------------------------------------------ public API */

@@ -34,6 +34,9 @@ typedef struct {
   double map_size;         /* 0.3 */
   double rew_scale;        /* 1 */
   double glob_frac;        /* 0 */
+  /* HighLevelEnv only (config.py:23,44) */
+  int32_t hier_action_assess;   /* bool, default True */
+  int32_t hier_opp_fight_ratio; /* percent, default 75 */
 } orc_args_t;
 
 typedef struct orc_env orc_env_t;
@@ -75,6 +78,14 @@ typedef struct {
 
 void orc_env_get_state(const orc_env_t* e, orc_state_t* out);
 int orc_obs_len(const orc_args_t* args, int agent_id);
+
+/* ---- HighLevelEnv (envs/env_hier.py): 3-vs-3 commander environment.  obs: float32 [num_agents][34];
+ * commander_actions: int32[num_agents] in {0,1,2}; rew: double[num_agents] (every agent has an entry);
+ * info[0] = number of low-level sub-steps taken, info[1..total_num] = commander action of unit id (after
+ * _action_assess, -1 for None).  The policy callback is used for ALL aircraft (env_hier.py:126-130). */
+#define ORC_OBS_HL 34
+void orc_hier_reset(orc_env_t* e, float* obs);
+int orc_hier_step(orc_env_t* e, const int32_t* commander_actions, float* obs, double* rew, int32_t* info);
 
 /* Throughput helper for bench.py's CPU baseline: runs `n_steps` env steps with auto-reset and
  * uniformly random MultiDiscrete actions (own xorshift stream, not the contract RNG). */

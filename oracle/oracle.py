@@ -36,7 +36,8 @@ def build(force: bool = False) -> str:
 class OrcArgs(ctypes.Structure):
     _fields_ = [("level", I32), ("agent_mode", I32), ("horizon", I32), ("num_agents", I32),
                 ("num_opps", I32), ("esc_dist_rew", I32), ("friendly_kill", I32),
-                ("friendly_punish", I32), ("map_size", D), ("rew_scale", D), ("glob_frac", D)]
+                ("friendly_punish", I32), ("map_size", D), ("rew_scale", D), ("glob_frac", D),
+                ("hier_action_assess", I32), ("hier_opp_fight_ratio", I32)]
 
 
 class OrcState(ctypes.Structure):
@@ -89,6 +90,10 @@ def lib():
         L.orc_env_get_state.restype = None
         L.orc_obs_len.argtypes = [P(OrcArgs), ctypes.c_int]
         L.orc_obs_len.restype = ctypes.c_int
+        L.orc_hier_reset.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.orc_hier_reset.restype = None
+        L.orc_hier_step.argtypes = [ctypes.c_void_p] * 5
+        L.orc_hier_step.restype = ctypes.c_int
         L.orc_env_run_random.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64]
         L.orc_env_run_random.restype = ctypes.c_uint64
         _lib = L
@@ -161,7 +166,17 @@ def make_args(level=1, agent_mode="fight", horizon=None, map_size=0.3, rew_scale
     return OrcArgs(level=level, agent_mode=0 if agent_mode == "fight" else 1, horizon=horizon,
                    num_agents=2, num_opps=2, esc_dist_rew=int(esc_dist_rew),
                    friendly_kill=int(friendly_kill), friendly_punish=int(friendly_punish),
-                   map_size=map_size, rew_scale=rew_scale, glob_frac=glob_frac)
+                   map_size=map_size, rew_scale=rew_scale, glob_frac=glob_frac, hier_action_assess=1,
+                   hier_opp_fight_ratio=75)
+
+
+def make_hier_args(horizon=500, map_size=0.5, rew_scale=1.0, glob_frac=0.0, friendly_kill=True,
+                   hier_action_assess=True, hier_opp_fight_ratio=75, level=1) -> OrcArgs:
+    """Config(1) defaults of the reference (config.py:17-57,98): 3-vs-3, map 0.5, horizon 500, level left at 1."""
+    return OrcArgs(level=level, agent_mode=0, horizon=horizon, num_agents=3, num_opps=3, esc_dist_rew=0,
+                   friendly_kill=int(friendly_kill), friendly_punish=0, map_size=map_size, rew_scale=rew_scale,
+                   glob_frac=glob_frac, hier_action_assess=int(hier_action_assess),
+                   hier_opp_fight_ratio=int(hier_opp_fight_ratio))
 
 
 class OracleEnv:
@@ -207,6 +222,53 @@ class OracleEnv:
 
     def run_random(self, n_steps: int, action_seed: int = 1) -> int:
         return lib().orc_env_run_random(self._h, n_steps, action_seed)
+
+    def close(self):
+        if self._h:
+            lib().orc_env_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class OracleHierEnv:
+    """Single-arena C oracle of the reference's HighLevelEnv (envs/env_hier.py)."""
+
+    def __init__(self, args: OrcArgs, seed: int, arena_id: int, policy_fn):
+        self.args = args
+        self._h = lib().orc_env_create(ctypes.byref(args), seed, arena_id)
+        self.obs = np.zeros((3, 34), np.float32)
+        self.rew = np.zeros(3, np.float64)
+        self.info = np.zeros(8, np.int32)
+        self.set_policy_fn(policy_fn)
+
+    def set_policy_fn(self, fn):
+        def _tramp(user, unit_id, ac_type, mode, pset, obs_p, obs_len, act_p):
+            obs = np.ctypeslib.as_array(obs_p, shape=(obs_len,)).copy()
+            act = fn(unit_id, ac_type, mode, pset, obs)
+            for i, a in enumerate(act):
+                act_p[i] = int(a)
+        self._cb = POLICY_FN(_tramp)
+        lib().orc_env_set_policy_fn(self._h, self._cb, None)
+
+    def reset(self):
+        lib().orc_hier_reset(self._h, self.obs.ctypes.data)
+        return self.obs.copy()
+
+    def step(self, commander_actions):
+        a = np.ascontiguousarray(commander_actions, dtype=np.int32)
+        done = lib().orc_hier_step(self._h, a.ctypes.data, self.obs.ctypes.data, self.rew.ctypes.data,
+                                   self.info.ctypes.data)
+        return self.obs.copy(), self.rew.copy(), bool(done), self.info.copy()
+
+    def state(self) -> OrcState:
+        s = OrcState()
+        lib().orc_env_get_state(self._h, ctypes.byref(s))
+        return s
 
     def close(self):
         if self._h:

@@ -65,4 +65,9 @@ static inline int orc_rng_randint(orc_rng_t* s, int a, int b) {
   return a + (int)(orc_rng_random(s) * (double)(b - a + 1));
 }
 
+/* random.choices([0, 1], weights=[w0, w1], k=1)[0]: bisect(cum_weights, random() * total) */
+static inline int orc_rng_choice2(orc_rng_t* s, double w0, double w1) {
+  return orc_rng_random(s) * (w0 + w1) >= w0 ? 1 : 0;
+}
+
 #endif

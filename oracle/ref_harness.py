@@ -315,3 +315,92 @@ def reference_models():
     install_model_stubs()
     import models.ac_models_hetero as m
     return m
+
+
+# ------------------------------------------------------------------ reference HighLevelEnv under stubs
+def make_hier_namespace(horizon=500, map_size=0.5, rew_scale=1, glob_frac=0.0, friendly_kill=True,
+                        hier_action_assess=True, hier_opp_fight_ratio=75, level=1) -> Namespace:
+    """Config(1) of the reference (config.py:17-57, 94-107) without argparse."""
+    return Namespace(level=level, horizon=horizon, agent_mode="fight", num_agents=3, num_opps=3, total_num=6,
+                     map_size=map_size, rew_scale=rew_scale, glob_frac=glob_frac, esc_dist_rew=False,
+                     friendly_kill=friendly_kill, friendly_punish=False, eval_info=False, eval_hl=True,
+                     eval_level_ag=5, eval_level_opp=5, hier_opp_fight_ratio=hier_opp_fight_ratio,
+                     hier_action_assess=hier_action_assess)
+
+
+class ReferenceHierEnv:
+    """The reference's HighLevelEnv under the RNG contract.  `policy_fn(unit_id, ac_type, mode, obs) -> action`
+    replaces the pickled RLlib policies (env_base.py:312-347) at the point where the reference calls
+    self.policy[...](input_dict=..., state=..., seq_lens=...) (env_base.py:392-396)."""
+
+    def __init__(self, args: Namespace, seed: int, arena_id: int, policy_fn):
+        install()
+        import torch
+        import envs.env_base as env_base
+        import envs.env_hier as env_hier
+        env_hier.random = _PROXY
+        self.g = orc.PhiloxStream(seed, arena_id, 0)
+        self.c = orc.PhiloxStream(seed, arena_id, 1)
+        outer = self
+
+        class _Pol:
+            def __init__(self, mode, ac_type):
+                self.mode, self.ac_type = mode, ac_type
+
+            def __call__(self, input_dict=None, state=None, seq_lens=None):
+                obs = input_dict["obs"]["obs_1_own"][0].numpy()
+                act = policy_fn(outer._cur_unit, self.ac_type, self.mode, obs)
+                heads = (13, 9, 2, 2) if self.ac_type == 1 else (13, 9, 2)
+                logits = torch.full((1, sum(heads)), -10.0)
+                o = 0
+                for h, a in zip(heads, act):
+                    logits[0, o + int(a)] = 10.0
+                    o += h
+                return logits, []
+
+        def _get(this, mode):
+            this.policy = {f"{m}_{t}": _Pol(0 if m == "fight" else 1, t) for m in ("fight", "escape") for t in (1, 2)}
+
+        orig_get = env_base.HHMARLBaseEnv._get_policies
+        orig_pa = env_base.HHMARLBaseEnv._policy_actions
+
+        def _pa(this, policy_type, agent_id, unit):
+            outer._cur_unit = agent_id
+            return orig_pa(this, policy_type, agent_id, unit)
+
+        env_base.HHMARLBaseEnv._get_policies = _get
+        try:
+            self.env = env_hier.HighLevelEnv({"args": args})
+        finally:
+            env_base.HHMARLBaseEnv._get_policies = orig_get
+        self.env._policy_actions = types.MethodType(_pa, self.env)
+
+    def reset(self):
+        _PROXY.stream = self.g
+        import envs.env_base as env_base
+        orig_sim = env_base.CmanoSimulator
+        c = self.c
+
+        def _sim(*a, **k):
+            s = orig_sim(*a, **k)
+            s.rnd_gen = c
+            return s
+
+        env_base.CmanoSimulator = _sim
+        try:
+            obs, _ = self.env.reset()
+        finally:
+            env_base.CmanoSimulator = orig_sim
+        return np.stack([obs[i] for i in (1, 2, 3)])
+
+    def step(self, commander_actions):
+        _PROXY.stream = self.g
+        ca = {i + 1: int(a) for i, a in enumerate(commander_actions)}
+        steps0 = self.env.steps
+        obs, rew, term, trunc, info = self.env.step(ca)
+        return (np.stack([obs[i] for i in (1, 2, 3)]), np.array([rew[i] for i in (1, 2, 3)], np.float64),
+                bool(term["__all__"]), self.env.steps - steps0, dict(ca))
+
+    def scalars(self):
+        e = self.env
+        return [e.steps, e.alive_agents, e.alive_opps, e.sim._next_unit_id, self.g.draw, self.c.draw]
