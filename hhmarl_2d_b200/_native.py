@@ -12,7 +12,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("HH_LIB_PATH") or os.path.join(CSRC, "libhhmarl_b200.so")
-SOURCES = ["hh_api.cu"]
+SOURCES = ["hh_api.cu", "hh_hier.cu"]
 HEADERS = ["hh_quad.cuh", "hh_core.cuh", "hh_geodesic.cuh", os.path.join("..", "..", "include", "hhmarl_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
@@ -40,6 +40,23 @@ _I32_1 = ("steps", "alive_agents", "alive_opps", "escaping", "escaping_time", "n
 _U64_1 = ("draws_g", "draws_c")
 STATE_FIELDS = ([(n, "f8", 4) for n in _F64_4] + [(n, "i4", 4) for n in _I32_4] + [(n, "f8", 2) for n in _F64_2]
                 + [(n, "i4", 2) for n in _I32_2] + [(n, "i4", 1) for n in _I32_1] + [(n, "u8", 1) for n in _U64_1])
+
+
+class HHHierConfig(ctypes.Structure):
+    _fields_ = [("horizon", I32), ("level", I32), ("friendly_kill", I32), ("hier_action_assess", I32),
+                ("hier_opp_fight_ratio", I32), ("autoreset", I32), ("map_size", D), ("rew_scale", D), ("glob_frac", D),
+                ("seed", U64), ("arena_base", U64)]
+
+
+class HHHierArena(ctypes.Structure):
+    _fields_ = ([(n, D * 6) for n in ("lat", "lon", "hdg", "spd", "nhdg", "nspd", "rlat", "rlon", "rhdg", "rnhdg")]
+                + [("ota_dn", (D * 3) * 6), ("rewards", D * 3), ("dg", U64)]
+                + [(n, I32 * 6) for n in ("crem", "burst", "mrem", "mwait", "rid")]
+                + [(n, I32) for n in ("steps", "alive_ag", "alive_op", "next_id", "sub", "kill_event",
+                                      "situation_event", "active", "err")]
+                + [("dc", ctypes.c_uint32), ("ca", ctypes.c_int8 * 6)]
+                + [(n, ctypes.c_uint8 * 6) for n in ("alive", "hasm", "actype", "ralive", "rage", "rtgt", "ota_n")]
+                + [("ota_id", (ctypes.c_uint8 * 3) * 6)])
 
 
 class HHStateView(ctypes.Structure):
@@ -106,6 +123,24 @@ def lib() -> ctypes.CDLL:
     L.hh_gae.restype = ctypes.c_int
     L.hh_debug_geodesic.argtypes = [I32, I32, VP, VP]
     L.hh_debug_geodesic.restype = ctypes.c_int
+    L.hh_hier_create.argtypes = [P(HHHierConfig), I32, I32, P(VP)]
+    L.hh_hier_create.restype = ctypes.c_int
+    L.hh_hier_destroy.argtypes = [VP]
+    L.hh_hier_destroy.restype = None
+    L.hh_hier_reset.argtypes = [VP, VP, VP, VP]
+    L.hh_hier_reset.restype = ctypes.c_int
+    for fn in ("hh_hier_begin", "hh_hier_agents", "hh_hier_tick"):
+        getattr(L, fn).argtypes = [VP, VP, VP, VP, VP]
+        getattr(L, fn).restype = ctypes.c_int
+    L.hh_hier_end.argtypes = [VP, VP, VP, VP, VP, VP]
+    L.hh_hier_end.restype = ctypes.c_int
+    L.hh_hier_get_state.argtypes = [VP, VP]
+    L.hh_hier_get_state.restype = ctypes.c_int
+    L.hh_hier_set_state.argtypes = [VP, VP]
+    L.hh_hier_set_state.restype = ctypes.c_int
+    L.hh_hier_launch_count.argtypes = [VP]
+    L.hh_hier_launch_count.restype = U64
+    L.hh_hier_last_error.restype = ctypes.c_char_p
     L.hh_last_error.restype = ctypes.c_char_p
     L.hh_version.restype = ctypes.c_char_p
     _lib = L
@@ -113,12 +148,14 @@ def lib() -> ctypes.CDLL:
 
 
 EXPORTS = ["hh_create", "hh_destroy", "hh_n_arenas", "hh_obs_dim", "hh_reset", "hh_step", "hh_step_begin", "hh_step_finish", "hh_reset_host",
-           "hh_step_host", "hh_host_buffers", "hh_get_state", "hh_set_state", "hh_launch_count", "hh_gae", "hh_debug_geodesic", "hh_last_error", "hh_version"]
+           "hh_step_host", "hh_host_buffers", "hh_get_state", "hh_set_state", "hh_launch_count", "hh_gae", "hh_debug_geodesic", "hh_last_error", "hh_version",
+           "hh_hier_create", "hh_hier_destroy", "hh_hier_reset", "hh_hier_begin", "hh_hier_agents", "hh_hier_tick",
+           "hh_hier_end", "hh_hier_get_state", "hh_hier_set_state", "hh_hier_launch_count", "hh_hier_last_error"]
 
 
 def check(rc: int, what: str):
     if rc != 0:
-        msg = lib().hh_last_error().decode()
+        msg = (lib().hh_hier_last_error() if what.startswith("hh_hier") else lib().hh_last_error()).decode()
         if rc == -1:
             raise ValueError(f"{what}: {msg}")
         raise RuntimeError(f"{what}: {msg} (code {rc})")

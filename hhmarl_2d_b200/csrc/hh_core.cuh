@@ -46,7 +46,7 @@ __device__ __forceinline__ double rocket_speed(int life) {
 // ------------------------------------------------------------------------------------- RNG
 // Philox4x32-10, key = seed, counter = (draw_lo, draw_hi, arena_id, stream); SURVEY.md A.5.
 // One block per draw; random() = ((w0 >> 5) * 2^26 + (w1 >> 6)) * 2^-53.
-__device__ __noinline__ double philox_u53(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2,
+static __device__ __noinline__ double philox_u53(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2,
                                           uint32_t c3) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {

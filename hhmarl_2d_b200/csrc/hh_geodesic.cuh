@@ -23,12 +23,12 @@ namespace hh {
 // profile (profiles/r1b_*) shows instruction fetch as the top stall.  One shared copy of each keeps
 // the hot math inside the 32 KB L1.5 instruction cache; the call costs ~10 cycles.
 namespace m {
-__device__ __noinline__ void sincos_(double x, double* s, double* c) { ::sincos(x, s, c); }
-__device__ __noinline__ void sincospi_(double x, double* s, double* c) { ::sincospi(x, s, c); }
-__device__ __noinline__ double atan2_(double y, double x) { return ::atan2(y, x); }
-__device__ __noinline__ double acos_(double x) { return ::acos(x); }
+static __device__ __noinline__ void sincos_(double x, double* s, double* c) { ::sincos(x, s, c); }
+static __device__ __noinline__ void sincospi_(double x, double* s, double* c) { ::sincospi(x, s, c); }
+static __device__ __noinline__ double atan2_(double y, double x) { return ::atan2(y, x); }
+static __device__ __noinline__ double acos_(double x) { return ::acos(x); }
 __device__ __forceinline__ double hypot_(double x, double y) { return sqrt(x * x + y * y); }  // operands are O(1): no scaling needed
-__device__ __noinline__ double fmod_(double x, double y) { return ::fmod(x, y); }
+static __device__ __noinline__ double fmod_(double x, double y) { return ::fmod(x, y); }
 }  // namespace m
 
 namespace geo {
@@ -260,7 +260,7 @@ __device__ __forceinline__ double S5(double s, double c, const C5& k) {
 // ---------------------------------------------------------------------------------------------
 // Direct problem. Returns (lat2, lon2) in degrees. azi1 in degrees (any range), s12 in metres.
 // ---------------------------------------------------------------------------------------------
-__device__ __noinline__ double2 direct(double lat1, double lon1, double azi1, double s12) {
+static __device__ __noinline__ double2 direct(double lat1, double lon1, double azi1, double s12) {
   double salp1, calp1, sbet1, cbet1;
   sincosd(ang_round(ang_normalize(azi1)), salp1, calp1);
   sincosd(ang_round(lat1), sbet1, cbet1);
@@ -379,7 +379,7 @@ __device__ __forceinline__ void lambda12(double sbet1, double cbet1, double dn1,
   o.eps = eps;
 }
 
-__device__ __noinline__ double2 inverse(double lat1, double lon1, double lat2, double lon2) {
+static __device__ __noinline__ double2 inverse(double lat1, double lon1, double lat2, double lon2) {
   // lon12 = AngDiff(lon1, lon2) with its error term (both |lon| < 180 here, so the
   // remainder() calls of the general formulation are identities)
   double u = ang_normalize(-lon1), v = ang_normalize(lon2);

@@ -1,0 +1,148 @@
+"""VecHighLevelEnv -- the reference's HighLevelEnv (envs/env_hier.py; 3-vs-3 commander environment, BASELINE
+config 5) for N arenas in lock-step on the GPU (csrc/hh_hier.cu through the hh_hier_* C ABI).
+
+A commander step runs _action_assess, then up to 16 low-level sub-steps in which EVERY live aircraft queries a
+frozen fight or escape policy (env_hier.py:114-140).  The reference does that with one batch-1 forward per
+aircraft per sub-step; here each sub-step is two kernel launches around two batched forwards (agents, then
+opponents -- the opponents observe the agents' fresh fire decisions), arenas whose loop has ended idle.
+
+Low-level policies follow the reference's container (env_base.py:332-341): {"fight_1", "fight_2", "escape_1",
+"escape_2"} -> networks of hhmarl_2d_b200.models (seeded stand-ins when no weights are given: the reference
+loads pickled RLlib models that are not in its repository).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _native as nat
+from . import models as M
+from .spaces import Box, Discrete
+
+OBS_HL, N_ACTIONS_HL = 34, 3   # env_hier.py:20-37
+
+
+def default_lowlevel_policies(seed: int = 0, device="cpu"):
+    import torch  # noqa: F401
+    f1, f2 = M.build_policy_pair("fight")
+    e1, e2 = M.build_policy_pair("escape")
+    for k, m in enumerate((f1, f2, e1, e2)):
+        M.fill_from_seed(m, seed + 200 + k)
+        m.to(device).eval()
+    return {"fight_1": f1, "fight_2": f2, "escape_1": e1, "escape_2": e2}
+
+
+def make_hier_args(horizon=500, map_size=0.5, rew_scale=1.0, glob_frac=0.0, friendly_kill=True,
+                   hier_action_assess=True, hier_opp_fight_ratio=75, level=1):
+    """Config(1) defaults of the reference (config.py:17-57, 98)."""
+    from argparse import Namespace
+    return Namespace(level=level, horizon=horizon, agent_mode="fight", num_agents=3, num_opps=3, total_num=6,
+                     map_size=map_size, rew_scale=rew_scale, glob_frac=glob_frac, friendly_kill=friendly_kill,
+                     hier_action_assess=hier_action_assess, hier_opp_fight_ratio=hier_opp_fight_ratio, eval_hl=True)
+
+
+class VecHighLevelEnv:
+    def __init__(self, n_arenas: int, args=None, device: int = 0, seed: int = 0, arena_base: int = 0,
+                 autoreset: bool = True, lowlevel_policies=None):
+        import torch
+        self._torch = torch
+        self.args = args if args is not None else make_hier_args()
+        a = self.args
+        self.n_arenas, self.device_index = int(n_arenas), int(device)
+        cfg = nat.HHHierConfig(horizon=a.horizon, level=a.level, friendly_kill=int(bool(a.friendly_kill)),
+                               hier_action_assess=int(bool(a.hier_action_assess)),
+                               hier_opp_fight_ratio=int(a.hier_opp_fight_ratio), autoreset=int(bool(autoreset)),
+                               map_size=float(a.map_size), rew_scale=float(a.rew_scale), glob_frac=float(a.glob_frac),
+                               seed=int(seed), arena_base=int(arena_base))
+        self._h = nat.VP()
+        nat.check(nat.lib().hh_hier_create(ctypes.byref(cfg), self.n_arenas, self.device_index, ctypes.byref(self._h)),
+                  "hh_hier_create")
+        self.observation_space = Box(np.zeros(OBS_HL), np.ones(OBS_HL), dtype=np.float32)   # env_hier.py:36
+        self.action_space = Discrete(N_ACTIONS_HL)                                            # env_hier.py:37
+        self._agent_ids = {1, 2, 3}
+        dev = torch.device("cuda", self.device_index)
+        self.dev = dev
+        n = self.n_arenas
+        self.policies = lowlevel_policies if lowlevel_policies is not None else default_lowlevel_policies(0, dev)
+        self.obs = torch.empty((n, 3, OBS_HL), dtype=torch.float32, device=dev)
+        self.rew = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        self.done = torch.empty((n,), dtype=torch.uint8, device=dev)
+        self.substeps = torch.empty((n,), dtype=torch.int32, device=dev)
+        self.ll_obs = torch.zeros((n, 6, 30), dtype=torch.float32, device=dev)
+        self.ll_info = torch.zeros((n, 6), dtype=torch.uint8, device=dev)
+        self.ll_act = torch.zeros((n, 6, 4), dtype=torch.int32, device=dev)
+        self.trace = None   # set to a list to record (phase, ll_obs, ll_info, ll_act) per sub-step (tests)
+
+    def _stream(self):
+        return self._torch.cuda.current_stream(self.device_index).cuda_stream
+
+    def reset(self, mask=None):
+        mp = None if mask is None else mask.data_ptr()
+        nat.check(nat.lib().hh_hier_reset(self._h, mp, self.obs.data_ptr(), self._stream()), "hh_hier_reset")
+        return self.obs
+
+    # frozen low-level policies, batched: env_base.py:349-398 (per-head argmax of the actor)
+    def _infer(self, first: int):
+        t = self._torch
+        info = self.ll_info[:, first:first + 3]
+        obs = self.ll_obs[:, first:first + 3]
+        act = self.ll_act[:, first:first + 3]
+        with t.no_grad():
+            for mode, mbit in (("fight", 0), ("escape", 2)):
+                for ac, abit in ((1, 0), (2, 4)):
+                    sel = (info & 7) == (1 | mbit | abit)
+                    idx = t.nonzero(sel.reshape(-1), as_tuple=False).flatten()
+                    if idx.numel() == 0:
+                        continue
+                    d = {("fight", 1): 26, ("fight", 2): 24, ("escape", 1): 30, ("escape", 2): 29}[(mode, ac)]
+                    x = obs.reshape(-1, 30).index_select(0, idx)[:, :d]
+                    a = M.deterministic_actions(self.policies[f"{mode}_{ac}"].actor(x), ac).to(t.int32)
+                    flat = act.reshape(-1, 4)
+                    rows = t.zeros((idx.numel(), 4), dtype=t.int32, device=self.dev)
+                    rows[:, :a.shape[1]] = a
+                    # act is a view of ll_act with a non-contiguous arena stride: scatter through global row ids
+                    g_rows = (idx // 3) * 6 + first + (idx % 3)
+                    self.ll_act.reshape(-1, 4)[g_rows] = rows
+
+    def step(self, commander_actions):
+        """commander_actions: int32 CUDA tensor [N, 3] in {0: escape, 1: nearest opponent, 2: second nearest}.
+        Returns (obs [N,3,34], rew [N,3], done [N] u8); `self.substeps` holds the sub-step counts."""
+        L, h, st = nat.lib(), self._h, self._stream()
+        t = self._torch
+        assert commander_actions.is_cuda and commander_actions.dtype == t.int32 and commander_actions.numel() == self.n_arenas * 3
+        lo, li, la = self.ll_obs.data_ptr(), self.ll_info.data_ptr(), self.ll_act.data_ptr()
+        nat.check(L.hh_hier_begin(h, commander_actions.contiguous().data_ptr(), lo, li, st), "hh_hier_begin")
+        for s in range(16):   # n_sub_steps = 15 -> at most 16 iterations (env_hier.py:33,125)
+            self._infer(0)
+            if self.trace is not None:
+                self.trace.append(("agents", self.ll_obs.cpu().numpy().copy(), self.ll_info.cpu().numpy().copy(), None))
+            nat.check(L.hh_hier_agents(h, la, lo, li, st), "hh_hier_agents")
+            self._infer(3)
+            if self.trace is not None:
+                self.trace.append(("opps", self.ll_obs.cpu().numpy().copy(), self.ll_info.cpu().numpy().copy(),
+                                   self.ll_act.cpu().numpy().copy()))
+            nat.check(L.hh_hier_tick(h, la, lo, li, st), "hh_hier_tick")
+        nat.check(L.hh_hier_end(h, self.obs.data_ptr(), self.rew.data_ptr(), self.done.data_ptr(),
+                                self.substeps.data_ptr(), st), "hh_hier_end")
+        return self.obs, self.rew, self.done
+
+    def get_state(self):
+        arr = (nat.HHHierArena * self.n_arenas)()
+        nat.check(nat.lib().hh_hier_get_state(self._h, ctypes.cast(arr, nat.VP)), "hh_hier_get_state")
+        return arr
+
+    @property
+    def launch_count(self):
+        return int(nat.lib().hh_hier_launch_count(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            nat.lib().hh_hier_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -130,6 +130,63 @@ int hh_debug_geodesic(int32_t mode, int32_t n, const double* in_host, double* ou
 const char* hh_last_error(void);
 const char* hh_version(void);
 
+/* ============================================================================================
+ * HighLevelEnv (envs/env_hier.py): the 3-vs-3 commander environment (BASELINE config 5).
+ *   hh_hier_create  <- HighLevelEnv.__init__(env_config)          env_hier.py:31-42
+ *   hh_hier_reset   <- HighLevelEnv.reset()                       env_hier.py:44-47
+ *   one HHMARLBaseEnv.step(commander_actions) (env_base.py:79-109 -> _take_action env_hier.py:114-140) is
+ *     hh_hier_begin  : _action_assess (env_hier.py:142-190) + low-level observations of the agents
+ *     16 x { [agents' networks]  hh_hier_agents : agents' _take_base_action + opponents' low-level observations
+ *            [opponents' networks] hh_hier_tick : opponents' _take_base_action, do_tick, _get_rewards,
+ *                                                 _surrounding_event, next observations of the agents }
+ *     hh_hier_end    : termination (env_base.py:89-90), optional auto-reset, HighLevelEnv.state() (34-d)
+ *   Arenas whose sub-step loop has ended idle through the remaining sub-step calls.
+ * Shapes: commander_actions int32[N][3] in {0,1,2}; ll_obs f32[N][6][30] (row of unit id-1; fight 26/24,
+ * escape 30/29 entries used); ll_info u8[N][6]: bit0 = unit queries its policy now, bit1 = escape policy,
+ * bit2 = aircraft type 2; actions int32[N][6][4]; obs f32[N][3][34]; rew f32[N][3]; done u8[N]; substeps i32[N].
+ * ============================================================================================ */
+typedef struct hh_hier_env hh_hier_env;
+
+typedef struct {
+  int32_t horizon;              /* 500 (config.py:98) */
+  int32_t level;                /* args.level keeps its default 1 in train_hier.py: opponents start at speed 0 */
+  int32_t friendly_kill;        /* bool */
+  int32_t hier_action_assess;   /* bool (config.py:44) */
+  int32_t hier_opp_fight_ratio; /* percent (config.py:23) */
+  int32_t autoreset;
+  double map_size;              /* 0.5 */
+  double rew_scale, glob_frac;
+  uint64_t seed, arena_base;
+} hh_hier_config;
+
+/* Per-arena record, device layout == host layout (hh_hier_get_state / hh_hier_set_state copy it verbatim).
+ * Index u = aircraft id - 1 (ids 1-3 agents, 4-6 opponents); rocket fields belong to shooter u. */
+typedef struct {
+  double lat[6], lon[6], hdg[6], spd[6], nhdg[6], nspd[6];
+  double rlat[6], rlon[6], rhdg[6], rnhdg[6];
+  double ota_dn[6][3];          /* opp_to_attack[i][k][1]: normalised distance at the last commander step */
+  double rewards[3];
+  uint64_t dg;                  /* G-stream draw counter */
+  int32_t crem[6], burst[6], mrem[6], mwait[6], rid[6];
+  int32_t steps, alive_ag, alive_op, next_id, sub, kill_event, situation_event, active, err;
+  uint32_t dc;                  /* C-stream draw counter */
+  int8_t ca[6];                 /* commander actions after _action_assess, -1 = None */
+  uint8_t alive[6], hasm[6], actype[6], ralive[6], rage[6], rtgt[6];
+  uint8_t ota_n[6], ota_id[6][3]; /* opp_to_attack lists (0-based unit indices) */
+} hh_hier_arena;
+
+int hh_hier_create(const hh_hier_config* cfg, int32_t n_arenas, int32_t device, hh_hier_env** out);
+void hh_hier_destroy(hh_hier_env* env);
+int hh_hier_reset(hh_hier_env* env, const uint8_t* mask_dev, float* obs_dev, void* stream);
+int hh_hier_begin(hh_hier_env* env, const int32_t* commander_actions_dev, float* ll_obs_dev, uint8_t* ll_info_dev, void* stream);
+int hh_hier_agents(hh_hier_env* env, const int32_t* actions_dev, float* ll_obs_dev, uint8_t* ll_info_dev, void* stream);
+int hh_hier_tick(hh_hier_env* env, const int32_t* actions_dev, float* ll_obs_dev, uint8_t* ll_info_dev, void* stream);
+int hh_hier_end(hh_hier_env* env, float* obs_dev, float* rew_dev, uint8_t* done_dev, int32_t* substeps_dev, void* stream);
+int hh_hier_get_state(hh_hier_env* env, hh_hier_arena* out_host);
+int hh_hier_set_state(hh_hier_env* env, const hh_hier_arena* in_host);
+uint64_t hh_hier_launch_count(const hh_hier_env* env);
+const char* hh_hier_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,75 @@
+"""GPU HighLevelEnv (csrc/hh_hier.cu via hh_hier_*) against the C oracle of envs/env_hier.py.  The oracle's
+policy callback replays the actions the GPU path's batched networks chose (and checks the observation each
+query was made with), so the environment is compared exactly and the networks separately."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-5, 1e-6
+
+
+def _close(a, b, what):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    err = np.abs(a - b) - (ATOL + RTOL * np.abs(b))
+    assert (err <= 0).all(), f"{what}: max excess {err.max():.3e}"
+
+
+@pytest.mark.parametrize("kw", [{}, {"glob_frac": 0.3, "hier_action_assess": False, "hier_opp_fight_ratio": 40},
+                                {"friendly_kill": False, "rew_scale": 2.0}])
+def test_hier_matches_oracle(kw):
+    import oracle as orc
+    from hhmarl_2d_b200.env_hier import VecHighLevelEnv, make_hier_args
+    n, T, seed, base = 48, 40, 606, 300
+    env = VecHighLevelEnv(n, make_hier_args(**kw), device=0, seed=seed, arena_base=base, autoreset=True)
+    queue = [[] for _ in range(n)]     # per arena: FIFO of (unit_id, mode, ac_type, obs, action) the GPU produced
+
+    def make_fn(k):
+        def fn(unit_id, ac_type, mode, pset, obs):
+            assert queue[k], f"arena {k}: oracle asks for a policy query the GPU path did not make"
+            u, m, ty, gobs, act = queue[k].pop(0)
+            assert (u, m, ty) == (unit_id, mode, ac_type), (k, (u, m, ty), (unit_id, mode, ac_type))
+            _close(gobs[:len(obs)], obs, f"arena {k} unit {unit_id} low-level obs")
+            assert (gobs[len(obs):] == 0).all()
+            return act[:4 if ac_type == 1 else 3]
+        return fn
+
+    oracles = [orc.OracleHierEnv(orc.make_hier_args(**kw), seed, base + k, make_fn(k)) for k in range(n)]
+    obs = env.reset().cpu().numpy()
+    _close(obs, np.stack([o.reset() for o in oracles]), "reset obs")
+    rng = np.random.default_rng(1)
+    n_done = 0
+    for t in range(T):
+        ca = rng.integers(0, 3, (n, 3)).astype(np.int32)
+        env.trace = []
+        gobs, grew, gdone = env.step(torch.from_numpy(ca).cuda())
+        gobs, grew, gdone, gsub = gobs.cpu().numpy(), grew.cpu().numpy(), gdone.cpu().numpy(), env.substeps.cpu().numpy()
+        # rebuild, per arena, the sequence of policy queries in the reference's order: per sub-step units 1..6
+        for k in range(n):
+            queue[k].clear()
+        for i in range(0, len(env.trace), 2):
+            (_, oa, ia, _), (_, oo, io, act) = env.trace[i], env.trace[i + 1]
+            for k in range(n):
+                for u in range(6):
+                    info, o = (ia, oa) if u < 3 else (io, oo)
+                    if info[k, u] & 1:
+                        queue[k].append((u + 1, (info[k, u] >> 1) & 1, 2 if info[k, u] & 4 else 1, o[k, u], act[k, u]))
+        for k, o in enumerate(oracles):
+            eo, er, ed, info = o.step(ca[k])
+            assert not queue[k], f"arena {k}: GPU made {len(queue[k])} more policy queries than the oracle"
+            assert bool(gdone[k]) == ed and gsub[k] == info[0], (t, k, gsub[k], info[0])
+            _close(grew[k], er, f"t={t} arena={k} rew")
+            if ed:
+                eo = o.reset()
+                n_done += 1
+            _close(gobs[k], eo, f"t={t} arena={k} obs")
+        if t % 10 == 9:
+            st = env.get_state()
+            for k, o in enumerate(oracles):
+                s = o.state()
+                assert [st[k].steps, st[k].alive_ag, st[k].alive_op, st[k].next_id, st[k].dg, st[k].dc] == \
+                       [s.steps, s.alive_agents, s.alive_opps, s.next_unit_id, s.draws_g, s.draws_c], (t, k)
+                assert list(st[k].alive) == list(s.alive[:6]) and list(st[k].mrem) == list(s.missile_remain[:6])
+                _close(list(st[k].lat), list(s.lat[:6]), "lat"); _close(list(st[k].hdg), list(s.heading[:6]), "hdg")
+                assert st[k].err == 0
+    assert n_done >= n // 2
