@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--cpu-sample-steps", type=int, default=400_000, help="env-steps per host thread")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-rollout", action="store_true")
+    ap.add_argument("--no-hier", action="store_true")
     return ap.parse_args()
 
 
@@ -286,6 +287,43 @@ def run_b200(args):
     except Exception as ex:  # noqa: BLE001
         rollout = {"error": repr(ex)}
 
+    # ---- BASELINE config 5: 3-vs-3 hierarchical commander rollout (HighLevelEnv), random commander actions,
+    #      every aircraft's frozen low-level policy batched across arenas (random-init weights)
+    hier = None
+    try:
+        if args.no_hier:
+            raise RuntimeError("skipped (--no-hier)")
+        from hhmarl_2d_b200.env_hier import VecHighLevelEnv
+        henv = VecHighLevelEnv(n, device=local, seed=2, arena_base=rank * n, autoreset=True)
+        henv.reset()
+        gh = torch.Generator(device=dev)
+        gh.manual_seed(77 + rank)
+        cmd = torch.randint(0, 3, (8, n, 3), device=dev, generator=gh).to(torch.int32)
+        for w in range(2):
+            henv.step(cmd[w])
+        barrier()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        ticks = 0
+        HS = 5
+        for k in range(HS):
+            henv.step(cmd[2 + k])
+            ticks += int(henv.substeps.sum().item())
+        h1.record()
+        barrier()
+        ht = torch.tensor([h0.elapsed_time(h1)], dtype=torch.float64, device=dev)
+        tk = torch.tensor([float(ticks)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ht, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tk)
+        hier = {"commander_steps_per_s": world * n * HS / (float(ht.item()) * 1e-3),
+                "sim_ticks_per_s": float(tk.item()) / (float(ht.item()) * 1e-3), "commander_steps": HS,
+                "mean_substeps": float(tk.item()) / (world * n * HS), "arenas_per_gpu": n,
+                "note": "HighLevelEnv 3-vs-3, 16 masked sub-steps x (2 launches + fight/escape actor batches), fp32 cuBLAS"}
+        del henv
+    except Exception as ex:  # noqa: BLE001
+        hier = {"error": repr(ex)}
+
     # ---- end to end through the host entry point of the C ABI
     acts_host = acts.cpu().numpy()
     pin_act, *pin_out = env.host_buffers()       # the handle's pinned slab: the driver writes actions in place
@@ -334,6 +372,7 @@ def run_b200(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "hh_step_host on the pinned host buffers of hh_host_buffers (C ABI; 1 H2D + launch + 1 D2H + sync per call)"},
                 "rollout": rollout,
+                "hier": hier,
                 "gpu_launches": int(gpu_launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

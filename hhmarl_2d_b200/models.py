@@ -208,6 +208,59 @@ class Esc2(Esc1):
     ac_type = 2
 
 
+class CommanderGru(nn.Module):
+    """models/ac_models_hier.py:21-112: commander policy for the 3-vs-3 HighLevelEnv.  Actor: 4/20/10-wide
+    branches + GRU(200) over the RLlib time axis on the full 34-d observation; centralised critic: own and the
+    two team-mates' (observation, action) pairs + GRU(200); both through the shared 500x500 layer.
+    State = [actor GRU h (200), critic GRU h (200)]."""
+    OBS_DIM, N_OPP_HL, OBS_OPP = 34, 2, 10
+
+    def __init__(self, shared_layer: SlimFC | None = None, num_outputs: int = 3):
+        super().__init__()
+        self.num_outputs = num_outputs
+        self.shared_layer = shared_layer if shared_layer is not None else make_shared_layer()
+        self.rnn_act = nn.GRU(200, 200, batch_first=True)
+        self.rnn_val = nn.GRU(200, 200, batch_first=True)
+        self.inp1 = _fc(4, 50)
+        self.inp2 = _fc(self.N_OPP_HL * self.OBS_OPP, 200)
+        self.inp3 = _fc(10, 50)
+        self.inp4 = _fc(self.OBS_DIM, 200)
+        self.act_out = _fc(500, num_outputs, act=False)
+        self.v1 = _fc(self.OBS_DIM + 1, 100)
+        self.v2 = _fc(self.OBS_DIM + 1, 100)
+        self.v3 = _fc(self.OBS_DIM + 1, 100)
+        self.v4 = _fc(3 * (self.OBS_DIM + 1), 200)
+        self.val_out = _fc(500, 1, act=False)
+        self._val = None
+
+    def get_initial_state(self):
+        return [torch.zeros(200), torch.zeros(200)]
+
+    def forward(self, input_dict, state, seq_lens):
+        o = input_dict["obs"]
+        own = o["obs_1_own"]
+        k = 4 + self.N_OPP_HL * self.OBS_OPP
+        v1 = torch.cat((own, o["act_1_own"]), dim=1)
+        v2 = torch.cat((o["obs_2"], o["act_2"]), dim=1)
+        v3 = torch.cat((o["obs_3"], o["act_3"]), dim=1)
+        v4 = torch.cat((v1, v2, v3), dim=1)
+        x = torch.cat((self.inp1(own[:, :4]), self.inp2(own[:, 4:k]), self.inp3(own[:, k:])), dim=1)
+        x_full = self.inp4(own)
+        y, h = self.rnn_act(add_time_dimension(x_full, seq_lens), torch.unsqueeze(state[0], 0))
+        x_full = F.normalize(x_full + y.reshape(-1, 200))
+        x = self.act_out(self.shared_layer(torch.cat((x, x_full), dim=1)))
+        z = torch.cat((self.v1(v1), self.v2(v2), self.v3(v3)), dim=1)
+        z_full = self.v4(v4)
+        w, kk = self.rnn_val(add_time_dimension(z_full, seq_lens), torch.unsqueeze(state[1], 0))
+        z_full = F.normalize(z_full + w.reshape(-1, 200))
+        self._val = self.val_out(self.shared_layer(torch.cat((z, z_full), dim=1)))
+        return torch.reshape(x, [-1, self.num_outputs]), [torch.squeeze(h, 0), torch.squeeze(kk, 0)]
+
+    def value_function(self):
+        assert self._val is not None, "must call forward first!"
+        return torch.reshape(self._val, [-1])
+
+
 def build_policy_pair(mode: str = "fight", shared_layer: SlimFC | None = None):
     """(ac1_policy model, ac2_policy model) sharing one SHARED_LAYER, like the reference process does."""
     shared = shared_layer if shared_layer is not None else make_shared_layer()

@@ -40,6 +40,25 @@ def main():
                 out[f"{name}_{tag}_{k}"] = v
             out[f"{name}_{tag}_logits"] = logits.numpy()
             out[f"{name}_{tag}_value"] = val.numpy()
+    # CommanderGru (models/ac_models_hier.py), imported unmodified under the same stubs
+    import models.ac_models_hier as mh
+    torch.manual_seed(0)
+    cm = mh.CommanderGru(None, None, 3, {}, "commander")
+    fill_from_seed(cm, 777)
+    for tag, B, T in (("t1", 8, 1), ("t4", 12, 4)):
+        obs = {k: rng.random((B, 34), dtype=np.float32) for k in ("obs_1_own", "obs_2", "obs_3")}
+        obs.update({k: rng.integers(0, 3, (B, 1)).astype(np.float32) for k in ("act_1_own", "act_2", "act_3")})
+        nseq = B // T
+        state = [torch.from_numpy(rng.random((nseq, 200), dtype=np.float32)) for _ in range(2)]
+        with torch.no_grad():
+            logits, new_state = cm({"obs": {k: torch.from_numpy(v) for k, v in obs.items()}}, state,
+                                   torch.tensor([T] * nseq))
+            val = cm.value_function()
+        for k, v in obs.items():
+            out[f"Cmd_{tag}_{k}"] = v
+        out[f"Cmd_{tag}_h0"], out[f"Cmd_{tag}_h1"] = state[0].numpy(), state[1].numpy()
+        out[f"Cmd_{tag}_logits"], out[f"Cmd_{tag}_value"] = logits.numpy(), val.numpy()
+        out[f"Cmd_{tag}_nh0"], out[f"Cmd_{tag}_nh1"] = new_state[0].numpy(), new_state[1].numpy()
     path = os.path.join(ROOT, "tests", "golden", "models_forward.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")

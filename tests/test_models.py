@@ -37,3 +37,19 @@ def test_shared_layer_and_parameter_names():
         assert n in names
     a = M.deterministic_actions(torch.randn(5, 26), 1)
     assert a.shape == (5, 4) and (a[:, 0] < 13).all() and (a[:, 3] < 2).all()
+
+
+def test_commander_gru_matches_reference_model():
+    model = M.fill_from_seed(M.CommanderGru(), 777)
+    for tag, T in (("t1", 1), ("t4", 4)):
+        obs = {k: torch.from_numpy(G[f"Cmd_{tag}_{k}"]) for k in ("obs_1_own", "obs_2", "obs_3", "act_1_own", "act_2", "act_3")}
+        B = obs["obs_1_own"].shape[0]
+        state = [torch.from_numpy(G[f"Cmd_{tag}_h0"]), torch.from_numpy(G[f"Cmd_{tag}_h1"])]
+        with torch.no_grad():
+            logits, ns = model({"obs": obs}, state, torch.tensor([T] * (B // T)))
+            val = model.value_function()
+        np.testing.assert_allclose(logits.numpy(), G[f"Cmd_{tag}_logits"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(val.numpy(), G[f"Cmd_{tag}_value"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(ns[0].numpy(), G[f"Cmd_{tag}_nh0"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(ns[1].numpy(), G[f"Cmd_{tag}_nh1"], rtol=1e-5, atol=1e-6)
+        assert logits.shape == (B, 3)
