@@ -260,30 +260,35 @@ def run_b200(args):
             raise RuntimeError("skipped (--no-rollout)")
         from hhmarl_2d_b200 import VecSampler, TorchPolicy
         from hhmarl_2d_b200 import models as M
-        torch.manual_seed(rank)
-        m1, m2 = M.build_policy_pair("fight")
-        m1.to(dev); m2.to(dev)
-        env_r = VecLowLevelEnv(n, make_args(level=args.level), device=local, seed=1, arena_base=rank * n, autoreset=True)
+        rollout = {}
         Tf = 20
-        smp = VecSampler(env_r, TorchPolicy(m1, 1), TorchPolicy(m2, 2), fragment_len=Tf, use_cuda_graph=True)
-        for _ in range(3):
-            smp.collect()
-        R = max(2, K // Tf)
-        barrier()
-        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        r0.record()
-        for _ in range(R):
-            smp.collect()
-        r1.record()
-        barrier()
-        rt = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(rt, op=dist.ReduceOp.MAX)
-        rollout = {"value": world * n * Tf * R / (float(rt.item()) * 1e-3), "unit": UNIT, "fragment_len": Tf,
-                   "fragments": R, "ms_per_tick": float(rt.item()) / (R * Tf),
-                   "note": "policy forward (2 x Fight actor+critic, fp32 cuBLAS) + sampling + env step + GAE, "
-                           "CUDA-graph replay; random-init weights"}
-        del smp, env_r
+        for tag, kw in (("fp32", dict(allow_tf32=False)), ("tf32", dict(allow_tf32=True)),
+                        ("fp32_unpacked", dict(allow_tf32=False, packed=False))):
+            torch.manual_seed(rank)
+            m1, m2 = M.build_policy_pair("fight")
+            m1.to(dev); m2.to(dev)
+            env_r = VecLowLevelEnv(n, make_args(level=args.level), device=local, seed=1, arena_base=rank * n, autoreset=True)
+            smp = VecSampler(env_r, TorchPolicy(m1, 1), TorchPolicy(m2, 2), fragment_len=Tf, use_cuda_graph=True, **kw)
+            for _ in range(3):
+                smp.collect()
+            R = max(2, K // Tf)
+            barrier()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            for _ in range(R):
+                smp.collect()
+            r1.record()
+            barrier()
+            rt = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(rt, op=dist.ReduceOp.MAX)
+            rollout[tag] = {"value": world * n * Tf * R / (float(rt.item()) * 1e-3), "unit": UNIT,
+                            "ms_per_tick": float(rt.item()) / (R * Tf)}
+            del smp, env_r
+        rollout["fragment_len"] = Tf
+        rollout["note"] = ("both policies' actor + central critic (packed GEMMs, cuBLAS) + Gumbel-max sampling + env step + "
+                           "GAE + action write-back, one CUDA graph per 20-tick fragment; random-init weights; "
+                           "'tf32' = same with TF32 tensor-core GEMMs, 'fp32_unpacked' = per-layer forward of models.py")
     except Exception as ex:  # noqa: BLE001
         rollout = {"error": repr(ex)}
 

@@ -75,8 +75,14 @@ class VecSampler:
     (ac1_policy for agent 1, ac2_policy for agent 2; policy_mapping_fn of train_hetero.py:240)."""
 
     def __init__(self, env, policy1: TorchPolicy, policy2: TorchPolicy, fragment_len: int = 64,
-                 gamma: float = 0.99, lam: float = 0.95, use_cuda_graph: bool = True):
+                 gamma: float = 0.99, lam: float = 0.95, use_cuda_graph: bool = True, packed: bool = True,
+                 allow_tf32: bool = False):
         self.env, self.p1, self.p2, self.T = env, policy1, policy2, fragment_len
+        self.allow_tf32 = allow_tf32
+        self.packed = None
+        if packed:
+            from .fused_forward import PackedPolicyPair
+            self.packed = PackedPolicyPair(policy1.model, policy2.model)
         self.gamma, self.lam = gamma, lam
         n, T = env.n_arenas, fragment_len
         d1, d2 = env.obs_dim
@@ -108,10 +114,25 @@ class VecSampler:
         self.cur2[:, 7:7 + d2] = obs2
         self.cur2[:, 7 + d2:] = obs1
 
+    def refresh_policy(self):
+        """Call after the learner changed the weights (re-packs in place; a captured graph stays valid)."""
+        if self.packed is not None:
+            self.packed.refresh()
+
+    def _forward_both(self, f1, f2):
+        if self.packed is not None:
+            return self.packed.forward(f1, f2)
+        l1, v1 = self.p1.model.forward_flat(f1)
+        l2, v2 = self.p2.model.forward_flat(f2)
+        return l1, v1, l2, v2
+
     def _tick(self, t):
         b = self.buf
-        a1, _, x1 = self.p1.compute_actions(self.cur1)
-        a2, _, x2 = self.p2.compute_actions(self.cur2)
+        l1, v1, l2, v2 = self._forward_both(self.cur1, self.cur2)
+        a1, lp1 = multicategorical_sample(l1, self.p1.splits, True)
+        a2, lp2 = multicategorical_sample(l2, self.p2.splits, True)
+        x1 = {"action_logp": lp1, "action_dist_inputs": l1, "vf_preds": v1}
+        x2 = {"action_logp": lp2, "action_dist_inputs": l2, "vf_preds": v2}
         b["flat1"][t] = self.cur1
         b["flat2"][t] = self.cur2
         act = b["actions"][t]
@@ -129,8 +150,7 @@ class VecSampler:
         for t in range(self.T):
             self._tick(t)
         b = self.buf
-        _, v1 = self.p1.model.forward_flat(self.cur1)
-        _, v2 = self.p2.model.forward_flat(self.cur2)
+        _, v1, _, v2 = self._forward_both(self.cur1, self.cur2)
         b["last_vf"][:, 0], b["last_vf"][:, 1] = v1, v2
         st = torch.cuda.current_stream(self.dev).cuda_stream
         nat.check(nat.lib().hh_gae(self.T, self.env.n_arenas, b["rew"].data_ptr(), b["vf"].data_ptr(),
@@ -150,6 +170,14 @@ class VecSampler:
             obs1, obs2 = self.env.reset()
             self._set_obs(obs1, obs2)
             self._started = True
+        prev_tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = bool(self.allow_tf32)
+        try:
+            return self._collect()
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+
+    def _collect(self):
         if not self.use_graph:
             self._fragment()
             return self.buf

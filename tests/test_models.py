@@ -53,3 +53,26 @@ def test_commander_gru_matches_reference_model():
         np.testing.assert_allclose(ns[0].numpy(), G[f"Cmd_{tag}_nh0"], rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(ns[1].numpy(), G[f"Cmd_{tag}_nh1"], rtol=1e-5, atol=1e-6)
         assert logits.shape == (B, 3)
+
+
+@pytest.mark.parametrize("mode", ["fight", "escape"])
+def test_packed_pair_forward_equals_per_model_forward(mode):
+    from hhmarl_2d_b200.fused_forward import PackedPolicyPair
+    torch.manual_seed(1)
+    m1, m2 = M.build_policy_pair(mode)
+    M.fill_from_seed(m1, 5); M.fill_from_seed(m2, 6)
+    packed = PackedPolicyPair(m1, m2)
+    B = 64
+    f1, f2 = torch.rand(B, m1.central_dim), torch.rand(B, m2.central_dim)
+    with torch.no_grad():
+        l1, v1 = m1.forward_flat(f1)
+        l2, v2 = m2.forward_flat(f2)
+        p1, q1, p2, q2 = packed.forward(f1, f2)
+    for a, b in ((l1, p1), (v1, q1), (l2, p2), (v2, q2)):
+        np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=2e-5, atol=2e-6)
+    # re-packing follows weight updates
+    with torch.no_grad():
+        m1.act_out._model[0].weight.add_(0.01)
+    packed.refresh()
+    with torch.no_grad():
+        np.testing.assert_allclose(m1.forward_flat(f1)[0].numpy(), packed.forward(f1, f2)[0].numpy(), rtol=2e-5, atol=2e-6)
