@@ -610,6 +610,68 @@ __global__ void gae_kernel(int T, int n_pairs, const float* __restrict__ rew, co
 }
 
 // ------------------------------------------------------------------------------------------
+// sampler glue: MultiCategorical sampling of both policies' actions and the central-critic observation layout
+// ------------------------------------------------------------------------------------------
+// One thread per (arena, agent): inverse-CDF sample of every MultiDiscrete head from its logits (RLlib's
+// TorchMultiCategorical.sample / logp), Philox stream 2 keyed by (seed, global arena id), per-arena counter.
+__global__ void sample_actions_kernel(int n, const float* __restrict__ logits1, const float* __restrict__ logits2,
+                                      uint32_t seed_lo, uint32_t seed_hi, uint32_t arena_base, uint32_t* __restrict__ ctr,
+                                      int explore, int32_t* __restrict__ actions, float* __restrict__ logp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * n) return;
+  const int a = i >> 1, agent = i & 1;
+  const float* lg = agent == 0 ? logits1 + (size_t)a * 26 : logits2 + (size_t)a * 24;
+  const int n_heads = agent == 0 ? 4 : 3;
+  const uint32_t c = ctr[i];
+  float lp = 0.0f;
+  int o = 0;
+  int32_t out[4] = {0, 0, 0, 0};
+  for (int h = 0; h < n_heads; ++h) {
+    const int w = h == 0 ? 13 : (h == 1 ? 9 : 2);
+    float mx = lg[o];
+    for (int k = 1; k < w; ++k) mx = fmaxf(mx, lg[o + k]);
+    float e[13], sum = 0.0f;
+    for (int k = 0; k < w; ++k) {
+      e[k] = expf(lg[o + k] - mx);
+      sum += e[k];
+    }
+    int pick = 0;
+    if (explore) {
+      const float u = (float)philox_u53(seed_lo, seed_hi, c, (uint32_t)h, arena_base + (uint32_t)a, 2u + (uint32_t)agent) * sum;
+      float acc = 0.0f;
+      pick = w - 1;
+      for (int k = 0; k < w; ++k) {
+        acc += e[k];
+        if (u < acc) { pick = k; break; }
+      }
+    } else {
+      for (int k = 1; k < w; ++k)
+        if (lg[o + k] > lg[o + pick]) pick = k;
+    }
+    out[h] = pick;
+    lp += lg[o + pick] - mx - logf(sum);
+    o += w;
+  }
+  ctr[i] = c + 1;
+  reinterpret_cast<int4*>(actions)[i] = make_int4(out[0], out[1], out[2], out[3]);
+  logp[i] = lp;
+}
+
+// central_critic_observer (train_hetero.py:162-181): flat_p = [act_own | act_other | obs_own | obs_other] with the
+// action columns zero at sampling time; writes the observation columns of both policies' inputs.
+__global__ void pack_central_kernel(int n, int d1, int d2, const float* __restrict__ obs1, const float* __restrict__ obs2,
+                                    float* __restrict__ flat1, float* __restrict__ flat2) {
+  const int D = 7 + d1 + d2;
+  const size_t total = (size_t)n * (d1 + d2);
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+    const int a = (int)(k / (d1 + d2)), c = (int)(k % (d1 + d2));
+    const float v = c < d1 ? obs1[(size_t)a * d1 + c] : obs2[(size_t)a * d2 + (c - d1)];
+    flat1[(size_t)a * D + 7 + c] = v;                                   // [.. | obs1 | obs2]
+    flat2[(size_t)a * D + 7 + (c < d1 ? d2 + c : c - d1)] = v;          // [.. | obs2 | obs1]
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // test access to the device geodesics (hh_debug_geodesic)
 // ------------------------------------------------------------------------------------------
 __global__ void geodesic_debug_kernel(int mode, int n, const double* __restrict__ in, double* __restrict__ out) {
@@ -683,6 +745,28 @@ extern "C" int hh_gae(int32_t T, int32_t n_arenas, const float* rew_dev, const f
   const int n_pairs = n_arenas * 2;
   gae_kernel<<<(n_pairs + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(T, n_pairs, rew_dev, vf_dev, last_vf_dev,
                                                                                  done_dev, gamma, lam, adv_dev, vtarg_dev);
+  HH_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int hh_sample_actions(int32_t n_arenas, const float* logits1_dev, const float* logits2_dev, uint64_t seed,
+                                 uint64_t arena_base, uint32_t* counters_dev, int32_t explore, int32_t* actions_dev,
+                                 float* logp_dev, void* stream) {
+  if (n_arenas <= 0 || !logits1_dev || !logits2_dev || !counters_dev || !actions_dev || !logp_dev)
+    return fail(-1, "hh_sample_actions: bad argument");
+  sample_actions_kernel<<<(2 * n_arenas + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      n_arenas, logits1_dev, logits2_dev, (uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)arena_base, counters_dev, explore,
+      actions_dev, logp_dev);
+  HH_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int hh_pack_central(int32_t n_arenas, int32_t d1, int32_t d2, const float* obs1_dev, const float* obs2_dev,
+                               float* flat1_dev, float* flat2_dev, void* stream) {
+  if (n_arenas <= 0 || d1 <= 0 || d2 <= 0 || !obs1_dev || !obs2_dev || !flat1_dev || !flat2_dev)
+    return fail(-1, "hh_pack_central: bad argument");
+  pack_central_kernel<<<592, 256, 0, static_cast<cudaStream_t>(stream)>>>(n_arenas, d1, d2, obs1_dev, obs2_dev, flat1_dev,
+                                                                          flat2_dev);
   HH_CUDA(cudaGetLastError());
   return 0;
 }

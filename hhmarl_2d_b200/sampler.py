@@ -101,6 +101,9 @@ class VecSampler:
         self.cur1 = torch.zeros((n, 7 + d1 + d2), **f32)   # [act_1_own(4) | act_2(3) | obs_1_own | obs_2], actions 0
         self.cur2 = torch.zeros((n, 7 + d1 + d2), **f32)   # [act_1_own(3) | act_2(4) | obs_1_own | obs_2]
         self.d1, self.d2 = d1, d2
+        self.native_glue = (d1, d2) == (26, 24)        # hh_sample_actions is written for the fight-mode head layout
+        self.ctr = torch.zeros((n, 2), dtype=torch.int32, device=dev)
+        self.seed = int(getattr(env, "_cfg").seed) + 0x5A17
         self.scale = ACT_SCALE.to(dev)
         self.use_graph = use_cuda_graph
         self._graph = None
@@ -109,6 +112,11 @@ class VecSampler:
     # central_critic_observer, train_hetero.py:162-181
     def _set_obs(self, obs1, obs2):
         d1, d2 = self.d1, self.d2
+        if self.native_glue:
+            st = torch.cuda.current_stream(self.dev).cuda_stream
+            nat.check(nat.lib().hh_pack_central(self.env.n_arenas, d1, d2, obs1.data_ptr(), obs2.data_ptr(),
+                                                self.cur1.data_ptr(), self.cur2.data_ptr(), st), "hh_pack_central")
+            return
         self.cur1[:, 7:7 + d1] = obs1
         self.cur1[:, 7 + d1:] = obs2
         self.cur2[:, 7:7 + d2] = obs2
@@ -129,6 +137,21 @@ class VecSampler:
     def _tick(self, t):
         b = self.buf
         l1, v1, l2, v2 = self._forward_both(self.cur1, self.cur2)
+        if self.native_glue:
+            b["flat1"][t] = self.cur1
+            b["flat2"][t] = self.cur2
+            b["logits1"][t], b["logits2"][t] = l1, l2
+            b["vf"][t, :, 0], b["vf"][t, :, 1] = v1, v2
+            act = b["actions"][t]
+            st = torch.cuda.current_stream(self.dev).cuda_stream
+            nat.check(nat.lib().hh_sample_actions(self.env.n_arenas, b["logits1"][t].data_ptr(), b["logits2"][t].data_ptr(),
+                                                  self.seed, int(self.env._cfg.arena_base), self.ctr.data_ptr(), 1,
+                                                  act.data_ptr(), b["logp"][t].data_ptr(), st), "hh_sample_actions")
+            obs1, obs2, rew, done = self.env.step(act)
+            b["rew"][t] = rew
+            b["done"][t] = done
+            self._set_obs(obs1, obs2)
+            return
         a1, lp1 = multicategorical_sample(l1, self.p1.splits, True)
         a2, lp2 = multicategorical_sample(l2, self.p2.splits, True)
         x1 = {"action_logp": lp1, "action_dist_inputs": l1, "vf_preds": v1}

@@ -120,6 +120,18 @@ uint64_t hh_launch_count(const hh_env* env);
 int hh_gae(int32_t T, int32_t n_arenas, const float* rew_dev, const float* vf_dev, const float* last_vf_dev,
            const uint8_t* done_dev, float gamma, float lam, float* adv_dev, float* vtarg_dev, void* stream);
 
+/* Sampler glue (what RLlib's sampler does between the policy forward and env.step):
+ * hh_sample_actions: TorchMultiCategorical.sample()/logp() of both policies in one launch.  logits1 f32[N][26]
+ *   (heads 13|9|2|2, agent 1), logits2 f32[N][24] (13|9|2, agent 2); counters u32[N][2] (per (arena, agent) draw
+ *   counter, advanced by the call); explore = 0 takes the per-head argmax; actions int32[N][2][4]; logp f32[N][2].
+ * hh_pack_central: central_critic_observer (train_hetero.py:162-181): writes obs1/obs2 into the observation
+ *   columns of flat1 = [act(4)|act(3)|obs1|obs2] and flat2 = [act(3)|act(4)|obs2|obs1] (row length 7+d1+d2). */
+int hh_sample_actions(int32_t n_arenas, const float* logits1_dev, const float* logits2_dev, uint64_t seed,
+                      uint64_t arena_base, uint32_t* counters_dev, int32_t explore, int32_t* actions_dev, float* logp_dev,
+                      void* stream);
+int hh_pack_central(int32_t n_arenas, int32_t d1, int32_t d2, const float* obs1_dev, const float* obs2_dev,
+                    float* flat1_dev, float* flat2_dev, void* stream);
+
 /* Test access to the device WGS84 solvers (replacing geographiclib's Geodesic.WGS84 as used at
  * warsim/utils/geodesics.py:12-24).  in_host: f64[4][n], out_host: f64[2][n].
  *   mode 0: direct  (lat1, lon1, azi1 [deg], s12 [m]) -> (lat2, lon2)

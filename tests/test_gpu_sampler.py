@@ -88,3 +88,41 @@ def test_ppo_update_on_gpu():
     st = learner.update(smp.collect())
     assert st["minibatches"] == 4 and np.isfinite(st["loss"]) and not torch.equal(w0, m1.act_out._model[0].weight)
     assert all(k >= 0 for k in st["kl"])
+
+
+def test_native_multicategorical_sampler():
+    """hh_sample_actions: frequencies follow softmax, logp matches torch, explore=0 is the per-head argmax,
+    and the per-(arena, agent) counters make successive calls draw fresh, reproducible numbers."""
+    from hhmarl_2d_b200 import _native as nat
+    from hhmarl_2d_b200 import models as M
+    from hhmarl_2d_b200.sampler import multicategorical_logp_entropy_kl
+    torch.manual_seed(0)
+    n = 40000
+    row1, row2 = torch.randn(26), torch.randn(24)
+    l1, l2 = row1.repeat(n, 1).cuda().contiguous(), row2.repeat(n, 1).cuda().contiguous()
+    ctr = torch.zeros((n, 2), dtype=torch.int32, device="cuda")
+    act = torch.empty((n, 2, 4), dtype=torch.int32, device="cuda")
+    logp = torch.empty((n, 2), device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+
+    def call(explore, counters):
+        nat.check(nat.lib().hh_sample_actions(n, l1.data_ptr(), l2.data_ptr(), 123, 0, counters.data_ptr(), explore,
+                                              act.data_ptr(), logp.data_ptr(), st), "hh_sample_actions")
+        return act.clone(), logp.clone()
+
+    a, lp = call(1, ctr)
+    assert (ctr == 1).all() and (a[:, 1, 3] == 0).all()
+    o = 0
+    for h, w in enumerate((13, 9, 2, 2)):
+        freq = torch.bincount(a[:, 0, h].long().cpu(), minlength=w).float() / n
+        assert (freq - torch.softmax(row1[o:o + w], 0)).abs().max() < 0.012
+        o += w
+    ref1, _, _ = multicategorical_logp_entropy_kl(l1, a[:, 0, :], (13, 9, 2, 2))
+    ref2, _, _ = multicategorical_logp_entropy_kl(l2, a[:, 1, :3], (13, 9, 2))
+    assert torch.allclose(lp[:, 0], ref1, atol=2e-5) and torch.allclose(lp[:, 1], ref2, atol=2e-5)
+    b, _ = call(1, ctr)
+    assert not torch.equal(a, b)                                   # counters advanced -> new draws
+    c, _ = call(1, torch.zeros_like(ctr))
+    assert torch.equal(a, c)                                       # same counters -> same draws
+    d, _ = call(0, ctr)
+    assert (d[:, 0, :].long() == M.deterministic_actions(l1, 1)).all() and (d[:, 1, :3].long() == M.deterministic_actions(l2, 2)).all()
