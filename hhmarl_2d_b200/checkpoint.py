@@ -1,0 +1,51 @@
+"""Ray-free policy files with the reference's naming, so the curriculum chain L3 -> L4 -> L5 (self-play against
+previously trained policies) works end to end.
+
+The reference exports whole-module pickles of RLlib models as `policies/L{level}_AC{i}_{mode}.pt`
+(train_hetero.py:98-107) and torch.load()s them in the env (env_base.py:312-347).  Those pickles need ray to
+load; here the same file names hold plain state_dicts of hhmarl_2d_b200.models (identical parameter names).
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from . import models as M
+
+
+def policy_path(policy_dir: str, level: int, ac: int, mode: str) -> str:
+    return os.path.join(policy_dir, f"L{level}_AC{ac}_{mode}.pt")
+
+
+def save_policies(policy_dir: str, level: int, mode: str, model1, model2):
+    """train_hetero.py:101-105: export ac1_policy / ac2_policy of this level."""
+    os.makedirs(policy_dir, exist_ok=True)
+    for ac, m in ((1, model1), (2, model2)):
+        torch.save({"class": type(m).__name__, "state_dict": m.state_dict()}, policy_path(policy_dir, level, ac, mode))
+
+
+def load_pair(policy_dir: str, level: int, mode: str, device="cpu"):
+    m1, m2 = M.build_policy_pair("fight" if mode == "fight" else "escape")
+    for ac, m in ((1, m1), (2, m2)):
+        blob = torch.load(policy_path(policy_dir, level, ac, mode), map_location=device)
+        m.load_state_dict(blob["state_dict"])
+        m.to(device).eval()
+    return m1, m2
+
+
+def load_opponent_policies(policy_dir: str, level: int, agent_mode: str, device="cpu"):
+    """HHMARLBaseEnv._get_policies("LowLevel") (env_base.py:318-331) with the reference's file selection."""
+    if agent_mode == "fight":
+        if level == 4:
+            f1, f2 = load_pair(policy_dir, 3, "fight", device)
+            return {"fight_1": f1, "fight_2": f2}
+        out = {}
+        for k in (3, 4):
+            f1, f2 = load_pair(policy_dir, k, "fight", device)
+            out[k] = {"fight_1": f1, "fight_2": f2}
+        e1, e2 = load_pair(policy_dir, 3, "escape", device)
+        out[5] = {"escape_1": e1, "escape_2": e2}
+        return out
+    f1, f2 = load_pair(policy_dir, 5, "fight", device)   # escape-vs-L5_fight
+    return {"fight_1": f1, "fight_2": f2}
