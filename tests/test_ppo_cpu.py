@@ -94,10 +94,12 @@ def test_gradient_allreduce_keeps_two_ranks_in_sync():
 def test_policy_files_round_trip_with_reference_naming(tmp_path):
     from hhmarl_2d_b200 import checkpoint
     d = str(tmp_path / "policies")
+    saved = {}
     for level in (3, 4):
         f1, f2 = M.build_policy_pair("fight")
-        M.fill_from_seed(f1, level); M.fill_from_seed(f2, level + 10)
+        M.fill_from_seed(f1, level); M.fill_from_seed(f2, level + 10)     # (the pair shares SHARED_LAYER)
         checkpoint.save_policies(d, level, "fight", f1, f2)
+        saved[level] = f1
     e1, e2 = M.build_policy_pair("escape")
     checkpoint.save_policies(d, 3, "escape", e1, e2)
     assert sorted(os.listdir(d)) == ["L3_AC1_escape.pt", "L3_AC1_fight.pt", "L3_AC2_escape.pt", "L3_AC2_fight.pt",
@@ -106,7 +108,7 @@ def test_policy_files_round_trip_with_reference_naming(tmp_path):
     assert set(l4) == {"fight_1", "fight_2"}
     l5 = checkpoint.load_opponent_policies(d, 5, "fight")
     assert set(l5) == {3, 4, 5} and set(l5[5]) == {"escape_1", "escape_2"}
-    ref = M.fill_from_seed(M.build_policy_pair("fight")[0], 3)
     x = torch.rand(4, 26)
     with torch.no_grad():
-        assert torch.equal(l5[3]["fight_1"].actor(x), ref.actor(x))
+        assert torch.equal(l5[3]["fight_1"].actor(x), saved[3].actor(x))
+        assert torch.equal(l5[4]["fight_1"].actor(x), saved[4].actor(x))
