@@ -83,6 +83,7 @@ def best_thread_count(level: int):
         v, _ = cpu_oracle_throughput(level, 15_000, c)
         if v > best_v * 1.03:
             best, best_v = c, v
+    best_thread_count.rate = best_v
     return best
 
 
@@ -91,7 +92,9 @@ def run_reference(args):
     if rank != 0:
         return
     cores = best_thread_count(args.level)
-    per_step = max(20_000, args.cpu_sample_steps // 8)
+    # bounded sample per bench step: the whole --steps/--warmup run stays within ~2 minutes on this box
+    budget = 100.0 * best_thread_count.rate / max(1, args.steps + args.warmup) / cores
+    per_step = int(min(max(20_000, args.cpu_sample_steps // 8), max(2_000, budget)))
     for _ in range(args.warmup):
         cpu_oracle_throughput(args.level, per_step // 10, cores)
     t_total, n_total = 0.0, 0
