@@ -126,14 +126,11 @@ __device__ __forceinline__ bool in_boundary(const Geom& g, double lat, double lo
   return 7.0 <= lon && lon <= g.right && 5.0 <= lat && lat <= g.top;
 }
 
-// (the feature helpers below are deliberately NOT inlined: each is 60-120 instructions with an FP64 divide /
-// sqrt expansion, called from ~25 sites of the step; one shared copy keeps the step's code in the
-// instruction caches -- profiles/README.md)
 // heading unit vector of env_base.py:428 / :452: (cos, sin) of ((90 - heading) % 360) * pi/180
 struct HVec {
   double c, s, n;
 };
-static __device__ __noinline__ HVec heading_vec(double heading) {
+__device__ __forceinline__ HVec heading_vec(double heading) {
   HVec h;
   double th = pymod(90.0 - heading, 360.0) * (geo::kPi / 180.0);
   m::sincos_(th, &h.s, &h.c);
@@ -141,7 +138,7 @@ static __device__ __noinline__ HVec heading_vec(double heading) {
   return h;
 }
 // env_base.py:424-432 -- degrees
-static __device__ __noinline__ double focus_deg(const HVec ha, double lat_a, double lon_a, double lat_b, double lon_b) {
+__device__ __forceinline__ double focus_deg(const HVec& ha, double lat_a, double lon_a, double lat_b, double lon_b) {
   double v0 = lon_b - lon_a, v1 = lat_b - lat_a;
   double x = clip((ha.c * v0 + ha.s * v1) / (ha.n * sqrt(v0 * v0 + v1 * v1) + 1e-10), -1.0, 1.0);
   return m::acos_(x) * (180.0 / geo::kPi);
@@ -150,7 +147,7 @@ __device__ __forceinline__ double focus_norm_from_deg(double deg) { return clip(
 // env_base.py:441-446
 __device__ __forceinline__ double aspect_from_deg(double deg) { return clip((180.0 - deg) / 180.0, 0.0, 1.0); }
 // env_base.py:448-456
-static __device__ __noinline__ double hdiff_norm(const HVec a, const HVec b) {
+__device__ __forceinline__ double hdiff_norm(const HVec& a, const HVec& b) {
   double x = clip((a.c * b.c + a.s * b.s) / (a.n * b.n + 1e-10), -1.0, 1.0);
   return clip((m::acos_(x) * (180.0 / geo::kPi)) / 180.0, 0.0, 1.0);
 }
@@ -159,7 +156,7 @@ __device__ __forceinline__ double dist_raw(double lat_a, double lon_a, double la
   const double dx = lon_b - lon_a, dy = lat_b - lat_a;  // math.hypot of two O(0.1) numbers
   return sqrt(dx * dx + dy * dy);
 }
-static __device__ __noinline__ double hdg_feature(double heading) {
+__device__ __forceinline__ double hdg_feature(double heading) {
   return clip(pymod(heading, 359.0) / 359.0, 0.0, 1.0);
 }
 

@@ -571,7 +571,7 @@ constexpr double kPhi0 = 5.25 * kDeg;
 constexpr double kSinPhi0 = 0.09150161866340238;   // sin(5.25 deg)
 constexpr double kCosPhi0 = 0.9958049275746618;   // cos(5.25 deg)
 
-static __device__ __noinline__ double2 inverse_local(double lat1, double lon1, double lat2, double lon2) {
+__device__ __forceinline__ double2 inverse_local(double lat1, double lon1, double lat2, double lon2) {
   const double phim = 0.5 * (lat1 + lat2) * kDeg;
   const double hp = 0.5 * (lat2 - lat1) * kDeg, hl = 0.5 * (lon2 - lon1) * kDeg;
   double sm, cm;
