@@ -177,11 +177,12 @@ __device__ int lowlevel_obs(Arena& A, const Geom& g, int i, float* out) {
 
 __device__ void write_ll(Arena& A, const Geom& g, int first, float* ll_obs, uint8_t* ll_info) {
   for (int i = first; i < first + NA; ++i) {
-    uint8_t info = 0;
+    // bits 1-2 (policy kind) are constant for the whole commander step, bit 0 = the unit queries its policy now
+    uint8_t info = (A.ca[i] == 0 ? 2 : 0) | (A.actype[i] == 2 ? 4 : 0);
     float* row = ll_obs + i * LL_STRIDE;
     if (A.active && A.alive[i]) {
       lowlevel_obs(A, g, i, row);
-      info = 1 | (A.ca[i] == 0 ? 2 : 0) | (A.actype[i] == 2 ? 4 : 0);
+      info |= 1;
     } else {
       for (int k = 0; k < LL_STRIDE; ++k) row[k] = 0.0f;
     }
@@ -517,6 +518,8 @@ __global__ void __launch_bounds__(64) begin_kernel(Arena* arenas, HParams P, con
   A.kill_event = A.situation_event = 0;
   A.active = 1;
   write_ll(A, g, 0, ll_obs + (size_t)a * NU * LL_STRIDE, ll_info + (size_t)a * NU);
+  for (int i = NA; i < NU; ++i)   // opponents' policy kinds are known already (their observations come later)
+    ll_info[(size_t)a * NU + i] = (A.ca[i] == 0 ? 2 : 0) | (A.actype[i] == 2 ? 4 : 0);
 }
 
 __global__ void __launch_bounds__(64) agents_kernel(Arena* arenas, HParams P, const int32_t* act, float* ll_obs, uint8_t* ll_info) {

@@ -82,28 +82,35 @@ class VecHighLevelEnv:
         nat.check(nat.lib().hh_hier_reset(self._h, mp, self.obs.data_ptr(), self._stream()), "hh_hier_reset")
         return self.obs
 
-    # frozen low-level policies, batched: env_base.py:349-398 (per-head argmax of the actor)
+    # frozen low-level policies, batched: env_base.py:349-398 (per-head argmax of the actor).  Which network a
+    # unit uses (fight/escape x aircraft type) is fixed for the whole commander step, so the row lists are built
+    # once per step (4 host syncs) and reused by all 16 sub-steps; rows of units that do not query right now
+    # (dead, or arena already out of its sub-step loop) are computed and ignored by the kernels.
+    _KINDS = (("fight", 1, 0), ("fight", 2, 4), ("escape", 1, 2), ("escape", 2, 6))
+    _DIMS = {("fight", 1): 26, ("fight", 2): 24, ("escape", 1): 30, ("escape", 2): 29}
+
+    def _build_rows(self):
+        t = self._torch
+        kind = (self.ll_info & 6).reshape(-1)
+        self._rows = []
+        for mode, ac, bits in self._KINDS:
+            for first in (0, 3):
+                unit = t.arange(self.n_arenas * 6, device=self.dev) % 6
+                sel = (kind == bits) & (unit >= first) & (unit < first + 3)
+                self._rows.append((mode, ac, first, t.nonzero(sel, as_tuple=False).flatten()))
+
     def _infer(self, first: int):
         t = self._torch
-        info = self.ll_info[:, first:first + 3]
-        obs = self.ll_obs[:, first:first + 3]
-        act = self.ll_act[:, first:first + 3]
+        obs_flat, act_flat = self.ll_obs.reshape(-1, 30), self.ll_act.reshape(-1, 4)
         with t.no_grad():
-            for mode, mbit in (("fight", 0), ("escape", 2)):
-                for ac, abit in ((1, 0), (2, 4)):
-                    sel = (info & 7) == (1 | mbit | abit)
-                    idx = t.nonzero(sel.reshape(-1), as_tuple=False).flatten()
-                    if idx.numel() == 0:
-                        continue
-                    d = {("fight", 1): 26, ("fight", 2): 24, ("escape", 1): 30, ("escape", 2): 29}[(mode, ac)]
-                    x = obs.reshape(-1, 30).index_select(0, idx)[:, :d]
-                    a = M.deterministic_actions(self.policies[f"{mode}_{ac}"].actor(x), ac).to(t.int32)
-                    flat = act.reshape(-1, 4)
-                    rows = t.zeros((idx.numel(), 4), dtype=t.int32, device=self.dev)
-                    rows[:, :a.shape[1]] = a
-                    # act is a view of ll_act with a non-contiguous arena stride: scatter through global row ids
-                    g_rows = (idx // 3) * 6 + first + (idx % 3)
-                    self.ll_act.reshape(-1, 4)[g_rows] = rows
+            for mode, ac, f, idx in self._rows:
+                if f != first or idx.numel() == 0:
+                    continue
+                x = obs_flat.index_select(0, idx)[:, :self._DIMS[(mode, ac)]]
+                a = M.deterministic_actions(self.policies[f"{mode}_{ac}"].actor(x), ac).to(t.int32)
+                if a.shape[1] == 3:
+                    a = t.nn.functional.pad(a, (0, 1))
+                act_flat.index_copy_(0, idx, a)
 
     def step(self, commander_actions):
         """commander_actions: int32 CUDA tensor [N, 3] in {0: escape, 1: nearest opponent, 2: second nearest}.
@@ -113,6 +120,7 @@ class VecHighLevelEnv:
         assert commander_actions.is_cuda and commander_actions.dtype == t.int32 and commander_actions.numel() == self.n_arenas * 3
         lo, li, la = self.ll_obs.data_ptr(), self.ll_info.data_ptr(), self.ll_act.data_ptr()
         nat.check(L.hh_hier_begin(h, commander_actions.contiguous().data_ptr(), lo, li, st), "hh_hier_begin")
+        self._build_rows()
         for s in range(16):   # n_sub_steps = 15 -> at most 16 iterations (env_hier.py:33,125)
             self._infer(0)
             if self.trace is not None:

@@ -303,3 +303,41 @@ def test_pinned_host_buffers_zero_copy_path_matches_device_path():
     z1, z2, zr, zd = a.step_host(act)
     w1, w2, wr, wd = b.step(torch.from_numpy(act).cuda())
     assert np.array_equal(z1, w1.cpu().numpy()) and np.array_equal(zd, wd.cpu().numpy())
+
+
+def test_state_round_trip_masked_reset_and_large_batch():
+    import torch
+    n = 4096
+    env = _vec(n, 3, "fight", 21)
+    env.reset()
+    torch.manual_seed(3)
+    acts = torch.stack([torch.randint(0, 13, (40, n, 2)), torch.randint(0, 9, (40, n, 2)), torch.randint(0, 2, (40, n, 2)),
+                        torch.randint(0, 2, (40, n, 2))], dim=-1).to(torch.int32).cuda()
+    for t in range(20):
+        env.step(acts[t])
+    st = env.get_state()
+    # (1) set_state(get_state()) is the identity: a clone continues bit-identically
+    twin = _vec(n, 3, "fight", 21)
+    twin.set_state(st)
+    for t in range(20, 40):
+        a = [x.clone() for x in env.step(acts[t])]
+        b = twin.step(acts[t])
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+    # (2) masked reset touches exactly the selected arenas
+    before = env.get_state()
+    mask = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    mask[::7] = 1
+    env.reset(mask)
+    after = env.get_state()
+    m = mask.cpu().numpy().astype(bool)
+    assert (after["steps"][m] == 0).all() and (after["alive"][m] == 1).all()
+    for k in ("lat", "lon", "heading", "steps", "draws_g", "alive", "cannon_remain"):
+        assert np.array_equal(after[k][~m], before[k][~m]), k
+    assert (after["draws_g"][m] > before["draws_g"][m]).all()       # the G stream keeps counting across episodes
+    # (3) a large batch (BASELINE config 4's total arena count on one device) steps and stays in range
+    big = _vec(65536, 3, "fight", 1)
+    o1, o2 = big.reset()
+    for t in range(3):
+        o1, o2, r, d = big.step(acts[t].repeat(16, 1, 1).contiguous())
+    assert torch.isfinite(o1).all() and (o1 >= 0).all() and (o1 <= 1).all() and (big.get_state()["error"] == 0).all()
