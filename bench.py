@@ -328,7 +328,21 @@ def run_b200(args):
                 "sim_ticks_per_s": float(tk.item()) / (float(ht.item()) * 1e-3), "commander_steps": HS,
                 "mean_substeps": float(tk.item()) / (world * n * HS), "arenas_per_gpu": n,
                 "note": "HighLevelEnv 3-vs-3, 16 masked sub-steps x (2 launches + fight/escape actor batches), fp32 cuBLAS"}
-        del henv
+        from hhmarl_2d_b200.env_hier import CommanderSampler
+        from hhmarl_2d_b200 import models as MM
+        cs = CommanderSampler(henv, MM.CommanderGru().to(dev), fragment_len=4)
+        cs.collect()
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        cs.collect()
+        c1.record()
+        barrier()
+        ct = torch.tensor([c0.elapsed_time(c1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ct, op=dist.ReduceOp.MAX)
+        hier["commander_rollout_steps_per_s"] = world * n * 4 / (float(ct.item()) * 1e-3)
+        del henv, cs
     except Exception as ex:  # noqa: BLE001
         hier = {"error": repr(ex)}
 

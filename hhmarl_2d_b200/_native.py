@@ -121,6 +121,8 @@ def lib() -> ctypes.CDLL:
     L.hh_launch_count.restype = U64
     L.hh_gae.argtypes = [I32, I32, VP, VP, VP, VP, ctypes.c_float, ctypes.c_float, VP, VP, VP]
     L.hh_gae.restype = ctypes.c_int
+    L.hh_gae_agents.argtypes = [I32, I32, I32, VP, VP, VP, VP, ctypes.c_float, ctypes.c_float, VP, VP, VP]
+    L.hh_gae_agents.restype = ctypes.c_int
     L.hh_sample_actions.argtypes = [I32, VP, VP, U64, U64, VP, I32, VP, VP, VP]
     L.hh_sample_actions.restype = ctypes.c_int
     L.hh_pack_central.argtypes = [I32, I32, I32, VP, VP, VP, VP, VP]
@@ -152,7 +154,7 @@ def lib() -> ctypes.CDLL:
 
 
 EXPORTS = ["hh_create", "hh_destroy", "hh_n_arenas", "hh_obs_dim", "hh_reset", "hh_step", "hh_step_begin", "hh_step_finish", "hh_reset_host",
-           "hh_step_host", "hh_host_buffers", "hh_get_state", "hh_set_state", "hh_launch_count", "hh_gae", "hh_sample_actions", "hh_pack_central", "hh_debug_geodesic", "hh_last_error", "hh_version",
+           "hh_step_host", "hh_host_buffers", "hh_get_state", "hh_set_state", "hh_launch_count", "hh_gae", "hh_gae_agents", "hh_sample_actions", "hh_pack_central", "hh_debug_geodesic", "hh_last_error", "hh_version",
            "hh_hier_create", "hh_hier_destroy", "hh_hier_reset", "hh_hier_begin", "hh_hier_agents", "hh_hier_tick",
            "hh_hier_end", "hh_hier_get_state", "hh_hier_set_state", "hh_hier_launch_count", "hh_hier_last_error"]
 

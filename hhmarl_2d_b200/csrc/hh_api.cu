@@ -591,12 +591,12 @@ reset_kernel(StatePtrs S, Params P, const uint8_t* __restrict__ mask, int first_
 // compute_advantages with use_gae=True): one thread per (arena, agent), backward scan over t;
 // consecutive threads touch consecutive addresses in every [t] slab.
 // ------------------------------------------------------------------------------------------
-__global__ void gae_kernel(int T, int n_pairs, const float* __restrict__ rew, const float* __restrict__ vf,
+__global__ void gae_kernel(int T, int n_pairs, int n_agents, const float* __restrict__ rew, const float* __restrict__ vf,
                            const float* __restrict__ last_vf, const uint8_t* __restrict__ done, float gamma,
                            float lam, float* __restrict__ adv, float* __restrict__ vtarg) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // i = arena * 2 + agent
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // i = arena * n_agents + agent
   if (i >= n_pairs) return;
-  const int arena = i >> 1, n_arenas = n_pairs >> 1;
+  const int arena = i / n_agents, n_arenas = n_pairs / n_agents;
   float next_v = last_vf[i], gae = 0.0f;
   for (int t = T - 1; t >= 0; --t) {
     const size_t k = (size_t)t * n_pairs + i;
@@ -743,8 +743,21 @@ extern "C" int hh_gae(int32_t T, int32_t n_arenas, const float* rew_dev, const f
   if (T <= 0 || n_arenas <= 0 || !rew_dev || !vf_dev || !last_vf_dev || !done_dev || !adv_dev || !vtarg_dev)
     return fail(-1, "hh_gae: bad argument");
   const int n_pairs = n_arenas * 2;
-  gae_kernel<<<(n_pairs + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(T, n_pairs, rew_dev, vf_dev, last_vf_dev,
+  gae_kernel<<<(n_pairs + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(T, n_pairs, 2, rew_dev, vf_dev, last_vf_dev,
                                                                                  done_dev, gamma, lam, adv_dev, vtarg_dev);
+  HH_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int hh_gae_agents(int32_t T, int32_t n_arenas, int32_t n_agents, const float* rew_dev, const float* vf_dev,
+                             const float* last_vf_dev, const uint8_t* done_dev, float gamma, float lam, float* adv_dev,
+                             float* vtarg_dev, void* stream) {
+  if (T <= 0 || n_arenas <= 0 || n_agents <= 0 || !rew_dev || !vf_dev || !last_vf_dev || !done_dev || !adv_dev || !vtarg_dev)
+    return fail(-1, "hh_gae_agents: bad argument");
+  const int n_pairs = n_arenas * n_agents;
+  gae_kernel<<<(n_pairs + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(T, n_pairs, n_agents, rew_dev, vf_dev,
+                                                                                 last_vf_dev, done_dev, gamma, lam, adv_dev,
+                                                                                 vtarg_dev);
   HH_CUDA(cudaGetLastError());
   return 0;
 }

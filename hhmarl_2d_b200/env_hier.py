@@ -154,3 +154,73 @@ class VecHighLevelEnv:
             self.close()
         except Exception:
             pass
+
+
+class CommanderSampler:
+    """On-device rollout of the commander policy (train_hier.py): one CommanderGru shared by the three agents
+    (policy_mapping_fn -> "commander_policy"), central observation = sorted-key flattening of
+    central_critic_observer (train_hier.py:134-165): [act_1_own, act_2, act_3 | obs_1_own | obs_2 | obs_3] (105),
+    actions zero while sampling and written back as act / N_OPP_HL afterwards (train_hier.py:131-132);
+    GRU state carried per (arena, agent) and zeroed when the arena's episode ends."""
+
+    def __init__(self, env: VecHighLevelEnv, model, fragment_len: int = 8, gamma: float = 0.99, lam: float = 1.0):
+        import torch
+        self.env, self.model, self.T, self.gamma, self.lam = env, model, fragment_len, gamma, lam
+        n, dev = env.n_arenas, env.dev
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.buf = dict(flat=torch.zeros((fragment_len, n, 3, 105), **f32), actions=torch.zeros((fragment_len, n, 3), dtype=torch.int32, device=dev),
+                        logp=torch.zeros((fragment_len, n, 3), **f32), vf=torch.zeros((fragment_len, n, 3), **f32),
+                        logits=torch.zeros((fragment_len, n, 3, 3), **f32), rew=torch.zeros((fragment_len, n, 3), **f32),
+                        done=torch.zeros((fragment_len, n), dtype=torch.uint8, device=dev),
+                        h0=torch.zeros((fragment_len, n, 3, 200), **f32), h1=torch.zeros((fragment_len, n, 3, 200), **f32),
+                        adv=torch.zeros((fragment_len, n, 3), **f32), vtarg=torch.zeros((fragment_len, n, 3), **f32),
+                        last_vf=torch.zeros((n, 3), **f32), substeps=torch.zeros((fragment_len, n), dtype=torch.int32, device=dev))
+        self.h = [torch.zeros((n * 3, 200), **f32), torch.zeros((n * 3, 200), **f32)]
+        self.others = torch.tensor([[1, 2], [0, 2], [0, 1]], device=dev)
+        self.obs = None
+
+    def _flat(self, obs):   # obs [N,3,34] -> [N,3,105]
+        t = self.env._torch
+        o = obs[:, self.others]                                      # [N,3,2,34]: the two team-mates in id order
+        return t.cat((t.zeros((obs.shape[0], 3, 3), device=obs.device), obs, o[:, :, 0], o[:, :, 1]), dim=2)
+
+    def _forward(self, flat):
+        x = flat.reshape(-1, 105)
+        d = {"act_1_own": x[:, 0:1], "act_2": x[:, 1:2], "act_3": x[:, 2:3], "obs_1_own": x[:, 3:37], "obs_2": x[:, 37:71],
+             "obs_3": x[:, 71:105]}
+        logits, new_h = self.model({"obs": d}, self.h, self.env._torch.ones(x.shape[0], dtype=self.env._torch.int32))
+        return logits, self.model.value_function(), new_h
+
+    def collect(self):
+        t = self.env._torch
+        b = self.buf
+        n = self.env.n_arenas
+        with t.no_grad():
+            if self.obs is None:
+                self.obs = self.env.reset().clone()
+            for k in range(self.T):
+                flat = self._flat(self.obs)
+                b["h0"][k], b["h1"][k] = self.h[0].view(n, 3, 200), self.h[1].view(n, 3, 200)
+                logits, vf, new_h = self._forward(flat)
+                g = -t.log(-t.log(t.rand_like(logits).clamp_(1e-20, 1 - 1e-7)))
+                a = t.argmax(logits + g, dim=-1)
+                lsm = t.log_softmax(logits, dim=-1)
+                b["flat"][k], b["logits"][k], b["vf"][k] = flat, logits.view(n, 3, 3), vf.view(n, 3)
+                b["actions"][k] = a.view(n, 3).to(t.int32)
+                b["logp"][k] = lsm.gather(1, a[:, None])[:, 0].view(n, 3)
+                obs, rew, done = self.env.step(b["actions"][k].contiguous())
+                b["rew"][k], b["done"][k], b["substeps"][k] = rew, done, self.env.substeps
+                keep = (1 - done.float()).repeat_interleave(3)[:, None]
+                self.h = [new_h[0] * keep, new_h[1] * keep]          # new episode -> initial state (zeros)
+                self.obs = obs.clone()
+            _, last_v, _ = self._forward(self._flat(self.obs))
+            b["last_vf"].copy_(last_v.view(n, 3))
+            st = t.cuda.current_stream(self.env.dev).cuda_stream
+            nat.check(nat.lib().hh_gae_agents(self.T, n, 3, b["rew"].data_ptr(), b["vf"].data_ptr(), b["last_vf"].data_ptr(),
+                                              b["done"].data_ptr(), self.gamma, self.lam, b["adv"].data_ptr(),
+                                              b["vtarg"].data_ptr(), st), "hh_gae_agents")
+            act = b["actions"].float() / 2.0                          # N_OPP_HL = 2 (train_hier.py:131-132)
+            b["flat"][..., 0] = act
+            b["flat"][..., 1] = act[:, :, self.others[:, 0]]
+            b["flat"][..., 2] = act[:, :, self.others[:, 1]]
+        return b

@@ -119,6 +119,10 @@ uint64_t hh_launch_count(const hh_env* env);
  *   done: u8[T][N] (episode ended at that step: no bootstrap across it); adv, vtarg: f32[T][N][2] out. */
 int hh_gae(int32_t T, int32_t n_arenas, const float* rew_dev, const float* vf_dev, const float* last_vf_dev,
            const uint8_t* done_dev, float gamma, float lam, float* adv_dev, float* vtarg_dev, void* stream);
+/* same with n_agents learning agents per arena (3 for the commander policy of train_hier.py): [T][N][n_agents] */
+int hh_gae_agents(int32_t T, int32_t n_arenas, int32_t n_agents, const float* rew_dev, const float* vf_dev,
+                  const float* last_vf_dev, const uint8_t* done_dev, float gamma, float lam, float* adv_dev,
+                  float* vtarg_dev, void* stream);
 
 /* Sampler glue (what RLlib's sampler does between the policy forward and env.step):
  * hh_sample_actions: TorchMultiCategorical.sample()/logp() of both policies in one launch.  logits1 f32[N][26]

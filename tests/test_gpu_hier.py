@@ -73,3 +73,25 @@ def test_hier_matches_oracle(kw):
                 _close(list(st[k].lat), list(s.lat[:6]), "lat"); _close(list(st[k].hdg), list(s.heading[:6]), "hdg")
                 assert st[k].err == 0
     assert n_done >= n // 2
+
+
+def test_commander_sampler_fragment():
+    from hhmarl_2d_b200.env_hier import CommanderSampler, VecHighLevelEnv
+    from hhmarl_2d_b200 import models as M
+    torch.manual_seed(0)
+    env = VecHighLevelEnv(256, device=0, seed=5)
+    model = M.CommanderGru().cuda()
+    smp = CommanderSampler(env, model, fragment_len=6)
+    b = smp.collect()
+    n = 256
+    assert b["flat"].shape == (6, n, 3, 105) and (b["actions"] >= 0).all() and (b["actions"] <= 2).all()
+    # central observation: own obs then the two team-mates in id order (train_hier.py:134-165)
+    f = b["flat"]
+    assert torch.equal(f[:, :, 1, 3:37], f[:, :, 0, 37:71]) and torch.equal(f[:, :, 0, 3:37], f[:, :, 1, 37:71])
+    assert torch.equal(f[:, :, 2, 37:71], f[:, :, 0, 3:37]) and torch.equal(f[:, :, 2, 71:105], f[:, :, 1, 3:37])
+    # action write-back, own first then team-mates, scaled by 1 / N_OPP_HL
+    a = b["actions"].float() / 2
+    assert torch.equal(f[:, :, 0, 0], a[:, :, 0]) and torch.equal(f[:, :, 0, 1], a[:, :, 1]) and torch.equal(f[:, :, 1, 1], a[:, :, 0])
+    assert torch.isfinite(b["adv"]).all() and (b["substeps"] >= 1).all() and (b["substeps"] <= 16).all()
+    lsm = torch.log_softmax(b["logits"], -1).gather(3, b["actions"].long()[..., None])[..., 0]
+    assert torch.allclose(lsm, b["logp"], atol=1e-5)
