@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -21,6 +22,7 @@
 
 #include "../../include/hhmarl_b200.h"
 #include "hh_quad.cuh"
+#include "hh_cta.cuh"
 
 namespace hh {
 
@@ -477,6 +479,16 @@ step_kernel(StatePtrs S, Params P, const int32_t* __restrict__ actions, float* _
   finish_step<MODE>(L, rng, g, P, S, a, u, valid, done, rew, obs1, obs2, rew_out, done_out, s1, s2, arena0, n_valid);
 }
 
+// Same step, "v3" work distribution (hh_cta.cuh): 32 arenas per 128-thread CTA staged in shared memory, each
+// phase executed by exactly the threads that have work in it.
+template <int LEVEL, int MODE>
+__global__ void __launch_bounds__(cta::kThreads)
+step_kernel_cta(StatePtrs S, Params P, const int32_t* __restrict__ actions, float* __restrict__ obs1,
+                float* __restrict__ obs2, float* __restrict__ rew_out, uint8_t* __restrict__ done_out) {
+  __shared__ __align__(16) cta::Smem sm;
+  cta::step_body<LEVEL, MODE>(sm, S, P, actions, obs1, obs2, rew_out, done_out);
+}
+
 // ------------------------------------------------------------------------------------------
 // step, levels 4-5 (frozen-policy opponents, env_base.py:349-398): the opponent's observation is
 // needed mid-step -- after the agents' fire decisions, before the tick -- so the step is split:
@@ -716,6 +728,7 @@ struct hh_env {
   Params P{};
   bool initialised = false;
   bool mid_step = false;
+  bool use_cta = false;   // HH_STEP_IMPL=cta|quad (levels 1-3 fused step)
   float* rew_pre = nullptr;
   uint64_t launches = 0;
   // host-variant staging
@@ -863,6 +876,10 @@ extern "C" int hh_create(const hh_config* cfg, int32_t n_arenas, int32_t device,
   P.seed_lo = (uint32_t)cfg->seed;
   P.seed_hi = (uint32_t)(cfg->seed >> 32);
   P.arena_base = (uint32_t)cfg->arena_base;
+  {
+    const char* impl = getenv("HH_STEP_IMPL");
+    e->use_cta = impl ? (std::string(impl) == "cta") : false;
+  }
   *out = e;
   return 0;
 }
@@ -903,6 +920,14 @@ extern "C" int hh_reset(hh_env* e, const uint8_t* mask_dev, float* obs1, float* 
 template <int LEVEL>
 static void launch_step(hh_env* e, const int32_t* actions, float* obs1, float* obs2, float* rew, uint8_t* done,
                         cudaStream_t st) {
+  if (e->use_cta) {
+    const int cblocks = (e->n + cta::kArenas - 1) / cta::kArenas;
+    if (e->cfg.agent_mode == 0)
+      step_kernel_cta<LEVEL, 0><<<cblocks, cta::kThreads, 0, st>>>(e->S, e->P, actions, obs1, obs2, rew, done);
+    else
+      step_kernel_cta<LEVEL, 1><<<cblocks, cta::kThreads, 0, st>>>(e->S, e->P, actions, obs1, obs2, rew, done);
+    return;
+  }
   const int blocks = (e->n + kArenasPerCta - 1) / kArenasPerCta;
   if (e->cfg.agent_mode == 0)
     step_kernel<LEVEL, 0><<<blocks, kThreads, 0, st>>>(e->S, e->P, actions, obs1, obs2, rew, done);
