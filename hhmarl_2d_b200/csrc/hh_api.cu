@@ -728,7 +728,7 @@ struct hh_env {
   Params P{};
   bool initialised = false;
   bool mid_step = false;
-  bool use_cta = false;   // HH_STEP_IMPL=cta|quad (levels 1-3 fused step)
+  bool use_cta = true;    // HH_STEP_IMPL=cta|quad (levels 1-3 fused step)
   float* rew_pre = nullptr;
   uint64_t launches = 0;
   // host-variant staging
@@ -878,7 +878,7 @@ extern "C" int hh_create(const hh_config* cfg, int32_t n_arenas, int32_t device,
   P.arena_base = (uint32_t)cfg->arena_base;
   {
     const char* impl = getenv("HH_STEP_IMPL");
-    e->use_cta = impl ? (std::string(impl) == "cta") : false;
+    e->use_cta = impl ? (std::string(impl) != "quad") : true;   // default: v3 (hh_cta.cuh)
   }
   *out = e;
   return 0;

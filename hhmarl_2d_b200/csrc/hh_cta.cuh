@@ -21,28 +21,32 @@
 namespace hh {
 namespace cta {
 
-constexpr int kArenas = 32;
-constexpr int kThreads = 128;
+#ifndef HH_CTA_ARENAS
+#define HH_CTA_ARENAS 32
+#endif
+constexpr int kArenas = HH_CTA_ARENAS;        // arenas per CTA (multiple of 8: whole warps in every mapping)
+constexpr int kThreads = 4 * kArenas;
+constexpr int A4 = 4 * kArenas, A2 = 2 * kArenas, A1 = kArenas;
 
 struct Smem {
-  double lat[128], lon[128], hdg[128], spd[128], nhdg[128], nspd[128];
-  double rlat[128], rlon[128], rhdg[128], rnhdg[128];  // rocket of the AC1 shooter in that unit slot
-  double nlat[128], nlon[128];
-  double hvc[128], hvs[128], hvn[128];
-  double rel_focus[128], near_dn[128];
-  double rew[64], opp_focus[64];
-  unsigned long long dg[32], dg0[32];
-  int crem[128], burst[128], cmax[128], mrem[128], rmax[128], mwait[128];
-  int rage[128], rtgt[128], rid[128], ota[128];
-  int near_t[128], rel_sign[128], tgt[128], new_wait[128], inr[128];
-  unsigned char alive[128], hasm[128], ralive[128], want[128], launched[128], upd[128], rocket0[128], hit_t[128],
-      hit_f[128], exploded[128], firing[128];
-  int steps[32], alive_ag[32], alive_op[32], esc_time[32], next_id[32], pset[32], opp_mode[32], err[32], escaping[32];
-  unsigned int dc[32];
-  unsigned int killer_pack[32];
-  int by_rocket[32], done[32], alive_pre[32];
-  int4 act[64];
-  float obs1[32 * OBS_ESC_AC1], obs2[32 * OBS_ESC_AC2];
+  double lat[A4], lon[A4], hdg[A4], spd[A4], nhdg[A4], nspd[A4];
+  double rlat[A4], rlon[A4], rhdg[A4], rnhdg[A4];  // rocket of the AC1 shooter in that unit slot
+  double nlat[A4], nlon[A4];
+  double hvc[A4], hvs[A4], hvn[A4];
+  double rel_focus[A4], near_dn[A4];
+  double rew[A2], opp_focus[A2];
+  unsigned long long dg[A1], dg0[A1];
+  int crem[A4], burst[A4], cmax[A4], mrem[A4], rmax[A4], mwait[A4];
+  int rage[A4], rtgt[A4], rid[A4], ota[A4];
+  int near_t[A4], rel_sign[A4], tgt[A4], new_wait[A4], inr[A4];
+  unsigned char alive[A4], hasm[A4], ralive[A4], want[A4], launched[A4], upd[A4], rocket0[A4], hit_t[A4],
+      hit_f[A4], exploded[A4], firing[A4];
+  int steps[A1], alive_ag[A1], alive_op[A1], esc_time[A1], next_id[A1], pset[A1], opp_mode[A1], err[A1], escaping[A1];
+  unsigned int dc[A1];
+  unsigned int killer_pack[A1];
+  int by_rocket[A1], done[A1], alive_pre[A1];
+  int4 act[A2];
+  float obs1[A1 * OBS_ESC_AC1], obs2[A1 * OBS_ESC_AC2];
 };
 
 __device__ __forceinline__ HVec sm_hv(const Smem& S, int i) {
@@ -184,7 +188,7 @@ __device__ __forceinline__ void step_body(Smem& S, const StatePtrs& G, const Par
       S.pset[ul] = L.pset; S.opp_mode[ul] = L.opp_mode; S.err[ul] = L.err; S.escaping[ul] = L.escaping;
       S.dg[ul] = L.dg; S.dg0[ul] = L.dg; S.dc[ul] = L.dc;
     }
-    if (tid < 64) {
+    if (tid < A2) {
       const int al = tid >> 1;
       const int a = arena0 + (al < n_valid ? al : n_valid - 1);
       S.act[tid] = reinterpret_cast<const int4*>(actions)[(size_t)a * 2 + (tid & 1)];
@@ -220,14 +224,14 @@ __device__ __forceinline__ void step_body(Smem& S, const StatePtrs& G, const Par
     S.want[tid] = 0;
     S.tgt[tid] = -1;
     S.new_wait[tid] = 0;
-    if (tid < 64) S.rew[tid] = 0.0;
+    if (tid < A2) S.rew[tid] = 0.0;
   }
   __syncthreads();
 
   // ---------------------------------------------------------------- P2: actions
   // warps 0-1: agents' _take_base_action (env_base.py:214-238), one thread per agent
   // warp 2   : scripted opponents (env_hetero.py:118-158), one thread per arena, ids 3 then 4
-  if (tid < 64) {
+  if (tid < A2) {
     const int al = tid >> 1, au = tid & 1, us = al * 4 + au;
     S.opp_focus[tid] = focus_norm_from_deg(S.rel_focus[us]);
     if (S.alive[us]) {
@@ -249,8 +253,8 @@ __device__ __forceinline__ void step_body(Smem& S, const StatePtrs& G, const Par
         S.new_wait[us] = randint_from(7, 17, g_random_at(rng, S.dg0[al]));   // drawn iff attempted (env_base.py:228-230)
       }
     }
-  } else if (tid < 96) {
-    const int al = tid - 64, b = al * 4;
+  } else if (tid < A2 + A1) {
+    const int al = tid - A2, b = al * 4;
     const Rng rng{P.seed_lo, P.seed_hi, P.arena_base + (uint32_t)(arena0 + min(al, n_valid - 1))};
     // agent 1's attempt consumes one G draw before the opponents' (same predicate as above)
     const int4 a0 = S.act[al * 2];
@@ -376,7 +380,7 @@ __device__ __forceinline__ void step_body(Smem& S, const StatePtrs& G, const Par
   __syncthreads();
 
   // ---------------------------------------------------------------- P6: kill resolution + missile noise (arena-mapped)
-  if (tid < 32) {
+  if (tid < A1) {
     const int al = tid, b = al * 4;
     const Rng rng{P.seed_lo, P.seed_hi, P.arena_base + (uint32_t)(arena0 + min(al, n_valid - 1))};
     int alive_m = S.alive_pre[al];
@@ -431,7 +435,7 @@ __device__ __forceinline__ void step_body(Smem& S, const StatePtrs& G, const Par
   __syncthreads();
 
   // ---------------------------------------------------------------- P8: rocket resolution in launch order (arena-mapped)
-  if (tid < 32) {
+  if (tid < A1) {
     const int al = tid, b = al * 4;
     const int r0 = S.rocket0[b], r2 = S.rocket0[b + 2];
     if (r0 || r2) {
@@ -493,7 +497,7 @@ __device__ __forceinline__ void step_body(Smem& S, const StatePtrs& G, const Par
   __syncthreads();
 
   // ---------------------------------------------------------------- P10: rewards, termination (arena-mapped)
-  if (tid < 32) {
+  if (tid < A1) {
     const int al = tid, b = al * 4;
     const double s = P.rew_scale;
     const int oob_m = S.firing[b] | (S.firing[b + 1] << 1) | (S.firing[b + 2] << 2) | (S.firing[b + 3] << 3);
@@ -620,14 +624,14 @@ __device__ __forceinline__ void step_body(Smem& S, const StatePtrs& G, const Par
   __syncthreads();
 
   // ---------------------------------------------------------------- P13: observations (agent-mapped)
-  if (tid < 64) {
+  if (tid < A2) {
     const int al = tid >> 1, au = tid & 1, b = al * 4;
     const int alive_m = S.alive[b] | (S.alive[b + 1] << 1) | (S.alive[b + 2] << 2) | (S.alive[b + 3] << 3);
     const int shot_m = S.firing[b] | (S.firing[b + 1] << 1) | (S.firing[b + 2] << 2) | (S.firing[b + 3] << 3);
     float* row = au == 0 ? S.obs1 + al * D1 : S.obs2 + al * D2;
     S.ota[b + au] = sm_observation(S, g, b, au, MODE, alive_m, shot_m, row);
   } else {
-    const int k = tid - 64;             // opponents' opp_to_attack stays None at levels 1-3
+    const int k = tid - A2;             // opponents' opp_to_attack stays None at levels 1-3
     const int al = k >> 1, ou = 2 + (k & 1);
     S.ota[al * 4 + ou] = 0;
   }

@@ -341,3 +341,29 @@ def test_state_round_trip_masked_reset_and_large_batch():
     for t in range(3):
         o1, o2, r, d = big.step(acts[t].repeat(16, 1, 1).contiguous())
     assert torch.isfinite(o1).all() and (o1 >= 0).all() and (o1 <= 1).all() and (big.get_state()["error"] == 0).all()
+
+
+def test_quad_and_cta_step_kernels_agree_bitwise(monkeypatch):
+    """Both work distributions of the fused level 1-3 step (hh_quad.cuh lanes-per-arena, hh_cta.cuh
+    phases-per-CTA) produce identical bits for observations, rewards, done flags and the whole state."""
+    import torch
+    n, T = 2000, 120
+    torch.manual_seed(9)
+    acts = torch.stack([torch.randint(0, 13, (T, n, 2)), torch.randint(0, 9, (T, n, 2)), torch.randint(0, 2, (T, n, 2)),
+                        torch.randint(0, 2, (T, n, 2))], dim=-1).to(torch.int32).cuda()
+    outs = {}
+    for impl in ("quad", "cta"):
+        monkeypatch.setenv("HH_STEP_IMPL", impl)
+        for level, mode in ((1, "fight"), (2, "fight"), (3, "fight"), (3, "escape")):
+            env = _vec(n, level, mode, 77, esc_dist_rew=(mode == "escape"))
+            rec = [torch.cat(env.reset(), 1).clone()]
+            for t in range(T):
+                o1, o2, r, d = env.step(acts[t])
+                rec.append(torch.cat([o1, o2, r, d.float()[:, None]], 1).clone())
+            outs[(impl, level, mode)] = (rec, env.get_state())
+    for level, mode in ((1, "fight"), (2, "fight"), (3, "fight"), (3, "escape")):
+        (ra, sa), (rb, sb) = outs[("quad", level, mode)], outs[("cta", level, mode)]
+        for x, y in zip(ra, rb):
+            assert torch.equal(x, y), (level, mode)
+        for k in sa:
+            assert np.array_equal(sa[k], sb[k]), (level, mode, k)
