@@ -399,8 +399,9 @@ def run_b200(args):
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * n,
-                             "kernel": "hh::step_kernel<3,0>", "kernel_ms": kern_ms,
-                             "note": "FP64-issue/latency bound, not DRAM bound: see DESIGN.md section 4"},
+                             "kernel": "hh::step_kernel_cta<3,0>" if os.environ.get("HH_STEP_IMPL", "cta") != "quad" else "hh::step_kernel<3,0>",
+                             "kernel_ms": kern_ms,
+                             "note": "bound by the dependent FP64 instruction chain of one CTA's step phases, not by DRAM: see DESIGN.md section 4"},
                 "clocks": clocks}
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
