@@ -364,6 +364,28 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = world * n * K / float(e2e_t.item())
+    # the other host mode of the same entry point (hh_set_host_mode), for comparison
+    e2e_alt = None
+    try:
+        default_mode = os.environ.get("HH_HOST_MODE", "staged")
+        alt_mode = "zerocopy" if default_mode != "zerocopy" else "staged"
+        env.set_host_mode(alt_mode)
+        for w in range(3):
+            env.step_host(pin_act, out=outs)
+        barrier()
+        ta0 = time.perf_counter()
+        for k in range(K):
+            pin_act[...] = acts_host[k % n_act]
+            env.step_host(pin_act, out=outs)
+        torch.cuda.synchronize()
+        ta1 = time.perf_counter()
+        alt_t = torch.tensor([ta1 - ta0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(alt_t, op=dist.ReduceOp.MAX)
+        e2e_alt = {"mode": alt_mode, "value": world * n * K / float(alt_t.item()), "unit": UNIT}
+        env.set_host_mode(default_mode)
+    except Exception as ex:  # noqa: BLE001
+        e2e_alt = {"error": repr(ex)}
     d1, d2 = env.obs_dim
     h2d, d2h = n * 8 * 4, n * ((d1 + d2 + 2) * 4 + 1)
 
@@ -392,14 +414,18 @@ def run_b200(args):
                 "back_to_back": {"value": world * n * K / (b2b_ms * 1e-3), "unit": UNIT,
                                  "note": "no L2 flush, K launches under one event pair (rank 0)"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "api": "hh_step_host on the pinned host buffers of hh_host_buffers (C ABI; 1 H2D + launch + 1 D2H + sync per call)"},
+                        "api": "hh_step_host on the pinned host buffers of hh_host_buffers (C ABI), host mode "
+                               + os.environ.get("HH_HOST_MODE", "staged") + " (staged = 1 H2D + launch + 1 D2H + sync per call; "
+                               "zerocopy = the kernel reads / writes the pinned slab over PCIe, launch + sync per call)",
+                        "other_host_mode": e2e_alt},
                 "rollout": rollout,
                 "hier": hier,
                 "gpu_launches": int(gpu_launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * n,
-                             "kernel": "hh::step_kernel_cta<3,0>" if os.environ.get("HH_STEP_IMPL", "cta") != "quad" else "hh::step_kernel<3,0>",
+                             "kernel": {"quad": "hh::step_kernel<3,0>", "cta": "hh::step_kernel_cta<3,0>"}.get(
+                                 os.environ.get("HH_STEP_IMPL", "v4"), "hh::step_kernel_v4<3,0>"),
                              "kernel_ms": kern_ms,
                              "note": "bound by the dependent FP64 instruction chain of one CTA's step phases, not by DRAM: see DESIGN.md section 4"},
                 "clocks": clocks}

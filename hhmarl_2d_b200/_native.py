@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("HH_LIB_PATH") or os.path.join(CSRC, "libhhmarl_b200.so")
 SOURCES = ["hh_api.cu", "hh_hier.cu"]
-HEADERS = ["hh_quad.cuh", "hh_core.cuh", "hh_geodesic.cuh", os.path.join("..", "..", "include", "hhmarl_b200.h")]
+HEADERS = ["hh_quad.cuh", "hh_cta.cuh", "hh_v4.cuh", "hh_state_pack.h", "hh_core.cuh", "hh_geodesic.cuh", os.path.join("..", "..", "include", "hhmarl_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared"]
@@ -89,7 +89,33 @@ def lib() -> ctypes.CDLL:
         raise RuntimeError(
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a). hhmarl_2d_b200 has no CPU fallback.")
-    L = ctypes.CDLL(LIB_PATH)
+    _lib = bind(ctypes.CDLL(LIB_PATH))
+    return _lib
+
+
+class _Partial:
+    """Proxy used by bind(partial=True): prototypes of entry points a library does not export are dropped."""
+
+    def __init__(self, L):
+        object.__setattr__(self, "_L", L)
+
+    def __getattr__(self, name):
+        try:
+            return getattr(self._L, name)
+        except AttributeError:
+            return _Missing()
+
+
+class _Missing:
+    argtypes = restype = None
+
+
+def bind(L: ctypes.CDLL, partial: bool = False) -> ctypes.CDLL:
+    """Attach the prototypes of include/hhmarl_b200.h to a loaded library.  `partial` is for the test harness
+    (tests/emu), which implements only the host subset of the ABI; the product library must export everything."""
+    real = L
+    if partial:
+        L = _Partial(L)
     P = ctypes.POINTER
     L.hh_create.argtypes = [P(HHConfig), I32, I32, P(VP)]
     L.hh_create.restype = ctypes.c_int
@@ -113,6 +139,8 @@ def lib() -> ctypes.CDLL:
     L.hh_step_host.restype = ctypes.c_int
     L.hh_host_buffers.argtypes = [VP] + [P(VP)] * 5
     L.hh_host_buffers.restype = ctypes.c_int
+    L.hh_set_host_mode.argtypes = [VP, I32]
+    L.hh_set_host_mode.restype = ctypes.c_int
     L.hh_get_state.argtypes = [VP, P(HHStateView)]
     L.hh_get_state.restype = ctypes.c_int
     L.hh_set_state.argtypes = [VP, P(HHStateView)]
@@ -149,12 +177,11 @@ def lib() -> ctypes.CDLL:
     L.hh_hier_last_error.restype = ctypes.c_char_p
     L.hh_last_error.restype = ctypes.c_char_p
     L.hh_version.restype = ctypes.c_char_p
-    _lib = L
-    return L
+    return real
 
 
 EXPORTS = ["hh_create", "hh_destroy", "hh_n_arenas", "hh_obs_dim", "hh_reset", "hh_step", "hh_step_begin", "hh_step_finish", "hh_reset_host",
-           "hh_step_host", "hh_host_buffers", "hh_get_state", "hh_set_state", "hh_launch_count", "hh_gae", "hh_gae_agents", "hh_sample_actions", "hh_pack_central", "hh_debug_geodesic", "hh_last_error", "hh_version",
+           "hh_step_host", "hh_host_buffers", "hh_set_host_mode", "hh_get_state", "hh_set_state", "hh_launch_count", "hh_gae", "hh_gae_agents", "hh_sample_actions", "hh_pack_central", "hh_debug_geodesic", "hh_last_error", "hh_version",
            "hh_hier_create", "hh_hier_destroy", "hh_hier_reset", "hh_hier_begin", "hh_hier_agents", "hh_hier_tick",
            "hh_hier_end", "hh_hier_get_state", "hh_hier_set_state", "hh_hier_launch_count", "hh_hier_last_error"]
 

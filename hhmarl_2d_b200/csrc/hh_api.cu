@@ -23,6 +23,8 @@
 #include "../../include/hhmarl_b200.h"
 #include "hh_quad.cuh"
 #include "hh_cta.cuh"
+#include "hh_v4.cuh"
+#include "hh_state_pack.h"
 
 namespace hh {
 
@@ -489,6 +491,18 @@ step_kernel_cta(StatePtrs S, Params P, const int32_t* __restrict__ actions, floa
   cta::step_body<LEVEL, MODE>(sm, S, P, actions, obs1, obs2, rew_out, done_out);
 }
 
+// Same step, "v4" schedule (hh_v4.cuh, default): stages of concurrent roles on a 256-thread CTA -- random draws
+// prepared ahead, rocket pipeline beside the aircraft pipeline, one arena-serial resolution stage, pair-parallel
+// observation features, short-arc direct solve.  2 CTAs per SM (<= 128 registers) so that 8 192 arenas = 256 CTAs
+// are resident at once.
+template <int LEVEL, int MODE>
+__global__ void __launch_bounds__(v4::kThreads, 2)
+step_kernel_v4(StatePtrs S, Params P, const int32_t* __restrict__ actions, float* __restrict__ obs1,
+               float* __restrict__ obs2, float* __restrict__ rew_out, uint8_t* __restrict__ done_out) {
+  __shared__ __align__(16) v4::Smem sm;
+  v4::step_body<LEVEL, MODE>(sm, S, P, actions, obs1, obs2, rew_out, done_out, blockIdx.x);
+}
+
 // ------------------------------------------------------------------------------------------
 // step, levels 4-5 (frozen-policy opponents, env_base.py:349-398): the opponent's observation is
 // needed mid-step -- after the agents' fire decisions, before the tick -- so the step is split:
@@ -728,7 +742,7 @@ struct hh_env {
   Params P{};
   bool initialised = false;
   bool mid_step = false;
-  bool use_cta = true;    // HH_STEP_IMPL=cta|quad (levels 1-3 fused step)
+  int step_impl = 4;      // HH_STEP_IMPL=v4|cta|quad (levels 1-3 fused step): 4 = hh_v4.cuh, 3 = hh_cta.cuh, 2 = hh_quad.cuh
   float* rew_pre = nullptr;
   uint64_t launches = 0;
   // host-variant staging
@@ -738,7 +752,9 @@ struct hh_env {
   float *d_obs1 = nullptr, *d_obs2 = nullptr, *d_rew = nullptr;
   uint8_t *d_done = nullptr, *d_mask = nullptr;
   void* pinned = nullptr;
+  void* pinned_dev = nullptr;   // device-side address of the pinned slab (zero-copy host mode)
   size_t pinned_bytes = 0;
+  int host_mode = 0;            // 0: staged (H2D, launch, D2H); 1: zero-copy (kernels read / write the pinned slab)
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -878,7 +894,9 @@ extern "C" int hh_create(const hh_config* cfg, int32_t n_arenas, int32_t device,
   P.arena_base = (uint32_t)cfg->arena_base;
   {
     const char* impl = getenv("HH_STEP_IMPL");
-    e->use_cta = impl ? (std::string(impl) != "quad") : true;   // default: v3 (hh_cta.cuh)
+    const char* hm = getenv("HH_HOST_MODE");
+    e->host_mode = (hm && std::string(hm) == "zerocopy") ? 1 : 0;
+    e->step_impl = !impl ? 4 : (std::string(impl) == "quad" ? 2 : (std::string(impl) == "cta" ? 3 : 4));
   }
   *out = e;
   return 0;
@@ -920,7 +938,15 @@ extern "C" int hh_reset(hh_env* e, const uint8_t* mask_dev, float* obs1, float* 
 template <int LEVEL>
 static void launch_step(hh_env* e, const int32_t* actions, float* obs1, float* obs2, float* rew, uint8_t* done,
                         cudaStream_t st) {
-  if (e->use_cta) {
+  if (e->step_impl == 4) {
+    const int vblocks = (e->n + v4::kArenas - 1) / v4::kArenas;
+    if (e->cfg.agent_mode == 0)
+      step_kernel_v4<LEVEL, 0><<<vblocks, v4::kThreads, 0, st>>>(e->S, e->P, actions, obs1, obs2, rew, done);
+    else
+      step_kernel_v4<LEVEL, 1><<<vblocks, v4::kThreads, 0, st>>>(e->S, e->P, actions, obs1, obs2, rew, done);
+    return;
+  }
+  if (e->step_impl == 3) {
     const int cblocks = (e->n + cta::kArenas - 1) / cta::kArenas;
     if (e->cfg.agent_mode == 0)
       step_kernel_cta<LEVEL, 0><<<cblocks, cta::kThreads, 0, st>>>(e->S, e->P, actions, obs1, obs2, rew, done);
@@ -1009,8 +1035,9 @@ static int ensure_staging(hh_env* e) {
   HH_CUDA(cudaSetDevice(e->device));
   HH_CUDA(cudaStreamCreateWithFlags(&e->hstream, cudaStreamNonBlocking));
   HH_CUDA(cudaMalloc(&e->d_slab, h.total));
-  HH_CUDA(cudaMallocHost(&e->pinned, h.total));
+  HH_CUDA(cudaHostAlloc(&e->pinned, h.total, cudaHostAllocMapped | cudaHostAllocPortable));
   memset(e->pinned, 0, h.total);
+  HH_CUDA(cudaHostGetDevicePointer(&e->pinned_dev, e->pinned, 0));
   e->pinned_bytes = h.total;
   char* d = static_cast<char*>(e->d_slab);
   e->d_actions = reinterpret_cast<int32_t*>(d + h.o_act);
@@ -1053,6 +1080,13 @@ extern "C" int hh_host_buffers(hh_env* e, int32_t** actions, float** obs1, float
   return 0;
 }
 
+extern "C" int hh_set_host_mode(hh_env* e, int32_t mode) {
+  if (!e) return fail(-1, "hh_set_host_mode: null env");
+  if (mode != 0 && mode != 1) return fail(-1, "hh_set_host_mode: mode must be 0 (staged copies) or 1 (zero-copy)");
+  e->host_mode = mode;
+  return 0;
+}
+
 extern "C" int hh_reset_host(hh_env* e, const uint8_t* mask_host, float* obs1_host, float* obs2_host) {
   if (!e) return fail(-1, "hh_reset_host: null env");
   int rc = ensure_staging(e);
@@ -1065,10 +1099,17 @@ extern "C" int hh_reset_host(hh_env* e, const uint8_t* mask_host, float* obs1_ho
     memcpy(pin + h.o_mask, mask_host, N);
     HH_CUDA(cudaMemcpyAsync(e->d_mask, pin + h.o_mask, N, cudaMemcpyHostToDevice, e->hstream));
   }
-  rc = hh_reset(e, mask_host ? e->d_mask : nullptr, e->d_obs1, e->d_obs2, e->hstream);
-  if (rc) return rc;
-  HH_CUDA(cudaMemcpyAsync(pin + h.o_obs1, e->d_obs1, h.o_obs2 + N * d2 * sizeof(float) - h.o_obs1, cudaMemcpyDeviceToHost,
-                          e->hstream));
+  if (e->host_mode == 1) {
+    char* pd = static_cast<char*>(e->pinned_dev);
+    rc = hh_reset(e, mask_host ? e->d_mask : nullptr, reinterpret_cast<float*>(pd + h.o_obs1),
+                  reinterpret_cast<float*>(pd + h.o_obs2), e->hstream);
+    if (rc) return rc;
+  } else {
+    rc = hh_reset(e, mask_host ? e->d_mask : nullptr, e->d_obs1, e->d_obs2, e->hstream);
+    if (rc) return rc;
+    HH_CUDA(cudaMemcpyAsync(pin + h.o_obs1, e->d_obs1, h.o_obs2 + N * d2 * sizeof(float) - h.o_obs1, cudaMemcpyDeviceToHost,
+                            e->hstream));
+  }
   HH_CUDA(cudaStreamSynchronize(e->hstream));
   if (obs1_host && obs1_host != reinterpret_cast<float*>(pin + h.o_obs1)) memcpy(obs1_host, pin + h.o_obs1, N * d1 * sizeof(float));
   if (obs2_host && obs2_host != reinterpret_cast<float*>(pin + h.o_obs2)) memcpy(obs2_host, pin + h.o_obs2, N * d2 * sizeof(float));
@@ -1086,10 +1127,20 @@ extern "C" int hh_step_host(hh_env* e, const int32_t* actions_host, float* obs1_
   const HostLayout h = host_layout(e);
   char* pin = static_cast<char*>(e->pinned);
   if (reinterpret_cast<const char*>(actions_host) != pin + h.o_act) memcpy(pin + h.o_act, actions_host, N * 8 * sizeof(int32_t));
-  HH_CUDA(cudaMemcpyAsync(e->d_actions, pin + h.o_act, N * 8 * sizeof(int32_t), cudaMemcpyHostToDevice, e->hstream));
-  rc = hh_step(e, e->d_actions, e->d_obs1, e->d_obs2, e->d_rew, e->d_done, e->hstream);
-  if (rc) return rc;
-  HH_CUDA(cudaMemcpyAsync(pin + h.o_obs1, e->d_obs1, h.out_bytes, cudaMemcpyDeviceToHost, e->hstream));
+  if (e->host_mode == 1) {
+    // zero-copy: the step kernel loads the actions from, and stores observations / rewards / done flags to, the
+    // pinned slab through its device-side mapping -- no staging copies, the PCIe traffic rides on the kernel
+    char* pd = static_cast<char*>(e->pinned_dev);
+    rc = hh_step(e, reinterpret_cast<const int32_t*>(pd + h.o_act), reinterpret_cast<float*>(pd + h.o_obs1),
+                 reinterpret_cast<float*>(pd + h.o_obs2), reinterpret_cast<float*>(pd + h.o_rew),
+                 reinterpret_cast<uint8_t*>(pd + h.o_done), e->hstream);
+    if (rc) return rc;
+  } else {
+    HH_CUDA(cudaMemcpyAsync(e->d_actions, pin + h.o_act, N * 8 * sizeof(int32_t), cudaMemcpyHostToDevice, e->hstream));
+    rc = hh_step(e, e->d_actions, e->d_obs1, e->d_obs2, e->d_rew, e->d_done, e->hstream);
+    if (rc) return rc;
+    HH_CUDA(cudaMemcpyAsync(pin + h.o_obs1, e->d_obs1, h.out_bytes, cudaMemcpyDeviceToHost, e->hstream));
+  }
   HH_CUDA(cudaStreamSynchronize(e->hstream));
   if (obs1_host && reinterpret_cast<char*>(obs1_host) != pin + h.o_obs1) memcpy(obs1_host, pin + h.o_obs1, N * d1 * sizeof(float));
   if (obs2_host && reinterpret_cast<char*>(obs2_host) != pin + h.o_obs2) memcpy(obs2_host, pin + h.o_obs2, N * d2 * sizeof(float));
@@ -1131,47 +1182,7 @@ extern "C" int hh_get_state(hh_env* e, hh_state_view* o) {
   HH_CUDA(cudaMemcpy(h.ri.data(), e->S.rint, N * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
   HH_CUDA(cudaMemcpy(h.meta.data(), e->S.meta, N * sizeof(uint4), cudaMemcpyDeviceToHost));
   HH_CUDA(cudaMemcpy(h.dg.data(), e->S.draws_g, N * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-  for (size_t a = 0; a < N; ++a) {
-    for (int u = 0; u < 4; ++u) {
-      const uint2 w = h.ac[a * 4 + u];
-      const size_t i = a * 4 + u;
-      if (o->cannon_remain) o->cannon_remain[i] = w.x & 0xFFFF;
-      if (o->cannon_burst) o->cannon_burst[i] = (w.x >> 16) & 0xFF;
-      if (o->missile_remain) o->missile_remain[i] = (w.x >> 24) & 0xFF;
-      if (o->cannon_max) o->cannon_max[i] = w.y & 0xFFFF;
-      if (o->missile_wait) o->missile_wait[i] = (w.y >> 16) & 0xFF;
-      if (o->rocket_max) o->rocket_max[i] = (w.y >> 24) & 0xF;
-      if (o->alive) o->alive[i] = (w.y >> 28) & 1;
-      if (o->has_missile) o->has_missile[i] = (w.y >> 29) & 1;
-    }
-    for (int s = 0; s < 2; ++s) {
-      const uint32_t w = h.ri[a * 2 + s];
-      const size_t i = a * 2 + s;
-      if (o->r_alive) o->r_alive[i] = w & 1;
-      if (o->r_age) o->r_age[i] = (w >> 1) & 0xF;
-      if (o->r_target) o->r_target[i] = (w >> 5) & 0x7;
-      if (o->r_id) o->r_id[i] = (w >> 8) & 0xFFFF;
-    }
-    const uint4 m = h.meta[a];
-    if (o->steps) o->steps[a] = m.x & 0xFFFF;
-    if (o->alive_agents) o->alive_agents[a] = (m.x >> 16) & 0xF;
-    if (o->alive_opps) o->alive_opps[a] = (m.x >> 20) & 0xF;
-    if (o->escaping) o->escaping[a] = (m.x >> 24) & 1;
-    if (o->policy_set) o->policy_set[a] = (m.x >> 25) & 0x7;
-    if (o->opp_mode) o->opp_mode[a] = (m.x >> 28) & 1;
-    if (o->escaping_time) o->escaping_time[a] = m.y & 0xFF;
-    if (o->next_unit_id) o->next_unit_id[a] = (m.y >> 8) & 0xFF;
-    if (o->opp_to_attack) {
-      const int t0 = (m.y >> 24) & 3, t1 = (m.y >> 26) & 3;
-      o->opp_to_attack[a * 4 + 0] = t0 ? t0 + 2 : 0;
-      o->opp_to_attack[a * 4 + 1] = t1 ? t1 + 2 : 0;
-      o->opp_to_attack[a * 4 + 2] = (m.y >> 28) & 3;
-      o->opp_to_attack[a * 4 + 3] = (m.y >> 30) & 3;
-    }
-    if (o->draws_c) o->draws_c[a] = m.z;
-    if (o->error) o->error[a] = (int32_t)m.w;
-    if (o->draws_g) o->draws_g[a] = h.dg[a];
-  }
+  unpack_state(N, h.ac.data(), h.ri.data(), h.meta.data(), h.dg.data(), o);
   return 0;
 }
 
@@ -1190,32 +1201,7 @@ extern "C" int hh_set_state(hh_env* e, const hh_state_view* in) {
   HH_CUDA(cudaSetDevice(e->device));
   HH_CUDA(cudaDeviceSynchronize());
   HostPacked h(N);
-  for (size_t a = 0; a < N; ++a) {
-    for (int u = 0; u < 4; ++u) {
-      const size_t i = a * 4 + u;
-      uint2 w;
-      w.x = (uint32_t)in->cannon_remain[i] | ((uint32_t)in->cannon_burst[i] << 16) | ((uint32_t)in->missile_remain[i] << 24);
-      w.y = (uint32_t)in->cannon_max[i] | ((uint32_t)in->missile_wait[i] << 16) | ((uint32_t)in->rocket_max[i] << 24) |
-            ((uint32_t)(in->alive[i] & 1) << 28) | ((uint32_t)(in->has_missile[i] & 1) << 29);
-      h.ac[i] = w;
-    }
-    for (int s = 0; s < 2; ++s) {
-      const size_t i = a * 2 + s;
-      h.ri[i] = (uint32_t)(in->r_alive[i] & 1) | ((uint32_t)in->r_age[i] << 1) | ((uint32_t)in->r_target[i] << 5) |
-                ((uint32_t)in->r_id[i] << 8);
-    }
-    uint4 m;
-    m.x = (uint32_t)in->steps[a] | ((uint32_t)in->alive_agents[a] << 16) | ((uint32_t)in->alive_opps[a] << 20) |
-          ((uint32_t)(in->escaping[a] & 1) << 24) | ((uint32_t)in->policy_set[a] << 25) | ((uint32_t)(in->opp_mode[a] & 1) << 28);
-    const int t0 = in->opp_to_attack[a * 4 + 0], t1 = in->opp_to_attack[a * 4 + 1];
-    m.y = (uint32_t)in->escaping_time[a] | ((uint32_t)in->next_unit_id[a] << 8) | ((uint32_t)(t0 ? t0 - 2 : 0) << 24) |
-          ((uint32_t)(t1 ? t1 - 2 : 0) << 26) | ((uint32_t)in->opp_to_attack[a * 4 + 2] << 28) |
-          ((uint32_t)in->opp_to_attack[a * 4 + 3] << 30);
-    m.z = (uint32_t)in->draws_c[a];
-    m.w = (uint32_t)in->error[a];
-    h.meta[a] = m;
-    h.dg[a] = in->draws_g[a];
-  }
+  pack_state(N, in, h.ac.data(), h.ri.data(), h.meta.data(), h.dg.data());
   const double* dsrc[6] = {in->lat, in->lon, in->heading, in->speed, in->new_heading, in->new_speed};
   double* ddst[6] = {e->S.lat, e->S.lon, e->S.hdg, e->S.spd, e->S.nhdg, e->S.nspd};
   for (int k = 0; k < 6; ++k) HH_CUDA(cudaMemcpy(ddst[k], dsrc[k], N * 4 * sizeof(double), cudaMemcpyHostToDevice));

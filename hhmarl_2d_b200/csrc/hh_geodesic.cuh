@@ -308,6 +308,102 @@ static __device__ __noinline__ double2 direct(double lat1, double lon1, double a
 }
 
 // ---------------------------------------------------------------------------------------------
+// Direct problem for one simulator tick: s12 <= 3 km (aircraft <= 463 m, rockets <= 1029 m per 1 s tick,
+// cmano_simulator.py:65-72) from a latitude within 1.1 deg of the map centre.  Same series as direct()
+// (Karney order 6: A1, C1, C1', A3, C3), but every angle that is small in this regime -- B11 (<= 8.4e-4 rad),
+// tau12 / sig12 / omg12 / the latitude change (<= 4.8e-4 rad) -- goes through a Taylor polynomial whose
+// truncation error is below 1e-20 instead of through sincos / atan2, the reduced latitude comes from an
+// expansion about the map centre (as in inverse_local), and the sine / cosine of the azimuth are the
+// caller's (the step kernel has them as the heading vector of env_base.py:428).  Agreement with direct():
+// <= 2e-15 deg in both coordinates (tests/test_emu_v4.py, tests/test_gpu_geodesic.py), i.e. the last bit or
+// two of a coordinate.  Outside the regime it hands over to direct().
+// ---------------------------------------------------------------------------------------------
+constexpr double kPhi0d = 5.25 * (3.14159265358979323846 / 180.0);
+constexpr double kSinPhi0d = 0.09150161866340238;   // sin(5.25 deg)
+constexpr double kCosPhi0d = 0.9958049275746618;    // cos(5.25 deg)
+
+static __device__ __noinline__ double2 direct_short(double lat1, double lon1, double azi1, double salp1, double calp1,
+                                                double s12) {
+  const double dl = lat1 * kDeg - kPhi0d;
+  if (!(fabs(dl) < 0.02 && fabs(s12) <= 3000.0 && fabs(lon1) < 170.0)) return direct(lat1, lon1, azi1, s12);
+  double sbet1, cbet1;
+  {
+    const double d2 = dl * dl;
+    const double sd = dl * (1.0 + d2 * (-1.0 / 6.0 + d2 * (1.0 / 120.0 - d2 * (1.0 / 5040.0))));
+    const double cd = 1.0 + d2 * (-0.5 + d2 * (1.0 / 24.0 - d2 * (1.0 / 720.0)));
+    sbet1 = kF1 * (kSinPhi0d * cd + kCosPhi0d * sd);
+    cbet1 = kCosPhi0d * cd - kSinPhi0d * sd;
+    const double r = rsqrt(sbet1 * sbet1 + cbet1 * cbet1);
+    sbet1 *= r;
+    cbet1 *= r;
+  }
+  const double salp0 = salp1 * cbet1;
+  const double calp0 = sqrt(calp1 * calp1 + sq(salp1 * sbet1));
+  // (ssig1, csig1) = (sbet1, cbet1 calp1) / calp0  (hypot(sbet1, cbet1 calp1) = calp0 for unit vectors)
+  const double icalp0 = 1.0 / calp0;
+  const double ssig1 = sbet1 * icalp0, csig1 = cbet1 * calp1 * icalp0;
+  const double k2 = sq(calp0) * kEp2;
+  const double eps = k2 / (2.0 * (1.0 + sqrt(1.0 + k2)) + k2);
+  const double B11 = S6(ssig1, csig1, C1f(eps));
+  double s, c;
+  {
+    const double x2 = B11 * B11;
+    s = B11 * (1.0 + x2 * (-1.0 / 6.0 + x2 * (1.0 / 120.0)));
+    c = 1.0 + x2 * (-0.5 + x2 * (1.0 / 24.0 - x2 * (1.0 / 720.0)));
+  }
+  const double stau1 = ssig1 * c + csig1 * s;
+  const double ctau1 = csig1 * c - ssig1 * s;
+  const C5 c3 = C3f(eps);
+  const double A3c = -kF * salp0 * A3f(eps);
+  const double B31 = S5(ssig1, csig1, c3);
+  // 1 + A1m1 = (1 + t) / (1 - eps),  t = eps^2 (64 + eps^2 (4 + eps^2)) / 256
+  const double e2 = eps * eps;
+  const double t1 = ((e2 + 4.0) * e2 + 64.0) * e2 * (1.0 / 256.0);
+  const double tau12 = s12 * (1.0 - eps) / (kB * (1.0 + t1));
+  {
+    const double x2 = tau12 * tau12;
+    s = tau12 * (1.0 + x2 * (-1.0 / 6.0 + x2 * (1.0 / 120.0)));
+    c = 1.0 + x2 * (-0.5 + x2 * (1.0 / 24.0));
+  }
+  const double B12 = -S6(stau1 * c + ctau1 * s, ctau1 * c - stau1 * s, C1pf(eps));
+  const double sig12 = tau12 - (B12 - B11);
+  double ssig12, csig12m1;   // sin(sig12), cos(sig12) - 1
+  {
+    const double x2 = sig12 * sig12;
+    ssig12 = sig12 * (1.0 + x2 * (-1.0 / 6.0 + x2 * (1.0 / 120.0)));
+    csig12m1 = x2 * (-0.5 + x2 * (1.0 / 24.0));
+  }
+  const double ssig2 = ssig1 + (ssig1 * csig12m1 + csig1 * ssig12);
+  const double csig2 = csig1 + (csig1 * csig12m1 - ssig1 * ssig12);
+  const double sbet2 = calp0 * ssig2;
+  const double cbet2 = sqrt(salp0 * salp0 + sq(calp0 * csig2));
+  double omg12;
+  {
+    // tan(omg) = salp0 tan(sig)  =>  tan(omg2 - omg1) = salp0 sin(sig12) / (csig1 csig2 + salp0^2 ssig1 ssig2):
+    // no cancellation (direct() takes the difference of two O(0.1) products, which costs ~20 ulp of the
+    // longitude for azimuths near 90 / 270 deg); the denominator is ~cos^2(beta) ~ 0.99
+    const double t = salp0 * ssig12 / (csig1 * csig2 + salp0 * salp0 * (ssig1 * ssig2));
+    const double t2 = t * t;
+    omg12 = t * (1.0 + t2 * (-1.0 / 3.0 + t2 * (1.0 / 5.0)));
+  }
+  const double lam12 = omg12 + A3c * (sig12 + (S5(ssig2, csig2, c3) - B31));
+  double dphi;
+  {
+    // sin(bet2 - bet1) without cancellation: dsb (cbet1 + sbet1 (sbet1 + sbet2) / (cbet1 + cbet2)),
+    // dsb = sbet2 - sbet1 = calp0 (ssig2 - ssig1);  tan(phi2 - phi1) = f1 sin(dbet) / (f1^2 cb1 cb2 + sb1 sb2)
+    const double dsb = calp0 * (ssig1 * csig12m1 + csig1 * ssig12);
+    const double sdb = dsb * (cbet1 + sbet1 * (sbet1 + sbet2) / (cbet1 + cbet2));
+    const double t = kF1 * sdb / (kF1 * kF1 * cbet1 * cbet2 + sbet1 * sbet2);
+    const double t2 = t * t;
+    dphi = t * (1.0 + t2 * (-1.0 / 3.0 + t2 * (1.0 / 5.0)));
+  }
+  double2 out;
+  out.x = lat1 + dphi * (180.0 / kPi);
+  out.y = lon1 + lam12 * (180.0 / kPi);
+  return out;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Inverse problem. Returns (s12 [m], azi1 [deg in (-180, 180]]).
 // ---------------------------------------------------------------------------------------------
 struct Lam12Out {

@@ -213,11 +213,13 @@ struct OppDecision {
   int tgt;  // index of the agent to shoot at
 };
 
-template <int LEVEL>
-__device__ __forceinline__ OppDecision scripted_opponent(Lane& L, const Rng& rng, const Geom& g, int k, bool k_alive,
-                                                         bool k_hasm, int k_mwait, double k_lat, double k_lon,
-                                                         double k_hdg, int k_near, double k_dn, double k_focus,
-                                                         int k_sign) {
+// `next(i)` returns G-stream draw number i of the arena (L.dg counts them): either computed on the spot
+// (scripted_opponent below) or read from a table drawn ahead by other threads (hh_v4.cuh).
+template <int LEVEL, class NextDraw>
+__device__ __forceinline__ OppDecision scripted_opponent_g(Lane& L, NextDraw next, const Geom& g, int k, bool k_alive,
+                                                           bool k_hasm, int k_mwait, double k_lat, double k_lon,
+                                                           double k_hdg, int k_near, double k_dn, double k_focus,
+                                                           int k_sign) {
   OppDecision d;
   d.heading = k_hdg;
   d.speed = 0.0;
@@ -228,8 +230,8 @@ __device__ __forceinline__ OppDecision scripted_opponent(Lane& L, const Rng& rng
   if (!k_alive) return d;
   if (LEVEL == 3) {  // __opp_level3
     if (L.steps % 60 == 0 && !L.escaping) {
-      L.escaping = randint_from(0, 1, g_random_at(rng, L.dg++)) != 0;
-      if (L.escaping) L.esc_time = (int)uniform_from(20.0, 30.0, g_random_at(rng, L.dg++));
+      L.escaping = randint_from(0, 1, next(L.dg++)) != 0;
+      if (L.escaping) L.esc_time = (int)uniform_from(20.0, 30.0, next(L.dg++));
     }
     d.set_hs = true;
     bool fire_m = false;
@@ -237,21 +239,21 @@ __device__ __forceinline__ OppDecision scripted_opponent(Lane& L, const Rng& rng
       double y, x;
       rel_pos(g, k_lat, k_lon, y, x);
       const double lo = y < 0.5 ? (x < 0.5 ? 30.0 : 300.0) : (x < 0.5 ? 120.0 : 210.0);
-      d.heading = (double)(int)uniform_from(lo, lo + 30.0, g_random_at(rng, L.dg++));
-      d.speed = (double)(int)uniform_from(300.0, 600.0, g_random_at(rng, L.dg++));
-      d.fire = randint_from(0, 1, g_random_at(rng, L.dg++)) != 0;
+      d.heading = (double)(int)uniform_from(lo, lo + 30.0, next(L.dg++));
+      d.speed = (double)(int)uniform_from(300.0, 600.0, next(L.dg++));
+      d.fire = randint_from(0, 1, next(L.dg++)) != 0;
       L.esc_time -= 1;
       if (L.esc_time <= 0) L.escaping = false;
       d.tgt = -1;
     } else {  // _hardcoded_opp
-      d.speed = (double)(int)uniform_from(100.0, 400.0, g_random_at(rng, L.dg++));
+      d.speed = (double)(int)uniform_from(100.0, 400.0, next(L.dg++));
       if (k_near >= 0) {
-        const double r = uniform_from(0.7, 1.3, g_random_at(rng, L.dg++));
+        const double r = uniform_from(0.7, 1.3, next(L.dg++));
         if (k_dn > 0.008 && k_focus > 4.0)
           d.heading = pymod(__dadd_rn(k_hdg, __dmul_rn(__dmul_rn(r, (double)k_sign), k_focus)), 360.0);
         if (k_dn > 0.05)
-          d.speed = k_focus < 30.0 ? (double)(int)uniform_from(500.0, 800.0, g_random_at(rng, L.dg++))
-                                   : (double)(int)uniform_from(100.0, 500.0, g_random_at(rng, L.dg++));
+          d.speed = k_focus < 30.0 ? (double)(int)uniform_from(500.0, 800.0, next(L.dg++))
+                                   : (double)(int)uniform_from(100.0, 500.0, next(L.dg++));
         d.fire = k_dn < 0.03 && k_focus < 10.0;
         fire_m = k_dn < 0.09 && k_focus < 5.0;
       }
@@ -262,20 +264,30 @@ __device__ __forceinline__ OppDecision scripted_opponent(Lane& L, const Rng& rng
     if (LEVEL == 2) {  // __opp_level2: fire_cannon every step, occasional +-90 deg turn
       d.fire = true;
       bool turn = L.steps <= 5;
-      if (!turn) turn = (L.steps % randint_from(35, 45, g_random_at(rng, L.dg++))) <= 5;
+      if (!turn) turn = (L.steps % randint_from(35, 45, next(L.dg++))) <= 5;
       if (turn) {
-        const int r = randint_from(0, 1, g_random_at(rng, L.dg++));
+        const int r = randint_from(0, 1, next(L.dg++));
         d.set_hs = true;
         d.heading = pymod(k_hdg + (r ? -90.0 : 90.0), 360.0);
-        d.speed = (double)(100 + randint_from(0, 4, g_random_at(rng, L.dg++)) * 75);
+        d.speed = (double)(100 + randint_from(0, 4, next(L.dg++)) * 75);
       }
     }
     // __opp_level1 missile rule (also the tail of __opp_level2); short-circuit order of the reference
     bool w = !k_hasm && (L.steps % 40) < 3;
-    if (w) w = randint_from(0, 1, g_random_at(rng, L.dg++)) != 0;
+    if (w) w = randint_from(0, 1, next(L.dg++)) != 0;
     d.want_missile = w && k_mwait == 0 && is_ac1(k) && k_near >= 0;
   }
   return d;
+}
+
+template <int LEVEL>
+__device__ __forceinline__ OppDecision scripted_opponent(Lane& L, const Rng& rng, const Geom& g, int k, bool k_alive,
+                                                         bool k_hasm, int k_mwait, double k_lat, double k_lon,
+                                                         double k_hdg, int k_near, double k_dn, double k_focus,
+                                                         int k_sign) {
+  return scripted_opponent_g<LEVEL>(
+      L, [&rng](unsigned long long i) { return g_random_at(rng, i); }, g, k, k_alive, k_hasm, k_mwait, k_lat, k_lon, k_hdg,
+      k_near, k_dn, k_focus, k_sign);
 }
 
 // ------------------------------------------------------------------------------------- observations

@@ -159,6 +159,12 @@ class VecLowLevelEnv:
                 view(ptrs[2], ctypes.c_float, (n, d2)), view(ptrs[3], ctypes.c_float, (n, 2)),
                 view(ptrs[4], ctypes.c_uint8, (n,)))
 
+    def set_host_mode(self, mode: str):
+        """'staged' (default: H2D, launch, D2H) or 'zerocopy' (the kernel reads / writes the pinned slab directly)."""
+        if mode not in ("staged", "zerocopy"):
+            raise ValueError("mode must be 'staged' or 'zerocopy'")
+        nat.check(nat.lib().hh_set_host_mode(self._h, 1 if mode == "zerocopy" else 0), "hh_set_host_mode")
+
     def step_host(self, actions: np.ndarray, out=None):
         """actions: int32 [N, 2, 4] host array -> (obs1, obs2, rew, done) host arrays.
         Host->device and device->host copies happen inside the call."""

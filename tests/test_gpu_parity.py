@@ -305,6 +305,34 @@ def test_pinned_host_buffers_zero_copy_path_matches_device_path():
     assert np.array_equal(z1, w1.cpu().numpy()) and np.array_equal(zd, wd.cpu().numpy())
 
 
+def test_zero_copy_host_mode_matches_staged_host_mode():
+    """hh_set_host_mode(1): the step kernel reads the actions from and writes the results to the pinned slab through
+    its device mapping (no staging copies).  Same bits as the staged path, ragged arena count, both agent modes."""
+    for mode in ("fight", "escape"):
+        n = 1000 + 13
+        a = _vec(n, 3, mode, 9)
+        b = _vec(n, 3, mode, 9)
+        b.set_host_mode("zerocopy")
+        act_pin, o1, o2, r, d = b.host_buffers()
+        x = a.reset_host()
+        y = b.reset_host()
+        assert np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1])
+        rng = np.random.default_rng(5)
+        for t in range(40):
+            act = np.stack([rng.integers(0, 13, (n, 2)), rng.integers(0, 9, (n, 2)), rng.integers(0, 2, (n, 2)),
+                            rng.integers(0, 2, (n, 2))], axis=-1).astype(np.int32)
+            x1, x2, xr, xd = a.step_host(act)
+            if t % 2:
+                act_pin[...] = act
+                y1, y2, yr, yd = b.step_host(act_pin, out=(o1, o2, r, d))     # in place in the slab
+            else:
+                y1, y2, yr, yd = b.step_host(act)                             # pageable arrays, staged through it
+            assert np.array_equal(x1, y1) and np.array_equal(x2, y2) and np.array_equal(xr, yr) and np.array_equal(xd, yd)
+        sa, sb = a.get_state(), b.get_state()
+        for k in sa:
+            assert np.array_equal(sa[k], sb[k]), k
+
+
 def test_state_round_trip_masked_reset_and_large_batch():
     import torch
     n = 4096
@@ -343,16 +371,17 @@ def test_state_round_trip_masked_reset_and_large_batch():
     assert torch.isfinite(o1).all() and (o1 >= 0).all() and (o1 <= 1).all() and (big.get_state()["error"] == 0).all()
 
 
-def test_quad_and_cta_step_kernels_agree(monkeypatch):
-    """Both work distributions of the fused level 1-3 step (hh_quad.cuh lanes-per-arena, hh_cta.cuh
-    phases-per-CTA) agree: identical discrete state and done flags, floats within the parity tolerance."""
+def test_quad_cta_and_v4_step_kernels_agree(monkeypatch):
+    """The three work distributions of the fused level 1-3 step (hh_quad.cuh lanes-per-arena, hh_cta.cuh
+    phases-per-CTA, hh_v4.cuh staged roles = default) agree: identical discrete state and done flags, floats
+    within the parity tolerance."""
     import torch
     n, T = 2000, 120
     torch.manual_seed(9)
     acts = torch.stack([torch.randint(0, 13, (T, n, 2)), torch.randint(0, 9, (T, n, 2)), torch.randint(0, 2, (T, n, 2)),
                         torch.randint(0, 2, (T, n, 2))], dim=-1).to(torch.int32).cuda()
     outs = {}
-    for impl in ("quad", "cta"):
+    for impl in ("quad", "cta", "v4"):
         monkeypatch.setenv("HH_STEP_IMPL", impl)
         for level, mode in ((1, "fight"), (2, "fight"), (3, "fight"), (3, "escape")):
             env = _vec(n, level, mode, 77, esc_dist_rew=(mode == "escape"))
@@ -362,17 +391,18 @@ def test_quad_and_cta_step_kernels_agree(monkeypatch):
                 rec.append(torch.cat([o1, o2, r, d.float()[:, None]], 1).clone())
             outs[(impl, level, mode)] = (rec, env.get_state())
     for level, mode in ((1, "fight"), (2, "fight"), (3, "fight"), (3, "escape")):
-        (ra, sa), (rb, sb) = outs[("quad", level, mode)], outs[("cta", level, mode)]
-        # discrete bookkeeping must be identical; floats may differ in the last bits (the two kernels give the
-        # compiler different FMA-contraction opportunities), never beyond the parity tolerance
+      for other in ("cta", "v4"):
+        (ra, sa), (rb, sb) = outs[("quad", level, mode)], outs[(other, level, mode)]
+        # discrete bookkeeping must be identical; floats may differ in the last bits (different FMA-contraction
+        # opportunities; v4 moves units with geo::direct_short), never beyond the parity tolerance
         for k in sa:
             if sa[k].dtype.kind in "iu":
-                assert np.array_equal(sa[k], sb[k]), (level, mode, k)
+                assert np.array_equal(sa[k], sb[k]), (other, level, mode, k)
             else:
-                _close(sa[k], sb[k], f"L{level} {mode} {k}")
+                _close(sa[k], sb[k], f"{other} L{level} {mode} {k}")
         n_diff = 0
         for t, (x, y) in enumerate(zip(ra, rb)):
-            assert torch.equal(x[:, -1], y[:, -1]), (level, mode, t)          # done flags
-            _close(x.cpu().numpy(), y.cpu().numpy(), f"L{level} {mode} t={t}")
+            assert torch.equal(x[:, -1], y[:, -1]), (other, level, mode, t)          # done flags
+            _close(x.cpu().numpy(), y.cpu().numpy(), f"{other} L{level} {mode} t={t}")
             n_diff += int((x != y).sum())
-        print(f"L{level} {mode}: {n_diff} of {len(ra) * ra[0].numel()} output values differ in the last bits")
+        print(f"{other} vs quad, L{level} {mode}: {n_diff} of {len(ra) * ra[0].numel()} output values differ in the last bits")
