@@ -367,7 +367,7 @@ def run_b200(args):
     # the other host mode of the same entry point (hh_set_host_mode), for comparison
     e2e_alt = None
     try:
-        default_mode = os.environ.get("HH_HOST_MODE", "staged")
+        default_mode = os.environ.get("HH_HOST_MODE", "zerocopy")
         alt_mode = "zerocopy" if default_mode != "zerocopy" else "staged"
         env.set_host_mode(alt_mode)
         for w in range(3):
@@ -415,7 +415,7 @@ def run_b200(args):
                                  "note": "no L2 flush, K launches under one event pair (rank 0)"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "hh_step_host on the pinned host buffers of hh_host_buffers (C ABI), host mode "
-                               + os.environ.get("HH_HOST_MODE", "staged") + " (staged = 1 H2D + launch + 1 D2H + sync per call; "
+                               + os.environ.get("HH_HOST_MODE", "zerocopy") + " (staged = 1 H2D + launch + 1 D2H + sync per call; "
                                "zerocopy = the kernel reads / writes the pinned slab over PCIe, launch + sync per call)",
                         "other_host_mode": e2e_alt},
                 "rollout": rollout,

@@ -495,12 +495,22 @@ step_kernel_cta(StatePtrs S, Params P, const int32_t* __restrict__ actions, floa
 // prepared ahead, rocket pipeline beside the aircraft pipeline, one arena-serial resolution stage, pair-parallel
 // observation features, short-arc direct solve.  2 CTAs per SM (<= 128 registers) so that 8 192 arenas = 256 CTAs
 // are resident at once.
+#ifndef HH_V4_MIN_CTAS
+#define HH_V4_MIN_CTAS (v4::kThreads <= 256 ? 2 : 1)   // <= 128 registers per thread either way
+#endif
+constexpr int kV4MinCtas = HH_V4_MIN_CTAS;
 template <int LEVEL, int MODE>
-__global__ void __launch_bounds__(v4::kThreads, 2)
+__global__ void __launch_bounds__(v4::kThreads, kV4MinCtas)
 step_kernel_v4(StatePtrs S, Params P, const int32_t* __restrict__ actions, float* __restrict__ obs1,
                float* __restrict__ obs2, float* __restrict__ rew_out, uint8_t* __restrict__ done_out) {
-  __shared__ __align__(16) v4::Smem sm;
-  v4::step_body<LEVEL, MODE>(sm, S, P, actions, obs1, obs2, rew_out, done_out, blockIdx.x);
+  extern __shared__ __align__(16) unsigned char v4_smem[];
+  v4::step_body<LEVEL, MODE>(*reinterpret_cast<v4::Smem*>(v4_smem), S, P, actions, obs1, obs2, rew_out, done_out,
+                             blockIdx.x);
+}
+template <int LEVEL, int MODE>
+static cudaError_t v4_opt_in_smem() {
+  return cudaFuncSetAttribute(step_kernel_v4<LEVEL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)sizeof(v4::Smem));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -754,7 +764,7 @@ struct hh_env {
   void* pinned = nullptr;
   void* pinned_dev = nullptr;   // device-side address of the pinned slab (zero-copy host mode)
   size_t pinned_bytes = 0;
-  int host_mode = 0;            // 0: staged (H2D, launch, D2H); 1: zero-copy (kernels read / write the pinned slab)
+  int host_mode = 1;            // 0: staged (H2D, launch, D2H); 1: zero-copy (kernels read / write the pinned slab)
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -827,6 +837,16 @@ extern "C" int hh_debug_geodesic(int32_t mode, int32_t n, const double* in_host,
   return 0;
 }
 
+#ifdef HH_V4_PROFILE
+// profiling builds only (profiles/stage_clocks.py): per-CTA clock64() at the stage boundaries of the last v4 step
+extern "C" int hh_debug_v4_profile(long long* out_host, int32_t n_ctas) {
+  if (!out_host || n_ctas <= 0 || n_ctas > 4096) return fail(-1, "hh_debug_v4_profile: bad argument");
+  HH_CUDA(cudaDeviceSynchronize());
+  HH_CUDA(cudaMemcpyFromSymbol(out_host, v4::g_stage_clock, sizeof(long long) * 16 * (size_t)n_ctas));
+  return 0;
+}
+#endif
+
 extern "C" int hh_create(const hh_config* cfg, int32_t n_arenas, int32_t device, hh_env** out) {
   if (!cfg || !out) return fail(-1, "hh_create: null argument");
   if (n_arenas <= 0) return fail(-1, "hh_create: n_arenas must be positive");
@@ -892,10 +912,23 @@ extern "C" int hh_create(const hh_config* cfg, int32_t n_arenas, int32_t device,
   P.seed_lo = (uint32_t)cfg->seed;
   P.seed_hi = (uint32_t)(cfg->seed >> 32);
   P.arena_base = (uint32_t)cfg->arena_base;
+  P.geom = make_geom(P.map_size);
   {
     const char* impl = getenv("HH_STEP_IMPL");
+    if (sizeof(v4::Smem) > 48 * 1024) {   // opt in to > 48 KB of dynamic shared memory (per device, idempotent)
+      cudaError_t ce2 = v4_opt_in_smem<1, 0>();
+      if (ce2 == cudaSuccess) ce2 = v4_opt_in_smem<1, 1>();
+      if (ce2 == cudaSuccess) ce2 = v4_opt_in_smem<2, 0>();
+      if (ce2 == cudaSuccess) ce2 = v4_opt_in_smem<2, 1>();
+      if (ce2 == cudaSuccess) ce2 = v4_opt_in_smem<3, 0>();
+      if (ce2 == cudaSuccess) ce2 = v4_opt_in_smem<3, 1>();
+      if (ce2 != cudaSuccess) {
+        hh_destroy(e);
+        return fail(-2, std::string("cudaFuncSetAttribute(step_kernel_v4, max dynamic smem): ") + cudaGetErrorString(ce2));
+      }
+    }
     const char* hm = getenv("HH_HOST_MODE");
-    e->host_mode = (hm && std::string(hm) == "zerocopy") ? 1 : 0;
+    e->host_mode = (hm && std::string(hm) == "staged") ? 0 : 1;   // default: zero-copy (+23 % e2e, profiles/README.md)
     e->step_impl = !impl ? 4 : (std::string(impl) == "quad" ? 2 : (std::string(impl) == "cta" ? 3 : 4));
   }
   *out = e;
@@ -941,9 +974,9 @@ static void launch_step(hh_env* e, const int32_t* actions, float* obs1, float* o
   if (e->step_impl == 4) {
     const int vblocks = (e->n + v4::kArenas - 1) / v4::kArenas;
     if (e->cfg.agent_mode == 0)
-      step_kernel_v4<LEVEL, 0><<<vblocks, v4::kThreads, 0, st>>>(e->S, e->P, actions, obs1, obs2, rew, done);
+      step_kernel_v4<LEVEL, 0><<<vblocks, v4::kThreads, sizeof(v4::Smem), st>>>(e->S, e->P, actions, obs1, obs2, rew, done);
     else
-      step_kernel_v4<LEVEL, 1><<<vblocks, v4::kThreads, 0, st>>>(e->S, e->P, actions, obs1, obs2, rew, done);
+      step_kernel_v4<LEVEL, 1><<<vblocks, v4::kThreads, sizeof(v4::Smem), st>>>(e->S, e->P, actions, obs1, obs2, rew, done);
     return;
   }
   if (e->step_impl == 3) {

@@ -14,6 +14,20 @@ constexpr int OBS_AC1 = 26, OBS_AC2 = 24, OBS_ESC_AC1 = 30, OBS_ESC_AC2 = 29;
 // error bits (where the reference would raise)
 enum : int { ERR_HEADING = 1, ERR_SPEED = 2 };
 
+struct Geom {  // per-launch constants of the map (env_base.py:43, map_limits.py)
+  double ext_lat, ext_lon, top, right;
+  double inv_diag;  // (1 - 0) / (sqrt(2 ms^2) - 0)   (env_base.py:439,458-462)
+};
+__host__ __device__ __forceinline__ Geom make_geom(double ms) {
+  Geom g;
+  g.top = 5.0 + ms;
+  g.right = 7.0 + ms;
+  g.ext_lat = g.top - 5.0;
+  g.ext_lon = g.right - 7.0;
+  g.inv_diag = 1.0 / sqrt(2.0 * (ms * ms));
+  return g;
+}
+
 struct Params {
   int n_arenas;
   int level;       // 1..5
@@ -23,6 +37,7 @@ struct Params {
   double map_size, rew_scale, glob_frac;
   uint32_t seed_lo, seed_hi;
   uint32_t arena_base;  // global id of local arena 0 (multi-GPU sharding)
+  Geom geom;            // make_geom(map_size), filled on the host (IEEE sqrt / division: same bits as on the device)
 };
 
 // rocket_unit.py:16-21 -- scipy quadratic spline through (0,500),(10,2000),(20,1400),(30,600)
@@ -79,8 +94,25 @@ __device__ __forceinline__ double c_random_at(const Rng& r, unsigned int idx) {
 }
 
 // ------------------------------------------------------------------------------------- scalar helpers
+// C fmod(x, m) for the moduli of this code (m = 360 or 359: q m is exact for every quotient below 2^44) and
+// |x| < 1e9: r = x - trunc(x / m) m in one fma, which is exact because r is representable; the quotient estimated
+// through the reciprocal can be off by one next to a multiple of m, which the compares repair (again exactly).
+// libdevice's fmod is a ~60-instruction loop and was 4 % of the step's stall samples (profiles/r1i_*).
+__device__ __forceinline__ double fmod_small(double x, double m) {
+  if (!(fabs(x) < 1e9)) return m::fmod_(x, m);
+  const double q = trunc(x * (1.0 / m));
+  double r = fma(-q, m, x);
+  if (x >= 0.0) {
+    if (r < 0.0) r += m;
+    else if (r >= m) r -= m;
+  } else {
+    if (r > 0.0) r -= m;
+    else if (r <= -m) r += m;
+  }
+  return r;
+}
 __device__ __forceinline__ double pymod(double x, double m) {  // CPython float %, m > 0
-  double r = m::fmod_(x, m);
+  double r = fmod_small(x, m);
   if (r != 0.0 && r < 0.0) r += m;
   return r;
 }
@@ -103,19 +135,6 @@ __device__ __forceinline__ double normalize_angle(double a) {
 __device__ __forceinline__ bool is_ac1(int u) { return (u & 1) == 0; }
 __device__ __forceinline__ double max_speed(int u) { return is_ac1(u) ? 900.0 : 600.0; }
 
-struct Geom {  // per-launch constants of the map (env_base.py:43, map_limits.py)
-  double ext_lat, ext_lon, top, right;
-  double inv_diag;  // (1 - 0) / (sqrt(2 ms^2) - 0)   (env_base.py:439,458-462)
-};
-__device__ __forceinline__ Geom make_geom(double ms) {
-  Geom g;
-  g.top = 5.0 + ms;
-  g.right = 7.0 + ms;
-  g.ext_lat = g.top - 5.0;
-  g.ext_lon = g.right - 7.0;
-  g.inv_diag = 1.0 / sqrt(2.0 * (ms * ms));
-  return g;
-}
 // map_limits.py:37-40
 __device__ __forceinline__ void rel_pos(const Geom& g, double lat, double lon, double& lat_rel, double& lon_rel) {
   lat_rel = clip((lat - 5.0) / g.ext_lat, 0.0, 1.0);
@@ -178,6 +197,21 @@ __device__ __forceinline__ int correct_angle_sign(double lat_o, double lon_o, do
   return val < 0.0 ? 1 : -1;
 }
 
+// the two halves of correct_angle_sign: the heading's unit offsets rounded to 3 decimals (depends on the opponent
+// only), and the cross product with the line of sight (never fused: CPython evaluates a*b - c*d in three roundings)
+__device__ __forceinline__ void angle_sign_offsets(double hdg_o, double& sx, double& cx) {
+  double s, c;
+  m::sincos_(pymod(hdg_o, 360.0) * (geo::kPi / 180.0), &s, &c);
+  sx = rint(s * 1000.0) / 1000.0;
+  cx = rint(c * 1000.0) / 1000.0;
+}
+__device__ __forceinline__ int angle_sign_from(double lat_o, double lon_o, double sx, double cx, double lat_a,
+                                               double lon_a) {
+  const double x1 = lon_o + sx, y1 = lat_o + cx;
+  const double val = __dadd_rn(__dmul_rn(x1 - lon_o, lat_a - lat_o), -__dmul_rn(lon_a - lon_o, y1 - lat_o));
+  return val < 0.0 ? 1 : -1;
+}
+
 // ------------------------------------------------------------------------------------- range tests
 // The reference decides cannon hits and rocket proximity from the WGS84 geodesic distance
 // (units_distance_km, cmano_simulator.py:167-169).  On the ellipsoid the metric satisfies
@@ -194,6 +228,13 @@ constexpr double kMarginDistM = 1e-3;     // 1 mm  (local error <= 10 um up to 7
 constexpr double kMarginAziDeg = 1e-5;    //       (local error <= 3e-8 deg up to 7 km)
 constexpr double kMarginAziFarDeg = 1e-3; //       (local error <= 1e-5 deg up to 80 km)
 
+// Cheap superset of the pairs that pass the flat prefilter of unit_in_cannon_range / within_1km (squared distance, a
+// hair wider): a pair outside it is out of range with certainty, a pair inside it goes through the full test.
+__device__ __forceinline__ bool maybe_within_km(double lat_s, double lon_s, double lat_t, double lon_t, double range_km) {
+  const double dx = lon_t - lon_s, dy = lat_t - lat_s;
+  const double r = range_km * (1.000001 / kKmPerDegLower);
+  return dx * dx + dy * dy < r * r;
+}
 // ac1.py:135-142 / ac2.py:109-116
 __device__ __forceinline__ bool unit_in_cannon_range(double lat_s, double lon_s, double hdg_s, double lat_t,
                                                      double lon_t, double range_km, double half_width) {

@@ -322,8 +322,18 @@ constexpr double kPhi0d = 5.25 * (3.14159265358979323846 / 180.0);
 constexpr double kSinPhi0d = 0.09150161866340238;   // sin(5.25 deg)
 constexpr double kCosPhi0d = 0.9958049275746618;    // cos(5.25 deg)
 
+// 1 / x for the well-scaled denominators of direct_short (0.9 .. 2.1): one rounding in the reciprocal, one in the
+// product that follows -- the quotient may differ from a correctly rounded division in the last bit
+__device__ __forceinline__ double rcp_(double x) {
+#if defined(__CUDA_ARCH__)
+  return __drcp_rn(x);
+#else
+  return 1.0 / x;
+#endif
+}
+
 static __device__ __noinline__ double2 direct_short(double lat1, double lon1, double azi1, double salp1, double calp1,
-                                                double s12) {
+                                                    double s12) {
   const double dl = lat1 * kDeg - kPhi0d;
   if (!(fabs(dl) < 0.02 && fabs(s12) <= 3000.0 && fabs(lon1) < 170.0)) return direct(lat1, lon1, azi1, s12);
   double sbet1, cbet1;
@@ -338,12 +348,20 @@ static __device__ __noinline__ double2 direct_short(double lat1, double lon1, do
     cbet1 *= r;
   }
   const double salp0 = salp1 * cbet1;
-  const double calp0 = sqrt(calp1 * calp1 + sq(salp1 * sbet1));
-  // (ssig1, csig1) = (sbet1, cbet1 calp1) / calp0  (hypot(sbet1, cbet1 calp1) = calp0 for unit vectors)
-  const double icalp0 = 1.0 / calp0;
+  // (ssig1, csig1) = (sbet1, cbet1 calp1) / calp0  (hypot(sbet1, cbet1 calp1) = calp0 for unit vectors);
+  // calp0 >= |sbet1| ~ 0.09 at these latitudes
+  const double calp0sq = calp1 * calp1 + sq(salp1 * sbet1);
+  const double icalp0 = rsqrt(calp0sq);
+  const double calp0 = calp0sq * icalp0;
   const double ssig1 = sbet1 * icalp0, csig1 = cbet1 * calp1 * icalp0;
-  const double k2 = sq(calp0) * kEp2;
-  const double eps = k2 / (2.0 * (1.0 + sqrt(1.0 + k2)) + k2);
+  // eps = k2 / (2 (1 + sqrt(1 + k2)) + k2) as its Taylor series: k2 <= e'^2 = 0.00674, degree 8 is exact to 3e-19
+  const double k2 = calp0sq * kEp2;
+  const double eps =
+      k2 * (1.0 / 4.0 +
+            k2 * (-1.0 / 8.0 +
+                  k2 * (5.0 / 64.0 +
+                        k2 * (-7.0 / 128.0 +
+                              k2 * (21.0 / 512.0 + k2 * (-33.0 / 1024.0 + k2 * (429.0 / 16384.0 + k2 * (-715.0 / 32768.0))))))));
   const double B11 = S6(ssig1, csig1, C1f(eps));
   double s, c;
   {
@@ -356,10 +374,10 @@ static __device__ __noinline__ double2 direct_short(double lat1, double lon1, do
   const C5 c3 = C3f(eps);
   const double A3c = -kF * salp0 * A3f(eps);
   const double B31 = S5(ssig1, csig1, c3);
-  // 1 + A1m1 = (1 + t) / (1 - eps),  t = eps^2 (64 + eps^2 (4 + eps^2)) / 256
+  // 1 + A1m1 = (1 + t) / (1 - eps),  t = eps^2 (64 + eps^2 (4 + eps^2)) / 256 <= 7.1e-7:  1 / (1 + t) = 1 - t + t^2
   const double e2 = eps * eps;
   const double t1 = ((e2 + 4.0) * e2 + 64.0) * e2 * (1.0 / 256.0);
-  const double tau12 = s12 * (1.0 - eps) / (kB * (1.0 + t1));
+  const double tau12 = s12 * (1.0 / kB) * ((1.0 - eps) * (1.0 - t1 * (1.0 - t1)));
   {
     const double x2 = tau12 * tau12;
     s = tau12 * (1.0 + x2 * (-1.0 / 6.0 + x2 * (1.0 / 120.0)));
@@ -373,7 +391,8 @@ static __device__ __noinline__ double2 direct_short(double lat1, double lon1, do
     ssig12 = sig12 * (1.0 + x2 * (-1.0 / 6.0 + x2 * (1.0 / 120.0)));
     csig12m1 = x2 * (-0.5 + x2 * (1.0 / 24.0));
   }
-  const double ssig2 = ssig1 + (ssig1 * csig12m1 + csig1 * ssig12);
+  const double dss = ssig1 * csig12m1 + csig1 * ssig12;      // ssig2 - ssig1
+  const double ssig2 = ssig1 + dss;
   const double csig2 = csig1 + (csig1 * csig12m1 - ssig1 * ssig12);
   const double sbet2 = calp0 * ssig2;
   const double cbet2 = sqrt(salp0 * salp0 + sq(calp0 * csig2));
@@ -382,7 +401,7 @@ static __device__ __noinline__ double2 direct_short(double lat1, double lon1, do
     // tan(omg) = salp0 tan(sig)  =>  tan(omg2 - omg1) = salp0 sin(sig12) / (csig1 csig2 + salp0^2 ssig1 ssig2):
     // no cancellation (direct() takes the difference of two O(0.1) products, which costs ~20 ulp of the
     // longitude for azimuths near 90 / 270 deg); the denominator is ~cos^2(beta) ~ 0.99
-    const double t = salp0 * ssig12 / (csig1 * csig2 + salp0 * salp0 * (ssig1 * ssig2));
+    const double t = salp0 * ssig12 * rcp_(csig1 * csig2 + salp0 * salp0 * (ssig1 * ssig2));
     const double t2 = t * t;
     omg12 = t * (1.0 + t2 * (-1.0 / 3.0 + t2 * (1.0 / 5.0)));
   }
@@ -391,9 +410,8 @@ static __device__ __noinline__ double2 direct_short(double lat1, double lon1, do
   {
     // sin(bet2 - bet1) without cancellation: dsb (cbet1 + sbet1 (sbet1 + sbet2) / (cbet1 + cbet2)),
     // dsb = sbet2 - sbet1 = calp0 (ssig2 - ssig1);  tan(phi2 - phi1) = f1 sin(dbet) / (f1^2 cb1 cb2 + sb1 sb2)
-    const double dsb = calp0 * (ssig1 * csig12m1 + csig1 * ssig12);
-    const double sdb = dsb * (cbet1 + sbet1 * (sbet1 + sbet2) / (cbet1 + cbet2));
-    const double t = kF1 * sdb / (kF1 * kF1 * cbet1 * cbet2 + sbet1 * sbet2);
+    const double sdb = calp0 * dss * (cbet1 + sbet1 * (sbet1 + sbet2) * rcp_(cbet1 + cbet2));
+    const double t = kF1 * sdb * rcp_(kF1 * kF1 * cbet1 * cbet2 + sbet1 * sbet2);
     const double t2 = t * t;
     dphi = t * (1.0 + t2 * (-1.0 / 3.0 + t2 * (1.0 / 5.0)));
   }

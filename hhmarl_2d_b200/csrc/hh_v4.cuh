@@ -48,20 +48,21 @@ struct Smem {
   double pf[A1 * kPF];                  // pair features, degrees (hdiff: normalised)
   double pdn[A4];                       // [al*4 + au*2 + {0,1}] normalised distance agent -> nearest / second enemy
   double rew[A2], opp_focus[A2];
+  double sgn_x[A2], sgn_y[A2];          // level 3: heading offsets of the opponents' turn-sign test
   unsigned long long dg[A1], dg0[A1], dg_out[A1];
   alignas(16) int4 act[A2];
   alignas(16) float obs1[A1 * OBS_ESC_AC1];
   alignas(16) float obs2[A1 * OBS_ESC_AC2];
   alignas(16) float uf[A4 * 4];         // per-unit features: lat_rel, lon_rel, speed, heading
   int crem[A4], burst[A4], cmax[A4], mrem[A4], rmax[A4], mwait[A4], ota[A4];
-  int near_t[A4], rel_sign[A4], inr[A4];
+  int near_t[A4], inr[A4];
   int po[A4];                           // [al*4 + au*2 + {0,1}] nearest / second enemy unit (-1: none)
   int rage[A2], rtgt[A2], rid[A2];
   int steps[A1], alive_ag[A1], alive_op[A1], esc_time[A1], next_id[A1], pset[A1], opp_mode[A1], err[A1], escaping[A1];
   int dgi[A1];                          // G draws consumed by the action phase
   int done[A1], alive_fin[A1], alive_pre[A1];
   unsigned int dc[A1];
-  unsigned char alive[A4], hasm[A4], upd[A4], firing[A4], launched[A4], shot[A4];
+  unsigned char alive[A4], hasm[A4], upd[A4], firing[A4], launched[A4], shot[A4], oob[A4];
   unsigned char ralive[A2], rocket0[A2], hit_t[A2], hit_f[A2], exploded[A2];
   unsigned char want0[A1];
 };
@@ -153,15 +154,11 @@ __device__ __forceinline__ void s1_pretick(const Ctx& C, int t) {
     ry = nt;
   }
   double rf = 0.0;
-  int rs = 1;
-  if (rx >= 0) {
+  if (rx >= 0)
     rf = focus_deg(heading_vec(S.hdg[ub + rx]), S.lat[ub + rx], S.lon[ub + rx], S.lat[ub + ry], S.lon[ub + ry]);
-    if (u >= 2) rs = correct_angle_sign(S.lat[ub + rx], S.lon[ub + rx], S.hdg[ub + rx], S.lat[ub + ry], S.lon[ub + ry]);
-  }
   S.near_t[t] = nt;
   S.near_dn[t] = ndn;
   S.rel_focus[t] = rf;
-  S.rel_sign[t] = rs;
   S.upd[t] = S.alive[t];            // CmanoSimulator.do_tick's snapshot: nothing dies in the action phase
   S.launched[t] = 0;
   if (u < 2) S.rew[al * 2 + u] = 0.0;
@@ -180,6 +177,16 @@ __device__ __forceinline__ void s1_draws(const Ctx& C, int t) {
   const unsigned long long base = C.S.dg0[al] + (unsigned long long)j;
 #pragma unroll
   for (int q = 0; q < 4; ++q) C.S.rnd[al * kDraws + j + q] = g_random_at(rng, base + q);
+}
+// level 3: the heading part of the opponents' turn-sign test (env_base.py:469-475) runs on the draw warps, after the
+// draws: the unit warps' chain (nearest-agent scan, heading vector, focus angle) is the longer one
+__device__ __forceinline__ void s1_sign_offsets(const Ctx& C, int t) {
+  const int al = t >> 2, k = t & 3;
+  if (k >= 2) return;
+  double sx = 0.0, cx = 0.0;
+  if (C.S.alive[al * 4 + 2 + k]) angle_sign_offsets(C.S.hdg[al * 4 + 2 + k], sx, cx);
+  C.S.sgn_x[al * 2 + k] = sx;
+  C.S.sgn_y[al * 2 + k] = cx;
 }
 
 // ===================================================================================== S2: actions
@@ -236,8 +243,13 @@ __device__ __forceinline__ void s2_script(const Ctx& C, int t) {
   for (int k = 2; k < 4; ++k) {
     const int us = b + k;
     const bool k_alive = S.alive[us];
+    const int k_near = S.near_t[us];
+    int k_sign = 1;
+    if (LEVEL == 3 && k_alive && k_near >= 0)
+      k_sign = angle_sign_from(S.lat[us], S.lon[us], S.sgn_x[al * 2 + k - 2], S.sgn_y[al * 2 + k - 2], S.lat[b + k_near],
+                               S.lon[b + k_near]);
     const OppDecision d = scripted_opponent_g<LEVEL>(L, next, C.g, k, k_alive, S.hasm[us], S.mwait[us], S.lat[us], S.lon[us],
-                                                     S.hdg[us], S.near_t[us], S.near_dn[us], S.rel_focus[us], S.rel_sign[us]);
+                                                     S.hdg[us], k_near, S.near_dn[us], S.rel_focus[us], k_sign);
     if (!k_alive) continue;
     if (d.set_hs) {
       if (d.heading >= 360.0 || d.heading < 0.0) atomicOr(&S.err[al], ERR_HEADING);
@@ -337,16 +349,29 @@ __device__ __forceinline__ void s5_cannon(const Ctx& C, int t) {
   if (S.firing[t]) {
     const int alive0 = S.alive_pre[al];
     const double range = is_ac1(u) ? 2.0 : 4.5, half_w = (is_ac1(u) ? 10.0 : 7.0) / 2.0;
-#pragma unroll 1
+    // candidates first (three squared distances), then the full test for the few that are near: the warp makes as
+    // many passes through the geodesic code as its busiest lane has candidates, usually 0 or 1
+    int cand = 0;
+#pragma unroll
     for (int j = 0; j < 4; ++j) {
-      if (j == u || !((alive0 >> j) & 1)) continue;
-      if (!(C.P.friendly_kill || ((u < 2) != (j < 2)))) continue;
+      const bool ok = j != u && ((alive0 >> j) & 1) && (C.P.friendly_kill || ((u < 2) != (j < 2)));
+      const double jl = j < u ? S.nlat[ub + j] : S.lat[ub + j];
+      const double jo = j < u ? S.nlon[ub + j] : S.lon[ub + j];
+      if (ok && maybe_within_km(S.lat[t], S.lon[t], jl, jo, range)) cand |= 1 << j;
+    }
+#pragma unroll 1
+    while (cand) {
+      const int j = __ffs(cand) - 1;
+      cand &= cand - 1;
       const double jl = j < u ? S.nlat[ub + j] : S.lat[ub + j];
       const double jo = j < u ? S.nlon[ub + j] : S.lon[ub + j];
       if (unit_in_cannon_range(S.lat[t], S.lon[t], S.hdg[t], jl, jo, range, half_w)) in_range |= 1 << j;
     }
   }
   S.inr[t] = in_range;
+  // out-of-bounds test of the post-tick position (env_base.py:244-255); combined with the alive mask in S6
+  const bool upd = S.upd[t];
+  S.oob[t] = !in_boundary(C.g, upd ? S.nlat[t] : S.lat[t], upd ? S.nlon[t] : S.lon[t]);
 }
 // rocket proximity (rocket_unit.py:39,49): every aircraft has already moved
 __device__ __forceinline__ void s5_rocket(const Ctx& C, int t) {
@@ -355,8 +380,11 @@ __device__ __forceinline__ void s5_rocket(const Ctx& C, int t) {
   bool ht = false, hf = false;
   if (S.rocket0[t]) {
     const int tq = S.rtgt[t] > 0 ? S.rtgt[t] - 1 : 0;
-    ht = within_1km(S.rlat[t], S.rlon[t], S.nlat[b + tq], S.nlon[b + tq]);
-    if (C.P.friendly_kill) hf = within_1km(S.rlat[t], S.rlon[t], S.nlat[b + 1], S.nlon[b + 1]);   // "friendly" is always id 2
+    ht = maybe_within_km(S.rlat[t], S.rlon[t], S.nlat[b + tq], S.nlon[b + tq], 1.0) &&
+         within_1km(S.rlat[t], S.rlon[t], S.nlat[b + tq], S.nlon[b + tq]);
+    if (C.P.friendly_kill)   // "friendly" is always id 2
+      hf = maybe_within_km(S.rlat[t], S.rlon[t], S.nlat[b + 1], S.nlon[b + 1], 1.0) &&
+           within_1km(S.rlat[t], S.rlon[t], S.nlat[b + 1], S.nlon[b + 1]);
   }
   S.hit_t[t] = ht;
   S.hit_f[t] = hf;
@@ -434,18 +462,8 @@ __device__ __forceinline__ void s6_resolve(const Ctx& C, int t) {
       }
     }
   }
-  // post-tick positions (committed to S.lat / S.lon by the unit threads in S7)
-  double pl[4], po[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    pl[j] = S.upd[b + j] ? S.nlat[b + j] : S.lat[b + j];
-    po[j] = S.upd[b + j] ? S.nlon[b + j] : S.lon[b + j];
-  }
   const double s = P.rew_scale;
-  int oob_m = 0;
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-    if (((alive_m >> j) & 1) && !in_boundary(C.g, pl[j], po[j])) oob_m |= 1 << j;
+  const int oob_m = alive_m & (S.oob[b] | (S.oob[b + 1] << 1) | (S.oob[b + 2] << 2) | (S.oob[b + 3] << 3));
   alive_m &= ~oob_m;
   const int present_m = (S.upd[b] ? 1 : 0) | (S.upd[b + 1] ? 2 : 0);   // alive at step start (reward-dict membership)
   double rews0 = 0.0, rews1 = 0.0;
@@ -492,7 +510,13 @@ __device__ __forceinline__ void s6_resolve(const Ctx& C, int t) {
       rews1 += add1;
     }
   }
-  if (MODE == 1 && P.esc_dist_rew) {           // env_hetero.py:198-214
+  if (MODE == 1 && P.esc_dist_rew) {           // env_hetero.py:198-214, on the post-tick positions
+    double pl[4], po[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      pl[j] = S.upd[b + j] ? S.nlat[b + j] : S.lat[b + j];
+      po[j] = S.upd[b + j] ? S.nlon[b + j] : S.lon[b + j];
+    }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       if (!((alive_m >> i) & 1)) continue;
@@ -602,7 +626,9 @@ __device__ __forceinline__ void s7_commit_rocket(const Ctx& C, int t) {
 
 // ===================================================================================== S8: pair features
 // Per arena: for each agent (nearest enemy o) focus(self->o), focus(o->self), hdiff(self, o); the team-mate pair
-// focus(1->2), focus(2->1); in escape mode the same three for the second enemy.  One task per thread.
+// focus(1->2), focus(2->1); in escape mode the same three for the second enemy.  One task per thread; every task
+// is the angle between a heading vector and either a line of sight (env_base.py:424-432) or another heading vector
+// (:448-456), so the tasks only select their two vectors and share ONE arccos evaluation (no divergent copies).
 template <int MODE>
 __device__ __forceinline__ void s8_pairs(const Ctx& C, int t) {
   Smem& S = C.S;
@@ -611,12 +637,10 @@ __device__ __forceinline__ void s8_pairs(const Ctx& C, int t) {
   const int alive_m = alive_mask(S, b);
 #pragma unroll 1
   for (int j = t & 7; j < kTasks; j += 8) {
-    double v = 0.0;
+    int x = -1, y = -1;          // unit slots: angle at x towards y (line of sight) or between the headings of x and y
+    bool heading_pair = false;
     if (j == 6 || j == 7) {
-      if ((alive_m & 3) == 3) {
-        const int x = b + (j - 6), y = b + (7 - j);
-        v = focus_deg(sm_hv(S, x), S.lat[x], S.lon[x], S.lat[y], S.lon[y]);
-      }
+      if ((alive_m & 3) == 3) { x = b + (j - 6); y = b + (7 - j); }
     } else {
       const int jj = j < 6 ? j : j - 8, au = jj / 3, kind = jj - 3 * au, second = j >= 8;
       const int us = b + au;
@@ -632,11 +656,20 @@ __device__ __forceinline__ void s8_pairs(const Ctx& C, int t) {
         S.pdn[b + au * 2 + second] = dn;
       }
       if (o >= 0) {
-        const int os = b + o;
-        if (kind == 0) v = focus_deg(sm_hv(S, us), S.lat[us], S.lon[us], S.lat[os], S.lon[os]);
-        else if (kind == 1) v = focus_deg(sm_hv(S, os), S.lat[os], S.lon[os], S.lat[us], S.lon[us]);
-        else v = hdiff_norm(sm_hv(S, us), sm_hv(S, os));
+        x = kind == 1 ? b + o : us;
+        y = kind == 1 ? us : b + o;
+        heading_pair = kind == 2;
       }
+    }
+    double v = 0.0;
+    if (x >= 0) {
+      const HVec a = sm_hv(S, x);
+      double w0 = S.lon[y] - S.lon[x], w1 = S.lat[y] - S.lat[x];
+      double wn = sqrt(w0 * w0 + w1 * w1);
+      if (heading_pair) { w0 = S.hvc[y]; w1 = S.hvs[y]; wn = S.hvn[y]; }
+      const double cs = clip((a.c * w0 + a.s * w1) / (a.n * wn + 1e-10), -1.0, 1.0);
+      const double deg = m::acos_(cs) * (180.0 / geo::kPi);
+      v = heading_pair ? clip(deg / 180.0, 0.0, 1.0) : deg;
     }
     S.pf[al * kPF + j] = v;
   }
@@ -644,7 +677,8 @@ __device__ __forceinline__ void s8_pairs(const Ctx& C, int t) {
 
 // ===================================================================================== S9: observation rows
 // lowlevel_state (env_hetero.py:65-103): fight_state_values / esc_state_values (env_base.py:111-164),
-// opp_ac_values (:185-212), friendly_ac_values (:166-183) assembled from the unit and pair features
+// opp_ac_values (:185-212), friendly_ac_values (:166-183) assembled from the unit and pair features.
+// Three threads per agent row: own part, enemy block(s), friend block.
 __device__ __forceinline__ int put_unit(const Smem& S, int us, float* out) {
   const float4 f = reinterpret_cast<const float4*>(S.uf)[us];
   out[0] = f.x; out[1] = f.y; out[2] = f.z; out[3] = f.w;
@@ -654,74 +688,88 @@ template <int MODE>
 __device__ __forceinline__ void s9_rows(const Ctx& C, int t) {
   Smem& S = C.S;
   constexpr int D1 = MODE == 0 ? OBS_AC1 : OBS_ESC_AC1, D2 = MODE == 0 ? OBS_AC2 : OBS_ESC_AC2;
-  const int al = t >> 1, au = t & 1, b = al * 4, us = b + au;
-  float* out = au == 0 ? S.obs1 + al * D1 : S.obs2 + al * D2;
-  const int len = au == 0 ? D1 : D2;
+  const int part = t / A2, ag = t - part * A2;       // part: 0 own, 1 enemies, 2 friend (warp-uniform)
+  const int al = ag >> 1, au = ag & 1, b = al * 4, us = b + au;
+  float* row = au == 0 ? S.obs1 + al * D1 : S.obs2 + al * D2;
+  const int n_own = MODE == 0 ? (au == 0 ? 12 : 10) : (au == 0 ? 7 : 6);
+  const int n_enemy = MODE == 0 ? 9 : 18;
   const int o = S.po[b + au * 2];
-  const double* pf = S.pf + al * kPF + au * 3;
-  if (o < 0) {
-    for (int k = 0; k < len; ++k) out[k] = 0.0f;
-    S.ota[us] = 0;
-    S.ota[b + 2 + au] = 0;      // opponents' opp_to_attack stays None at levels 1-3
+  if (o < 0) {                  // dead, or no enemy left: the whole row is zero (env_hetero.py:77-79)
+    const int lo = part == 0 ? 0 : (part == 1 ? n_own : n_own + n_enemy);
+    const int hi = part == 0 ? n_own : (part == 1 ? n_own + n_enemy : n_own + n_enemy + 5);
+    for (int k = lo; k < hi; ++k) row[k] = 0.0f;
+    if (part == 0) {
+      S.ota[us] = 0;
+      S.ota[b + 2 + au] = 0;    // opponents' opp_to_attack stays None at levels 1-3
+    }
     return;
   }
+  const double* pf = S.pf + al * kPF + au * 3;
   const double f_uo = pf[0], f_ou = pf[1], hd = pf[2], dn = S.pdn[b + au * 2];
-  int n = put_unit(S, us, out);
-  if (MODE == 0) {
-    out[n++] = (float)focus_norm_from_deg(f_uo);
-    out[n++] = (float)aspect_from_deg(f_ou);
-    out[n++] = (float)hd;
-    out[n++] = (float)dn;
-    out[n++] = (float)clip((double)S.crem[us] / (double)S.cmax[us], 0.0, 1.0);
-    if (au == 0) {
-      out[n++] = (float)clip((double)S.mrem[us] / (double)S.rmax[us], 0.0, 1.0);
-      out[n++] = S.mwait[us] == 0 ? 1.0f : 0.0f;
-      out[n++] = (S.hasm[us] || S.burst[us] > 0) ? 1.0f : 0.0f;
+  if (part == 0) {
+    float* out = row;
+    int n = put_unit(S, us, out);
+    if (MODE == 0) {
+      out[n++] = (float)focus_norm_from_deg(f_uo);
+      out[n++] = (float)aspect_from_deg(f_ou);
+      out[n++] = (float)hd;
+      out[n++] = (float)dn;
+      out[n++] = (float)clip((double)S.crem[us] / (double)S.cmax[us], 0.0, 1.0);
+      if (au == 0) {
+        out[n++] = (float)clip((double)S.mrem[us] / (double)S.rmax[us], 0.0, 1.0);
+        out[n++] = S.mwait[us] == 0 ? 1.0f : 0.0f;
+        out[n++] = (S.hasm[us] || S.burst[us] > 0) ? 1.0f : 0.0f;
+      } else {
+        out[n++] = S.burst[us] > 0 ? 1.0f : 0.0f;
+      }
     } else {
-      out[n++] = S.burst[us] > 0 ? 1.0f : 0.0f;
+      out[n++] = (float)clip((double)S.crem[us] / (double)S.cmax[us], 0.0, 1.0);
+      if (au == 0) out[n++] = (float)clip((double)S.mrem[us] / (double)S.rmax[us], 0.0, 1.0);
+      out[n++] = S.shot[us] ? 1.0f : 0.0f;
     }
-    n += put_unit(S, b + o, out + n);
+    S.ota[us] = o + 1;
+    S.ota[b + 2 + au] = 0;
+  } else if (part == 1) {
+    float* out = row + n_own;
+    int n = put_unit(S, b + o, out);
     out[n++] = (float)hd;
-    out[n++] = (float)focus_norm_from_deg(f_ou);
-    out[n++] = (float)aspect_from_deg(f_uo);
+    if (MODE == 0) {
+      out[n++] = (float)focus_norm_from_deg(f_ou);
+      out[n++] = (float)aspect_from_deg(f_uo);
+    } else {
+      out[n++] = (float)focus_norm_from_deg(f_uo);
+      out[n++] = (float)focus_norm_from_deg(f_ou);
+    }
     out[n++] = (float)dn;
     out[n++] = S.shot[b + o] ? 1.0f : 0.0f;
+    if (MODE == 1) {
+      const int o2 = S.po[b + au * 2 + 1];
+      if (o2 >= 0) {
+        const double* pq = S.pf + al * kPF + 8 + au * 3;
+        n += put_unit(S, b + o2, out + n);
+        out[n++] = (float)pq[2];
+        out[n++] = (float)focus_norm_from_deg(pq[0]);
+        out[n++] = (float)focus_norm_from_deg(pq[1]);
+        out[n++] = (float)S.pdn[b + au * 2 + 1];
+        out[n++] = S.shot[b + o2] ? 1.0f : 0.0f;
+      } else {
+        for (int z = 0; z < 9; ++z) out[n++] = 0.0f;
+      }
+    }
   } else {
-    out[n++] = (float)clip((double)S.crem[us] / (double)S.cmax[us], 0.0, 1.0);
-    if (au == 0) out[n++] = (float)clip((double)S.mrem[us] / (double)S.rmax[us], 0.0, 1.0);
-    out[n++] = S.shot[us] ? 1.0f : 0.0f;
-    n += put_unit(S, b + o, out + n);
-    out[n++] = (float)hd;
-    out[n++] = (float)focus_norm_from_deg(f_uo);
-    out[n++] = (float)focus_norm_from_deg(f_ou);
-    out[n++] = (float)dn;
-    out[n++] = S.shot[b + o] ? 1.0f : 0.0f;
-    const int o2 = S.po[b + au * 2 + 1];
-    if (o2 >= 0) {
-      const double* pq = S.pf + al * kPF + 8 + au * 3;
-      n += put_unit(S, b + o2, out + n);
-      out[n++] = (float)pq[2];
-      out[n++] = (float)focus_norm_from_deg(pq[0]);
-      out[n++] = (float)focus_norm_from_deg(pq[1]);
-      out[n++] = (float)S.pdn[b + au * 2 + 1];
-      out[n++] = S.shot[b + o2] ? 1.0f : 0.0f;
+    float* out = row + n_own + n_enemy;
+    const int fri = b + (au ^ 1);
+    if (S.alive[fri]) {
+      const float4 f = reinterpret_cast<const float4*>(S.uf)[fri];
+      out[0] = f.x;
+      out[1] = f.y;
+      out[2] = (float)focus_norm_from_deg(S.pf[al * kPF + 6 + au]);        // focus(self -> friend)
+      out[3] = (float)focus_norm_from_deg(S.pf[al * kPF + 7 - au]);        // focus(friend -> self)
+      out[4] = (float)(C.g.inv_diag * dist_raw(S.lat[us], S.lon[us], S.lat[fri], S.lon[fri]));
     } else {
-      for (int z = 0; z < 9; ++z) out[n++] = 0.0f;
+      for (int k = 0; k < 5; ++k) out[k] = 0.0f;
     }
   }
-  const int fri = b + (au ^ 1);
-  if (S.alive[fri]) {
-    const float4 f = reinterpret_cast<const float4*>(S.uf)[fri];
-    out[n++] = f.x;
-    out[n++] = f.y;
-    out[n++] = (float)focus_norm_from_deg(S.pf[al * kPF + 6 + au]);        // focus(self -> friend)
-    out[n++] = (float)focus_norm_from_deg(S.pf[al * kPF + 7 - au]);        // focus(friend -> self)
-    out[n++] = (float)(C.g.inv_diag * dist_raw(S.lat[us], S.lon[us], S.lat[fri], S.lon[fri]));
-  } else {
-    for (int k = 0; k < 5; ++k) out[n++] = 0.0f;
-  }
-  S.ota[us] = o + 1;
-  S.ota[b + 2 + au] = 0;
 }
 
 // ===================================================================================== S10: store
@@ -808,6 +856,15 @@ __device__ __forceinline__ void s10_store_rows(const Ctx& C, int t, int n_thread
 static bool emu_reverse = false;
 #endif
 
+// Optional stage clocks (build with -DHH_V4_PROFILE; profiles/ only): thread 0 of each CTA records clock64() at
+// every stage boundary, hh_debug_v4_profile() reads them back.
+#if defined(HH_V4_PROFILE) && defined(__CUDACC__)
+__device__ long long g_stage_clock[4096 * 16];
+#define HH_MARK(k) if (tid == 0 && block < 4096) g_stage_clock[block * 16 + (k)] = clock64();
+#else
+#define HH_MARK(k)
+#endif
+
 template <int LEVEL, int MODE>
 __device__ __forceinline__ void step_body(Smem& S, const StatePtrs& G, const Params& P, const int32_t* __restrict__ actions,
                                           float* __restrict__ obs1, float* __restrict__ obs2,
@@ -817,33 +874,44 @@ __device__ __forceinline__ void step_body(Smem& S, const StatePtrs& G, const Par
   const int arena0 = block * kArenas;
   const int n_valid_ = P.n_arenas - arena0;
   const Ctx C{S, G, P, actions, obs1, obs2, rew_out, done_out, arena0, n_valid_ < kArenas ? n_valid_ : kArenas,
-              make_geom(P.map_size)};
+              P.geom};
+  HH_MARK(0)
   HH_ROLE(0, A4, s0_load_unit(C, t))
   HH_ROLE(A4, A2, s0_load_actions(C, t))
   HH_BARRIER();
+  HH_MARK(1)
   HH_ROLE(0, A4, s1_pretick<LEVEL>(C, t))
-  HH_ROLE(A4, A4, s1_draws<LEVEL>(C, t))
+  HH_ROLE(A4, A4, s1_draws<LEVEL>(C, t); if (LEVEL == 3) s1_sign_offsets(C, t))
   HH_BARRIER();
+  HH_MARK(2)
   HH_ROLE(0, A2, s2_agents<MODE>(C, t))
   HH_ROLE(A4, A1, s2_script<LEVEL>(C, t))
   HH_BARRIER();
+  HH_MARK(3)
   HH_ROLE(0, A4, s4_move_unit(C, t))
   HH_ROLE(A4, A2, s4_move_rocket(C, t))
   HH_BARRIER();
+  HH_MARK(4)
   HH_ROLE(0, A4, s5_cannon(C, t))
   HH_ROLE(A4, A2, s5_rocket(C, t))
   HH_BARRIER();
+  HH_MARK(5)
   HH_ROLE(0, A1, s6_resolve<MODE>(C, t))
   HH_BARRIER();
+  HH_MARK(6)
   HH_ROLE(0, A4, s7_commit_unit(C, t))
   HH_ROLE(A4, A2, s7_commit_rocket(C, t))
   HH_BARRIER();
+  HH_MARK(7)
   HH_ROLE(0, A8, s8_pairs<MODE>(C, t))
   HH_BARRIER();
-  HH_ROLE(0, A2, s9_rows<MODE>(C, t))
+  HH_MARK(8)
+  HH_ROLE(0, 3 * A2, s9_rows<MODE>(C, t))
   HH_BARRIER();
+  HH_MARK(9)
   HH_ROLE(0, A4, s10_store_unit(C, t))
   HH_ROLE(0, A8, s10_store_rows(C, t, A8, D1, D2))
+  HH_MARK(10)
 }
 
 // Masked reset + first observation through the same stages (first_time: state is created, not loaded).
@@ -891,7 +959,7 @@ __device__ __forceinline__ void reset_body(Smem& S, const StatePtrs& G, const Pa
   const int arena0 = block * kArenas;
   const int n_valid_ = P.n_arenas - arena0;
   const Ctx C{S, G, P, nullptr, obs1, obs2, nullptr, nullptr, arena0, n_valid_ < kArenas ? n_valid_ : kArenas,
-              make_geom(P.map_size)};
+              P.geom};
   if (!first_time) {
     HH_ROLE(0, A4, r0_load_unit(C, t))
   }
@@ -901,7 +969,7 @@ __device__ __forceinline__ void reset_body(Smem& S, const StatePtrs& G, const Pa
   HH_BARRIER();
   HH_ROLE(0, A8, s8_pairs<MODE>(C, t))
   HH_BARRIER();
-  HH_ROLE(0, A2, s9_rows<MODE>(C, t))
+  HH_ROLE(0, 3 * A2, s9_rows<MODE>(C, t))
   HH_BARRIER();
   HH_ROLE(0, A4, s10_store_unit(C, t))
   HH_ROLE(0, A8, s10_store_rows(C, t, A8, D1, D2))

@@ -160,7 +160,7 @@ class VecLowLevelEnv:
                 view(ptrs[4], ctypes.c_uint8, (n,)))
 
     def set_host_mode(self, mode: str):
-        """'staged' (default: H2D, launch, D2H) or 'zerocopy' (the kernel reads / writes the pinned slab directly)."""
+        """'zerocopy' (default: the kernel reads / writes the pinned slab directly) or 'staged' (H2D, launch, D2H)."""
         if mode not in ("staged", "zerocopy"):
             raise ValueError("mode must be 'staged' or 'zerocopy'")
         nat.check(nat.lib().hh_set_host_mode(self._h, 1 if mode == "zerocopy" else 0), "hh_set_host_mode")

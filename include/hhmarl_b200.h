@@ -106,9 +106,10 @@ int hh_step_host(hh_env* env, const int32_t* actions_host, float* obs1_host, flo
  * passing exactly these pointers to hh_step_host / hh_reset_host makes the call zero-copy on the host side
  * (one H2D of the actions, one D2H of obs1|obs2|rew|done, one stream synchronise). */
 int hh_host_buffers(hh_env* env, int32_t** actions, float** obs1, float** obs2, float** rew, uint8_t** done);
-/* How hh_reset_host / hh_step_host move data: 0 = staged (one H2D of the actions, the launch, one D2H of the results;
- * default), 1 = zero-copy (the kernels read the actions from and write the results to the handle's pinned slab
- * through its device mapping; levels 1-3).  Either way the call returns after the results are in host memory. */
+/* How hh_reset_host / hh_step_host move data: 1 = zero-copy (default: the kernels read the actions from and write the
+ * results to the handle's pinned slab through its device mapping), 0 = staged (one H2D of the actions, the launch,
+ * one D2H of the results; also selected by HH_HOST_MODE=staged).  Either way the call returns after the results are
+ * in host memory. */
 int hh_set_host_mode(hh_env* env, int32_t mode);
 
 int hh_get_state(hh_env* env, hh_state_view* out_host);

@@ -46,3 +46,4 @@ static inline T __shfl_sync(unsigned, T, int, int = 32) { abort(); }
 template <typename T>
 static inline T __shfl_xor_sync(unsigned, T, int, int = 32) { abort(); }
 static inline unsigned __ballot_sync(unsigned, bool) { abort(); }
+static inline int __ffs(int x) { return __builtin_ffs(x); }

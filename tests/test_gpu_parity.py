@@ -311,6 +311,7 @@ def test_zero_copy_host_mode_matches_staged_host_mode():
     for mode in ("fight", "escape"):
         n = 1000 + 13
         a = _vec(n, 3, mode, 9)
+        a.set_host_mode("staged")
         b = _vec(n, 3, mode, 9)
         b.set_host_mode("zerocopy")
         act_pin, o1, o2, r, d = b.host_buffers()
