@@ -265,8 +265,9 @@ def run_b200(args):
         from hhmarl_2d_b200 import models as M
         rollout = {}
         Tf = 20
-        for tag, kw in (("fp32", dict(allow_tf32=False)), ("tf32", dict(allow_tf32=True)),
-                        ("fp32_unpacked", dict(allow_tf32=False, packed=False))):
+        for tag, kw in (("fused_3xtf32", dict(fused="3xtf32")), ("fused_tf32", dict(fused="tf32")),
+                        ("fp32", dict(allow_tf32=False, fused=None)), ("tf32", dict(allow_tf32=True, fused=None)),
+                        ("fp32_unpacked", dict(allow_tf32=False, packed=False, fused=None))):
             torch.manual_seed(rank)
             m1, m2 = M.build_policy_pair("fight")
             m1.to(dev); m2.to(dev)
@@ -289,9 +290,11 @@ def run_b200(args):
                             "ms_per_tick": float(rt.item()) / (R * Tf)}
             del smp, env_r
         rollout["fragment_len"] = Tf
-        rollout["note"] = ("both policies' actor + central critic (packed GEMMs, cuBLAS) + Gumbel-max sampling + env step + "
-                           "GAE + action write-back, one CUDA graph per 20-tick fragment; random-init weights; "
-                           "'tf32' = same with TF32 tensor-core GEMMs, 'fp32_unpacked' = per-layer forward of models.py")
+        rollout["note"] = ("both policies' actor + central critic + Gumbel-max sampling + env step + GAE + action "
+                           "write-back, one CUDA graph per 20-tick fragment; random-init weights.  'fused_3xtf32' (the "
+                           "sampler's default) / 'fused_tf32': the hand-written forward kernel csrc/hh_policy.cu (one launch "
+                           "per tick, 3xTF32 = fp32-equivalent / plain TF32 tensor-core products); 'fp32' / 'tf32': packed "
+                           "cuBLAS GEMMs (fused_forward.PackedPolicyPair); 'fp32_unpacked': per-layer forward of models.py")
     except Exception as ex:  # noqa: BLE001
         rollout = {"error": repr(ex)}
 

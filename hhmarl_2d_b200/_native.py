@@ -12,7 +12,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("HH_LIB_PATH") or os.path.join(CSRC, "libhhmarl_b200.so")
-SOURCES = ["hh_api.cu", "hh_hier.cu"]
+SOURCES = ["hh_api.cu", "hh_hier.cu", "hh_policy.cu"]
 HEADERS = ["hh_quad.cuh", "hh_cta.cuh", "hh_v4.cuh", "hh_state_pack.h", "hh_core.cuh", "hh_geodesic.cuh", os.path.join("..", "..", "include", "hhmarl_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
@@ -57,6 +57,11 @@ class HHHierArena(ctypes.Structure):
                 + [("dc", ctypes.c_uint32), ("ca", ctypes.c_int8 * 6)]
                 + [(n, ctypes.c_uint8 * 6) for n in ("alive", "hasm", "actype", "ralive", "rage", "rtgt", "ota_n")]
                 + [("ota_id", (ctypes.c_uint8 * 3) * 6)])
+
+
+class HHPolicyChain(ctypes.Structure):
+    _fields_ = ([(n, VP) for n in ("x", "w1", "b1", "watt", "batt", "wh", "bh", "out")]
+                + [(n, I32) for n in ("ldx", "d_in", "k1_pad", "att_lo", "att_n", "att_pad", "n_out", "ld_out")])
 
 
 class HHStateView(ctypes.Structure):
@@ -155,6 +160,9 @@ def bind(L: ctypes.CDLL, partial: bool = False) -> ctypes.CDLL:
     L.hh_sample_actions.restype = ctypes.c_int
     L.hh_pack_central.argtypes = [I32, I32, I32, VP, VP, VP, VP, VP]
     L.hh_pack_central.restype = ctypes.c_int
+    L.hh_policy_forward.argtypes = [I32, P(HHPolicyChain), VP, VP, I32, VP]
+    L.hh_policy_forward.restype = ctypes.c_int
+    L.hh_policy_last_error.restype = ctypes.c_char_p
     L.hh_debug_geodesic.argtypes = [I32, I32, VP, VP]
     L.hh_debug_geodesic.restype = ctypes.c_int
     L.hh_hier_create.argtypes = [P(HHHierConfig), I32, I32, P(VP)]
@@ -181,14 +189,15 @@ def bind(L: ctypes.CDLL, partial: bool = False) -> ctypes.CDLL:
 
 
 EXPORTS = ["hh_create", "hh_destroy", "hh_n_arenas", "hh_obs_dim", "hh_reset", "hh_step", "hh_step_begin", "hh_step_finish", "hh_reset_host",
-           "hh_step_host", "hh_host_buffers", "hh_set_host_mode", "hh_get_state", "hh_set_state", "hh_launch_count", "hh_gae", "hh_gae_agents", "hh_sample_actions", "hh_pack_central", "hh_debug_geodesic", "hh_last_error", "hh_version",
+           "hh_step_host", "hh_host_buffers", "hh_set_host_mode", "hh_get_state", "hh_set_state", "hh_launch_count", "hh_gae", "hh_gae_agents", "hh_sample_actions", "hh_pack_central", "hh_debug_geodesic", "hh_last_error", "hh_version", "hh_policy_forward", "hh_policy_last_error",
            "hh_hier_create", "hh_hier_destroy", "hh_hier_reset", "hh_hier_begin", "hh_hier_agents", "hh_hier_tick",
            "hh_hier_end", "hh_hier_get_state", "hh_hier_set_state", "hh_hier_launch_count", "hh_hier_last_error"]
 
 
 def check(rc: int, what: str):
     if rc != 0:
-        msg = (lib().hh_hier_last_error() if what.startswith("hh_hier") else lib().hh_last_error()).decode()
+        msg = (lib().hh_hier_last_error() if what.startswith("hh_hier") else
+               lib().hh_policy_last_error() if what.startswith("hh_policy") else lib().hh_last_error()).decode()
         if rc == -1:
             raise ValueError(f"{what}: {msg}")
         raise RuntimeError(f"{what}: {msg} (code {rc})")

@@ -15,9 +15,12 @@ tests/test_models.py (CPU) to ~1e-6.
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 import torch.nn.functional as F
 
+from . import _native as nat
 from . import models as M
 
 
@@ -129,3 +132,115 @@ class PackedPolicyPair:
         l2 = torch.addmm(self.bact[1], Z[2 * B:3 * B], self.Wact[1])
         v2 = torch.addmm(self.bval[1], Z[3 * B:], self.Wval[1])[:, 0]
         return l1, v1, l2, v2
+
+
+class FusedPolicyPair:
+    """The same forward as PackedPolicyPair.forward in ONE launch of the hand-written kernel csrc/hh_policy.cu
+    (C ABI hh_policy_forward): per 64-row tile and chain the activations stay in shared memory, every GEMM runs on
+    the tensor cores as 3xTF32 (fp32-equivalent, precision=0) or plain TF32 (precision=1).  Weights are re-packed
+    into the zero-padded layouts the kernel expects; `refresh()` re-packs in place (CUDA-graph safe)."""
+
+    NP, NW, NH = 504, 512, 32     # K extent / N extent (row stride) of the 500-wide layers, head width
+
+    def __init__(self, model1, model2, precision: int = 0):
+        self.packed = PackedPolicyPair(model1, model2)
+        self.fight = self.packed.fight
+        self.precision = int(precision)
+        self.dev = next(model1.parameters()).device
+        self._alloc()
+        self._fill()
+        self._out = None
+
+    def _alloc(self):
+        z = lambda *shape: torch.zeros(shape, device=self.dev, dtype=torch.float32)  # noqa: E731
+        self.k1_pad = [((w.shape[0] + 7) // 8) * 8 for w in self.packed.W1]
+        self.w1 = [[z(self.k1_pad[p], self.NW) for _ in range(2)] for p in range(2)]      # [policy][actor, critic]
+        self.b1 = [[z(self.NW) for _ in range(2)] for p in range(2)]
+        self.att = [(400, 100, 104), (350, 150, 152)]                                     # (att_lo, att_n, att_pad)
+        self.watt = [[z(self.att[k][2], self.att[k][2]) for k in range(2)] for p in range(2)] if self.fight else None
+        self.batt = [[z(self.att[k][2]) for k in range(2)] for p in range(2)] if self.fight else None
+        self.wh = [[z(self.NP, self.NH) for _ in range(2)] for p in range(2)]
+        self.bh = [[z(self.NH) for _ in range(2)] for p in range(2)]
+        self.ws, self.bs = z(self.NP, self.NW), z(self.NW)
+
+    @staticmethod
+    def _to_fragments(dst: torch.Tensor, w: torch.Tensor):
+        """Row-major zero-padded [K, N] -> MMA fragment order [K/8][N/8][lane = 4 g + t][(b0, b1)] with
+        b0 = w[8 ks + t, 8 nt + g], b1 = w[8 ks + t + 4, 8 nt + g] (in place into dst, same number of elements)."""
+        K, N = w.shape
+        v = w.reshape(K // 8, 2, 4, N // 8, 8).permute(0, 3, 4, 2, 1)      # (ks, q, t, nt, g) -> (ks, nt, g, t, q)
+        dst.view(-1).copy_(v.reshape(-1))
+
+    @torch.no_grad()
+    def _fill(self):
+        self._fill_row_major()
+        for p in range(2):
+            for k in range(2):
+                self._to_fragments(self.w1[p][k], self._rm["w1"][p][k])
+                self._to_fragments(self.wh[p][k], self._rm["wh"][p][k])
+                if self.fight:
+                    self._to_fragments(self.watt[p][k], self._rm["watt"][p][k])
+        self._to_fragments(self.ws, self._rm["ws"])
+
+    @torch.no_grad()
+    def _fill_row_major(self):
+        """Zero-padded row-major copies (staging for _to_fragments; the kernel reads the fragment-ordered tensors)."""
+        if not hasattr(self, "_rm"):
+            self._rm = {"w1": [[torch.zeros_like(t) for t in row] for row in self.w1],
+                        "wh": [[torch.zeros_like(t) for t in row] for row in self.wh],
+                        "watt": [[torch.zeros_like(t) for t in row] for row in self.watt] if self.fight else None,
+                        "ws": torch.zeros_like(self.ws)}
+        rm = self._rm
+        pk = self.packed
+        for p in range(2):
+            D = pk.W1[p].shape[0]
+            for k, cols in enumerate((slice(0, 500), slice(500, 1000))):
+                rm["w1"][p][k][:D, :500].copy_(pk.W1[p][:, cols])
+                self.b1[p][k][:500].copy_(pk.b1[p][cols])
+            if self.fight:
+                for k, blk in enumerate((slice(0, 100), slice(100, 250))):
+                    n = self.att[k][1]
+                    rm["watt"][p][k][:n, :n].copy_(pk.Watt[p][blk, blk])
+                    self.batt[p][k][:n].copy_(pk.batt[p][blk])
+            n_act = pk.Wact[p].shape[1]
+            rm["wh"][p][0][:500, :n_act].copy_(pk.Wact[p])
+            self.bh[p][0][:n_act].copy_(pk.bact[p])
+            rm["wh"][p][1][:500, :1].copy_(pk.Wval[p])
+            self.bh[p][1][:1].copy_(pk.bval[p])
+        rm["ws"][:500, :500].copy_(pk.Ws)
+        self.bs[:500].copy_(pk.bs)
+
+    @torch.no_grad()
+    def refresh(self):
+        self.packed.refresh()
+        self._fill()
+
+    @torch.no_grad()
+    def forward(self, flat1, flat2, out=None):
+        """-> (logits1 [B,26|..], value1 [B], logits2, value2); `out` = preallocated tuple of the same tensors."""
+        B = flat1.shape[0]
+        n_act = [self.packed.Wact[p].shape[1] for p in range(2)]
+        if out is None:
+            if self._out is None or self._out[0].shape[0] != B:
+                self._out = (torch.empty((B, n_act[0]), device=self.dev), torch.empty((B,), device=self.dev),
+                             torch.empty((B, n_act[1]), device=self.dev), torch.empty((B,), device=self.dev))
+            out = self._out
+        chains = (nat.HHPolicyChain * 4)()
+        for p, x in enumerate((flat1, flat2)):
+            assert x.is_contiguous() and x.dtype == torch.float32 and x.is_cuda
+            for k in range(2):
+                c = chains[2 * p + k]
+                c.x, c.w1, c.b1 = x.data_ptr(), self.w1[p][k].data_ptr(), self.b1[p][k].data_ptr()
+                if self.fight:
+                    c.watt, c.batt = self.watt[p][k].data_ptr(), self.batt[p][k].data_ptr()
+                    c.att_lo, c.att_n, c.att_pad = self.att[k]
+                else:
+                    c.watt, c.batt, c.att_lo, c.att_n, c.att_pad = None, None, 0, 0, 0
+                c.wh, c.bh = self.wh[p][k].data_ptr(), self.bh[p][k].data_ptr()
+                o = out[2 * p + k]
+                c.out, c.ld_out, c.n_out = o.data_ptr(), (o.shape[1] if o.dim() == 2 else 1), (n_act[p] if k == 0 else 1)
+                c.ldx, c.d_in, c.k1_pad = x.stride(0), x.shape[1], self.k1_pad[p]
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        nat.check(nat.lib().hh_policy_forward(B, chains, self.ws.data_ptr(), self.bs.data_ptr(), self.precision, st),
+                  "hh_policy_forward")
+        return out

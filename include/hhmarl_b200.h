@@ -146,6 +146,25 @@ int hh_pack_central(int32_t n_arenas, int32_t d1, int32_t d2, const float* obs1_
  *   mode 0: direct  (lat1, lon1, azi1 [deg], s12 [m]) -> (lat2, lon2)
  *   mode 1: inverse (lat1, lon1, lat2, lon2)          -> (s12 [m], azi1 [deg])   exact series
  *   mode 2: inverse, local closed form used for threshold decisions (same outputs) */
+/* ---- fused forward of the sampler's network chains (models/ac_models_hetero.py:86-103, 256-291, 368-404; the
+ * Policy.compute_actions -> TorchModelV2.forward call of the rollout worker).
+ * One chain = x [n_rows, d_in] -> tanh(x W1 + b1) [500] -> optional single-token attention block on columns
+ * [att_lo, 500) (residual + L2 normalisation) -> tanh(. Ws + bs) with the shared 500x500 layer -> head [n_out].
+ * Weight matrices are [in, out], zero-padded -- w1 [k1_pad, 512], watt [att_pad, att_pad], ws [504, 512],
+ * wh [504, 32] -- and stored in MMA FRAGMENT ORDER: [in / 8][out / 8][lane = 4 (out % 8) + (in % 4)][(in % 8) / 4],
+ * i.e. the (b0, b1) operand pair of mma.m16n8k8 of every lane, block by block.  Biases are plain vectors: b1 [512],
+ * batt [att_pad], bs [512], bh [32]; att_n = 0 means no attention block (Esc1 / Esc2).
+ * The four chains (policy 1 actor, policy 1 critic, policy 2 actor, policy 2 critic) run in ONE launch.
+ * precision 0: 3xTF32 tensor-core products (fp32-equivalent results); 1: plain TF32. */
+typedef struct {
+  const float *x, *w1, *b1, *watt, *batt, *wh, *bh;   /* device pointers */
+  float* out;                                         /* [n_rows, ld_out], first n_out columns written */
+  int32_t ldx, d_in, k1_pad, att_lo, att_n, att_pad, n_out, ld_out;
+} hh_policy_chain;
+int hh_policy_forward(int32_t n_rows, const hh_policy_chain* chains /* host array of 4 */, const float* ws_dev,
+                      const float* bs_dev, int32_t precision, void* stream);
+const char* hh_policy_last_error(void);
+
 int hh_debug_geodesic(int32_t mode, int32_t n, const double* in_host, double* out_host);
 
 const char* hh_last_error(void);

@@ -126,3 +126,55 @@ def test_native_multicategorical_sampler():
     assert torch.equal(a, c)                                       # same counters -> same draws
     d, _ = call(0, ctr)
     assert (d[:, 0, :].long() == M.deterministic_actions(l1, 1)).all() and (d[:, 1, :3].long() == M.deterministic_actions(l2, 2)).all()
+
+
+@pytest.mark.parametrize("mode", ["fight", "escape"])
+def test_fused_policy_forward_matches_torch(mode):
+    """csrc/hh_policy.cu (one launch: both policies' actor + central critic) against the fp32 torch forward of
+    models.py and the packed cuBLAS forward: 3xTF32 reproduces fp32 to ~1e-5, plain TF32 to ~1e-2; ragged batch."""
+    from hhmarl_2d_b200 import models as M
+    from hhmarl_2d_b200.fused_forward import FusedPolicyPair, PackedPolicyPair
+    torch.manual_seed(1)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        m1, m2 = M.build_policy_pair(mode)
+        m1.cuda(); m2.cuda()
+        for m in (m1, m2):                       # non-trivial biases (the initialiser sets them to zero)
+            for prm in m.parameters():
+                if prm.dim() == 1:
+                    torch.nn.init.normal_(prm, std=0.1)
+        B = 1000 + 37
+        d = m1.central_dim
+        f1 = torch.rand(B, d, device="cuda")
+        f2 = torch.rand(B, d, device="cuda")
+        f1[:, :7] = 0; f2[:, :7] = 0            # the sampler feeds zero actions (SURVEY A.6.15) ...
+        f1[5:50, :7] = torch.rand(45, 7, device="cuda")   # ... the learner real ones
+        with torch.no_grad():
+            rl1, rv1 = m1.forward_flat(f1)
+            rl2, rv2 = m2.forward_flat(f2)
+        ref = (rl1, rv1, rl2, rv2)
+        pk = PackedPolicyPair(m1, m2).forward(f1, f2)
+        for a, b in zip(pk, ref):
+            assert torch.allclose(a, b, atol=2e-5, rtol=1e-5)
+        for prec, atol in ((0, 3e-5), (1, 2e-2)):
+            fu = FusedPolicyPair(m1, m2, precision=prec)
+            out = [o.clone() for o in fu.forward(f1, f2)]
+            for name, a, b in zip(("logits1", "value1", "logits2", "value2"), out, ref):
+                assert a.shape == b.shape and torch.isfinite(a).all()
+                err = (a - b).abs().max().item()
+                assert err <= atol, (mode, prec, name, err)
+            # weights changed by the learner -> refresh() re-packs in place
+            with torch.no_grad():
+                m1.act_out._model[0].weight.mul_(0.5)
+                m1.shared_layer._model[0].bias.add_(0.01)
+            fu.refresh()
+            with torch.no_grad():
+                nl1, nv1 = m1.forward_flat(f1)
+            out = fu.forward(f1, f2)
+            assert (out[0] - nl1).abs().max().item() <= atol and (out[1] - nv1).abs().max().item() <= atol
+            with torch.no_grad():
+                m1.act_out._model[0].weight.mul_(2.0)
+                m1.shared_layer._model[0].bias.sub_(0.01)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
