@@ -430,10 +430,13 @@ __device__ __forceinline__ int unit_observation(const Lane& L, const World& W, c
 // LowLevelEnv.reset (env_hetero.py:53-60).  Each lane samples its own aircraft; the G-stream
 // draw order of the reference is r, then per unit (x, y[, heading]) in id order, then (level 5,
 // fight) k -- so every lane knows its draw indices without communication.
-__device__ __forceinline__ void reset_lane(Lane& L, const Rng& rng, const Params& P, int u) {
+// `next(i)` returns G-stream draw number i (absolute index): computed on the spot (reset_lane below) or read from a
+// table that several threads filled in parallel (hh_v4.cuh).
+template <class NextDraw>
+__device__ __forceinline__ void reset_lane_g(Lane& L, NextDraw next, const Params& P, int u) {
   const int level = P.level;
   const unsigned long long base = L.dg;
-  const int r = randint_from(1, 2, g_random_at(rng, base));
+  const int r = randint_from(1, 2, next(base));
   const int opp_draws = level == 1 ? 2 : 3;
   const int off = u == 0 ? 0 : (u == 1 ? 3 : (u == 2 ? 6 : 6 + opp_draws));
   const unsigned long long d = base + 1 + off;
@@ -444,16 +447,16 @@ __device__ __forceinline__ void reset_lane(Lane& L, const Rng& rng, const Params
   else { xw0 = 7.07; xw1 = 7.12; xe0 = 7.18; xe1 = 7.23; y0 = 5.09; y1 = 5.12; }
   const bool west = (group == 0) == (r == 1);  // agents start west when r == 1, opponents east
   const double di = (double)i * 0.1;
-  const double x = west ? uniform_from(xw0, xw1, g_random_at(rng, d)) : uniform_from(xe0, xe1, g_random_at(rng, d));
-  const double y = uniform_from(__dadd_rn(y0, di), __dadd_rn(y1, di), g_random_at(rng, d + 1));
+  const double x = west ? uniform_from(xw0, xw1, next(d)) : uniform_from(xe0, xe1, next(d));
+  const double y = uniform_from(__dadd_rn(y0, di), __dadd_rn(y1, di), next(d + 1));
   int a = 0;
   if (group == 0) {
-    const double rr = g_random_at(rng, d + 2);
+    const double rr = next(d + 2);
     if (level == 1) a = r == 1 ? randint_from(30, 150, rr) : randint_from(200, 330, rr);
     else if (level == 2) a = r == 1 ? randint_from(0, 180, rr) : randint_from(180, 359, rr);
     else a = r == 1 ? randint_from(0, 270, rr) : randint_from(90, 359, rr);
   } else if (level >= 2) {
-    a = randint_from(0, 359, g_random_at(rng, d + 2));
+    a = randint_from(0, 359, next(d + 2));
   }
   L.lat = y;
   L.lon = x;
@@ -476,12 +479,16 @@ __device__ __forceinline__ void reset_lane(Lane& L, const Rng& rng, const Params
   L.pset = 0; L.opp_mode = 0;
   unsigned long long used = 1 + 6 + 2 * opp_draws;
   if (level == 5 && P.agent_mode == 0) {
-    const int k = randint_from(3, 5, g_random_at(rng, base + used));
+    const int k = randint_from(3, 5, next(base + used));
     used += 1;
     L.pset = k;
     L.opp_mode = k == 5 ? 1 : 0;
   }
   L.dg = base + used;
+}
+
+__device__ __forceinline__ void reset_lane(Lane& L, const Rng& rng, const Params& P, int u) {
+  reset_lane_g(L, [&rng](unsigned long long i) { return g_random_at(rng, i); }, P, u);
 }
 
 }  // namespace hh

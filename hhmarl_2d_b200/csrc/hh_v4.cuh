@@ -65,6 +65,7 @@ struct Smem {
   unsigned char alive[A4], hasm[A4], upd[A4], firing[A4], launched[A4], shot[A4], oob[A4];
   unsigned char ralive[A2], rocket0[A2], hit_t[A2], hit_f[A2], exploded[A2];
   unsigned char want0[A1];
+  int any_reset;                        // some arena of the CTA auto-resets in this launch
 };
 
 struct Ctx {
@@ -109,6 +110,19 @@ __device__ __forceinline__ int sm_nearest(const Smem& S, const Geom& g, int b, i
   return best;
 }
 
+// Bulky code that a stage executes rarely is kept OUT OF LINE: a stage's common path then is a compact, sequential
+// instruction stream (the step is bound by instruction fetch), not a series of jumps over it.
+static __device__ __noinline__ bool cold_cannon_range(double lat_s, double lon_s, double hdg_s, double lat_t, double lon_t,
+                                                      double range_km, double half_width) {
+  return unit_in_cannon_range(lat_s, lon_s, hdg_s, lat_t, lon_t, range_km, half_width);
+}
+static __device__ __noinline__ bool cold_within_1km(double lat_r, double lon_r, double lat_t, double lon_t) {
+  return within_1km(lat_r, lon_r, lat_t, lon_t);
+}
+static __device__ __noinline__ bool cold_launch_gate(double lat_s, double lon_s, double hdg_s, double lat_t, double lon_t) {
+  return launch_gate(lat_s, lon_s, hdg_s, lat_t, lon_t);
+}
+
 // ===================================================================================== S0: load
 __device__ __forceinline__ void s0_load_unit(const Ctx& C, int t) {
   Smem& S = C.S;
@@ -128,6 +142,7 @@ __device__ __forceinline__ void s0_load_unit(const Ctx& C, int t) {
     S.alive_ag[al] = L.alive_ag; S.alive_op[al] = L.alive_op; S.esc_time[al] = L.esc_time; S.next_id[al] = L.next_id;
     S.pset[al] = L.pset; S.opp_mode[al] = L.opp_mode; S.err[al] = L.err; S.escaping[al] = L.escaping;
     S.dg[al] = L.dg; S.dg0[al] = L.dg; S.dc[al] = L.dc;
+    if (al == 0) S.any_reset = 0;
   }
 }
 __device__ __forceinline__ void s0_load_actions(const Ctx& C, int t) {
@@ -194,7 +209,7 @@ __device__ __forceinline__ void s1_sign_offsets(const Ctx& C, int t) {
 __device__ __forceinline__ void launch(Smem& S, int us, int rs, int b, int tgt) {
   if (!S.hasm[us] && S.mrem[us] > 0) {
     const int tq = tgt < 0 ? 0 : tgt;
-    if (launch_gate(S.lat[us], S.lon[us], S.hdg[us], S.lat[b + tq], S.lon[b + tq])) {
+    if (cold_launch_gate(S.lat[us], S.lon[us], S.hdg[us], S.lat[b + tq], S.lon[b + tq])) {
       S.rlat[rs] = S.lat[us]; S.rlon[rs] = S.lon[us]; S.rhdg[rs] = S.hdg[us]; S.rnhdg[rs] = S.hdg[us];
       S.ralive[rs] = 1; S.rage[rs] = 0; S.rtgt[rs] = tq + 1;
       S.hasm[us] = 1;
@@ -365,7 +380,7 @@ __device__ __forceinline__ void s5_cannon(const Ctx& C, int t) {
       cand &= cand - 1;
       const double jl = j < u ? S.nlat[ub + j] : S.lat[ub + j];
       const double jo = j < u ? S.nlon[ub + j] : S.lon[ub + j];
-      if (unit_in_cannon_range(S.lat[t], S.lon[t], S.hdg[t], jl, jo, range, half_w)) in_range |= 1 << j;
+      if (cold_cannon_range(S.lat[t], S.lon[t], S.hdg[t], jl, jo, range, half_w)) in_range |= 1 << j;
     }
   }
   S.inr[t] = in_range;
@@ -381,13 +396,37 @@ __device__ __forceinline__ void s5_rocket(const Ctx& C, int t) {
   if (S.rocket0[t]) {
     const int tq = S.rtgt[t] > 0 ? S.rtgt[t] - 1 : 0;
     ht = maybe_within_km(S.rlat[t], S.rlon[t], S.nlat[b + tq], S.nlon[b + tq], 1.0) &&
-         within_1km(S.rlat[t], S.rlon[t], S.nlat[b + tq], S.nlon[b + tq]);
+         cold_within_1km(S.rlat[t], S.rlon[t], S.nlat[b + tq], S.nlon[b + tq]);
     if (C.P.friendly_kill)   // "friendly" is always id 2
       hf = maybe_within_km(S.rlat[t], S.rlon[t], S.nlat[b + 1], S.nlon[b + 1], 1.0) &&
-           within_1km(S.rlat[t], S.rlon[t], S.nlat[b + 1], S.nlon[b + 1]);
+           cold_within_1km(S.rlat[t], S.rlon[t], S.nlat[b + 1], S.nlon[b + 1]);
   }
   S.hit_t[t] = ht;
   S.hit_f[t] = hf;
+}
+
+// cannon kill resolution in (shooter, target) id order; C-stream draws only for live in-range targets (ac1.py:105-115)
+__device__ __forceinline__ void cold_kill_resolution(const Ctx& C, int al, int& alive_m, unsigned& killer_pack) {
+  Smem& S = C.S;
+  const int b = al * 4;
+  const Rng rng = C.rng(al);
+  unsigned dc = S.dc[al];
+#pragma unroll 1
+  for (int k = 0; k < 4; ++k) {
+    const int row = S.inr[b + k];
+    if (row == 0) continue;
+    const double p_hit = (k & 1) ? 0.9 / (3.0 / 1.0) : 0.75 / (5.0 / 1.0);
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      if (((row >> j) & 1) && ((alive_m >> j) & 1)) {
+        if (c_random_at(rng, dc++) < p_hit) {
+          alive_m &= ~(1 << j);
+          killer_pack |= (unsigned)(k + 1) << (4 * j);
+        }
+      }
+    }
+  }
+  S.dc[al] = dc;
 }
 
 // ===================================================================================== S6: resolution (arena-mapped)
@@ -400,29 +439,7 @@ __device__ __forceinline__ void s6_resolve(const Ctx& C, int t) {
   const int al = t, b = al * 4;
   int alive_m = S.alive_pre[al];
   unsigned killer_pack = 0;      // 4 bits per victim: killer id (0 = none)
-  {
-    const int any = S.inr[b] | S.inr[b + 1] | S.inr[b + 2] | S.inr[b + 3];
-    if (any) {
-      const Rng rng = C.rng(al);
-      unsigned dc = S.dc[al];
-#pragma unroll 1
-      for (int k = 0; k < 4; ++k) {
-        const int row = S.inr[b + k];
-        if (row == 0) continue;
-        const double p_hit = (k & 1) ? 0.9 / (3.0 / 1.0) : 0.75 / (5.0 / 1.0);
-#pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
-          if (((row >> j) & 1) && ((alive_m >> j) & 1)) {
-            if (c_random_at(rng, dc++) < p_hit) {
-              alive_m &= ~(1 << j);
-              killer_pack |= (unsigned)(k + 1) << (4 * j);
-            }
-          }
-        }
-      }
-      S.dc[al] = dc;
-    }
-  }
+  if (S.inr[b] | S.inr[b + 1] | S.inr[b + 2] | S.inr[b + 3]) cold_kill_resolution(C, al, alive_m, killer_pack);
   // missile bookkeeping of the shooters (ac1.py:117-128); the noise itself was applied in S4
   {
     int noise = 0;
@@ -549,6 +566,7 @@ __device__ __forceinline__ void s6_resolve(const Ctx& C, int t) {
   S.alive_fin[al] = alive_m;
   const bool done = alive_ag <= 0 || alive_op <= 0 || S.steps[al] >= P.horizon;
   S.done[al] = done ? 1 : 0;
+  if (done && P.autoreset) S.any_reset = 1;      // every writer stores the same value
   if (al < C.n_valid) {
     const int a = C.arena0 + al;
     if (C.rew_out) reinterpret_cast<float2*>(C.rew_out)[a] = make_float2((float)r0, (float)r1);
@@ -571,14 +589,34 @@ __device__ __forceinline__ void unit_features(const Ctx& C, int t) {
   S.shot[t] = S.burst[t] > 0 || (is_ac1(u) && S.hasm[t]);      // env_base.py:208-211
 }
 // HHMARLBaseEnv.reset for one unit of arena al (reset_lane, hh_quad.cuh); arena scalars by unit 0
-__device__ __forceinline__ void reset_unit(const Ctx& C, int t, unsigned long long dg, unsigned int dc, int err) {
+// in-launch auto-reset: the 16 G draws from dg on were prepared by s7a_reset_draws (8 threads per arena)
+__device__ __forceinline__ void s7a_reset_draws(const Ctx& C, int t) {
+  Smem& S = C.S;
+  const int al = t >> 3, j = (t & 7) * 2;
+  if (!(S.done[al] && C.P.autoreset)) return;
+  const Rng rng = C.rng(al);
+  const unsigned long long base = S.dg[al] + (unsigned long long)j;
+  S.rnd[al * kDraws + j] = g_random_at(rng, base);
+  S.rnd[al * kDraws + j + 1] = g_random_at(rng, base + 1);
+}
+// (forceinline: a noinline callee taking the context by reference forces Ctx -- and with it every stage's accesses to
+// it -- into local memory: 552-byte stack frame, launch 24 -> 32 us, profiles/r1o_*)
+__device__ __forceinline__ void reset_unit(const Ctx& C, int t, unsigned long long dg, unsigned int dc, int err,
+                                           bool from_table) {
   Smem& S = C.S;
   const int al = t >> 2, u = t & 3;
   Lane L;
   L.dg = dg;
   L.dc = dc;
   L.err = err;
-  reset_lane(L, C.rng(al), C.P, u);
+  if (from_table) {
+    const double* tab = S.rnd + al * kDraws;
+    const Rng rng = C.rng(al);
+    reset_lane_g(L, [tab, dg, &rng](unsigned long long i) { return i - dg < (unsigned long long)kDraws ? tab[i - dg] : g_random_at(rng, i); },
+                 C.P, u);
+  } else {
+    reset_lane(L, C.rng(al), C.P, u);
+  }
   S.lat[t] = L.lat; S.lon[t] = L.lon; S.hdg[t] = L.hdg; S.spd[t] = L.spd; S.nhdg[t] = L.nhdg; S.nspd[t] = L.nspd;
   S.crem[t] = L.crem; S.burst[t] = 0; S.cmax[t] = L.cmax; S.mrem[t] = L.mrem; S.rmax[t] = L.rmax; S.mwait[t] = 0;
   S.alive[t] = 1; S.hasm[t] = 0; S.ota[t] = 0;
@@ -595,7 +633,7 @@ __device__ __forceinline__ void s7_commit_unit(const Ctx& C, int t) {
   Smem& S = C.S;
   const int al = t >> 2, u = t & 3;
   if (S.done[al] && C.P.autoreset) {
-    reset_unit(C, t, S.dg[al], S.dc[al], S.err[al]);
+    reset_unit(C, t, S.dg[al], S.dc[al], S.err[al], true);
   } else {
     if (S.upd[t]) {
       S.lat[t] = S.nlat[t];
@@ -698,10 +736,6 @@ __device__ __forceinline__ void s9_rows(const Ctx& C, int t) {
     const int lo = part == 0 ? 0 : (part == 1 ? n_own : n_own + n_enemy);
     const int hi = part == 0 ? n_own : (part == 1 ? n_own + n_enemy : n_own + n_enemy + 5);
     for (int k = lo; k < hi; ++k) row[k] = 0.0f;
-    if (part == 0) {
-      S.ota[us] = 0;
-      S.ota[b + 2 + au] = 0;    // opponents' opp_to_attack stays None at levels 1-3
-    }
     return;
   }
   const double* pf = S.pf + al * kPF + au * 3;
@@ -727,8 +761,6 @@ __device__ __forceinline__ void s9_rows(const Ctx& C, int t) {
       if (au == 0) out[n++] = (float)clip((double)S.mrem[us] / (double)S.rmax[us], 0.0, 1.0);
       out[n++] = S.shot[us] ? 1.0f : 0.0f;
     }
-    S.ota[us] = o + 1;
-    S.ota[b + 2 + au] = 0;
   } else if (part == 1) {
     float* out = row + n_own;
     int n = put_unit(S, b + o, out);
@@ -802,11 +834,12 @@ __device__ __forceinline__ void s10_store_unit(const Ctx& C, int t) {
   }
   if (u == 0) {
     // agents store target id - 2, opponents the id itself (load_lane)
+    // opp_to_attack after lowlevel_state: the agents' nearest enemy (S8), None for the opponents at levels 1-3
     uint32_t packed = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int o = S.ota[b + k];
-      packed |= (uint32_t)(o == 0 ? 0 : (k < 2 ? o - 2 : o)) << (2 * k);
+    for (int k = 0; k < 2; ++k) {
+      const int o = S.po[b + k * 2];          // enemy unit 2 / 3, or -1
+      packed |= (uint32_t)(o < 0 ? 0 : o - 1) << (2 * k);
     }
     uint4 m;
     m.x = (uint32_t)S.steps[al] | ((uint32_t)S.alive_ag[al] << 16) | ((uint32_t)S.alive_op[al] << 20) |
@@ -899,6 +932,10 @@ __device__ __forceinline__ void step_body(Smem& S, const StatePtrs& G, const Par
   HH_ROLE(0, A1, s6_resolve<MODE>(C, t))
   HH_BARRIER();
   HH_MARK(6)
+  if (S.any_reset) {                 // CTA-uniform (written before the barrier above)
+    HH_ROLE(0, A8, s7a_reset_draws(C, t))
+    HH_BARRIER();
+  }
   HH_ROLE(0, A4, s7_commit_unit(C, t))
   HH_ROLE(A4, A2, s7_commit_rocket(C, t))
   HH_BARRIER();
@@ -909,7 +946,7 @@ __device__ __forceinline__ void step_body(Smem& S, const StatePtrs& G, const Par
   HH_ROLE(0, 3 * A2, s9_rows<MODE>(C, t))
   HH_BARRIER();
   HH_MARK(9)
-  HH_ROLE(0, A4, s10_store_unit(C, t))
+  HH_ROLE(0, A4, s10_store_unit(C, t))     // (storing the state during S9 instead was measured slower: r1o)
   HH_ROLE(0, A8, s10_store_rows(C, t, A8, D1, D2))
   HH_MARK(10)
 }
@@ -927,13 +964,13 @@ __device__ __forceinline__ void r1_reset_unit(const Ctx& C, const uint8_t* mask,
   const int al = t >> 2;
   if (r_selected(C, mask, first_time, al)) {
     if (first_time) {
-      reset_unit(C, t, 0ull, 0u, 0);
+      reset_unit(C, t, 0ull, 0u, 0, false);
       if ((t & 3) == 0) {
         S.dc[al] = 0;
         S.err[al] = 0;
       }
     } else {
-      reset_unit(C, t, S.dg[al], S.dc[al], S.err[al]);
+      reset_unit(C, t, S.dg[al], S.dc[al], S.err[al], false);
     }
   } else {
     const HVec hv = heading_vec(S.hdg[t]);
