@@ -144,6 +144,10 @@ def bind(L: ctypes.CDLL, partial: bool = False) -> ctypes.CDLL:
     L.hh_step_host.restype = ctypes.c_int
     L.hh_host_buffers.argtypes = [VP] + [P(VP)] * 5
     L.hh_host_buffers.restype = ctypes.c_int
+    L.hh_step_host_begin.argtypes = [VP, VP]
+    L.hh_step_host_begin.restype = ctypes.c_int
+    L.hh_step_host_end.argtypes = [VP, VP, VP, VP, VP]
+    L.hh_step_host_end.restype = ctypes.c_int
     L.hh_set_host_mode.argtypes = [VP, I32]
     L.hh_set_host_mode.restype = ctypes.c_int
     L.hh_get_state.argtypes = [VP, P(HHStateView)]
@@ -189,7 +193,7 @@ def bind(L: ctypes.CDLL, partial: bool = False) -> ctypes.CDLL:
 
 
 EXPORTS = ["hh_create", "hh_destroy", "hh_n_arenas", "hh_obs_dim", "hh_reset", "hh_step", "hh_step_begin", "hh_step_finish", "hh_reset_host",
-           "hh_step_host", "hh_host_buffers", "hh_set_host_mode", "hh_get_state", "hh_set_state", "hh_launch_count", "hh_gae", "hh_gae_agents", "hh_sample_actions", "hh_pack_central", "hh_debug_geodesic", "hh_last_error", "hh_version", "hh_policy_forward", "hh_policy_last_error",
+           "hh_step_host", "hh_step_host_begin", "hh_step_host_end", "hh_host_buffers", "hh_set_host_mode", "hh_get_state", "hh_set_state", "hh_launch_count", "hh_gae", "hh_gae_agents", "hh_sample_actions", "hh_pack_central", "hh_debug_geodesic", "hh_last_error", "hh_version", "hh_policy_forward", "hh_policy_last_error",
            "hh_hier_create", "hh_hier_destroy", "hh_hier_reset", "hh_hier_begin", "hh_hier_agents", "hh_hier_tick",
            "hh_hier_end", "hh_hier_get_state", "hh_hier_set_state", "hh_hier_launch_count", "hh_hier_last_error"]
 

@@ -764,6 +764,7 @@ struct hh_env {
   void* pinned = nullptr;
   void* pinned_dev = nullptr;   // device-side address of the pinned slab (zero-copy host mode)
   size_t pinned_bytes = 0;
+  bool host_pending = false;    // a step enqueued by hh_step_host_begin has not been collected yet
   int host_mode = 1;            // 0: staged (H2D, launch, D2H); 1: zero-copy (kernels read / write the pinned slab)
 };
 
@@ -1149,14 +1150,17 @@ extern "C" int hh_reset_host(hh_env* e, const uint8_t* mask_host, float* obs1_ho
   return 0;
 }
 
-extern "C" int hh_step_host(hh_env* e, const int32_t* actions_host, float* obs1_host, float* obs2_host,
-                            float* rew_host, uint8_t* done_host) {
-  if (!e) return fail(-1, "hh_step_host: null env");
-  if (!actions_host) return fail(-1, "hh_step_host: null actions");
+// send / poll halves of a host step (RLlib's own asynchronous env interface is BaseEnv.send_actions() / poll()):
+// _begin enqueues the step on the handle's private stream and returns; _end waits for it and delivers the results.
+// Several handles (e.g. two halves of a batch) can be in flight at once, so that one handle's PCIe traffic and the
+// caller's preparation of the next actions overlap another handle's kernel.
+extern "C" int hh_step_host_begin(hh_env* e, const int32_t* actions_host) {
+  if (!e) return fail(-1, "hh_step_host_begin: null env");
+  if (!actions_host) return fail(-1, "hh_step_host_begin: null actions");
+  if (e->host_pending) return fail(-4, "hh_step_host_begin: the previous step was not collected (hh_step_host_end)");
   int rc = ensure_staging(e);
   if (rc) return rc;
   const size_t N = (size_t)e->n;
-  const int d1 = obs_dim(e->cfg, 1), d2 = obs_dim(e->cfg, 2);
   const HostLayout h = host_layout(e);
   char* pin = static_cast<char*>(e->pinned);
   if (reinterpret_cast<const char*>(actions_host) != pin + h.o_act) memcpy(pin + h.o_act, actions_host, N * 8 * sizeof(int32_t));
@@ -1174,12 +1178,31 @@ extern "C" int hh_step_host(hh_env* e, const int32_t* actions_host, float* obs1_
     if (rc) return rc;
     HH_CUDA(cudaMemcpyAsync(pin + h.o_obs1, e->d_obs1, h.out_bytes, cudaMemcpyDeviceToHost, e->hstream));
   }
+  e->host_pending = true;
+  return 0;
+}
+
+extern "C" int hh_step_host_end(hh_env* e, float* obs1_host, float* obs2_host, float* rew_host, uint8_t* done_host) {
+  if (!e) return fail(-1, "hh_step_host_end: null env");
+  if (!e->host_pending) return fail(-4, "hh_step_host_end: no step in flight (hh_step_host_begin)");
+  const size_t N = (size_t)e->n;
+  const int d1 = obs_dim(e->cfg, 1), d2 = obs_dim(e->cfg, 2);
+  const HostLayout h = host_layout(e);
+  char* pin = static_cast<char*>(e->pinned);
+  e->host_pending = false;
   HH_CUDA(cudaStreamSynchronize(e->hstream));
   if (obs1_host && reinterpret_cast<char*>(obs1_host) != pin + h.o_obs1) memcpy(obs1_host, pin + h.o_obs1, N * d1 * sizeof(float));
   if (obs2_host && reinterpret_cast<char*>(obs2_host) != pin + h.o_obs2) memcpy(obs2_host, pin + h.o_obs2, N * d2 * sizeof(float));
   if (rew_host && reinterpret_cast<char*>(rew_host) != pin + h.o_rew) memcpy(rew_host, pin + h.o_rew, N * 2 * sizeof(float));
   if (done_host && reinterpret_cast<char*>(done_host) != pin + h.o_done) memcpy(done_host, pin + h.o_done, N);
   return 0;
+}
+
+extern "C" int hh_step_host(hh_env* e, const int32_t* actions_host, float* obs1_host, float* obs2_host,
+                            float* rew_host, uint8_t* done_host) {
+  const int rc = hh_step_host_begin(e, actions_host);
+  if (rc) return rc;
+  return hh_step_host_end(e, obs1_host, obs2_host, rew_host, done_host);
 }
 
 // ------------------------------------------------------------------------------------------ state access

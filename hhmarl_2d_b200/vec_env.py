@@ -184,6 +184,26 @@ class VecLowLevelEnv:
                                          d.ctypes.data), "hh_step_host")
         return o1, o2, r, d
 
+    def send_actions_host(self, actions: np.ndarray):
+        """First half of step_host (RLlib BaseEnv.send_actions): enqueue the step, return immediately."""
+        a = np.ascontiguousarray(actions, np.int32)
+        if a.size != self.n_arenas * 8:
+            raise ValueError("actions must have shape [N, 2, 4]")
+        if self.level >= 4:
+            raise ValueError("send_actions_host / poll_host: levels 1-3 (levels 4/5 step through the tensor API)")
+        nat.check(nat.lib().hh_step_host_begin(self._h, a.ctypes.data), "hh_step_host_begin")
+
+    def poll_host(self, out=None):
+        """Second half (RLlib BaseEnv.poll): wait for the enqueued step -> (obs1, obs2, rew, done) host arrays."""
+        if out is None:
+            out = (np.empty((self.n_arenas, self.obs_dim[0]), np.float32),
+                   np.empty((self.n_arenas, self.obs_dim[1]), np.float32),
+                   np.empty((self.n_arenas, 2), np.float32), np.empty((self.n_arenas,), np.uint8))
+        o1, o2, r, d = out
+        nat.check(nat.lib().hh_step_host_end(self._h, o1.ctypes.data, o2.ctypes.data, r.ctypes.data, d.ctypes.data),
+                  "hh_step_host_end")
+        return o1, o2, r, d
+
     # ------------------------------------------------------------------ state access
     def _alloc_view(self):
         n = self.n_arenas

@@ -105,6 +105,11 @@ int hh_step_host(hh_env* env, const int32_t* actions_host, float* obs1_host, flo
 /* Pointers into the handle's own PINNED host slab (valid until hh_destroy): filling `actions` in place and
  * passing exactly these pointers to hh_step_host / hh_reset_host makes the call zero-copy on the host side
  * (one H2D of the actions, one D2H of obs1|obs2|rew|done, one stream synchronise). */
+/* The two halves of hh_step_host, for callers that keep several handles in flight (RLlib's asynchronous env
+ * interface BaseEnv.send_actions() / poll()): _begin enqueues the step on the handle's private stream and returns,
+ * _end waits for it and delivers the results.  At most one step per handle may be pending. */
+int hh_step_host_begin(hh_env* env, const int32_t* actions_host);
+int hh_step_host_end(hh_env* env, float* obs1_host, float* obs2_host, float* rew_host, uint8_t* done_host);
 int hh_host_buffers(hh_env* env, int32_t** actions, float** obs1, float** obs2, float** rew, uint8_t** done);
 /* How hh_reset_host / hh_step_host move data: 1 = zero-copy (default: the kernels read the actions from and write the
  * results to the handle's pinned slab through its device mapping), 0 = staged (one H2D of the actions, the launch,

@@ -334,6 +334,32 @@ def test_zero_copy_host_mode_matches_staged_host_mode():
             assert np.array_equal(sa[k], sb[k]), k
 
 
+def test_send_poll_on_two_handles_matches_one_synchronous_env():
+    """hh_step_host_begin / _end (send_actions / poll): two half-batch handles kept in flight together reproduce the
+    synchronous full-batch env bit for bit (arena_base makes the halves the same arenas); misuse is an error."""
+    n = 1024
+    full = _vec(n, 3, "fight", 17)
+    lo = _vec(n // 2, 3, "fight", 17, arena_base=0)
+    hi = _vec(n // 2, 3, "fight", 17, arena_base=n // 2)
+    f = full.reset_host(); a = lo.reset_host(); b = hi.reset_host()
+    assert np.array_equal(f[0], np.concatenate([a[0], b[0]])) and np.array_equal(f[1], np.concatenate([a[1], b[1]]))
+    rng = np.random.default_rng(2)
+    with pytest.raises(RuntimeError):
+        lo.poll_host()                                   # nothing in flight
+    for t in range(60):
+        act = np.stack([rng.integers(0, 13, (n, 2)), rng.integers(0, 9, (n, 2)), rng.integers(0, 2, (n, 2)),
+                        rng.integers(0, 2, (n, 2))], axis=-1).astype(np.int32)
+        lo.send_actions_host(act[:n // 2])
+        hi.send_actions_host(act[n // 2:])
+        if t == 3:
+            with pytest.raises(RuntimeError):
+                lo.send_actions_host(act[:n // 2])       # previous step not collected
+        f = full.step_host(act)
+        a = lo.poll_host(); b = hi.poll_host()
+        for x, y, z in zip(f, a, b):
+            assert np.array_equal(x, np.concatenate([y, z]))
+
+
 def test_state_round_trip_masked_reset_and_large_batch():
     import torch
     n = 4096
