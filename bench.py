@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-rollout", action="store_true")
     ap.add_argument("--no-hier", action="store_true")
+    ap.add_argument("--no-l5", action="store_true")
     return ap.parse_args()
 
 
@@ -330,7 +331,8 @@ def run_b200(args):
         hier = {"commander_steps_per_s": world * n * HS / (float(ht.item()) * 1e-3),
                 "sim_ticks_per_s": float(tk.item()) / (float(ht.item()) * 1e-3), "commander_steps": HS,
                 "mean_substeps": float(tk.item()) / (world * n * HS), "arenas_per_gpu": n,
-                "note": "HighLevelEnv 3-vs-3, 16 masked sub-steps x (2 launches + fight/escape actor batches), fp32 cuBLAS"}
+                "note": "HighLevelEnv 3-vs-3, 16 masked sub-steps x (2 env launches + 2 launches of csrc/hh_policy.cu: the frozen "
+                        "fight / escape actors of all six aircraft as gathered chains, 3xTF32, argmax in the epilogue)"}
         from hhmarl_2d_b200.env_hier import CommanderSampler
         from hhmarl_2d_b200 import models as MM
         cs = CommanderSampler(henv, MM.CommanderGru().to(dev), fragment_len=4)
@@ -348,6 +350,38 @@ def run_b200(args):
         del henv, cs
     except Exception as ex:  # noqa: BLE001
         hier = {"error": repr(ex)}
+
+    # ---- BASELINE configs 3/4: level-5 self-play (frozen fight / escape policy sets as opponents, one set per arena and
+    #      episode): hh_step_begin -> opponents' actors -> hh_step_finish, random agent actions, random-init weights
+    l5 = None
+    try:
+        if args.no_l5:
+            raise RuntimeError("skipped (--no-l5)")
+        l5 = {}
+        for tag, fused in (("fused_actors", True), ("torch_actors", False)):
+            env5 = VecLowLevelEnv(n, make_args(level=5), device=local, seed=3, arena_base=rank * n, autoreset=True)
+            env5.fused_opponents = fused
+            env5.reset()
+            for w in range(5):
+                env5.step(acts[w % n_act])
+            barrier()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            S5 = 40
+            q0.record()
+            for k in range(S5):
+                env5.step(acts[k % n_act])
+            q1.record()
+            barrier()
+            qt = torch.tensor([q0.elapsed_time(q1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(qt, op=dist.ReduceOp.MAX)
+            l5[tag] = {"value": world * n * S5 / (float(qt.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(qt.item()) / S5}
+            del env5
+        l5["note"] = ("level 5 (horizon 400): split step around the opponents' frozen actors (3 policy sets x 2 aircraft types); "
+                      "'fused_actors' = csrc/hh_policy.cu chains (one launch, 3xTF32, argmax in the epilogue), 'torch_actors' = "
+                      "per-set gather + per-layer cuBLAS forward")
+    except Exception as ex:  # noqa: BLE001
+        l5 = {"error": repr(ex)}
 
     # ---- end to end through the host entry point of the C ABI
     acts_host = acts.cpu().numpy()
@@ -461,6 +495,7 @@ def run_b200(args):
                         "other_host_mode": e2e_alt, "send_poll_two_handles": e2e_pipe},
                 "rollout": rollout,
                 "hier": hier,
+                "level5": l5,
                 "gpu_launches": int(gpu_launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

@@ -39,15 +39,17 @@ constexpr int kThreads = 32 * kWarps;
 constexpr int NTW = 64 / kWarps;                  // n-tiles per warp, wide layers
 constexpr int NTA = (19 + kWarps - 1) / kWarps;   // attention block: <= 19 n-tiles
 
+constexpr int kMaxChains = 8;
 struct Chain {
-  const float *x, *w1, *b1, *watt, *batt, *wh, *bh;
-  float* out;
-  int ldx, d_in, k1_pad, att_lo, att_n, att_pad, n_out, ld_out;
+  const float *x, *w1, *b1, *watt, *batt, *ws, *bs, *wh, *bh;
+  float* out;                 // logits / value, may be null when act_out is given
+  const int* rows;            // optional gather: local row r is global row rows[begin + r] (input AND output)
+  const int* range_dev;       // optional {begin, count} in device memory (data-dependent row lists without a host sync)
+  int* act_out;               // optional per-head argmax, int32 [.., 4]
+  int n_rows, ldx, d_in, k1_pad, att_lo, att_n, att_pad, n_out, ld_out, n_heads, head[4];
 };
 struct Args {
-  Chain c[4];
-  const float *ws, *bs;
-  int n_rows;
+  Chain c[kMaxChains];
 };
 
 // TF32 operands are the upper 19 bits of an fp32 word; the tensor core ignores the rest, i.e. passing the raw bits
@@ -188,16 +190,28 @@ template <bool X3>
 __global__ void __launch_bounds__(kThreads, 1) policy_forward_kernel(Args args) {
   extern __shared__ __align__(16) float smem[];
   float* act = smem;                    // [TM][LDA] activation tile
-  float* xin = smem + TM * LDA;         // [TM][XLD] input tile
+  float* xin = smem + TM * LDA;         // [TM][XLD] input tile; later the staged logits [TM][33]
+  __shared__ int rowmap[TM];            // global row of every tile row, -1 beyond the chain's row list
   const Chain& C = args.c[blockIdx.y];
-  const int row0 = blockIdx.x * TM;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  int beg = 0, cnt = C.n_rows;
+  if (C.range_dev) {
+    beg = C.range_dev[0];
+    cnt = C.range_dev[1];
+  }
+  const int row0 = blockIdx.x * TM;
+  if (row0 >= cnt) return;              // CTA-uniform
+  if (tid < TM) {
+    const int lr = row0 + tid;
+    rowmap[tid] = lr < cnt ? (C.rows ? C.rows[beg + lr] : beg + lr) : -1;
+  }
+  __syncthreads();
 
-  // input rows (zero beyond d_in and beyond n_rows); the activation tile's padding columns start as zero
+  // input rows (zero beyond d_in and beyond the row list); the activation tile's padding columns start as zero
   for (int i = tid; i < TM * XLD; i += kThreads) {
     const int r = i / XLD, c = i - r * XLD;
-    const int gr = row0 + r;
-    xin[i] = (c < C.d_in && gr < args.n_rows) ? __ldg(C.x + (size_t)gr * C.ldx + c) : 0.0f;
+    const int gr = rowmap[r];
+    xin[i] = (c < C.d_in && gr >= 0) ? __ldg(C.x + (size_t)gr * C.ldx + c) : 0.0f;
   }
   for (int i = tid; i < TM * (LDA - 500); i += kThreads) {
     const int r = i / (LDA - 500), c = 500 + i - r * (LDA - 500);
@@ -233,24 +247,50 @@ __global__ void __launch_bounds__(kThreads, 1) policy_forward_kernel(Args args) 
 
   {  // Z = tanh(in Ws + bs), written back in place once every warp is done reading
     float acc[NTW][4][4];
-    gemm_tile<NTW, X3, false>(act, LDA, NP, args.ws, NW / 8, acc);
+    gemm_tile<NTW, X3, false>(act, LDA, NP, C.ws, NW / 8, acc);
     __syncthreads();
-    store_tile<NTW, true>(act, 0, 500, args.bs, NW / 8, acc, false);
+    store_tile<NTW, true>(act, 0, 500, C.bs, NW / 8, acc, false);
   }
   __syncthreads();
 
-  {  // head: logits or value
+  {  // head: logits or value (+ optional per-head argmax, env_base.py:373-382)
     float acc[1][4][4];
     gemm_tile<1, X3, true>(act, LDA, NP, C.wh, 4, acc);
+    float* lg = xin;                     // [TM][33]
     if (warp < 4) {
       const int c = warp * 8 + 2 * t;
 #pragma unroll
       for (int m = 0; m < 4; ++m)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int col = c + (q & 1), row = row0 + m * 16 + g + ((q >> 1) ? 8 : 0);
-          if (col < C.n_out && row < args.n_rows) C.out[(size_t)row * C.ld_out + col] = acc[0][m][q] + __ldg(C.bh + col);
+          const int col = c + (q & 1), r = m * 16 + g + ((q >> 1) ? 8 : 0);
+          const int gr = rowmap[r];
+          if (col < C.n_out) {
+            const float v = acc[0][m][q] + __ldg(C.bh + col);
+            if (gr >= 0 && C.out) C.out[(size_t)gr * C.ld_out + col] = v;
+            lg[r * 33 + col] = v;
+          }
         }
+    }
+    if (C.act_out) {
+      __syncthreads();
+      if (tid < TM && rowmap[tid] >= 0) {
+        const float* row = lg + tid * 33;
+        int4 a = make_int4(0, 0, 0, 0);
+        int o = 0;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          if (h < C.n_heads) {
+            int best = 0;
+            float bv = row[o];
+            for (int k = 1; k < C.head[h]; ++k)
+              if (row[o + k] > bv) { bv = row[o + k]; best = k; }      // first maximum, like torch.argmax
+            (h == 0 ? a.x : h == 1 ? a.y : h == 2 ? a.z : a.w) = best;
+            o += C.head[h];
+          }
+        }
+        reinterpret_cast<int4*>(C.act_out)[rowmap[tid]] = a;
+      }
     }
   }
 }
@@ -261,30 +301,8 @@ __global__ void __launch_bounds__(kThreads, 1) policy_forward_kernel(Args args) 
 static thread_local std::string g_pf_error;
 extern "C" const char* hh_policy_last_error(void) { return g_pf_error.c_str(); }
 
-extern "C" int hh_policy_forward(int32_t n_rows, const hh_policy_chain* chains, const float* ws_dev, const float* bs_dev,
-                                 int32_t precision, void* stream) {
+static int launch_policy(const hh::pf::Args& a, int n_chains, int max_rows, int precision, void* stream) {
   using namespace hh::pf;
-  if (n_rows <= 0 || !chains || !ws_dev || !bs_dev || (precision != 0 && precision != 1)) {
-    g_pf_error = "hh_policy_forward: bad argument";
-    return -1;
-  }
-  Args a;
-  for (int i = 0; i < 4; ++i) {
-    const hh_policy_chain& s = chains[i];
-    if (!s.x || !s.w1 || !s.b1 || !s.wh || !s.bh || !s.out || s.d_in <= 0 || s.d_in > 72 || s.k1_pad % 8 || s.k1_pad < s.d_in ||
-        s.k1_pad > 72 || s.n_out <= 0 || s.n_out > 32 || (s.att_n > 0 && (!s.watt || !s.batt || s.att_pad % 8 || s.att_pad < s.att_n ||
-                                                                             s.att_lo + s.att_n != 500 || s.att_pad > 152))) {
-      g_pf_error = "hh_policy_forward: inconsistent chain description";
-      return -1;
-    }
-    Chain& c = a.c[i];
-    c.x = s.x; c.w1 = s.w1; c.b1 = s.b1; c.watt = s.watt; c.batt = s.batt; c.wh = s.wh; c.bh = s.bh; c.out = s.out;
-    c.ldx = s.ldx; c.d_in = s.d_in; c.k1_pad = s.k1_pad; c.att_lo = s.att_lo; c.att_n = s.att_n; c.att_pad = s.att_pad;
-    c.n_out = s.n_out; c.ld_out = s.ld_out;
-  }
-  a.ws = ws_dev;
-  a.bs = bs_dev;
-  a.n_rows = n_rows;
   const size_t smem = sizeof(float) * (TM * LDA + TM * XLD);
   static bool opted[2] = {false, false};
   cudaError_t ce = cudaSuccess;
@@ -298,7 +316,7 @@ extern "C" int hh_policy_forward(int32_t n_rows, const hh_policy_chain* chains, 
     }
     opted[precision] = true;
   }
-  const dim3 grid((n_rows + TM - 1) / TM, 4);
+  const dim3 grid((max_rows + TM - 1) / TM, n_chains);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (precision == 0) policy_forward_kernel<true><<<grid, kThreads, smem, st>>>(a);
   else policy_forward_kernel<false><<<grid, kThreads, smem, st>>>(a);
@@ -308,4 +326,67 @@ extern "C" int hh_policy_forward(int32_t n_rows, const hh_policy_chain* chains, 
     return -2;
   }
   return 0;
+}
+
+static bool chain_ok(const hh_policy_chain_ex& s) {
+  if (!s.x || !s.w1 || !s.b1 || !s.ws || !s.bs || !s.wh || !s.bh || (!s.out && !s.act_out)) return false;
+  if (s.n_rows < 0 || s.d_in <= 0 || s.d_in > 72 || s.k1_pad % 8 || s.k1_pad < s.d_in || s.k1_pad > 72) return false;
+  if (s.n_out <= 0 || s.n_out > 32) return false;
+  if (s.att_n > 0 && (!s.watt || !s.batt || s.att_pad % 8 || s.att_pad < s.att_n || s.att_lo + s.att_n != 500 || s.att_pad > 152))
+    return false;
+  if (s.act_out) {
+    if (s.n_heads < 1 || s.n_heads > 4) return false;
+    int tot = 0;
+    for (int h = 0; h < s.n_heads; ++h) {
+      if (s.head[h] < 1) return false;
+      tot += s.head[h];
+    }
+    if (tot != s.n_out) return false;
+  }
+  return true;
+}
+
+extern "C" int hh_policy_forward_ex(int32_t n_chains, const hh_policy_chain_ex* chains, int32_t precision, void* stream) {
+  using namespace hh::pf;
+  if (n_chains <= 0 || n_chains > kMaxChains || !chains || (precision != 0 && precision != 1)) {
+    g_pf_error = "hh_policy_forward_ex: bad argument";
+    return -1;
+  }
+  Args a;
+  int max_rows = 0;
+  for (int i = 0; i < n_chains; ++i) {
+    const hh_policy_chain_ex& s = chains[i];
+    if (!chain_ok(s)) {
+      g_pf_error = "hh_policy_forward_ex: inconsistent chain description";
+      return -1;
+    }
+    Chain& c = a.c[i];
+    c.x = s.x; c.w1 = s.w1; c.b1 = s.b1; c.watt = s.watt; c.batt = s.batt; c.ws = s.ws; c.bs = s.bs; c.wh = s.wh; c.bh = s.bh;
+    c.out = s.out; c.rows = s.rows; c.range_dev = s.range_dev; c.act_out = s.act_out;
+    c.n_rows = s.n_rows; c.ldx = s.ldx; c.d_in = s.d_in; c.k1_pad = s.k1_pad; c.att_lo = s.att_lo; c.att_n = s.att_n;
+    c.att_pad = s.att_pad; c.n_out = s.n_out; c.ld_out = s.ld_out; c.n_heads = s.n_heads;
+    for (int h = 0; h < 4; ++h) c.head[h] = s.head[h];
+    if (s.n_rows > max_rows) max_rows = s.n_rows;   // with range_dev, n_rows is the capacity of the row list
+  }
+  if (max_rows == 0) return 0;
+  return launch_policy(a, n_chains, max_rows, precision, stream);
+}
+
+extern "C" int hh_policy_forward(int32_t n_rows, const hh_policy_chain* chains, const float* ws_dev, const float* bs_dev,
+                                 int32_t precision, void* stream) {
+  if (n_rows <= 0 || !chains || !ws_dev || !bs_dev || (precision != 0 && precision != 1)) {
+    g_pf_error = "hh_policy_forward: bad argument";
+    return -1;
+  }
+  hh_policy_chain_ex ex[4];
+  for (int i = 0; i < 4; ++i) {
+    const hh_policy_chain& s = chains[i];
+    hh_policy_chain_ex& c = ex[i];
+    c = hh_policy_chain_ex{};
+    c.x = s.x; c.w1 = s.w1; c.b1 = s.b1; c.watt = s.watt; c.batt = s.batt; c.ws = ws_dev; c.bs = bs_dev; c.wh = s.wh; c.bh = s.bh;
+    c.out = s.out;
+    c.n_rows = n_rows; c.ldx = s.ldx; c.d_in = s.d_in; c.k1_pad = s.k1_pad; c.att_lo = s.att_lo; c.att_n = s.att_n;
+    c.att_pad = s.att_pad; c.n_out = s.n_out; c.ld_out = s.ld_out;
+  }
+  return hh_policy_forward_ex(4, ex, precision, stream);
 }

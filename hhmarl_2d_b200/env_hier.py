@@ -73,6 +73,8 @@ class VecHighLevelEnv:
         self.ll_info = torch.zeros((n, 6), dtype=torch.uint8, device=dev)
         self.ll_act = torch.zeros((n, 6, 4), dtype=torch.int32, device=dev)
         self.trace = None   # set to a list to record (phase, ll_obs, ll_info, ll_act) per sub-step (tests)
+        self.fused_policies = True   # the frozen low-level actors through csrc/hh_policy.cu (False: torch forward)
+        self._fused = None
 
     def _stream(self):
         return self._torch.cuda.current_stream(self.device_index).cuda_stream
@@ -97,9 +99,27 @@ class VecHighLevelEnv:
             for first in (0, 3):
                 unit = t.arange(self.n_arenas * 6, device=self.dev) % 6
                 sel = (kind == bits) & (unit >= first) & (unit < first + 3)
-                self._rows.append((mode, ac, first, t.nonzero(sel, as_tuple=False).flatten()))
+                idx = t.nonzero(sel, as_tuple=False).flatten()
+                self._rows.append((mode, ac, first, idx.to(t.int32) if self.fused_policies else idx))
+
+    def _infer_fused(self, first: int):
+        """All (mode x aircraft type) row lists of this half-step as chains of ONE hh_policy_forward_ex launch: gather
+        by row index, actor forward on the tensor cores (3xTF32), per-head argmax written straight into ll_act."""
+        from .fused_forward import FusedActor, run_chains
+        if self._fused is None:
+            self._fused = {(mode, ac): FusedActor(self.policies[f"{mode}_{ac}"]) for mode, ac, _ in self._KINDS}
+        obs_flat, act_flat = self.ll_obs.reshape(-1, 30), self.ll_act.reshape(-1, 4)
+        fills = []
+        for mode, ac, f, idx in self._rows:
+            if f != first or idx.numel() == 0:
+                continue
+            fa = self._fused[(mode, ac)]
+            fills.append(lambda c, fa=fa, idx=idx: fa.fill_chain(c, obs_flat, idx.numel(), act_out=act_flat, rows=idx))
+        run_chains(fills, self.dev, 0)
 
     def _infer(self, first: int):
+        if self.fused_policies:
+            return self._infer_fused(first)
         t = self._torch
         obs_flat, act_flat = self.ll_obs.reshape(-1, 30), self.ll_act.reshape(-1, 4)
         with t.no_grad():

@@ -244,3 +244,97 @@ class FusedPolicyPair:
         nat.check(nat.lib().hh_policy_forward(B, chains, self.ws.data_ptr(), self.bs.data_ptr(), self.precision, st),
                   "hh_policy_forward")
         return out
+
+
+class FusedActor:
+    """One frozen actor network -- `model.actor(own_obs)` of Fight1/Fight2/Esc1/Esc2 -- packed for the general
+    entry point hh_policy_forward_ex: what HHMARLBaseEnv._policy_actions evaluates for a self-play opponent
+    (env_base.py:349-398) and for every aircraft inside HighLevelEnv (env_hier.py:114-140)."""
+
+    NP, NW, NH = 504, 512, 32
+
+    def __init__(self, model):
+        self.model = model
+        self.fight = isinstance(model, M.Fight1)
+        self.dev = next(model.parameters()).device
+        self.d_in = model.own_obs_dim
+        self.k1_pad = ((self.d_in + 7) // 8) * 8
+        self.splits = M.ACTION_SPLITS[model.ac_type]
+        self.n_out = sum(self.splits)
+        z = lambda *shape: torch.zeros(shape, device=self.dev, dtype=torch.float32)  # noqa: E731
+        self.w1, self.b1 = z(self.k1_pad, self.NW), z(self.NW)
+        self.watt, self.batt = (z(104, 104), z(104)) if self.fight else (None, None)
+        self.ws, self.bs = z(self.NP, self.NW), z(self.NW)
+        self.wh, self.bh = z(self.NP, self.NH), z(self.NH)
+        self.refresh()
+
+    @torch.no_grad()
+    def refresh(self):
+        m, own = self.model, self.d_in
+        W = torch.zeros((self.k1_pad, self.NW), device=self.dev)
+        if self.fight:
+            ss = m.ss
+            blocks = ((m.inp1, 0, 200, 0, ss), (m.inp2, 200, 400, ss, own), (m.inp3, 400, 500, 0, own))
+        else:
+            k1 = m.k1
+            blocks = ((m.inp1, 0, 150, 0, k1), (m.inp2, 150, 400, k1, k1 + 18), (m.inp3, 400, 500, k1 + 18, own))
+        self.b1.zero_()
+        for fc, c0, c1, r0, r1 in blocks:
+            w, b = _lin(fc)
+            W[r0:r1, c0:c1] = w.t()
+            self.b1[c0:c1] = b
+        FusedPolicyPair._to_fragments(self.w1, W)
+        if self.fight:
+            mha = m.att_act
+            e = mha.embed_dim
+            Wv, bv = mha.in_proj_weight[2 * e:], mha.in_proj_bias[2 * e:]
+            Wo, bo = mha.out_proj.weight, mha.out_proj.bias
+            Wa = torch.zeros((104, 104), device=self.dev)
+            Wa[:100, :100] = (Wo @ Wv).t()
+            self.batt.zero_()
+            self.batt[:100] = Wo @ bv + bo
+            FusedPolicyPair._to_fragments(self.watt, Wa)
+        ws, bs = _lin(m.shared_layer)
+        Wsp = torch.zeros((self.NP, self.NW), device=self.dev)
+        Wsp[:500, :500] = ws.t()
+        FusedPolicyPair._to_fragments(self.ws, Wsp)
+        self.bs.zero_()
+        self.bs[:500] = bs
+        wa, ba = _lin(m.act_out)
+        Wh = torch.zeros((self.NP, self.NH), device=self.dev)
+        Wh[:500, :self.n_out] = wa.t()
+        FusedPolicyPair._to_fragments(self.wh, Wh)
+        self.bh.zero_()
+        self.bh[:self.n_out] = ba
+
+    def fill_chain(self, c, x, n_rows, out=None, act_out=None, rows=None, range_dev=None):
+        """Fill one nat.HHPolicyChainEx: x [*, >= d_in] f32 (row stride x.stride(0)); out [*, n_out] f32 and / or
+        act_out [*, 4] i32 (per-head argmax); rows (i32) gathers; range_dev (i32 [2], device) = {begin, count}."""
+        c.x, c.ldx, c.d_in, c.k1_pad = x.data_ptr(), x.stride(0), self.d_in, self.k1_pad
+        c.w1, c.b1 = self.w1.data_ptr(), self.b1.data_ptr()
+        if self.fight:
+            c.watt, c.batt, c.att_lo, c.att_n, c.att_pad = self.watt.data_ptr(), self.batt.data_ptr(), 400, 100, 104
+        else:
+            c.watt, c.batt, c.att_lo, c.att_n, c.att_pad = None, None, 0, 0, 0
+        c.ws, c.bs, c.wh, c.bh = self.ws.data_ptr(), self.bs.data_ptr(), self.wh.data_ptr(), self.bh.data_ptr()
+        c.out = out.data_ptr() if out is not None else None
+        c.ld_out = out.stride(0) if out is not None else 0
+        c.act_out = act_out.data_ptr() if act_out is not None else None
+        c.rows = rows.data_ptr() if rows is not None else None
+        c.range_dev = range_dev.data_ptr() if range_dev is not None else None
+        c.n_rows, c.n_out, c.n_heads = int(n_rows), self.n_out, len(self.splits)
+        for h in range(4):
+            c.head[h] = self.splits[h] if h < len(self.splits) else 0
+
+
+def run_chains(fill_fns, device, precision: int = 0):
+    """One hh_policy_forward_ex launch for up to 8 chains; each fill_fn(chain) fills a nat.HHPolicyChainEx."""
+    n = len(fill_fns)
+    if n == 0:
+        return
+    assert n <= 8
+    chains = (nat.HHPolicyChainEx * n)()
+    for c, f in zip(chains, fill_fns):
+        f(c)
+    st = torch.cuda.current_stream(device).cuda_stream
+    nat.check(nat.lib().hh_policy_forward_ex(n, chains, precision, st), "hh_policy_forward_ex")

@@ -59,6 +59,43 @@ class OpponentPolicies:
             return d["fight_1"], d["fight_2"], "fight"
         return self.policies["fight_1"], self.policies["fight_2"], "fight"
 
+    # ---- fused path: every (policy set, opponent) actor is one chain of ONE hh_policy_forward_ex launch
+    def _fused_setup(self, n):
+        from .fused_forward import FusedActor
+        sets = (3, 4, 5) if self.per_set else (0,)
+        self._fa = {k: tuple(FusedActor(m) for m in self._models_for(k)[:2]) for k in sets}
+        dev = self.device
+        self._fa_act = (torch.zeros((n, 4), dtype=torch.int32, device=dev), torch.zeros((n, 4), dtype=torch.int32, device=dev))
+        self._fa_ks = torch.tensor(sets, dtype=torch.int32, device=dev)
+        self._fa_n = n
+
+    @torch.no_grad()
+    def act_fused(self, opp_obs3, opp_obs4, policy_set=None, precision: int = 0):
+        """Same result as act() (per-head argmax of the frozen actors), without host synchronisation: the rows of a
+        policy set are gathered through an argsort of the set ids, the per-set {begin, count} stays on the device."""
+        from .fused_forward import run_chains
+        n = opp_obs3.shape[0]
+        if getattr(self, "_fa_n", None) != n:
+            self._fused_setup(n)
+        a3, a4 = self._fa_act
+        fills = []
+        if self.per_set:
+            ps = policy_set.to(torch.int32)
+            order = torch.argsort(ps, stable=True).to(torch.int32)
+            counts = (ps[None, :] == self._fa_ks[:, None]).sum(1)
+            ranges = torch.stack((torch.cumsum(counts, 0) - counts, counts), dim=1).to(torch.int32).contiguous()
+            self._fa_keep = (order, ranges)          # alive until the launch has been enqueued and run
+            for j, k in enumerate((3, 4, 5)):
+                f1, f2 = self._fa[k]
+                fills.append(lambda c, f=f1, j=j: f.fill_chain(c, opp_obs3, n, act_out=a3, rows=order, range_dev=ranges[j]))
+                fills.append(lambda c, f=f2, j=j: f.fill_chain(c, opp_obs4, n, act_out=a4, rows=order, range_dev=ranges[j]))
+        else:
+            f1, f2 = self._fa[0]
+            fills.append(lambda c: f1.fill_chain(c, opp_obs3, n, act_out=a3))
+            fills.append(lambda c: f2.fill_chain(c, opp_obs4, n, act_out=a4))
+        run_chains(fills, self.device, precision)
+        return torch.stack((a3, a4), dim=1)
+
     @torch.no_grad()
     def act(self, opp_obs3: torch.Tensor, opp_obs4: torch.Tensor, policy_set: torch.Tensor | None = None,
             return_logits: bool = False):

@@ -168,6 +168,21 @@ typedef struct {
 } hh_policy_chain;
 int hh_policy_forward(int32_t n_rows, const hh_policy_chain* chains /* host array of 4 */, const float* ws_dev,
                       const float* bs_dev, int32_t precision, void* stream);
+/* General form: 1..8 chains per launch, each with its own shared-layer weights (frozen opponent policy sets have
+ * their own SHARED_LAYER), an optional row gather (rows: local row r reads x[rows[begin + r]] and writes the same global
+ * row), an optional {begin, count} pair in DEVICE memory (data-dependent row lists without a host synchronisation;
+ * n_rows is then the capacity) and an optional per-head argmax (act_out int32 [.., 4]: what _policy_actions does with
+ * the logits, env_base.py:373-382; head[] are the MultiDiscrete split sizes).  Used for the level-4/5 opponents and
+ * the low-level policies inside HighLevelEnv. */
+typedef struct {
+  const float *x, *w1, *b1, *watt, *batt, *ws, *bs, *wh, *bh;
+  float* out;
+  const int32_t* rows;
+  const int32_t* range_dev;
+  int32_t* act_out;
+  int32_t n_rows, ldx, d_in, k1_pad, att_lo, att_n, att_pad, n_out, ld_out, n_heads, head[4];
+} hh_policy_chain_ex;
+int hh_policy_forward_ex(int32_t n_chains, const hh_policy_chain_ex* chains, int32_t precision, void* stream);
 const char* hh_policy_last_error(void);
 
 int hh_debug_geodesic(int32_t mode, int32_t n, const double* in_host, double* out_host);

@@ -7,7 +7,7 @@ echo "== stage clocks"
 HH_LIB_PATH=$PWD/build/lib_v4prof.so timeout 200 python profiles/stage_clocks.py 8192 2>&1 | tee gpurun_out/r1o_stage_clocks_8192.txt
 echo "== sweep"
 for n in 8192 32768 131072; do
-  timeout 200 python bench.py --arenas $n --steps 200 --warmup 20 --no-cpu-baseline --no-rollout --no-hier 2>/dev/null | tail -1 > /tmp/l.json
+  timeout 200 python bench.py --arenas $n --steps 200 --warmup 20 --no-cpu-baseline --no-rollout --no-hier --no-l5 2>/dev/null | tail -1 > /tmp/l.json
   python - "v4.2" "$n" <<'PY' | tee -a gpurun_out/r1o_sweep.txt
 import json, sys
 d = json.load(open('/tmp/l.json'))

@@ -178,3 +178,75 @@ def test_fused_policy_forward_matches_torch(mode):
                 m1.shared_layer._model[0].bias.sub_(0.01)
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def test_fused_actor_chains_gather_range_and_argmax():
+    """hh_policy_forward_ex: the four frozen-actor kinds (Fight1/2, Esc1/2 .actor) as chains of one launch, with a
+    row gather, a device-side {begin, count} range and the per-head argmax epilogue, against the torch modules."""
+    from hhmarl_2d_b200 import models as M
+    from hhmarl_2d_b200.fused_forward import FusedActor, run_chains
+    torch.manual_seed(3)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        f1, f2 = M.build_policy_pair("fight")
+        e1, e2 = M.build_policy_pair("escape")
+        models = [m.cuda().eval() for m in (f1, f2, e1, e2)]
+        for m in models:
+            for prm in m.parameters():
+                if prm.dim() == 1:
+                    torch.nn.init.normal_(prm, std=0.1)
+        n = 3000
+        x = torch.rand(n, 30, device="cuda")
+        fas = [FusedActor(m) for m in models]
+        # chain j works on its own quarter of a shuffled row list, given once as a host count and once as a device range
+        perm = torch.randperm(n, device="cuda").to(torch.int32)
+        cuts = [0, 700, 1500, 2300, n]
+        outs = [torch.full((n, fa.n_out), float("nan"), device="cuda") for fa in fas]
+        acts = torch.full((n, 4), -1, dtype=torch.int32, device="cuda")
+        ranges = torch.tensor([[cuts[j], cuts[j + 1] - cuts[j]] for j in range(4)], dtype=torch.int32, device="cuda")
+        fills = []
+        for j, fa in enumerate(fas):
+            if j % 2 == 0:
+                rows = perm[cuts[j]:cuts[j + 1]].contiguous()
+                fills.append(lambda c, fa=fa, rows=rows, j=j: fa.fill_chain(c, x, rows.numel(), out=outs[j], act_out=acts, rows=rows))
+            else:
+                fills.append(lambda c, fa=fa, j=j: fa.fill_chain(c, x, n, out=outs[j], act_out=acts, rows=perm, range_dev=ranges[j]))
+        run_chains(fills, torch.device("cuda"), 0)
+        n_checked = 0
+        for j, (m, fa) in enumerate(zip(models, fas)):
+            rows = perm[cuts[j]:cuts[j + 1]].long()
+            with torch.no_grad():
+                ref = m.actor(x[rows][:, :fa.d_in])
+            got = outs[j][rows]
+            assert (got - ref).abs().max().item() < 3e-5, j
+            other = torch.ones(n, dtype=torch.bool, device="cuda"); other[rows] = False
+            assert torch.isnan(outs[j][other]).all()                 # rows of other chains untouched
+            want = M.deterministic_actions(ref, m.ac_type)
+            top = torch.stack([torch.topk(ref[:, o:o + w], 2).values for o, w in
+                               zip(np.cumsum((0,) + fa.splits[:-1]), fa.splits)], 1)     # [rows, heads, 2]
+            clear = ((top[..., 0] - top[..., 1]) > 1e-3).all(1)
+            a = acts[rows][:, :len(fa.splits)].long()
+            assert torch.equal(a[clear], want[clear])
+            if len(fa.splits) == 3:
+                assert (acts[rows][:, 3] == 0).all()
+            n_checked += int(clear.sum())
+        assert n_checked > 2000
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+@pytest.mark.parametrize("level,mode", [(4, "fight"), (5, "fight")])
+def test_fused_opponents_match_torch_opponents(level, mode):
+    from hhmarl_2d_b200.opponents import OpponentPolicies
+    torch.manual_seed(4)
+    n = 2500
+    opp = OpponentPolicies(level, mode, seed=0, device="cuda")
+    o3, o4 = torch.rand(n, 30, device="cuda"), torch.rand(n, 29, device="cuda")
+    pset = torch.randint(3, 6, (n,), device="cuda").to(torch.uint8)
+    o3[pset != 5, 26:] = 0; o4[pset != 5, 24:] = 0
+    ref, logits = opp.act(o3, o4, pset, return_logits=True)
+    got = opp.act_fused(o3, o4, pset)
+    assert got.shape == ref.shape and got.dtype == torch.int32
+    agree = (got == ref).all(2).all(1).float().mean().item()
+    assert agree > 0.995, agree                                     # differences only at near-ties of a head

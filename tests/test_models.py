@@ -76,3 +76,22 @@ def test_packed_pair_forward_equals_per_model_forward(mode):
     packed.refresh()
     with torch.no_grad():
         np.testing.assert_allclose(m1.forward_flat(f1)[0].numpy(), packed.forward(f1, f2)[0].numpy(), rtol=2e-5, atol=2e-6)
+
+
+def test_fragment_order_packing_of_the_fused_forward_weights():
+    """FusedPolicyPair._to_fragments: [K, N] row-major -> [K/8][N/8][lane = 4 g + t][(b0, b1)] with
+    b0 = w[8 ks + t, 8 nt + g], b1 = w[8 ks + t + 4, 8 nt + g] (the mma.m16n8k8 B operand of every lane)."""
+    import torch
+    from hhmarl_2d_b200.fused_forward import FusedPolicyPair
+    K, N = 24, 40
+    w = torch.arange(K * N, dtype=torch.float32).reshape(K, N)
+    dst = torch.zeros(K, N)
+    FusedPolicyPair._to_fragments(dst, w)
+    flat = dst.view(-1)
+    for ks in range(K // 8):
+        for nt in range(N // 8):
+            for g in range(8):
+                for t in range(4):
+                    for q in range(2):
+                        idx = ((ks * (N // 8) + nt) * 32 + g * 4 + t) * 2 + q
+                        assert flat[idx].item() == w[ks * 8 + t + 4 * q, nt * 8 + g].item()
