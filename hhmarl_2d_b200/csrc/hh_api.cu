@@ -717,7 +717,15 @@ __global__ void geodesic_debug_kernel(int mode, int n, const double* __restrict_
   double2 r;
   if (mode == 0) r = geo::direct(a, b, c, d);
   else if (mode == 1) r = geo::inverse(a, b, c, d);
-  else r = geo::inverse_local(a, b, c, d);
+  else if (mode == 2) r = geo::inverse_local(a, b, c, d);
+  else if (mode == 3) {          // the v4 step's aircraft move: azimuth through the heading vector (env_base.py:428)
+    const HVec hv = heading_vec(c);
+    r = geo::direct_short(a, b, c, hv.c, hv.s, d);
+  } else {                       // the v4 step's rocket move: azimuth through sincosd
+    double sa, ca;
+    geo::sincosd(geo::ang_round(geo::ang_normalize(c)), sa, ca);
+    r = geo::direct_short(a, b, c, sa, ca, d);
+  }
   out[i] = r.x;
   out[n + i] = r.y;
 }
@@ -825,7 +833,7 @@ extern "C" int hh_pack_central(int32_t n_arenas, int32_t d1, int32_t d2, const f
 }
 
 extern "C" int hh_debug_geodesic(int32_t mode, int32_t n, const double* in_host, double* out_host) {
-  if (mode < 0 || mode > 2 || n <= 0 || !in_host || !out_host) return fail(-1, "hh_debug_geodesic: bad argument");
+  if (mode < 0 || mode > 4 || n <= 0 || !in_host || !out_host) return fail(-1, "hh_debug_geodesic: bad argument");
   double *d_in = nullptr, *d_out = nullptr;
   HH_CUDA(cudaMalloc(&d_in, sizeof(double) * 4 * n));
   HH_CUDA(cudaMalloc(&d_out, sizeof(double) * 2 * n));

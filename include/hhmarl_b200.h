@@ -146,11 +146,6 @@ int hh_sample_actions(int32_t n_arenas, const float* logits1_dev, const float* l
 int hh_pack_central(int32_t n_arenas, int32_t d1, int32_t d2, const float* obs1_dev, const float* obs2_dev,
                     float* flat1_dev, float* flat2_dev, void* stream);
 
-/* Test access to the device WGS84 solvers (replacing geographiclib's Geodesic.WGS84 as used at
- * warsim/utils/geodesics.py:12-24).  in_host: f64[4][n], out_host: f64[2][n].
- *   mode 0: direct  (lat1, lon1, azi1 [deg], s12 [m]) -> (lat2, lon2)
- *   mode 1: inverse (lat1, lon1, lat2, lon2)          -> (s12 [m], azi1 [deg])   exact series
- *   mode 2: inverse, local closed form used for threshold decisions (same outputs) */
 /* ---- fused forward of the sampler's network chains (models/ac_models_hetero.py:86-103, 256-291, 368-404; the
  * Policy.compute_actions -> TorchModelV2.forward call of the rollout worker).
  * One chain = x [n_rows, d_in] -> tanh(x W1 + b1) [500] -> optional single-token attention block on columns
@@ -185,6 +180,12 @@ typedef struct {
 int hh_policy_forward_ex(int32_t n_chains, const hh_policy_chain_ex* chains, int32_t precision, void* stream);
 const char* hh_policy_last_error(void);
 
+/* Test access to the device WGS84 solvers (replacing geographiclib's Geodesic.WGS84 as used at
+ * warsim/utils/geodesics.py:12-24).  in_host: f64[4][n], out_host: f64[2][n].
+ *   mode 0: direct  (lat1, lon1, azi1 [deg], s12 [m]) -> (lat2, lon2)
+ *   mode 1: inverse (lat1, lon1, lat2, lon2)          -> (s12 [m], azi1 [deg])   exact series
+ *   mode 2: inverse, local closed form used for threshold decisions (same outputs)
+ *   mode 3 / 4: the short-arc direct solve as the step kernel calls it for aircraft / rockets (same in / out as 0) */
 int hh_debug_geodesic(int32_t mode, int32_t n, const double* in_host, double* out_host);
 
 const char* hh_last_error(void);

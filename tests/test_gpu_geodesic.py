@@ -37,6 +37,26 @@ def test_direct_matches_oracle():
     assert np.abs(got - exp).max() < 5e-14                                # degrees (~5 nm)
 
 
+def test_direct_short_on_device_matches_oracle_and_quadrature():
+    """geo::direct_short as the v4 step kernel calls it (mode 3: heading vector, mode 4: sincosd) on the device."""
+    import oracle as orc
+    from test_oracle_geodesic import _exact_direct
+    rng = np.random.default_rng(7)
+    n = 20000
+    x = np.stack([rng.uniform(4.99, 5.51, n), rng.uniform(6.99, 7.51, n),
+                  np.where(rng.random(n) < 0.5, rng.integers(0, 360, n).astype(float), rng.uniform(-20, 400, n)),
+                  np.where(rng.random(n) < 0.2, rng.uniform(250, 1030, n), rng.uniform(0.5, 463, n))])
+    exp = np.array([orc.geod_direct(*c)[:2] for c in x.T]).T
+    for mode in (3, 4):
+        got = _dev(mode, x)
+        d = np.abs(got - exp)
+        assert d[0].max() < 6e-15 and d[1].max() < 3e-14, (mode, d.max(1))   # Karney's own longitude noise near az 90 / 270
+        worst = list(d.max(0).argsort()[-8:]) + list(range(8))
+        for k in worst:                                                        # exact elliptic-integral quadrature
+            ex = np.array(_exact_direct(*x[:, k]))
+            assert np.abs(got[:, k] - ex).max() < 3e-15, (mode, x[:, k], got[:, k] - ex)
+
+
 def test_inverse_exact_and_local_match_oracle():
     import oracle as orc
     rng = np.random.default_rng(2)
