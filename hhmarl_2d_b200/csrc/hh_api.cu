@@ -947,6 +947,7 @@ extern "C" int hh_create(const hh_config* cfg, int32_t n_arenas, int32_t device,
 extern "C" void hh_destroy(hh_env* e) {
   if (!e) return;
   cudaSetDevice(e->device);
+  if (e->hstream) cudaStreamSynchronize(e->hstream);   // a step sent with hh_step_host_begin may still be in flight
   if (e->slab) cudaFree(e->slab);
   if (e->d_slab) cudaFree(e->d_slab);
   if (e->rew_pre) cudaFree(e->rew_pre);

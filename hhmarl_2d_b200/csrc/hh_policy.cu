@@ -305,8 +305,14 @@ extern "C" const char* hh_policy_last_error(void) { return g_pf_error.c_str(); }
 static int launch_policy(const hh::pf::Args& a, int n_chains, int max_rows, int precision, void* stream) {
   using namespace hh::pf;
   const size_t smem = sizeof(float) * (TM * LDA + TM * XLD);
-  static bool opted[2] = {false, false};
-  cudaError_t ce = cudaSuccess;
+  static bool opted_dev[64][2] = {};       // the opt-in is per device (one process may drive several)
+  int dev = 0;
+  cudaError_t ce = cudaGetDevice(&dev);
+  if (ce != cudaSuccess || dev < 0 || dev >= 64) {
+    g_pf_error = "hh_policy_forward: cudaGetDevice failed";
+    return -2;
+  }
+  bool* opted = opted_dev[dev];
   if (!opted[precision]) {
     ce = precision == 0
              ? cudaFuncSetAttribute(policy_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
