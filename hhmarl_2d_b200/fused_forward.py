@@ -238,7 +238,7 @@ class FusedPolicyPair:
                     c.watt, c.batt, c.att_lo, c.att_n, c.att_pad = None, None, 0, 0, 0
                 c.wh, c.bh = self.wh[p][k].data_ptr(), self.bh[p][k].data_ptr()
                 o = out[2 * p + k]
-                c.out, c.ld_out, c.n_out = o.data_ptr(), (o.shape[1] if o.dim() == 2 else 1), (n_act[p] if k == 0 else 1)
+                c.out, c.ld_out, c.n_out = o.data_ptr(), o.stride(0), (n_act[p] if k == 0 else 1)
                 c.ldx, c.d_in, c.k1_pad = x.stride(0), x.shape[1], self.k1_pad[p]
         st = torch.cuda.current_stream(self.dev).cuda_stream
         nat.check(nat.lib().hh_policy_forward(B, chains, self.ws.data_ptr(), self.bs.data_ptr(), self.precision, st),

@@ -109,6 +109,7 @@ class VecSampler:
         self.cur2 = torch.zeros((n, 7 + d1 + d2), **f32)   # [act_1_own(3) | act_2(4) | obs_1_own | obs_2]
         self.d1, self.d2 = d1, d2
         self.native_glue = (d1, d2) == (26, 24)        # hh_sample_actions is written for the fight-mode head layout
+        self.direct = self.native_glue and fused is not None and env.level <= 3   # kernels write into the buffers themselves
         self.ctr = torch.zeros((n, 2), dtype=torch.int32, device=dev)
         self.seed = int(getattr(env, "_cfg").seed) + 0x5A17
         self.scale = ACT_SCALE.to(dev)
@@ -141,8 +142,27 @@ class VecSampler:
         l2, v2 = self.p2.model.forward_flat(f2)
         return l1, v1, l2, v2
 
+    def _tick_direct(self, t):
+        """Tick with every kernel writing straight into the rollout buffers (fused forward + native glue): four
+        launches per tick -- forward, sample, env step, central-observation packing -- and no copies."""
+        b, n, T = self.buf, self.env.n_arenas, self.T
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        vf = b["vf"][t]
+        self.packed.forward(b["flat1"][t], b["flat2"][t], out=(b["logits1"][t], vf[:, 0], b["logits2"][t], vf[:, 1]))
+        act = b["actions"][t]
+        nat.check(nat.lib().hh_sample_actions(n, b["logits1"][t].data_ptr(), b["logits2"][t].data_ptr(), self.seed,
+                                              int(self.env._cfg.arena_base), self.ctr.data_ptr(), 1, act.data_ptr(),
+                                              b["logp"][t].data_ptr(), st), "hh_sample_actions")
+        eb = self.env._ensure_torch()
+        obs1, obs2, _, _ = self.env.step(act, out=dict(obs1=eb["obs1"], obs2=eb["obs2"], rew=b["rew"][t], done=b["done"][t]))
+        nxt1, nxt2 = (b["flat1"][t + 1], b["flat2"][t + 1]) if t + 1 < T else (self.cur1, self.cur2)
+        nat.check(nat.lib().hh_pack_central(n, self.d1, self.d2, obs1.data_ptr(), obs2.data_ptr(), nxt1.data_ptr(),
+                                            nxt2.data_ptr(), st), "hh_pack_central")
+
     def _tick(self, t):
         b = self.buf
+        if self.direct:
+            return self._tick_direct(t)
         l1, v1, l2, v2 = self._forward_both(self.cur1, self.cur2)
         if self.native_glue:
             b["flat1"][t] = self.cur1
@@ -177,9 +197,16 @@ class VecSampler:
         self._set_obs(obs1, obs2)
 
     def _fragment(self):
+        b = self.buf
+        if self.direct:
+            # the critic sees ZERO actions while sampling: clear what the previous fragment's write-back
+            # left in the action columns, then seed tick 0 with the current central observation
+            b["flat1"][:, :, :7].zero_()
+            b["flat2"][:, :, :7].zero_()
+            b["flat1"][0].copy_(self.cur1)
+            b["flat2"][0].copy_(self.cur2)
         for t in range(self.T):
             self._tick(t)
-        b = self.buf
         _, v1, _, v2 = self._forward_both(self.cur1, self.cur2)
         b["last_vf"][:, 0], b["last_vf"][:, 1] = v1, v2
         st = torch.cuda.current_stream(self.dev).cuda_stream
