@@ -62,3 +62,21 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(nat, "LIB_PATH", "/nonexistent/libhhmarl_b200.so")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         nat.lib()
+
+
+def test_policy_forward_validates_arguments_without_a_gpu():
+    """hh_policy_forward / _ex reject inconsistent chain descriptions before any CUDA call; struct layouts match."""
+    from hhmarl_2d_b200 import _native as nat
+    L = nat.lib()
+    assert ctypes.sizeof(nat.HHPolicyChain) == 8 * 8 + 8 * 4
+    assert ctypes.sizeof(nat.HHPolicyChainEx) == 13 * 8 + 10 * 4 + 4 * 4
+    one = (nat.HHPolicyChainEx * 1)()
+    assert L.hh_policy_forward_ex(0, one, 0, None) == -1            # no chains
+    assert L.hh_policy_forward_ex(9, one, 0, None) == -1            # more than 8
+    assert L.hh_policy_forward_ex(1, one, 2, None) == -1            # unknown precision
+    assert L.hh_policy_forward_ex(1, one, 0, None) == -1            # null pointers
+    assert b"chain" in L.hh_policy_last_error()
+    four = (nat.HHPolicyChain * 4)()
+    assert L.hh_policy_forward(0, four, None, None, 0, None) == -1
+    assert L.hh_step_host_begin(None, None) == -1 and L.hh_step_host_end(None, None, None, None, None) == -1
+    assert L.hh_set_host_mode(None, 0) == -1

@@ -95,3 +95,31 @@ def test_commander_sampler_fragment():
     assert torch.isfinite(b["adv"]).all() and (b["substeps"] >= 1).all() and (b["substeps"] <= 16).all()
     lsm = torch.log_softmax(b["logits"], -1).gather(3, b["actions"].long()[..., None])[..., 0]
     assert torch.allclose(lsm, b["logp"], atol=1e-5)
+
+
+def test_hier_full_size_properties():
+    """BASELINE config 5 size (8 192 arenas, 3-vs-3): two runs agree bit for bit, observations stay in Box(0, 1),
+    every arena makes between 1 and 16 sub-steps per commander step, a ragged slice of the arenas reproduces."""
+    from hhmarl_2d_b200.env_hier import VecHighLevelEnv
+    n, T = 8192, 3
+    torch.manual_seed(2)
+    ca = torch.randint(0, 3, (T, n, 3)).to(torch.int32).cuda()
+
+    def run(n_arenas, base, sl):
+        env = VecHighLevelEnv(n_arenas, device=0, seed=4, arena_base=base, autoreset=True)
+        outs = [env.reset().clone().reshape(n_arenas, -1)]
+        for t in range(T):
+            o, r, d = env.step(ca[t, sl].contiguous())
+            outs.append(torch.cat([o.reshape(n_arenas, -1), r, d.float()[:, None], env.substeps.float()[:, None]], dim=1).clone())
+        return outs
+
+    full = run(n, 0, slice(0, n))
+    again = run(n, 0, slice(0, n))
+    for a, b in zip(full, again):
+        assert torch.equal(a, b)
+    for o in full[1:]:
+        assert torch.isfinite(o).all() and (o[:, :102] >= 0).all() and (o[:, :102] <= 1).all()
+        assert (o[:, -1] >= 1).all() and (o[:, -1] <= 16).all()
+    part = run(333, 5000, slice(5000, 5333))
+    for a, b in zip(full, part):
+        assert torch.equal(a[5000:5333], b)

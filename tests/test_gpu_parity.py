@@ -433,3 +433,32 @@ def test_quad_cta_and_v4_step_kernels_agree(monkeypatch):
             _close(x.cpu().numpy(), y.cpu().numpy(), f"{other} L{level} {mode} t={t}")
             n_diff += int((x != y).sum())
         print(f"{other} vs quad, L{level} {mode}: {n_diff} of {len(ra) * ra[0].numel()} output values differ in the last bits")
+
+
+def test_level5_full_size_properties():
+    """BASELINE config 3 size (32 768 arenas, level 5, frozen fight / escape opponents through the fused actor chains):
+    determinism, Box(0, 1) range, all three policy sets in use, partition invariance of a ragged slice."""
+    import torch
+    n, T = 32768, 12
+    torch.manual_seed(1)
+    acts = torch.stack([torch.randint(0, 13, (T, n, 2)), torch.randint(0, 9, (T, n, 2)),
+                        torch.randint(0, 2, (T, n, 2)), torch.randint(0, 2, (T, n, 2))], dim=-1).to(torch.int32).cuda()
+
+    def run(n_arenas, base, sl):
+        env = _vec(n_arenas, 5, "fight", 8, arena_base=base)
+        outs = [torch.cat([x.clone() for x in env.reset()], dim=1)]
+        for t in range(T):
+            o1, o2, r, d = env.step(acts[t, sl].contiguous())
+            outs.append(torch.cat([o1, o2, r, d.float()[:, None], env.last_opp_actions.reshape(-1, 8).float()], dim=1).clone())
+        return outs, env.get_state()
+
+    full, st = run(n, 0, slice(0, n))
+    again, _ = run(n, 0, slice(0, n))
+    for a, b in zip(full, again):
+        assert torch.equal(a, b)
+    for o in full:
+        assert torch.isfinite(o).all() and (o[:, :50] >= 0).all() and (o[:, :50] <= 1).all()
+    assert set(np.unique(st["policy_set"]).tolist()) == {3, 4, 5} and (st["error"] == 0).all()
+    part, _ = run(1001, 20000, slice(20000, 21001))
+    for a, b in zip(full, part):
+        assert torch.equal(a[20000:21001], b)
