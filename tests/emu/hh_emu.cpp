@@ -185,3 +185,36 @@ extern "C" int hh_debug_geodesic(int32_t mode, int32_t n, const double* in, doub
   }
   return 0;
 }
+
+// scalar helpers of hh_core.cuh, one call per row of in[n][6] -> out[n][2] (property tests, tests/test_emu_v4.py)
+extern "C" int hh_emu_scalar(int32_t op, int32_t n, const double* in, double* out) {
+  const Geom g = make_geom(0.3);
+  for (int i = 0; i < n; ++i) {
+    const double* p = in + 6 * (size_t)i;
+    double a = 0.0, b = 0.0;
+    switch (op) {
+      case 0: a = pymod(p[0], p[1]); break;
+      case 1: a = signed_heading_diff(p[0], p[1]); break;
+      case 2: a = normalize_angle(p[0]); break;
+      case 3: a = angle_in_radar_range(p[0], p[1]) ? 1.0 : 0.0; break;
+      case 4: a = hdg_feature(p[0]); break;
+      case 5: a = focus_deg(heading_vec(p[0]), p[1], p[2], p[3], p[4]); break;
+      case 6: {
+        a = (double)correct_angle_sign(p[1], p[2], p[0], p[3], p[4]);
+        double sx, cx;
+        angle_sign_offsets(p[0], sx, cx);
+        b = (double)angle_sign_from(p[1], p[2], sx, cx, p[3], p[4]);
+        break;
+      }
+      case 7: a = rocket_speed((int)p[0]); break;
+      case 8: rel_pos(g, p[0], p[1], a, b); break;
+      case 9: a = in_boundary(g, p[0], p[1]) ? 1.0 : 0.0; break;
+      case 10: a = hdiff_norm(heading_vec(p[0]), heading_vec(p[1])); break;
+      case 11: a = fmod_small(p[0], p[1]); break;
+      default: return -1;
+    }
+    out[2 * (size_t)i] = a;
+    out[2 * (size_t)i + 1] = b;
+  }
+  return 0;
+}

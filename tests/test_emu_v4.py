@@ -122,3 +122,94 @@ def test_direct_short_agrees_with_karney_direct():
         ex = np.array(_exact_direct(*q[k]))
         assert np.abs(out[3][k] - ex).max() < 2e-15, (q[k], out[3][k] - ex)
         assert np.abs(out[4][k] - ex).max() < 2e-15, (q[k], out[4][k] - ex)
+
+
+# ------------------------------------------------------------------------------------------ scalar helpers (hh_core.cuh)
+def _scalar(op, rows):
+    import ctypes
+    a = np.zeros((len(rows), 6))
+    a[:, :np.asarray(rows).shape[1]] = rows
+    out = np.empty((len(rows), 2))
+    with emu_env.emulated() as L:
+        L.hh_emu_scalar.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
+        assert L.hh_emu_scalar(op, len(rows), a.ctypes.data, out.ctypes.data) == 0
+    return out
+
+
+def _ref_signed_heading_diff(actual, desired):        # warsim/utils/angles.py:22-29
+    delta = desired - actual
+    if delta < -180:
+        delta = 360 + delta
+    if delta > 180:
+        delta = -360 + delta
+    return delta
+
+
+def _ref_normalize(a):                                 # warsim/utils/angles.py:10-15
+    while a >= 360:
+        a -= 360
+    while a < 0:
+        a += 360
+    return a
+
+
+def _ref_focus(h, lat_a, lon_a, lat_b, lon_b):         # envs/env_base.py:424-432 (numpy, as the reference computes it)
+    th = ((90 - h) % 360) * (np.pi / 180)
+    u = np.array([np.cos(th), np.sin(th)])
+    v = np.array([lon_b - lon_a, lat_b - lat_a])
+    x = np.clip(np.dot(u, v) / (np.linalg.norm(u) * np.linalg.norm(v) + 1e-10), -1, 1)
+    return np.arccos(x) * 180 / np.pi
+
+
+def test_scalar_helpers_follow_python_semantics():
+    """The Python-semantics helpers of hh_core.cuh (the source the kernels compile) against CPython / numpy
+    restatements of the reference formulas: float %, heading differences, radar gate, angle features."""
+    import math
+    rng = np.random.default_rng(11)
+    # float % with positive modulus, incl. values next to multiples and the tiny-negative quirk (SURVEY A.6.14)
+    xs = np.concatenate([rng.uniform(-1500, 1500, 20000), np.arange(-4, 5) * 360.0, np.arange(-4, 5) * 359.0,
+                         np.nextafter(np.arange(1, 5) * 360.0, 0), np.nextafter(np.arange(1, 5) * 360.0, 1e9),
+                         [-1e-20, -1e-300, 1e-20, -0.0, 0.0, 719.9999999999999, -359.99999999999994]])
+    for m in (360.0, 359.0):
+        got = _scalar(0, np.stack([xs, np.full_like(xs, m)], 1))[:, 0]
+        want = np.array([x % m for x in xs.tolist()])
+        assert np.array_equal(got, want), (m, xs[got != want][:5])
+        gf = _scalar(11, np.stack([xs, np.full_like(xs, m)], 1))[:, 0]
+        assert np.array_equal(gf, np.array([math.fmod(x, m) for x in xs.tolist()]))
+    assert _scalar(0, [[-1e-20, 360.0]])[0, 0] == 360.0          # the reference's % returns the modulus itself here
+    # signed_heading_diff / normalize_angle
+    pairs = np.stack([rng.uniform(-50, 400, 5000), rng.uniform(-50, 400, 5000)], 1)
+    pairs[:50] = np.round(pairs[:50])
+    got = _scalar(1, pairs)[:, 0]
+    assert np.array_equal(got, np.array([_ref_signed_heading_diff(a, b) for a, b in pairs.tolist()]))
+    ang = np.concatenate([rng.uniform(-1000, 1000, 5000), [0.0, 360.0, -360.0, 359.99999999999994, 720.0]])
+    assert np.array_equal(_scalar(2, ang[:, None])[:, 0], np.array([_ref_normalize(a) for a in ang.tolist()]))
+    # radar gate (ac1.py:144-146): accepts relative bearings in (-1, 121) degrees (SURVEY A.6.3)
+    hd = rng.uniform(0, 360, 20000); rel = rng.uniform(-180, 180, 20000)
+    got = _scalar(3, np.stack([hd, (hd + rel) % 360], 1))[:, 0].astype(bool)
+    clear = (np.abs(rel + 1) > 1e-9) & (np.abs(rel - 121) > 1e-9)
+    assert np.array_equal(got[clear], ((rel > -1) & (rel < 121))[clear])
+    # heading feature (sic: % 359 / 359), focus angle, heading difference, map helpers
+    h = np.concatenate([rng.uniform(0, 360, 5000), np.arange(0, 361, 1.0)])
+    want = np.clip((h % 359) / 359, 0, 1)
+    assert np.abs(_scalar(4, h[:, None])[:, 0] - want).max() < 1e-15
+    rows = np.stack([rng.uniform(0, 360, 5000), rng.uniform(5, 5.3, 5000), rng.uniform(7, 7.3, 5000),
+                     rng.uniform(5, 5.3, 5000), rng.uniform(7, 7.3, 5000)], 1)
+    rows[:10, 3:5] = rows[:10, 1:3] + 1e-6 * rng.standard_normal((10, 2))        # ~100 m apart: the + 1e-10 term matters
+    got = _scalar(5, rows)[:, 0]
+    want = np.array([_ref_focus(*r) for r in rows.tolist()])
+    near = np.minimum(want, 180 - want) < 0.5      # arccos is ill-conditioned next to 0 / 180 deg: compare there loosely
+    assert np.abs(got - want)[~near].max() < 1e-9 and np.abs(got - want)[near].max() < 2e-6
+    sg = _scalar(6, rows)
+    assert np.array_equal(sg[:, 0], sg[:, 1]) and set(np.unique(sg[:, 0])) <= {-1.0, 1.0}   # split form == one-piece form
+    rp = _scalar(8, np.stack([rng.uniform(4.9, 5.4, 2000), rng.uniform(6.9, 7.4, 2000)], 1))
+    assert rp.min() >= 0.0 and rp.max() <= 1.0
+    assert [_scalar(7, [[k]])[0, 0] for k in (0, 5, 10, 11)] == [500.0, float.fromhex("0x1.8405555555554p+10"), 2000.0, 2000.0]
+    if os.path.isdir("/root/reference"):            # this container only: the reference's own helpers
+        sys.path.insert(0, "/root/reference/warsim")
+        try:
+            from utils.angles import signed_heading_diff, normalize_angle
+            assert all(signed_heading_diff(a, b) == g for (a, b), g in zip(pairs[:500].tolist(), _scalar(1, pairs[:500])[:, 0]))
+            assert all(normalize_angle(a) == g for a, g in zip(ang[:500].tolist(), _scalar(2, ang[:500, None])[:, 0]))
+        finally:
+            sys.path.pop(0)

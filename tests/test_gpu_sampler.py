@@ -250,3 +250,41 @@ def test_fused_opponents_match_torch_opponents(level, mode):
     assert got.shape == ref.shape and got.dtype == torch.int32
     agree = (got == ref).all(2).all(1).float().mean().item()
     assert agree > 0.995, agree                                     # differences only at near-ties of a head
+
+
+def test_sampler_graph_sees_refreshed_weights():
+    """After a learner update `refresh_policy()` re-packs the fused kernel's weight buffers IN PLACE, so the captured
+    CUDA graph samples with the new weights: recorded logits / values equal a torch forward of the updated modules."""
+    from hhmarl_2d_b200 import VecLowLevelEnv, make_args, VecSampler, TorchPolicy
+    from hhmarl_2d_b200 import models as M
+    torch.manual_seed(5)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        env = VecLowLevelEnv(300, make_args(level=3), device=0, seed=13)
+        m1, m2 = M.build_policy_pair("fight")
+        m1.cuda(); m2.cuda()
+        smp = VecSampler(env, TorchPolicy(m1, 1), TorchPolicy(m2, 2), fragment_len=6, use_cuda_graph=True)
+        for _ in range(3):
+            smp.collect()                                   # warm-up, capture, replay
+
+        def check():
+            b = smp.collect()
+            for t in (0, 5):
+                f1, f2 = b["flat1"][t].clone(), b["flat2"][t].clone()
+                f1[:, :7] = 0; f2[:, :7] = 0               # sampling saw zero actions (the write-back came later)
+                with torch.no_grad():
+                    l1, v1 = m1.forward_flat(f1)
+                    l2, v2 = m2.forward_flat(f2)
+                assert (b["logits1"][t] - l1).abs().max().item() < 5e-5 and (b["logits2"][t] - l2).abs().max().item() < 5e-5
+                assert (b["vf"][t][:, 0] - v1).abs().max().item() < 5e-5 and (b["vf"][t][:, 1] - v2).abs().max().item() < 5e-5
+
+        check()
+        with torch.no_grad():
+            for m in (m1, m2):
+                for prm in m.parameters():
+                    prm.add_(0.02 * torch.randn_like(prm))
+        smp.refresh_policy()
+        check()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
