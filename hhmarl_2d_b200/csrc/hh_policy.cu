@@ -46,7 +46,7 @@ struct Chain {
   const int* rows;            // optional gather: local row r is global row rows[begin + r] (input AND output)
   const int* range_dev;       // optional {begin, count} in device memory (data-dependent row lists without a host sync)
   int* act_out;               // optional per-head argmax, int32 [.., 4]
-  int n_rows, ldx, d_in, k1_pad, att_lo, att_n, att_pad, n_out, ld_out, n_heads, head[4];
+  int n_rows, ldx, d_in, k1_pad, att_lo, att_n, att_pad, n_out, ld_out, n_heads, head[4], ld_act;
 };
 struct Args {
   Chain c[kMaxChains];
@@ -290,12 +290,37 @@ __global__ void __launch_bounds__(kThreads, 1) policy_forward_kernel(Args args) 
             o += C.head[h];
           }
         }
-        reinterpret_cast<int4*>(C.act_out)[rowmap[tid]] = a;
+        reinterpret_cast<int4*>(C.act_out)[(size_t)rowmap[tid] * C.ld_act] = a;
       }
     }
   }
 }
 
+}  // namespace pf
+}  // namespace hh
+
+namespace hh {
+namespace pf {
+// Row lists per key without a host round trip (level 5: which frozen policy set an arena's opponents use,
+// env_hetero.py:55-59): rows[k][0 .. count_k) = the arenas whose key equals keys[k], ranges[k] = {k n, count_k}.
+// The order inside a list is whatever the atomics give; every row's result is independent of its neighbours.
+__global__ void rows_init_kernel(int n, int n_keys, int* __restrict__ ranges) {
+  const int k = threadIdx.x;
+  if (k < n_keys) {
+    ranges[2 * k] = k * n;
+    ranges[2 * k + 1] = 0;
+  }
+}
+__global__ void rows_fill_kernel(int n, int n_keys, int4 keys, const uint8_t* __restrict__ key, int* __restrict__ rows,
+                                 int* __restrict__ ranges) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int v = key[i];
+  const int k = v == keys.x ? 0 : (v == keys.y && n_keys > 1) ? 1 : (v == keys.z && n_keys > 2) ? 2 : (v == keys.w && n_keys > 3) ? 3 : -1;
+  if (k < 0) return;
+  const int pos = atomicAdd(&ranges[2 * k + 1], 1);
+  rows[(size_t)k * n + pos] = i;
+}
 }  // namespace pf
 }  // namespace hh
 
@@ -373,6 +398,7 @@ extern "C" int hh_policy_forward_ex(int32_t n_chains, const hh_policy_chain_ex* 
     c.n_rows = s.n_rows; c.ldx = s.ldx; c.d_in = s.d_in; c.k1_pad = s.k1_pad; c.att_lo = s.att_lo; c.att_n = s.att_n;
     c.att_pad = s.att_pad; c.n_out = s.n_out; c.ld_out = s.ld_out; c.n_heads = s.n_heads;
     for (int h = 0; h < 4; ++h) c.head[h] = s.head[h];
+    c.ld_act = s.ld_act > 0 ? s.ld_act : 1;
     if (s.n_rows > max_rows) max_rows = s.n_rows;   // with range_dev, n_rows is the capacity of the row list
   }
   if (max_rows == 0) return 0;
@@ -396,4 +422,23 @@ extern "C" int hh_policy_forward(int32_t n_rows, const hh_policy_chain* chains, 
     c.att_pad = s.att_pad; c.n_out = s.n_out; c.ld_out = s.ld_out;
   }
   return hh_policy_forward_ex(4, ex, precision, stream);
+}
+
+extern "C" int hh_policy_rows_by_key(int32_t n, const uint8_t* key_dev, int32_t n_keys, const int32_t* keys_host,
+                                     int32_t* rows_dev, int32_t* ranges_dev, void* stream) {
+  using namespace hh::pf;
+  if (n <= 0 || !key_dev || n_keys < 1 || n_keys > 4 || !keys_host || !rows_dev || !ranges_dev) {
+    g_pf_error = "hh_policy_rows_by_key: bad argument";
+    return -1;
+  }
+  int4 keys = make_int4(keys_host[0], n_keys > 1 ? keys_host[1] : -1, n_keys > 2 ? keys_host[2] : -1, n_keys > 3 ? keys_host[3] : -1);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rows_init_kernel<<<1, 32, 0, st>>>(n, n_keys, ranges_dev);
+  rows_fill_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, n_keys, keys, key_dev, rows_dev, ranges_dev);
+  const cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) {
+    g_pf_error = std::string("hh_policy_rows_by_key launch: ") + cudaGetErrorString(ce);
+    return -2;
+  }
+  return 0;
 }

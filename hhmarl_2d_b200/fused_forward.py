@@ -307,7 +307,7 @@ class FusedActor:
         self.bh.zero_()
         self.bh[:self.n_out] = ba
 
-    def fill_chain(self, c, x, n_rows, out=None, act_out=None, rows=None, range_dev=None):
+    def fill_chain(self, c, x, n_rows, out=None, act_out=None, rows=None, range_dev=None, act_ptr=None, ld_act=1):
         """Fill one nat.HHPolicyChainEx: x [*, >= d_in] f32 (row stride x.stride(0)); out [*, n_out] f32 and / or
         act_out [*, 4] i32 (per-head argmax); rows (i32) gathers; range_dev (i32 [2], device) = {begin, count}."""
         c.x, c.ldx, c.d_in, c.k1_pad = x.data_ptr(), x.stride(0), self.d_in, self.k1_pad
@@ -319,7 +319,8 @@ class FusedActor:
         c.ws, c.bs, c.wh, c.bh = self.ws.data_ptr(), self.bs.data_ptr(), self.wh.data_ptr(), self.bh.data_ptr()
         c.out = out.data_ptr() if out is not None else None
         c.ld_out = out.stride(0) if out is not None else 0
-        c.act_out = act_out.data_ptr() if act_out is not None else None
+        c.act_out = act_ptr if act_ptr is not None else (act_out.data_ptr() if act_out is not None else None)
+        c.ld_act = int(ld_act)
         c.rows = rows.data_ptr() if rows is not None else None
         c.range_dev = range_dev.data_ptr() if range_dev is not None else None
         c.n_rows, c.n_out, c.n_heads = int(n_rows), self.n_out, len(self.splits)

@@ -15,8 +15,11 @@ state_dict keys equal the reference's, initialised from a seed when no weights a
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
+from . import _native as nat
 from . import models as M
 
 OBS_FIGHT = {1: M.OBS_AC1, 2: M.OBS_AC2}
@@ -65,36 +68,40 @@ class OpponentPolicies:
         sets = (3, 4, 5) if self.per_set else (0,)
         self._fa = {k: tuple(FusedActor(m) for m in self._models_for(k)[:2]) for k in sets}
         dev = self.device
-        self._fa_act = (torch.zeros((n, 4), dtype=torch.int32, device=dev), torch.zeros((n, 4), dtype=torch.int32, device=dev))
-        self._fa_ks = torch.tensor(sets, dtype=torch.int32, device=dev)
+        self._fa_act = torch.zeros((n, 2, 4), dtype=torch.int32, device=dev)
+        self._fa_rows = torch.zeros((3, n), dtype=torch.int32, device=dev)
+        self._fa_ranges = torch.zeros((3, 2), dtype=torch.int32, device=dev)
+        self._fa_keys = (ctypes.c_int32 * 3)(3, 4, 5)
         self._fa_n = n
 
     @torch.no_grad()
     def act_fused(self, opp_obs3, opp_obs4, policy_set=None, precision: int = 0):
-        """Same result as act() (per-head argmax of the frozen actors), without host synchronisation: the rows of a
-        policy set are gathered through an argsort of the set ids, the per-set {begin, count} stays on the device."""
+        """Same result as act() (per-head argmax of the frozen actors) in three launches and without host
+        synchronisation: hh_policy_rows_by_key lists the arenas of every policy set on the device, then all
+        (set, opponent) actors run as chains of ONE hh_policy_forward_ex launch that writes the actions in place."""
         from .fused_forward import run_chains
         n = opp_obs3.shape[0]
         if getattr(self, "_fa_n", None) != n:
             self._fused_setup(n)
-        a3, a4 = self._fa_act
+        act = self._fa_act
+        p3, p4 = act.data_ptr(), act.data_ptr() + 16           # [n, 2, 4] int32: opponent id 3 / id 4 of every arena
         fills = []
         if self.per_set:
-            ps = policy_set.to(torch.int32)
-            order = torch.argsort(ps, stable=True).to(torch.int32)
-            counts = (ps[None, :] == self._fa_ks[:, None]).sum(1)
-            ranges = torch.stack((torch.cumsum(counts, 0) - counts, counts), dim=1).to(torch.int32).contiguous()
-            self._fa_keep = (order, ranges)          # alive until the launch has been enqueued and run
+            assert policy_set.dtype == torch.uint8 and policy_set.is_contiguous()
+            rows, ranges = self._fa_rows, self._fa_ranges
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            nat.check(nat.lib().hh_policy_rows_by_key(n, policy_set.data_ptr(), 3, self._fa_keys, rows.data_ptr(),
+                                                      ranges.data_ptr(), st), "hh_policy_rows_by_key")
             for j, k in enumerate((3, 4, 5)):
                 f1, f2 = self._fa[k]
-                fills.append(lambda c, f=f1, j=j: f.fill_chain(c, opp_obs3, n, act_out=a3, rows=order, range_dev=ranges[j]))
-                fills.append(lambda c, f=f2, j=j: f.fill_chain(c, opp_obs4, n, act_out=a4, rows=order, range_dev=ranges[j]))
+                fills.append(lambda c, f=f1, j=j: f.fill_chain(c, opp_obs3, n, rows=rows, range_dev=ranges[j], act_ptr=p3, ld_act=2))
+                fills.append(lambda c, f=f2, j=j: f.fill_chain(c, opp_obs4, n, rows=rows, range_dev=ranges[j], act_ptr=p4, ld_act=2))
         else:
             f1, f2 = self._fa[0]
-            fills.append(lambda c: f1.fill_chain(c, opp_obs3, n, act_out=a3))
-            fills.append(lambda c: f2.fill_chain(c, opp_obs4, n, act_out=a4))
+            fills.append(lambda c: f1.fill_chain(c, opp_obs3, n, act_ptr=p3, ld_act=2))
+            fills.append(lambda c: f2.fill_chain(c, opp_obs4, n, act_ptr=p4, ld_act=2))
         run_chains(fills, self.device, precision)
-        return torch.stack((a3, a4), dim=1)
+        return act
 
     @torch.no_grad()
     def act(self, opp_obs3: torch.Tensor, opp_obs4: torch.Tensor, policy_set: torch.Tensor | None = None,

@@ -176,8 +176,14 @@ typedef struct {
   const int32_t* range_dev;
   int32_t* act_out;
   int32_t n_rows, ldx, d_in, k1_pad, att_lo, att_n, att_pad, n_out, ld_out, n_heads, head[4];
+  int32_t ld_act;   /* row stride of act_out in units of 4 int32 (0 or 1: dense [.., 4]) */
 } hh_policy_chain_ex;
 int hh_policy_forward_ex(int32_t n_chains, const hh_policy_chain_ex* chains, int32_t precision, void* stream);
+/* Row lists per key, built on the device: rows_dev int32 [n_keys][n], ranges_dev int32 [n_keys][2] = {k n, count_k} for the
+ * arenas i with key_dev[i] == keys_host[k] (n_keys <= 4).  Level 5 draws the opponents' policy set per arena and episode
+ * (env_hetero.py:55-59); the lists feed hh_policy_chain_ex.rows / range_dev without a host synchronisation. */
+int hh_policy_rows_by_key(int32_t n, const uint8_t* key_dev, int32_t n_keys, const int32_t* keys_host, int32_t* rows_dev,
+                          int32_t* ranges_dev, void* stream);
 const char* hh_policy_last_error(void);
 
 /* Test access to the device WGS84 solvers (replacing geographiclib's Geodesic.WGS84 as used at

@@ -69,7 +69,7 @@ def test_policy_forward_validates_arguments_without_a_gpu():
     from hhmarl_2d_b200 import _native as nat
     L = nat.lib()
     assert ctypes.sizeof(nat.HHPolicyChain) == 8 * 8 + 8 * 4
-    assert ctypes.sizeof(nat.HHPolicyChainEx) == 13 * 8 + 10 * 4 + 4 * 4
+    assert ctypes.sizeof(nat.HHPolicyChainEx) == 13 * 8 + 16 * 4          # 15 int32 + padding
     one = (nat.HHPolicyChainEx * 1)()
     assert L.hh_policy_forward_ex(0, one, 0, None) == -1            # no chains
     assert L.hh_policy_forward_ex(9, one, 0, None) == -1            # more than 8
@@ -80,3 +80,4 @@ def test_policy_forward_validates_arguments_without_a_gpu():
     assert L.hh_policy_forward(0, four, None, None, 0, None) == -1
     assert L.hh_step_host_begin(None, None) == -1 and L.hh_step_host_end(None, None, None, None, None) == -1
     assert L.hh_set_host_mode(None, 0) == -1
+    assert L.hh_policy_rows_by_key(0, None, 3, None, None, None, None) == -1
