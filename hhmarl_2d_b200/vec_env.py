@@ -59,6 +59,7 @@ class VecLowLevelEnv:
         self._opp = None
         self._opp_policies_arg = opponent_policies
         self.fused_opponents = True     # levels 4/5: frozen actors through csrc/hh_policy.cu (False: per-layer torch forward)
+        self.opponent_precision = 0     # 0: 3xTF32 (fp32-equivalent logits before the argmax), 1: plain TF32
         self.level = int(a.level)
 
     # ------------------------------------------------------------------ device (torch) API
@@ -132,7 +133,7 @@ class VecLowLevelEnv:
         nat.check(nat.lib().hh_step_begin(self._h, actions.data_ptr(), ob["obs3"].data_ptr(), ob["obs4"].data_ptr(),
                                           ob["pset"].data_ptr(), self._stream()), "hh_step_begin")
         if self.fused_opponents and ob["obs3"].is_cuda:
-            self.last_opp_actions = opp.act_fused(ob["obs3"], ob["obs4"], ob["pset"]).contiguous()
+            self.last_opp_actions = opp.act_fused(ob["obs3"], ob["obs4"], ob["pset"], self.opponent_precision).contiguous()
         else:
             self.last_opp_actions = opp.act(ob["obs3"], ob["obs4"], ob["pset"]).contiguous()
         return self.last_opp_actions
