@@ -520,6 +520,10 @@ __global__ void __launch_bounds__(64) begin_kernel(Arena* arenas, HParams P, con
   write_ll(A, g, 0, ll_obs + (size_t)a * NU * LL_STRIDE, ll_info + (size_t)a * NU);
   for (int i = NA; i < NU; ++i)   // opponents' policy kinds are known already (their observations come later)
     ll_info[(size_t)a * NU + i] = (A.ca[i] == 0 ? 2 : 0) | (A.actype[i] == 2 ? 4 : 0);
+  // bit 3 (this call only): alive at the start of the commander step -- a unit that is dead now makes no policy query
+  // in any of the step's sub-steps, so the host leaves it out of the batched forwards
+  for (int i = 0; i < NU; ++i)
+    if (A.alive[i]) ll_info[(size_t)a * NU + i] |= 8;
 }
 
 __global__ void __launch_bounds__(64) agents_kernel(Arena* arenas, HParams P, const int32_t* act, float* ll_obs, uint8_t* ll_info) {

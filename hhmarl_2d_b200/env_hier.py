@@ -95,11 +95,12 @@ class VecHighLevelEnv:
     def _build_rows(self):
         t = self._torch
         kind = (self.ll_info & 6).reshape(-1)
+        live = (self.ll_info & 8).reshape(-1) != 0     # alive at the start of this commander step (hh_hier_begin)
         self._rows = []
         for mode, ac, bits in self._KINDS:
             for first in (0, 3):
                 unit = t.arange(self.n_arenas * 6, device=self.dev) % 6
-                sel = (kind == bits) & (unit >= first) & (unit < first + 3)
+                sel = (kind == bits) & live & (unit >= first) & (unit < first + 3)
                 idx = t.nonzero(sel, as_tuple=False).flatten()
                 self._rows.append((mode, ac, first, idx.to(t.int32) if self.fused_policies else idx))
 

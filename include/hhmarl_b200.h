@@ -210,7 +210,8 @@ const char* hh_version(void);
  *   Arenas whose sub-step loop has ended idle through the remaining sub-step calls.
  * Shapes: commander_actions int32[N][3] in {0,1,2}; ll_obs f32[N][6][30] (row of unit id-1; fight 26/24,
  * escape 30/29 entries used); ll_info u8[N][6]: bit0 = unit queries its policy now, bit1 = escape policy,
- * bit2 = aircraft type 2; actions int32[N][6][4]; obs f32[N][3][34]; rew f32[N][3]; done u8[N]; substeps i32[N].
+ * bit2 = aircraft type 2, bit3 (as written by hh_hier_begin only) = alive at the start of the commander step;
+ * actions int32[N][6][4]; obs f32[N][3][34]; rew f32[N][3]; done u8[N]; substeps i32[N].
  * ============================================================================================ */
 typedef struct hh_hier_env hh_hier_env;
 
