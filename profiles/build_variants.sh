@@ -1,0 +1,12 @@
+#!/bin/bash
+# profiles/build_variants.sh -- the library variants that the profiles/run_*.sh scripts select with HH_LIB_PATH
+# (cross-compiles here; build/ is git-ignored but travels to the GPU box with the gpurun snapshot).
+set -e
+cd "$(dirname "$0")/../hhmarl_2d_b200/csrc"
+mkdir -p ../../build
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --expt-relaxed-constexpr -Xcompiler -fPIC -shared"
+SRC="hh_api.cu hh_hier.cu hh_policy.cu"
+nvcc $FLAGS -DHH_V4_PROFILE -o ../../build/lib_v4prof.so $SRC      # per-stage clock64() stamps (profiles/stage_clocks.py)
+nvcc $FLAGS -DHH_V4_MIN_CTAS=3 -o ../../build/lib_v4occ3.so $SRC   # 3 CTAs per SM (80 registers)
+# others used during round 1: -DHH_V4_ARENAS=16|64 (arenas per CTA), -DHH_PF_WARPS=16 (policy kernel warps)
+ls -la ../../build
