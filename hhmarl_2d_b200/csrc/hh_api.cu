@@ -157,7 +157,9 @@ __device__ __forceinline__ void launch_phase(Lane& L, int u, const PreTick& p, b
 // CmanoSimulator.do_tick (cmano_simulator.py:138-157) + _get_rewards/_combat_rewards (env_hetero.py:188-225,
 // env_base.py:240-310).  `rew` enters with the action-phase penalties and leaves with the step reward of
 // the calling agent lane.  Returns done (env_base.py:89-90).
-template <int MODE>
+// SHORT: moves through geo::direct_tick (the short-arc solve of the v4 kernel) -- the level-4/5 product path; the quad
+// level 1-3 kernel keeps the full Karney solve as an independent cross-check (A/B test in tests/test_gpu_parity.py).
+template <int MODE, bool SHORT>
 __device__ __forceinline__ bool tick_and_rewards(Lane& L, const Rng& rng, const Geom& g, const Params& P, int u,
                                                  const PreTick& p, double opp_focus, bool present, double& rew) {
   const int alive0 = p.alive_m;                  // snapshot: nothing dies in the action phase
@@ -183,7 +185,8 @@ __device__ __forceinline__ bool tick_and_rewards(Lane& L, const Rng& rng, const 
   phase_sync();
   double nlat = L.lat, nlon = L.lon;
   if (upd && L.spd > 0.0) {
-    const double2 q = geo::direct(L.lat, L.lon, L.hdg, L.spd * kKnotsToMs * 1.0);
+    const double2 q = (SHORT && P.short_moves) ? geo::direct_tick(L.lat, L.lon, L.hdg, L.spd * kKnotsToMs * 1.0)
+                            : geo::direct(L.lat, L.lon, L.hdg, L.spd * kKnotsToMs * 1.0);
     nlat = q.x;
     nlon = q.y;
   }
@@ -289,7 +292,8 @@ __device__ __forceinline__ bool tick_and_rewards(Lane& L, const Rng& rng, const 
           const double delta = signed_heading_diff(L.rhdg, L.rnhdg);
           L.rhdg = fabs(delta) <= 10.0 ? L.rnhdg : L.rhdg + (delta >= 0.0 ? 10.0 : -10.0);
         }
-        const double2 q = geo::direct(L.rlat, L.rlon, L.rhdg, rocket_speed(L.rage) * kKnotsToMs * 1.0);
+        const double2 q = (SHORT && P.short_moves) ? geo::direct_tick(L.rlat, L.rlon, L.rhdg, rocket_speed(L.rage) * kKnotsToMs * 1.0)
+                                : geo::direct(L.rlat, L.rlon, L.rhdg, rocket_speed(L.rage) * kKnotsToMs * 1.0);
         L.rlat = q.x;
         L.rlon = q.y;
         L.rage += 1;
@@ -477,7 +481,7 @@ step_kernel(StatePtrs S, Params P, const int32_t* __restrict__ actions, float* _
   }
   if (u < 2 && L.alive && L.mwait > 0 && !L.hasm) L.mwait -= 1;  // env_base.py:235-236
 
-  const bool done = tick_and_rewards<MODE>(L, rng, g, P, u, p, opp_focus, present, rew);
+  const bool done = tick_and_rewards<MODE, false>(L, rng, g, P, u, p, opp_focus, present, rew);
   finish_step<MODE>(L, rng, g, P, S, a, u, valid, done, rew, obs1, obs2, rew_out, done_out, s1, s2, arena0, n_valid);
 }
 
@@ -587,7 +591,7 @@ step_finish_kernel(StatePtrs S, Params P, const int32_t* __restrict__ opp_action
   launch_phase(L, u, p, want_missile, tgt);
   if (want_missile) L.mwait = new_wait;
   if (u >= 2 && L.alive && L.mwait > 0 && !L.hasm) L.mwait -= 1;
-  const bool done = tick_and_rewards<MODE>(L, rng, g, P, u, p, opp_focus, present, rew);
+  const bool done = tick_and_rewards<MODE, true>(L, rng, g, P, u, p, opp_focus, present, rew);
   finish_step<MODE>(L, rng, g, P, S, a, u, valid, done, rew, obs1, obs2, rew_out, done_out, s1, s2, arena0, n_valid);
 }
 
@@ -922,6 +926,10 @@ extern "C" int hh_create(const hh_config* cfg, int32_t n_arenas, int32_t device,
   P.seed_hi = (uint32_t)(cfg->seed >> 32);
   P.arena_base = (uint32_t)cfg->arena_base;
   P.geom = make_geom(P.map_size);
+  {
+    const char* sm = getenv("HH_SHORT_MOVES");
+    P.short_moves = (sm && sm[0] == '0') ? 0 : 1;
+  }
   {
     const char* impl = getenv("HH_STEP_IMPL");
     if (sizeof(v4::Smem) > 48 * 1024) {   // opt in to > 48 KB of dynamic shared memory (per device, idempotent)

@@ -38,6 +38,7 @@ struct Params {
   uint32_t seed_lo, seed_hi;
   uint32_t arena_base;  // global id of local arena 0 (multi-GPU sharding)
   Geom geom;            // make_geom(map_size), filled on the host (IEEE sqrt / division: same bits as on the device)
+  int short_moves;      // levels 4/5 finish kernel: 1 = geo::direct_tick (default), 0 = full Karney direct (HH_SHORT_MOVES=0)
 };
 
 // rocket_unit.py:16-21 -- scipy quadratic spline through (0,500),(10,2000),(20,1400),(30,600)

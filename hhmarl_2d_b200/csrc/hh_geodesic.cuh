@@ -421,6 +421,13 @@ static __device__ __noinline__ double2 direct_short(double lat1, double lon1, do
   return out;
 }
 
+// One-tick move with the azimuth given in degrees (callers that do not keep a heading vector)
+__device__ __forceinline__ double2 direct_tick(double lat1, double lon1, double azi1, double s12) {
+  double sa, ca;
+  sincosd(ang_round(ang_normalize(azi1)), sa, ca);
+  return direct_short(lat1, lon1, azi1, sa, ca, s12);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Inverse problem. Returns (s12 [m], azi1 [deg in (-180, 180]]).
 // ---------------------------------------------------------------------------------------------

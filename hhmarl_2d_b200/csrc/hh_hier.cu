@@ -49,6 +49,7 @@ struct HParams {
   int n_arenas, horizon, level, friendly_kill, autoreset, action_assess, fight_p, fight_q;
   double map_size, rew_scale, glob_frac;
   uint32_t seed_lo, seed_hi, arena_base;
+  int short_moves;   // 1: one-tick moves through geo::direct_tick (default), 0: full Karney direct (HH_SHORT_MOVES=0)
 };
 
 __device__ __forceinline__ double g_next(const Rng& r, Arena& A) { return g_random_at(r, A.dg++); }
@@ -311,7 +312,8 @@ __device__ void do_tick(Arena& A, const Rng& rng, const HParams& P, Events& ev) 
       else A.rnhdg[i] = clip(__dmul_rn(A.rhdg[i], uniform_from(0.95, 1.05, g_next(rng, A))), 0.0, 359.0);
     }
     if (A.spd[i] > 0.0) {
-      const double2 q = geo::direct(A.lat[i], A.lon[i], A.hdg[i], A.spd[i] * kKnotsToMs * 1.0);
+      const double2 q = P.short_moves ? geo::direct_tick(A.lat[i], A.lon[i], A.hdg[i], A.spd[i] * kKnotsToMs * 1.0)
+                                     : geo::direct(A.lat[i], A.lon[i], A.hdg[i], A.spd[i] * kKnotsToMs * 1.0);
       A.lat[i] = q.x;
       A.lon[i] = q.y;
     }
@@ -351,7 +353,8 @@ __device__ void do_tick(Arena& A, const Rng& rng, const HParams& P, Events& ev) 
       const double d = signed_heading_diff(A.rhdg[s], A.rnhdg[s]);
       A.rhdg[s] = fabs(d) <= 10.0 ? A.rnhdg[s] : A.rhdg[s] + (d >= 0.0 ? 10.0 : -10.0);
     }
-    const double2 q = geo::direct(A.rlat[s], A.rlon[s], A.rhdg[s], rocket_speed(A.rage[s]) * kKnotsToMs * 1.0);
+    const double2 q = P.short_moves ? geo::direct_tick(A.rlat[s], A.rlon[s], A.rhdg[s], rocket_speed(A.rage[s]) * kKnotsToMs * 1.0)
+                                   : geo::direct(A.rlat[s], A.rlon[s], A.rhdg[s], rocket_speed(A.rage[s]) * kKnotsToMs * 1.0);
     A.rlat[s] = q.x;
     A.rlon[s] = q.y;
     A.rage[s] += 1;
@@ -618,6 +621,10 @@ extern "C" int hh_hier_create(const hh_hier_config* c, int32_t n_arenas, int32_t
   P.seed_lo = (uint32_t)c->seed;
   P.seed_hi = (uint32_t)(c->seed >> 32);
   P.arena_base = (uint32_t)c->arena_base;
+  {
+    const char* sm = getenv("HH_SHORT_MOVES");
+    P.short_moves = (sm && sm[0] == '0') ? 0 : 1;
+  }
   cudaError_t ce = cudaMalloc(&e->arenas, sizeof(Arena) * (size_t)n_arenas);
   if (ce != cudaSuccess) {
     delete e;

@@ -85,6 +85,7 @@ extern "C" int hh_create(const hh_config* cfg, int32_t n_arenas, int32_t, hh_env
   P.seed_hi = (uint32_t)(cfg->seed >> 32);
   P.arena_base = (uint32_t)cfg->arena_base;
   P.geom = make_geom(P.map_size);
+  P.short_moves = 1;
   e->sm = new v4::Smem();
   *out = e;
   return 0;
