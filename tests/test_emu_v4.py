@@ -22,7 +22,34 @@ def test_v4_schedule_replays_reference_golden(path):
         tgp.test_cuda_replays_reference_golden(path)
 
 
-def _many(level, mode, kw, n, T, reverse=False, arenas_per_cta=None):
+def pursuit_actions(states, rng, p_random=0.15):
+    """Actions that make the agents hunt: steer towards the nearest live opponent (15-degree heading steps), full speed
+    when far, always fire cannon and missile.  Engagements -- cannon cones, rocket proximity, kills, friendly fire --
+    then happen every few steps instead of once in a while as with uniformly random actions."""
+    n = len(states)
+    act = np.zeros((n, 2, 4), np.int32)
+    for k, s in enumerate(states):
+        for u in range(2):
+            if rng.random() < p_random or not s.alive[u]:
+                act[k, u] = (rng.integers(0, 13), rng.integers(0, 9), rng.integers(0, 2), rng.integers(0, 2))
+                continue
+            best, bd = None, 1e9
+            for e in (2, 3):
+                if s.alive[e]:
+                    d = np.hypot(s.lon[e] - s.lon[u], s.lat[e] - s.lat[u])
+                    if d < bd:
+                        best, bd = e, d
+            if best is None:
+                act[k, u] = (6, 4, 1, 1)
+                continue
+            bearing = np.degrees(np.arctan2(s.lon[best] - s.lon[u], s.lat[best] - s.lat[u])) % 360
+            err = (bearing - s.heading[u] + 180) % 360 - 180
+            act[k, u] = (int(np.clip(round(err / 15) + 6, 0, 12)), 8 if bd > 0.03 else 3, 1, 1)
+    act[:, 1, 3] = 0
+    return act
+
+
+def _many(level, mode, kw, n, T, reverse=False, arenas_per_cta=None, pursuit=False):
     import oracle as orc
     seed, base = 99173 + level, 1000
     with emu_env.emulated(reverse=reverse, arenas_per_cta=arenas_per_cta):
@@ -35,9 +62,14 @@ def _many(level, mode, kw, n, T, reverse=False, arenas_per_cta=None):
         rng = np.random.default_rng(level)
         n_done = 0
         trace = []
+        n_kill_steps = 0
         for t in range(T):
-            act = np.stack([rng.integers(0, 13, (n, 2)), rng.integers(0, 9, (n, 2)), rng.integers(0, 2, (n, 2)),
-                            rng.integers(0, 2, (n, 2))], axis=-1).astype(np.int32)
+            if pursuit:
+                act = pursuit_actions([o.state() for o in oracles], rng)
+            else:
+                act = np.stack([rng.integers(0, 13, (n, 2)), rng.integers(0, 9, (n, 2)), rng.integers(0, 2, (n, 2)),
+                                rng.integers(0, 2, (n, 2))], axis=-1).astype(np.int32)
+            alive_before = np.array([sum(o.state().alive[:4]) for o in oracles]) if pursuit else None
             g1, g2, grew, gdone = env.step_host(act)
             e1 = np.empty_like(g1); e2 = np.empty_like(g2); erew = np.empty((n, 2)); edone = np.empty(n, np.uint8)
             for k, o in enumerate(oracles):
@@ -51,6 +83,9 @@ def _many(level, mode, kw, n, T, reverse=False, arenas_per_cta=None):
             tgp._close(g1, e1, f"t={t} obs1")
             tgp._close(g2, e2, f"t={t} obs2")
             n_done += int(edone.sum())
+            if pursuit:   # arena-steps in which an aircraft was lost (shot down or out of bounds); resets excluded
+                after = np.array([sum(o.state().alive[:4]) for o in oracles])
+                n_kill_steps += int(np.count_nonzero((after < alive_before) & (edone == 0)))
             trace.append((g1.copy(), g2.copy(), grew.copy(), gdone.copy()))
             if t % 50 == 49 or t == T - 1:
                 st = env.get_state()
@@ -65,6 +100,8 @@ def _many(level, mode, kw, n, T, reverse=False, arenas_per_cta=None):
                     assert (st[fld] == np.array([getattr(s, fld) for s in os_])).all(), (t, fld)
                 assert (st["error"] == 0).all()
         assert n_done > n // 2
+        if pursuit:
+            assert n_kill_steps > n, n_kill_steps           # losses in the middle of episodes, in every arena on average
         return trace
 
 
@@ -76,6 +113,13 @@ CASES = [(1, "fight", {}), (2, "fight", {}), (3, "fight", {}), (3, "escape", {"e
 def test_v4_schedule_matches_oracle(level, mode, kw):
     """77 arenas (ragged: 2 full CTAs + 13) x 330 ticks with in-step auto-reset against 77 scalar C oracles."""
     _many(level, mode, kw, n=77, T=330)
+
+
+@pytest.mark.parametrize("level,mode,kw", [(3, "fight", {}), (2, "fight", {}), (3, "escape", {"esc_dist_rew": True}),
+                                           (3, "fight", {"friendly_punish": True, "glob_frac": 0.5})])
+def test_v4_schedule_matches_oracle_under_pursuit(level, mode, kw):
+    """Same comparison with agents that hunt the opponents: dense cannon / rocket engagements and kills."""
+    _many(level, mode, kw, n=48, T=400, pursuit=True)
 
 
 def test_v4_schedule_has_no_order_dependence_between_threads_of_a_stage():
