@@ -462,3 +462,47 @@ def test_level5_full_size_properties():
     part, _ = run(1001, 20000, slice(20000, 21001))
     for a, b in zip(full, part):
         assert torch.equal(a[20000:21001], b)
+
+
+@pytest.mark.parametrize("level,mode,kw", [(3, "fight", {}), (2, "fight", {"friendly_punish": True}),
+                                           (3, "escape", {"esc_dist_rew": True})])
+def test_cuda_matches_oracle_under_pursuit(level, mode, kw):
+    """Agents that hunt the opponents (tests/test_emu_v4.py: pursuit_actions) make cannon cones, rocket proximity tests,
+    kills and friendly fire frequent: the CUDA step against the C oracle on those trajectories."""
+    import oracle as orc
+    from test_emu_v4 import pursuit_actions
+    n, T, seed, base = 96, 320, 4711 + level, 50
+    env = _vec(n, level, mode, seed, arena_base=base, autoreset=True, **kw)
+    oracles = [orc.OracleEnv(orc.make_args(level=level, agent_mode=mode, **kw), seed, base + k) for k in range(n)]
+    o1, o2 = env.reset_host()
+    ref = [o.reset() for o in oracles]
+    _close(o1, np.stack([p[0] for p in ref]), "reset obs1")
+    rng = np.random.default_rng(level)
+    losses = 0
+    for t in range(T):
+        states = [o.state() for o in oracles]
+        act = pursuit_actions(states, rng)
+        before = np.array([sum(s.alive[:4]) for s in states])
+        g1, g2, grew, gdone = env.step_host(act)
+        e1 = np.empty_like(g1); e2 = np.empty_like(g2); erew = np.empty((n, 2)); edone = np.empty(n, np.uint8)
+        for k, o in enumerate(oracles):
+            a1, a2, r, pres, d = o.step(act[k])
+            edone[k], erew[k] = d, r
+            if not d:
+                losses += int(sum(o.state().alive[:4]) < before[k])
+            else:
+                a1, a2 = o.reset()
+            e1[k], e2[k] = a1, a2
+        assert (gdone == edone).all(), f"t={t} done mismatch at {np.nonzero(gdone != edone)[0][:8]}"
+        _close(grew, erew, f"t={t} rew")
+        _close(g1, e1, f"t={t} obs1")
+        _close(g2, e2, f"t={t} obs2")
+        if t % 40 == 39:
+            st = env.get_state()
+            os_ = [o.state() for o in oracles]
+            for fld in ("missile_remain", "missile_wait", "alive", "has_missile", "cannon_remain", "cannon_burst"):
+                assert (st[fld] == np.array([list(getattr(s, fld)[:4]) for s in os_])).all(), (t, fld)
+            for fld in ("steps", "alive_agents", "alive_opps", "next_unit_id", "draws_g", "draws_c"):
+                assert (st[fld] == np.array([getattr(s, fld) for s in os_])).all(), (t, fld)
+            assert (st["error"] == 0).all()
+    assert losses > n
