@@ -858,6 +858,12 @@ extern "C" int hh_debug_v4_profile(long long* out_host, int32_t n_ctas) {
   HH_CUDA(cudaMemcpyFromSymbol(out_host, v4::g_stage_clock, sizeof(long long) * 16 * (size_t)n_ctas));
   return 0;
 }
+extern "C" int hh_debug_v4_warp_arrivals(long long* out_host, int32_t n_ctas) {
+  if (!out_host || n_ctas <= 0 || n_ctas > 512) return fail(-1, "hh_debug_v4_warp_arrivals: bad argument");
+  HH_CUDA(cudaDeviceSynchronize());
+  HH_CUDA(cudaMemcpyFromSymbol(out_host, v4::g_warp_arrive, sizeof(long long) * 8 * 16 * (size_t)n_ctas));
+  return 0;
+}
 #endif
 
 extern "C" int hh_create(const hh_config* cfg, int32_t n_arenas, int32_t device, hh_env** out) {

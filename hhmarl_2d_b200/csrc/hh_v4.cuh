@@ -893,7 +893,17 @@ static bool emu_reverse = false;
 // every stage boundary, hh_debug_v4_profile() reads them back.
 #if defined(HH_V4_PROFILE) && defined(__CUDACC__)
 __device__ long long g_stage_clock[4096 * 16];
+__device__ long long g_warp_arrive[512 * 8 * 16];   // [CTA][warp][barrier]: when each warp reached each barrier
 #define HH_MARK(k) if (tid == 0 && block < 4096) g_stage_clock[block * 16 + (k)] = clock64();
+#undef HH_BARRIER
+#define HH_BARRIER()                                                                                          \
+  do {                                                                                                        \
+    if ((tid & 31) == 0 && block < 512 && hh_bar < 16) g_warp_arrive[(block * 8 + (tid >> 5)) * 16 + hh_bar] = clock64(); \
+    ++hh_bar;                                                                                                 \
+    __syncthreads();                                                                                          \
+  } while (0)
+#undef HH_TID_DECL
+#define HH_TID_DECL const int tid = threadIdx.x; int hh_bar = 0;
 #else
 #define HH_MARK(k)
 #endif
@@ -949,6 +959,9 @@ __device__ __forceinline__ void step_body(Smem& S, const StatePtrs& G, const Par
   HH_ROLE(0, A4, s10_store_unit(C, t))     // (storing the state during S9 instead was measured slower: r1o)
   HH_ROLE(0, A8, s10_store_rows(C, t, A8, D1, D2))
   HH_MARK(10)
+#if defined(HH_V4_PROFILE) && defined(__CUDACC__)
+  if ((tid & 31) == 0 && block < 512) g_warp_arrive[(block * 8 + (tid >> 5)) * 16 + 15] = hh_bar;   // barriers passed
+#endif
 }
 
 // Masked reset + first observation through the same stages (first_time: state is created, not loaded).
