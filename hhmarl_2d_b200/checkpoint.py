@@ -49,3 +49,18 @@ def load_opponent_policies(policy_dir: str, level: int, agent_mode: str, device=
         return out
     f1, f2 = load_pair(policy_dir, 5, "fight", device)   # escape-vs-L5_fight
     return {"fight_1": f1, "fight_2": f2}
+
+
+def load_highlevel_policies(policy_dir: str, eval_level_ag: int = 5, eval_level_opp: int = 5, eval_hl: bool = True,
+                            device="cpu"):
+    """HHMARLBaseEnv._get_policies("HighLevel") (env_base.py:332-346): the container VecHighLevelEnv takes as
+    `lowlevel_policies`.  Fight policies of level `eval_level_ag`; escape policies trained against L5 fight if
+    present, else the L3 ones; in the low-level evaluation mode (eval_hl False) the opponents fight with the
+    policies of level `eval_level_opp` ("fight_1_opp" / "fight_2_opp")."""
+    out = {}
+    out["fight_1"], out["fight_2"] = load_pair(policy_dir, eval_level_ag, "fight", device)
+    esc_level = 5 if all(os.path.exists(policy_path(policy_dir, 5, ac, "escape")) for ac in (1, 2)) else 3
+    out["escape_1"], out["escape_2"] = load_pair(policy_dir, esc_level, "escape", device)
+    if not eval_hl:
+        out["fight_1_opp"], out["fight_2_opp"] = load_pair(policy_dir, eval_level_opp, "fight", device)
+    return out

@@ -553,6 +553,43 @@ __global__ void __launch_bounds__(64) tick_kernel(Arena* arenas, HParams P, cons
   write_ll(A, g, 0, ll_obs + (size_t)a * NU * LL_STRIDE, ll_info + (size_t)a * NU);
 }
 
+// HHMARLBaseEnv.step with args.eval_info (env_base.py:91-107): the step's `info` dict as int32[12] per arena =
+// agents_win, opps_win, draw, agent_fight, agent_escape, opp_fight, opp_escape, agent_steps, opp_steps, opp1, opp2,
+// opp3.  Reads the record as the last tick left it (aircraft that exist NOW, the commander actions as
+// _action_assess left them), so it runs between the last hh_hier_tick and hh_hier_end (which may auto-reset).
+__global__ void __launch_bounds__(64) eval_info_kernel(const Arena* arenas, HParams P, int32_t* info) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= P.n_arenas) return;
+  const Arena& A = arenas[a];
+  int32_t o[12];
+  for (int k = 0; k < 12; ++k) o[k] = 0;
+  const bool before_horizon = A.steps < P.horizon;
+  o[0] = (A.alive_op <= 0 && before_horizon) ? 1 : 0;
+  o[1] = (A.alive_ag <= 0 && before_horizon) ? 1 : 0;
+  o[2] = (!before_horizon && A.alive_ag > 0 && A.alive_op > 0) ? 1 : 0;
+  for (int i = 0; i < NU; ++i) {
+    if (!A.alive[i]) continue;
+    const int v = A.ca[i];   // `if v:` -- None (-1) and 0 are falsy
+    if (v > 0) {
+      if (i < NA) {
+        o[3] += 1;
+        o[7] += 1;
+        if (v <= 3) o[8 + v] += 1;
+      } else {
+        o[5] += 1;
+        o[8] += 1;
+      }
+    } else if (i < NA) {
+      o[4] += 1;
+      o[7] += 1;
+    } else {
+      o[6] += 1;
+      o[8] += 1;
+    }
+  }
+  for (int k = 0; k < 12; ++k) info[(size_t)a * 12 + k] = o[k];
+}
+
 __global__ void __launch_bounds__(64) end_kernel(Arena* arenas, HParams P, float* obs, float* rew, uint8_t* done, int32_t* substeps) {
   HH_HIER_PROLOGUE
   const bool d = A.alive_ag <= 0 || A.alive_op <= 0 || A.steps >= P.horizon;
@@ -675,6 +712,15 @@ extern "C" int hh_hier_tick(hh_hier_env* e, const int32_t* act_dev, float* ll_ob
 extern "C" int hh_hier_end(hh_hier_env* e, float* obs_dev, float* rew_dev, uint8_t* done_dev, int32_t* substeps_dev, void* stream) {
   if (!e || !obs_dev || !rew_dev || !done_dev) return hfail(-1, "hh_hier_end: null argument");
   HIER_LAUNCH(end_kernel, obs_dev, rew_dev, done_dev, substeps_dev);
+  return 0;
+}
+extern "C" int hh_hier_eval_info(hh_hier_env* e, int32_t* info_dev, void* stream) {
+  if (!e || !info_dev) return hfail(-1, "hh_hier_eval_info: null argument");
+  if (!e->initialised) return hfail(-4, "hh_hier_eval_info: call hh_hier_reset first");
+  const int blocks = (e->P.n_arenas + 63) / 64;
+  hh::hier::eval_info_kernel<<<blocks, 64, 0, static_cast<cudaStream_t>(stream)>>>(e->arenas, e->P, info_dev);
+  HHH_CUDA(cudaGetLastError());
+  e->launches += 1;
   return 0;
 }
 extern "C" int hh_hier_get_state(hh_hier_env* e, hh_hier_arena* out_host) {

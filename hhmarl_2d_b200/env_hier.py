@@ -21,6 +21,9 @@ from . import models as M
 from .spaces import Box, Discrete
 
 OBS_HL, N_ACTIONS_HL = 34, 3   # env_hier.py:20-37
+# keys of the info dict of HHMARLBaseEnv.step under args.eval_info, in the reference's order (env_base.py:104-106)
+EVAL_INFO_KEYS = ("agents_win", "opps_win", "draw", "agent_fight", "agent_escape", "opp_fight", "opp_escape",
+                  "agent_steps", "opp_steps", "opp1", "opp2", "opp3")
 
 
 def default_lowlevel_policies(seed: int = 0, device="cpu"):
@@ -34,12 +37,13 @@ def default_lowlevel_policies(seed: int = 0, device="cpu"):
 
 
 def make_hier_args(horizon=500, map_size=0.5, rew_scale=1.0, glob_frac=0.0, friendly_kill=True,
-                   hier_action_assess=True, hier_opp_fight_ratio=75, level=1):
-    """Config(1) defaults of the reference (config.py:17-57, 98)."""
+                   hier_action_assess=True, hier_opp_fight_ratio=75, level=1, eval_info=False):
+    """Config(1) defaults of the reference (config.py:17-57, 98); eval_info=True is Config(2) (config.py:49)."""
     from argparse import Namespace
     return Namespace(level=level, horizon=horizon, agent_mode="fight", num_agents=3, num_opps=3, total_num=6,
                      map_size=map_size, rew_scale=rew_scale, glob_frac=glob_frac, friendly_kill=friendly_kill,
-                     hier_action_assess=hier_action_assess, hier_opp_fight_ratio=hier_opp_fight_ratio, eval_hl=True)
+                     hier_action_assess=hier_action_assess, hier_opp_fight_ratio=hier_opp_fight_ratio, eval_hl=True,
+                     eval_info=eval_info)
 
 
 class VecHighLevelEnv:
@@ -72,6 +76,10 @@ class VecHighLevelEnv:
         self.ll_obs = torch.zeros((n, 6, 30), dtype=torch.float32, device=dev)
         self.ll_info = torch.zeros((n, 6), dtype=torch.uint8, device=dev)
         self.ll_act = torch.zeros((n, 6, 4), dtype=torch.int32, device=dev)
+        # args.eval_info (config.py:49, env_base.py:91-107): when set, step() also fills `self.info` (int32 [N,12],
+        # columns EVAL_INFO_KEYS) with the reference's per-step info dict; hhmarl_2d_b200.evaluation sums it
+        self.eval_info = bool(getattr(self.args, "eval_info", False))
+        self.info = torch.zeros((n, len(EVAL_INFO_KEYS)), dtype=torch.int32, device=dev)
         self.trace = None   # set to a list to record (phase, ll_obs, ll_info, ll_act) per sub-step (tests)
         self.fused_policies = True   # the frozen low-level actors through csrc/hh_policy.cu (False: torch forward)
         self.policy_precision = 0    # 0: 3xTF32 (fp32-equivalent logits before the argmax), 1: plain TF32 (~2x faster forward)
@@ -104,18 +112,28 @@ class VecHighLevelEnv:
                 idx = t.nonzero(sel, as_tuple=False).flatten()
                 self._rows.append((mode, ac, first, idx.to(t.int32) if self.fused_policies else idx))
 
+    def _policy_key(self, mode: str, ac: int, first: int) -> str:
+        """env_base.py:385-390: every aircraft uses "{mode}_{ac_type}"; only in the low-level evaluation mode
+        (args.eval_hl False, env_base.py:343-346) the opponents (units 4-6) fight with "fight_{ac_type}_opp"."""
+        if first == 3 and mode == "fight" and not getattr(self.args, "eval_hl", True):
+            return f"fight_{ac}_opp"
+        return f"{mode}_{ac}"
+
     def _infer_fused(self, first: int):
         """All (mode x aircraft type) row lists of this half-step as chains of ONE hh_policy_forward_ex launch: gather
         by row index, actor forward on the tensor cores (3xTF32), per-head argmax written straight into ll_act."""
         from .fused_forward import FusedActor, run_chains
         if self._fused is None:
-            self._fused = {(mode, ac): FusedActor(self.policies[f"{mode}_{ac}"]) for mode, ac, _ in self._KINDS}
+            self._fused = {}
         obs_flat, act_flat = self.ll_obs.reshape(-1, 30), self.ll_act.reshape(-1, 4)
         fills = []
         for mode, ac, f, idx in self._rows:
             if f != first or idx.numel() == 0:
                 continue
-            fa = self._fused[(mode, ac)]
+            key = self._policy_key(mode, ac, first)
+            if key not in self._fused:
+                self._fused[key] = FusedActor(self.policies[key])
+            fa = self._fused[key]
             fills.append(lambda c, fa=fa, idx=idx: fa.fill_chain(c, obs_flat, idx.numel(), act_out=act_flat, rows=idx))
         run_chains(fills, self.dev, self.policy_precision)
 
@@ -129,7 +147,7 @@ class VecHighLevelEnv:
                 if f != first or idx.numel() == 0:
                     continue
                 x = obs_flat.index_select(0, idx)[:, :self._DIMS[(mode, ac)]]
-                a = M.deterministic_actions(self.policies[f"{mode}_{ac}"].actor(x), ac).to(t.int32)
+                a = M.deterministic_actions(self.policies[self._policy_key(mode, ac, first)].actor(x), ac).to(t.int32)
                 if a.shape[1] == 3:
                     a = t.nn.functional.pad(a, (0, 1))
                 act_flat.index_copy_(0, idx, a)
@@ -153,6 +171,8 @@ class VecHighLevelEnv:
                 self.trace.append(("opps", self.ll_obs.cpu().numpy().copy(), self.ll_info.cpu().numpy().copy(),
                                    self.ll_act.cpu().numpy().copy()))
             nat.check(L.hh_hier_tick(h, la, lo, li, st), "hh_hier_tick")
+        if self.eval_info:   # before hh_hier_end: its auto-reset replaces a finished episode
+            nat.check(L.hh_hier_eval_info(h, self.info.data_ptr(), st), "hh_hier_eval_info")
         nat.check(L.hh_hier_end(h, self.obs.data_ptr(), self.rew.data_ptr(), self.done.data_ptr(),
                                 self.substeps.data_ptr(), st), "hh_hier_end")
         return self.obs, self.rew, self.done

@@ -250,6 +250,12 @@ int hh_hier_begin(hh_hier_env* env, const int32_t* commander_actions_dev, float*
 int hh_hier_agents(hh_hier_env* env, const int32_t* actions_dev, float* ll_obs_dev, uint8_t* ll_info_dev, void* stream);
 int hh_hier_tick(hh_hier_env* env, const int32_t* actions_dev, float* ll_obs_dev, uint8_t* ll_info_dev, void* stream);
 int hh_hier_end(hh_hier_env* env, float* obs_dev, float* rew_dev, uint8_t* done_dev, int32_t* substeps_dev, void* stream);
+/* HHMARLBaseEnv.step with args.eval_info (env_base.py:91-107; summed by evaluation.py:59-60, reported by
+ * postprocess_eval evaluation.py:66-82): info int32[N][12] = agents_win, opps_win, draw, agent_fight, agent_escape,
+ * opp_fight, opp_escape, agent_steps, opp_steps, opp1, opp2, opp3 of the commander step in flight.  Call it after
+ * the last hh_hier_tick and BEFORE hh_hier_end (whose auto-reset replaces the finished episode). */
+#define HH_HIER_EVAL_INFO_LEN 12
+int hh_hier_eval_info(hh_hier_env* env, int32_t* info_dev, void* stream);
 int hh_hier_get_state(hh_hier_env* env, hh_hier_arena* out_host);
 int hh_hier_set_state(hh_hier_env* env, const hh_hier_arena* in_host);
 uint64_t hh_hier_launch_count(const hh_hier_env* env);

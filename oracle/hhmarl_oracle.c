@@ -1307,6 +1307,39 @@ int orc_hier_step(orc_env_t* e, const int32_t* commander_actions, float* obs, do
   return e->alive_agents <= 0 || e->alive_opps <= 0 || e->steps >= e->args.horizon;
 }
 
+/* the `info` dict of HHMARLBaseEnv.step when args.eval_info is set (env_base.py:91-107; consumed by
+ * evaluation.py:59-60, 66-82), evaluated on the env as orc_hier_step left it: units that exist NOW, the commander
+ * action dict as _action_assess left it (env_hier.py:142-190).  out[12] = agents_win, opps_win, draw, agent_fight,
+ * agent_escape, opp_fight, opp_escape, agent_steps, opp_steps, opp1, opp2, opp3. */
+void orc_hier_eval_info(const orc_env_t* e, int32_t* out) {
+  int i, na = e->args.num_agents;
+  const int before_horizon = e->steps < e->args.horizon;
+  memset(out, 0, 12 * sizeof(int32_t));
+  out[0] = e->alive_opps <= 0 && before_horizon;
+  out[1] = e->alive_agents <= 0 && before_horizon;
+  out[2] = !before_horizon && e->alive_agents > 0 && e->alive_opps > 0;
+  for (i = 1; i <= e->total_num; ++i) {
+    const int v = e->commander_actions[i];
+    if (!unit_exists(e, i)) continue;
+    if (v > 0) { /* `if v:` -- None and 0 are falsy */
+      if (i <= na) {
+        out[3] += 1;
+        out[7] += 1;
+        if (v <= 3) out[8 + v] += 1;
+      } else {
+        out[5] += 1;
+        out[8] += 1;
+      }
+    } else if (i <= na) {
+      out[4] += 1;
+      out[7] += 1;
+    } else {
+      out[6] += 1;
+      out[8] += 1;
+    }
+  }
+}
+
 /* ------------------------------------------------------------------ public API */
 orc_env_t* orc_env_create(const orc_args_t* args, uint64_t seed, uint32_t arena_id) {
   orc_env_t* e = (orc_env_t*)calloc(1, sizeof *e);

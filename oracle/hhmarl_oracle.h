@@ -86,6 +86,10 @@ int orc_obs_len(const orc_args_t* args, int agent_id);
 #define ORC_OBS_HL 34
 void orc_hier_reset(orc_env_t* e, float* obs);
 int orc_hier_step(orc_env_t* e, const int32_t* commander_actions, float* obs, double* rew, int32_t* info);
+/* env_base.py:91-107 (args.eval_info): out[12] = agents_win, opps_win, draw, agent_fight, agent_escape, opp_fight,
+ * opp_escape, agent_steps, opp_steps, opp1, opp2, opp3 for the step orc_hier_step just made (call before a reset). */
+#define ORC_EVAL_INFO_LEN 12
+void orc_hier_eval_info(const orc_env_t* e, int32_t* out);
 
 /* Throughput helper for bench.py's CPU baseline: runs `n_steps` env steps with auto-reset and
  * uniformly random MultiDiscrete actions (own xorshift stream, not the contract RNG). */

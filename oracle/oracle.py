@@ -94,6 +94,8 @@ def lib():
         L.orc_hier_reset.restype = None
         L.orc_hier_step.argtypes = [ctypes.c_void_p] * 5
         L.orc_hier_step.restype = ctypes.c_int
+        L.orc_hier_eval_info.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.orc_hier_eval_info.restype = None
         L.orc_env_run_random.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64]
         L.orc_env_run_random.restype = ctypes.c_uint64
         _lib = L
@@ -171,8 +173,9 @@ def make_args(level=1, agent_mode="fight", horizon=None, map_size=0.3, rew_scale
 
 
 def make_hier_args(horizon=500, map_size=0.5, rew_scale=1.0, glob_frac=0.0, friendly_kill=True,
-                   hier_action_assess=True, hier_opp_fight_ratio=75, level=1) -> OrcArgs:
-    """Config(1) defaults of the reference (config.py:17-57,98): 3-vs-3, map 0.5, horizon 500, level left at 1."""
+                   hier_action_assess=True, hier_opp_fight_ratio=75, level=1, eval_info=False) -> OrcArgs:
+    """Config(1) defaults of the reference (config.py:17-57,98): 3-vs-3, map 0.5, horizon 500, level left at 1.
+    `eval_info` changes nothing in the env (env_base.py:91 only builds the info dict): see OracleHierEnv.eval_info."""
     return OrcArgs(level=level, agent_mode=0, horizon=horizon, num_agents=3, num_opps=3, esc_dist_rew=0,
                    friendly_kill=int(friendly_kill), friendly_punish=0, map_size=map_size, rew_scale=rew_scale,
                    glob_frac=glob_frac, hier_action_assess=int(hier_action_assess),
@@ -235,6 +238,11 @@ class OracleEnv:
             pass
 
 
+# key order of the reference's info dict (env_base.py:104-106)
+EVAL_INFO_KEYS = ("agents_win", "opps_win", "draw", "agent_fight", "agent_escape", "opp_fight", "opp_escape",
+                  "agent_steps", "opp_steps", "opp1", "opp2", "opp3")
+
+
 class OracleHierEnv:
     """Single-arena C oracle of the reference's HighLevelEnv (envs/env_hier.py)."""
 
@@ -264,6 +272,12 @@ class OracleHierEnv:
         done = lib().orc_hier_step(self._h, a.ctypes.data, self.obs.ctypes.data, self.rew.ctypes.data,
                                    self.info.ctypes.data)
         return self.obs.copy(), self.rew.copy(), bool(done), self.info.copy()
+
+    def eval_info(self):
+        """env_base.py:91-107 for the step just made, as {key: int} in the reference's key order."""
+        out = np.zeros(len(EVAL_INFO_KEYS), np.int32)
+        lib().orc_hier_eval_info(self._h, out.ctypes.data)
+        return dict(zip(EVAL_INFO_KEYS, (int(v) for v in out)))
 
     def state(self) -> OrcState:
         s = OrcState()

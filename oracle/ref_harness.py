@@ -319,11 +319,11 @@ def reference_models():
 
 # ------------------------------------------------------------------ reference HighLevelEnv under stubs
 def make_hier_namespace(horizon=500, map_size=0.5, rew_scale=1, glob_frac=0.0, friendly_kill=True,
-                        hier_action_assess=True, hier_opp_fight_ratio=75, level=1) -> Namespace:
+                        hier_action_assess=True, hier_opp_fight_ratio=75, level=1, eval_info=False) -> Namespace:
     """Config(1) of the reference (config.py:17-57, 94-107) without argparse."""
     return Namespace(level=level, horizon=horizon, agent_mode="fight", num_agents=3, num_opps=3, total_num=6,
                      map_size=map_size, rew_scale=rew_scale, glob_frac=glob_frac, esc_dist_rew=False,
-                     friendly_kill=friendly_kill, friendly_punish=False, eval_info=False, eval_hl=True,
+                     friendly_kill=friendly_kill, friendly_punish=False, eval_info=eval_info, eval_hl=True,
                      eval_level_ag=5, eval_level_opp=5, hier_opp_fight_ratio=hier_opp_fight_ratio,
                      hier_action_assess=hier_action_assess)
 
@@ -398,6 +398,7 @@ class ReferenceHierEnv:
         ca = {i + 1: int(a) for i, a in enumerate(commander_actions)}
         steps0 = self.env.steps
         obs, rew, term, trunc, info = self.env.step(ca)
+        self.last_info = info   # {} unless args.eval_info (env_base.py:91-107)
         return (np.stack([obs[i] for i in (1, 2, 3)]), np.array([rew[i] for i in (1, 2, 3)], np.float64),
                 bool(term["__all__"]), self.env.steps - steps0, dict(ca))
 

@@ -17,7 +17,13 @@ SEED = 20260926
 MAXC = 96  # 16 sub-steps x 6 aircraft
 CASES = [("hier_default", 0, 90, {}), ("hier_shared", 1, 70, {"glob_frac": 0.3, "hier_action_assess": False,
                                                                "hier_opp_fight_ratio": 40}),
-         ("hier_nofk", 2, 70, {"friendly_kill": False, "rew_scale": 2})]
+         ("hier_nofk", 2, 70, {"friendly_kill": False, "rew_scale": 2}),
+         # args.eval_info (env_base.py:91-107): the info dict of every step, in the reference's key order
+         ("hier_evalinfo", 3, 200, {"eval_info": True, "horizon": 170})]
+
+
+EVAL_KEYS = ("agents_win", "opps_win", "draw", "agent_fight", "agent_escape", "opp_fight", "opp_escape", "agent_steps",
+             "opp_steps", "opp1", "opp2", "opp3")
 
 
 def pseudo_policy(unit_id, ac_type, mode, obs):
@@ -38,6 +44,8 @@ def generate(name, arena, n_steps, kw):
     rng = np.random.default_rng(arena)
     rec = {k: [] for k in ("ca", "obs", "rew", "done", "subs", "ca_out", "scalars", "n_calls", "c_unit", "c_type",
                            "c_mode", "c_act", "c_obs")}
+    if kw.get("eval_info"):
+        rec["eval"] = []
     resets = [env.reset()]
     for t in range(n_steps):
         ca = rng.integers(0, 3, 3)
@@ -46,6 +54,9 @@ def generate(name, arena, n_steps, kw):
         rec["ca"].append(ca); rec["obs"].append(o); rec["rew"].append(r); rec["done"].append(d); rec["subs"].append(ns)
         rec["ca_out"].append([(-1 if ca_out.get(i) is None else ca_out[i]) for i in range(1, 7)])
         rec["scalars"].append(env.scalars())
+        if kw.get("eval_info"):
+            assert tuple(env.last_info) == EVAL_KEYS
+            rec["eval"].append([int(v) for v in env.last_info.values()])
         cu = np.zeros(MAXC, np.int8); ct = np.zeros(MAXC, np.int8); cm = np.zeros(MAXC, np.int8)
         cact = np.zeros((MAXC, 4), np.int8); cobs = np.zeros((MAXC, 30), np.float32)
         for k, (u, ty, m, ob, a) in enumerate(calls):
@@ -65,5 +76,6 @@ def generate(name, arena, n_steps, kw):
 
 
 if __name__ == "__main__":
-    for c in CASES:
-        generate(*c)
+    for c in CASES:   # `python gen_golden_hier.py hier_evalinfo` regenerates one case
+        if len(sys.argv) == 1 or c[0] in sys.argv[1:]:
+            generate(*c)

@@ -22,6 +22,9 @@ def test_hier_matches_oracle(kw):
     from hhmarl_2d_b200.env_hier import VecHighLevelEnv, make_hier_args
     n, T, seed, base = 48, 40, 606, 300
     env = VecHighLevelEnv(n, make_hier_args(**kw), device=0, seed=seed, arena_base=base, autoreset=True)
+    env.eval_info = True               # args.eval_info (env_base.py:91-107) only adds the info counters
+    from hhmarl_2d_b200.evaluation import EvalStats
+    stats, want = EvalStats(env.dev), np.zeros(12, np.int64)
     queue = [[] for _ in range(n)]     # per arena: FIFO of (unit_id, mode, ac_type, obs, action) the GPU produced
 
     def make_fn(k):
@@ -44,6 +47,8 @@ def test_hier_matches_oracle(kw):
         env.trace = []
         gobs, grew, gdone = env.step(torch.from_numpy(ca).cuda())
         gobs, grew, gdone, gsub = gobs.cpu().numpy(), grew.cpu().numpy(), gdone.cpu().numpy(), env.substeps.cpu().numpy()
+        ginfo = env.info.cpu().numpy()
+        stats.update(env.info, env.done)
         # rebuild, per arena, the sequence of policy queries in the reference's order: per sub-step units 1..6
         for k in range(n):
             queue[k].clear()
@@ -59,6 +64,9 @@ def test_hier_matches_oracle(kw):
             assert not queue[k], f"arena {k}: GPU made {len(queue[k])} more policy queries than the oracle"
             assert bool(gdone[k]) == ed and gsub[k] == info[0], (t, k, gsub[k], info[0])
             _close(grew[k], er, f"t={t} arena={k} rew")
+            ei = list(o.eval_info().values())   # before the reset, like the reference's step()
+            assert list(ginfo[k]) == ei, (t, k, list(ginfo[k]), ei)
+            want += np.asarray(ei)
             if ed:
                 eo = o.reset()
                 n_done += 1
@@ -73,6 +81,9 @@ def test_hier_matches_oracle(kw):
                 _close(list(st[k].lat), list(s.lat[:6]), "lat"); _close(list(st[k].hdg), list(s.heading[:6]), "hdg")
                 assert st[k].err == 0
     assert n_done >= n // 2
+    tot = stats.totals()
+    assert [tot[k] for k in orc.EVAL_INFO_KEYS] == list(want) and tot["episodes"] == n_done and tot["total_n_actions"] == n * T
+    assert tot["agents_win"] + tot["opps_win"] + tot["draw"] <= n_done
 
 
 def test_commander_sampler_fragment():

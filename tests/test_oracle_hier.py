@@ -42,10 +42,14 @@ def test_hier_oracle_replays_golden(path):
         assert [st.steps, st.alive_agents, st.alive_opps, st.next_unit_id, st.draws_g, st.draws_c] == list(g["scalars"][t])
         np.testing.assert_allclose(obs, g["obs"][t], atol=1e-6)
         np.testing.assert_allclose(rew, g["rew"][t], atol=1e-9)
+        if "eval" in g:   # args.eval_info: the info dict of env_base.py:91-107, key by key
+            assert list(env.eval_info().values()) == list(g["eval"][t]), t
         if done:
             ep += 1
             np.testing.assert_allclose(env.reset(), g["resets"][ep], atol=1e-7)
     assert ep == len(g["resets"]) - 1 and ep >= 3
+    if "eval" in g:   # the fixture holds wins, losses and draws
+        assert tuple(env.eval_info()) == orc.EVAL_INFO_KEYS and all(g["eval"][:, k].sum() > 0 for k in (0, 1, 2))
 
 
 @pytest.mark.skipif(not rh.reference_available(), reason="/root/reference not present")

@@ -112,3 +112,18 @@ def test_policy_files_round_trip_with_reference_naming(tmp_path):
     with torch.no_grad():
         assert torch.equal(l5[3]["fight_1"].actor(x), saved[3].actor(x))
         assert torch.equal(l5[4]["fight_1"].actor(x), saved[4].actor(x))
+    # HighLevelEnv container (env_base.py:332-346): fight policies of eval_level_ag, escape L5 else L3, "_opp" pair
+    # only for the low-level evaluation mode
+    hl = checkpoint.load_highlevel_policies(d, eval_level_ag=4)
+    assert set(hl) == {"fight_1", "fight_2", "escape_1", "escape_2"}
+    hl = checkpoint.load_highlevel_policies(d, eval_level_ag=4, eval_level_opp=3, eval_hl=False)
+    assert set(hl) == {"fight_1", "fight_2", "escape_1", "escape_2", "fight_1_opp", "fight_2_opp"}
+    xe = torch.rand(4, 30)
+    with torch.no_grad():
+        assert torch.equal(hl["fight_1"].actor(x), saved[4].actor(x)) and torch.equal(hl["fight_1_opp"].actor(x), saved[3].actor(x))
+        assert torch.equal(hl["escape_1"].actor(xe), e1.actor(xe))
+    e51, e52 = M.build_policy_pair("escape")
+    M.fill_from_seed(e51, 77); M.fill_from_seed(e52, 78)
+    checkpoint.save_policies(d, 5, "escape", e51, e52)
+    with torch.no_grad():
+        assert torch.equal(checkpoint.load_highlevel_policies(d, 4)["escape_1"].actor(xe), e51.actor(xe))
