@@ -17,6 +17,12 @@ def __getattr__(name):   # torch-dependent pieces are imported lazily
     if name == "PPOLearner":
         from .ppo import PPOLearner
         return PPOLearner
+    if name in ("EvalStats", "evaluate"):
+        from . import evaluation
+        return getattr(evaluation, name)
+    if name == "TraceRecorder":
+        from .trace import TraceRecorder
+        return TraceRecorder
     if name == "OpponentPolicies":
         from .opponents import OpponentPolicies
         return OpponentPolicies
@@ -24,4 +30,4 @@ def __getattr__(name):   # torch-dependent pieces are imported lazily
 
 
 __all__ = ["VecLowLevelEnv", "LowLevelEnv", "make_args", "HORIZON_BY_LEVEL", "VecSampler", "TorchPolicy", "PPOLearner",
-           "OpponentPolicies"]
+           "OpponentPolicies", "EvalStats", "evaluate", "TraceRecorder"]
