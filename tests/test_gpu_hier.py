@@ -18,9 +18,15 @@ def _close(a, b, what):
 @pytest.mark.parametrize("kw", [{}, {"glob_frac": 0.3, "hier_action_assess": False, "hier_opp_fight_ratio": 40},
                                 {"friendly_kill": False, "rew_scale": 2.0}])
 def test_hier_matches_oracle(kw):
+    # the eval-info counters are compared here for the default configuration and, for the other two, in
+    # tests/test_gpu_zz_evaluation.py (same harness, run last)
+    _hier_vs_oracle(kw, check_eval=not kw)
+
+
+def _hier_vs_oracle(kw, check_eval, T=40):
     import oracle as orc
     from hhmarl_2d_b200.env_hier import VecHighLevelEnv, make_hier_args
-    n, T, seed, base = 48, 40, 606, 300
+    n, seed, base = 48, 606, 300
     env = VecHighLevelEnv(n, make_hier_args(**kw), device=0, seed=seed, arena_base=base, autoreset=True)
     env.eval_info = True               # args.eval_info (env_base.py:91-107) only adds the info counters
     from hhmarl_2d_b200.evaluation import EvalStats
@@ -64,9 +70,10 @@ def test_hier_matches_oracle(kw):
             assert not queue[k], f"arena {k}: GPU made {len(queue[k])} more policy queries than the oracle"
             assert bool(gdone[k]) == ed and gsub[k] == info[0], (t, k, gsub[k], info[0])
             _close(grew[k], er, f"t={t} arena={k} rew")
-            ei = list(o.eval_info().values())   # before the reset, like the reference's step()
-            assert list(ginfo[k]) == ei, (t, k, list(ginfo[k]), ei)
-            want += np.asarray(ei)
+            if check_eval:
+                ei = list(o.eval_info().values())   # before the reset, like the reference's step()
+                assert list(ginfo[k]) == ei, (t, k, list(ginfo[k]), ei)
+                want += np.asarray(ei)
             if ed:
                 eo = o.reset()
                 n_done += 1
@@ -80,10 +87,12 @@ def test_hier_matches_oracle(kw):
                 assert list(st[k].alive) == list(s.alive[:6]) and list(st[k].mrem) == list(s.missile_remain[:6])
                 _close(list(st[k].lat), list(s.lat[:6]), "lat"); _close(list(st[k].hdg), list(s.heading[:6]), "hdg")
                 assert st[k].err == 0
-    assert n_done >= n // 2
-    tot = stats.totals()
-    assert [tot[k] for k in orc.EVAL_INFO_KEYS] == list(want) and tot["episodes"] == n_done and tot["total_n_actions"] == n * T
-    assert tot["agents_win"] + tot["opps_win"] + tot["draw"] <= n_done
+    if T >= 40:
+        assert n_done >= n // 2
+    if check_eval:
+        tot = stats.totals()
+        assert [tot[k] for k in orc.EVAL_INFO_KEYS] == list(want) and tot["episodes"] == n_done and tot["total_n_actions"] == n * T
+        assert tot["agents_win"] + tot["opps_win"] + tot["draw"] <= n_done
 
 
 def test_commander_sampler_fragment():

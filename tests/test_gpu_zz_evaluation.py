@@ -11,6 +11,15 @@ from test_gpu_parity import _close, _vec
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("kw", [{"glob_frac": 0.3, "hier_action_assess": False, "hier_opp_fight_ratio": 40},
+                                {"friendly_kill": False, "rew_scale": 2.0}])
+def test_eval_info_matches_oracle_other_configs(kw):
+    """The info counters of step() under args.eval_info (env_base.py:91-107) against the oracle, every arena and step, for
+    the non-default configurations of tests/test_gpu_hier.py::test_hier_matches_oracle (which checks the default one)."""
+    from test_gpu_hier import _hier_vs_oracle
+    _hier_vs_oracle(kw, check_eval=True, T=24)
+
+
 def test_evaluate_commander(tmp_path):
     """evaluation.py on all arenas at once: the sums are consistent, the report has the reference's keys
     (postprocess_eval, evaluation.py:66-82), and the no-commander mode attacks the closest opponent only."""
