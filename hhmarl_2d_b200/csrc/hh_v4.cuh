@@ -908,6 +908,22 @@ __device__ long long g_warp_arrive[512 * 8 * 16];   // [CTA][warp][barrier]: whe
 #define HH_MARK(k)
 #endif
 
+// Experiment for round 2 (build with -DHH_V4_WARM, profiles/build_variants.sh; NOT in the default library): a warp that
+// idles during S2 makes one dry call of geo::direct_short so that the routine's 58 instruction-cache lines are in the
+// SM's L1.5 when the unit and rocket warps reach it in S4 (profiles/README.md: 41 % of the kernel's no_instruction stall
+// samples sit in that routine).  The call has no side effect: its result is compared with a value it cannot take.
+#if defined(HH_V4_WARM) && defined(__CUDACC__)
+__device__ __forceinline__ void s2_warm(const Ctx& C, int t) {
+  if (t & 31) return;   // lane 0 of the role's warp fetches for everyone
+  const double2 q = geo::direct_short(5.25 + 1e-9 * (double)(C.arena0 & 7), 7.1, 10.0, 0.17364817766693033,
+                                      0.984807753012208, 100.0);
+  if (q.x == 1234.5) C.S.any_reset = 2;
+}
+#define HH_WARM_S2 HH_ROLE(A2, A1, s2_warm(C, t))
+#else
+#define HH_WARM_S2
+#endif
+
 template <int LEVEL, int MODE>
 __device__ __forceinline__ void step_body(Smem& S, const StatePtrs& G, const Params& P, const int32_t* __restrict__ actions,
                                           float* __restrict__ obs1, float* __restrict__ obs2,
@@ -929,6 +945,7 @@ __device__ __forceinline__ void step_body(Smem& S, const StatePtrs& G, const Par
   HH_MARK(2)
   HH_ROLE(0, A2, s2_agents<MODE>(C, t))
   HH_ROLE(A4, A1, s2_script<LEVEL>(C, t))
+  HH_WARM_S2
   HH_BARRIER();
   HH_MARK(3)
   HH_ROLE(0, A4, s4_move_unit(C, t))
