@@ -74,6 +74,49 @@ def cpu_oracle_throughput(level: int, steps_per_thread: int, threads: int):
     return threads * steps_per_thread / dt, dt
 
 
+def cpu_sampler_equivalent(level: int, seconds: float = 4.0):
+    """SURVEY.md 8(d) CPU side-by-side (ii): what ONE rollout worker of the reference does per env step -- the env
+    step (C oracle here, so this is an upper bound for the Python env) plus a batch-1 torch-CPU forward of both
+    policies (actor + central critic, train_hetero.py:162-181 observation layout with zero team-mate actions) and
+    MultiCategorical sampling -- on one host core.  Returns env-steps/s of that single worker."""
+    import numpy as np
+    import torch
+    import oracle as orc
+    from hhmarl_2d_b200 import models as M
+    prev = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        torch.manual_seed(0)
+        m1, m2 = M.build_policy_pair("fight")
+        m1.eval(); m2.eval()
+        env = orc.OracleEnv(orc.make_args(level=level), 0, 0)
+        o1, o2 = env.reset()
+        z1, z = torch.zeros(1, 4), torch.zeros(1, 3)
+
+        def act(model, own, other, a_own, a_other, splits):
+            d = {"obs_1_own": torch.from_numpy(own[None]), "obs_2": torch.from_numpy(other[None]), "act_1_own": a_own, "act_2": a_other}
+            logits, _ = model({"obs": d}, [], None)
+            model.value_function()
+            out, o = [], 0
+            for n in splits:
+                out.append(int(torch.distributions.Categorical(logits=logits[0, o:o + n]).sample()))
+                o += n
+            return out
+
+        n_steps, t0 = 0, time.perf_counter()
+        with torch.no_grad():
+            while time.perf_counter() - t0 < seconds:
+                a1 = act(m1, o1, o2, z1, z, (13, 9, 2, 2))
+                a2 = act(m2, o2, o1, z, z1, (13, 9, 2)) + [0]
+                o1, o2, _, _, done = env.step(np.array([a1, a2], np.int32))
+                if done:
+                    o1, o2 = env.reset()
+                n_steps += 1
+        return n_steps / (time.perf_counter() - t0)
+    finally:
+        torch.set_num_threads(prev)
+
+
 def best_thread_count(level: int):
     """Host boxes may expose more logical CPUs than the cgroup lets us use: probe a few thread
     counts on a small sample and keep the fastest."""
@@ -291,6 +334,16 @@ def run_b200(args):
                             "ms_per_tick": float(rt.item()) / (R * Tf)}
             del smp, env_r
         rollout["fragment_len"] = Tf
+        if cpu_base is not None:   # N = 1, rank 0: the reference-style rollout worker on one host core, bounded sample
+            try:
+                v1 = cpu_sampler_equivalent(args.level)
+                rollout["cpu_sampler_equivalent"] = {
+                    "value_per_worker": v1, "unit": UNIT, "cores": 1,
+                    "sample": "4 s of one worker: C-oracle env step + batch-1 torch-CPU forward of both policies (actor + "
+                              "central critic) + MultiCategorical sampling, 1 torch thread; the reference runs one such "
+                              "worker per core (train_hetero.py:212) with the Python env instead of the C oracle"}
+            except Exception as ex:  # noqa: BLE001
+                rollout["cpu_sampler_equivalent"] = {"error": repr(ex)}
         rollout["note"] = ("both policies' actor + central critic + Gumbel-max sampling + env step + GAE + action "
                            "write-back, one CUDA graph per 20-tick fragment; random-init weights.  'fused_3xtf32' (the "
                            "sampler's default) / 'fused_tf32': the hand-written forward kernel csrc/hh_policy.cu (one launch "
