@@ -20,9 +20,9 @@ def __getattr__(name):   # torch-dependent pieces are imported lazily
     if name in ("EvalStats", "evaluate"):
         from . import evaluation
         return getattr(evaluation, name)
-    if name == "TraceRecorder":
-        from .trace import TraceRecorder
-        return TraceRecorder
+    if name in ("TraceRecorder", "HierTraceRecorder"):
+        from . import trace
+        return getattr(trace, name)
     if name == "OpponentPolicies":
         from .opponents import OpponentPolicies
         return OpponentPolicies
@@ -30,4 +30,4 @@ def __getattr__(name):   # torch-dependent pieces are imported lazily
 
 
 __all__ = ["VecLowLevelEnv", "LowLevelEnv", "make_args", "HORIZON_BY_LEVEL", "VecSampler", "TorchPolicy", "PPOLearner",
-           "OpponentPolicies", "EvalStats", "evaluate", "TraceRecorder"]
+           "OpponentPolicies", "EvalStats", "evaluate", "TraceRecorder", "HierTraceRecorder"]

@@ -80,6 +80,7 @@ class VecHighLevelEnv:
         # columns EVAL_INFO_KEYS) with the reference's per-step info dict; hhmarl_2d_b200.evaluation sums it
         self.eval_info = bool(getattr(self.args, "eval_info", False))
         self.info = torch.zeros((n, len(EVAL_INFO_KEYS)), dtype=torch.int32, device=dev)
+        self.tick_hook = None   # callable(sub_step) run after every hh_hier_tick (trace.HierTraceRecorder); None = no cost
         self.trace = None   # set to a list to record (phase, ll_obs, ll_info, ll_act) per sub-step (tests)
         self.fused_policies = True   # the frozen low-level actors through csrc/hh_policy.cu (False: torch forward)
         self.policy_precision = 0    # 0: 3xTF32 (fp32-equivalent logits before the argmax), 1: plain TF32 (~2x faster forward)
@@ -171,6 +172,8 @@ class VecHighLevelEnv:
                 self.trace.append(("opps", self.ll_obs.cpu().numpy().copy(), self.ll_info.cpu().numpy().copy(),
                                    self.ll_act.cpu().numpy().copy()))
             nat.check(L.hh_hier_tick(h, la, lo, li, st), "hh_hier_tick")
+            if self.tick_hook is not None:
+                self.tick_hook(s)
         if self.eval_info:   # before hh_hier_end: its auto-reset replaces a finished episode
             nat.check(L.hh_hier_eval_info(h, self.info.data_ptr(), st), "hh_hier_eval_info")
         nat.check(L.hh_hier_end(h, self.obs.data_ptr(), self.rew.data_ptr(), self.done.data_ptr(),

@@ -115,3 +115,91 @@ class TraceRecorder:
         with open(path, "w") as f:
             json.dump(out, f)
         return out
+
+
+class HierTraceRecorder:
+    """The same samples for selected arenas of a VecHighLevelEnv (3-vs-3, aircraft ids 1-6): the reference's evaluation
+    (evaluation.py:62-63) plots the commander episodes from sim.trace_record_units, one sample per simulator tick.  A
+    commander step makes up to 16 ticks inside `env.step`; the recorder hooks `env.tick_hook`, reads the arena records
+    after every tick (hh_hier_get_state) and appends a sample for the arenas whose tick counter moved.
+
+    rec = HierTraceRecorder(env, arenas); env.reset(); rec.start(); loop: env.step(actions); rec.after_step(env.done).
+    With auto-reset the record read after the last tick of an episode is still the finished episode's (the reset
+    happens in hh_hier_end), so the traces are complete; `after_step` then opens the next episode."""
+
+    N_UNITS = 6
+
+    def __init__(self, env, arenas):
+        self.env = env
+        self.arenas = [int(a) for a in arenas]
+        if any(a < 0 or a >= env.n_arenas for a in self.arenas):
+            raise ValueError("HierTraceRecorder: arena index out of range")
+        self.finished = {a: [] for a in self.arenas}
+        self._cur = {a: None for a in self.arenas}
+        self._last_steps = {a: -1 for a in self.arenas}
+        env.tick_hook = self._on_tick
+
+    def _sample(self, st, a):
+        rec = st[a]
+        ep = self._cur[a]
+        t = float(rec.steps)
+        for u in range(self.N_UNITS):
+            if rec.alive[u]:
+                ep[u + 1].append((t, float(rec.lat[u]), float(rec.lon[u]), float(rec.hdg[u]), float(rec.spd[u])))
+        self._last_steps[a] = int(rec.steps)
+
+    def _open(self, st, a):
+        self._cur[a] = {u + 1: [] for u in range(self.N_UNITS)}
+        self._sample(st, a)
+
+    def start(self):
+        st = self.env.get_state()
+        for a in self.arenas:
+            if self._cur[a] is not None:
+                self.finished[a].append(self._cur[a])
+            self._open(st, a)
+
+    def _on_tick(self, sub_step):
+        st = self.env.get_state()
+        for a in self.arenas:
+            if self._cur[a] is not None and int(st[a].steps) != self._last_steps[a]:   # idle arenas do not tick
+                self._sample(st, a)
+
+    def after_step(self, done):
+        done = np.asarray(done.cpu() if hasattr(done, "cpu") else done).astype(bool)
+        if not done[self.arenas].any():
+            return
+        st = self.env.get_state()
+        for a in self.arenas:
+            if done[a] and self._cur[a] is not None:
+                self.finished[a].append(self._cur[a])
+                self._cur[a] = None
+                if int(st[a].steps) == 0:          # auto-reset env: the next episode has begun
+                    self._open(st, a)
+
+    def after_reset(self, mask=None):
+        mask = None if mask is None else np.asarray(mask.cpu() if hasattr(mask, "cpu") else mask).astype(bool)
+        st = self.env.get_state()
+        for a in self.arenas:
+            if mask is None or mask[a]:
+                if self._cur[a] is not None:
+                    self.finished[a].append(self._cur[a])
+                self._open(st, a)
+
+    def episodes(self, arena, include_open=True):
+        eps = list(self.finished[int(arena)])
+        if include_open and self._cur[int(arena)] is not None:
+            eps.append(self._cur[int(arena)])
+        return [{"units": {u: np.asarray(rows, np.float64).reshape(-1, len(COLUMNS)) for u, rows in ep.items()},
+                 "truncated_last_tick": False} for ep in eps]
+
+    def export_json(self, path, include_open=True):
+        ms = float(self.env.args.map_size)
+        out = {"columns": list(COLUMNS),
+               "map": {"left_lon": 7.0, "bottom_lat": 5.0, "right_lon": 7.0 + ms, "top_lat": 5.0 + ms},
+               "arenas": {str(ar): [{"units": {str(u): v.tolist() for u, v in ep["units"].items()},
+                                     "truncated_last_tick": False} for ep in self.episodes(ar, include_open)]
+                          for ar in self.arenas}}
+        with open(path, "w") as f:
+            json.dump(out, f)
+        return out

@@ -92,3 +92,42 @@ def test_trace_recorder_on_device_env():
             w = np.asarray(want[k][u], np.float64).reshape(-1, 5)
             assert ep["units"][u + 1].shape == w.shape and len(w) >= 2
             _close(ep["units"][u + 1], w, f"arena {k} unit {u + 1}")
+
+
+def test_hier_trace_recorder_on_device_env():
+    """HierTraceRecorder on the real commander env: one sample per simulator tick and live aircraft (time stamps 0, 1, 2 ...
+    without gaps, as many ticks as the env reports sub-steps), the last sample of an open episode is the aircraft's current
+    state (the recorder's bookkeeping itself is tested on the CPU, tests/test_trace_cpu.py)."""
+    from hhmarl_2d_b200.env_hier import VecHighLevelEnv, make_hier_args
+    from hhmarl_2d_b200.trace import HierTraceRecorder
+    n, watch = 32, [0, 5, 31]
+    env = VecHighLevelEnv(n, make_hier_args(horizon=120), device=0, seed=21, autoreset=True)
+    env.reset()
+    rec = HierTraceRecorder(env, watch)
+    rec.start()
+    g = torch.Generator().manual_seed(3)
+    ticks = {a: 0 for a in watch}
+    n_done = 0
+    for t in range(14):
+        _, _, done = env.step(torch.randint(0, 3, (n, 3), generator=g).to(torch.int32).cuda())
+        sub = env.substeps.cpu().numpy()
+        d = done.cpu().numpy()
+        rec.after_step(done)
+        for a in watch:
+            ticks[a] = 0 if d[a] else ticks[a] + int(sub[a])
+            n_done += int(d[a])
+    assert n_done >= 2
+    st = env.get_state()
+    for a in watch:
+        eps = rec.episodes(a)
+        assert len(eps) >= 1
+        for i, ep in enumerate(eps):
+            longest = max(len(v) for v in ep["units"].values())
+            for u, v in ep["units"].items():
+                assert len(v) >= 1 and v[0, 0] == 0 and (np.diff(v[:, 0]) == 1).all()
+                assert ((v[:, 1] >= 4.9) & (v[:, 1] <= 5.6) & (v[:, 2] >= 6.9) & (v[:, 2] <= 7.6)).all()
+            if i == len(eps) - 1:      # the open episode: as many ticks as the env counted, last sample = current state
+                assert longest == ticks[a] + 1 == st[a].steps + 1
+                for u, v in ep["units"].items():
+                    if st[a].alive[u - 1]:
+                        assert len(v) == longest and v[-1, 1] == st[a].lat[u - 1] and v[-1, 3] == st[a].hdg[u - 1]

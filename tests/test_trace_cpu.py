@@ -125,3 +125,95 @@ def test_trace_matches_reference_trace_lists():
             tgp._close(got, want[:len(got)], f"unit {u}")
             n_cmp += len(got)
         assert n_cmp > 100
+
+
+class _Rec:
+    def __init__(self):
+        self.steps, self.alive = 0, [1] * 6
+        self.lat, self.lon, self.hdg, self.spd = [0.0] * 6, [0.0] * 6, [0.0] * 6, [0.0] * 6
+
+
+class _FakeHierEnv:
+    """Stands in for VecHighLevelEnv: arenas tick a varying number of times per commander step, idle afterwards, lose an
+    aircraft now and then, and auto-reset in the end phase of the step that finishes the episode."""
+
+    def __init__(self, n, horizon, autoreset, seed=0):
+        from argparse import Namespace
+        self.n_arenas, self.horizon, self.autoreset = n, horizon, autoreset
+        self.args = Namespace(map_size=0.5)
+        self.rng = np.random.default_rng(seed)
+        self.tick_hook = None
+        self.recs = [_Rec() for _ in range(n)]
+        self.truth = [[] for _ in range(n)]     # per arena: list of episodes {unit: [samples]}
+        self.done = np.zeros(n, np.uint8)
+
+    def _log(self, a):
+        r = self.recs[a]
+        for u in range(6):
+            if r.alive[u]:
+                self.truth[a][-1][u + 1].append((float(r.steps), r.lat[u], r.lon[u], r.hdg[u], r.spd[u]))
+
+    def _reset_arena(self, a):
+        r = self.recs[a] = _Rec()
+        r.lat = list(5.0 + self.rng.random(6) * 0.5); r.lon = list(7.0 + self.rng.random(6) * 0.5)
+        r.hdg = list(self.rng.random(6) * 360); r.spd = list(100 + self.rng.random(6) * 500)
+        self.truth[a].append({u + 1: [] for u in range(6)})
+        self._log(a)
+
+    def reset(self, mask=None):
+        for a in range(self.n_arenas):
+            if mask is None or mask[a]:
+                self._reset_arena(a)
+
+    def get_state(self):
+        return self.recs
+
+    def step(self, _actions=None):
+        n_ticks = self.rng.integers(11, 17, self.n_arenas)
+        finished = self.done.astype(bool) & (not self.autoreset)
+        for s in range(16):
+            for a in range(self.n_arenas):
+                r = self.recs[a]
+                if s < n_ticks[a] and not finished[a] and r.steps < self.horizon:
+                    r.steps += 1
+                    for u in range(6):
+                        r.lat[u] += 1e-4; r.lon[u] -= 2e-4; r.hdg[u] = (r.hdg[u] + 3.0) % 360
+                    if self.rng.random() < 0.03:
+                        r.alive[int(self.rng.integers(0, 6))] = 0
+                    self._log(a)
+            if self.tick_hook is not None:
+                self.tick_hook(s)
+        for a in range(self.n_arenas):
+            if finished[a]:
+                continue
+            self.done[a] = self.recs[a].steps >= self.horizon
+            if self.done[a] and self.autoreset:
+                self._reset_arena(a)
+        return self.done
+
+
+@pytest.mark.parametrize("autoreset", [True, False])
+def test_hier_trace_recorder_follows_every_tick(autoreset, tmp_path):
+    from hhmarl_2d_b200.trace import HierTraceRecorder
+    env = _FakeHierEnv(5, horizon=70, autoreset=autoreset)
+    env.reset()
+    rec = HierTraceRecorder(env, [0, 2, 4])
+    rec.start()
+    for t in range(30):
+        done = env.step()
+        rec.after_step(done)
+        if not autoreset and done.any():
+            mask = done.copy()
+            env.done[:] = 0
+            env.reset(mask)
+            rec.after_reset(mask)
+    for a in (0, 2, 4):
+        eps = rec.episodes(a)
+        assert len(eps) == len(env.truth[a]) >= 4
+        for ep, want in zip(eps, env.truth[a]):
+            for u in range(1, 7):
+                w = np.asarray(want[u], np.float64).reshape(-1, 5)
+                assert ep["units"][u].shape == w.shape and np.array_equal(ep["units"][u], w), (a, u)
+    out = rec.export_json(str(tmp_path / "hier_trace.json"))
+    assert out["map"]["top_lat"] == 5.5 and sorted(out["arenas"]) == ["0", "2", "4"]
+    assert json.loads((tmp_path / "hier_trace.json").read_text())["arenas"]["2"][1]["units"]["6"] == rec.episodes(2)[1]["units"][6].tolist()
