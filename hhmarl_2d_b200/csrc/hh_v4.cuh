@@ -851,19 +851,31 @@ __device__ __forceinline__ void s10_store_unit(const Ctx& C, int t) {
     G.draws_g[a] = S.dg_out[al];
   }
 }
-// contiguous, coalesced copy of the staged observation rows (16-byte aligned on both sides)
+// contiguous, coalesced copy of the staged observation rows (16-byte aligned on both sides).
+// HH_V4_ROLLED (variant build, round-2 experiment): the copy loops make at most one trip (<= 208 float4 for 256 threads), the
+// compiler's 4x unrolling only spreads ~80 executed instructions over 6 KB of code (profiles/README.md: 16 % of the kernel's
+// no_instruction samples)
+#if defined(HH_V4_ROLLED) && defined(__CUDACC__)
+#define HH_NO_UNROLL _Pragma("unroll 1")
+#else
+#define HH_NO_UNROLL
+#endif
 __device__ __forceinline__ void s10_store_rows(const Ctx& C, int t, int n_threads, int d1, int d2) {
   const Smem& S = C.S;
   if (C.obs1) {
     const int nf = C.n_valid * d1, n4 = nf >> 2;
     float* dst = C.obs1 + (size_t)C.arena0 * d1;
+    HH_NO_UNROLL
     for (int k = t; k < n4; k += n_threads) reinterpret_cast<float4*>(dst)[k] = reinterpret_cast<const float4*>(S.obs1)[k];
+    HH_NO_UNROLL
     for (int k = (n4 << 2) + t; k < nf; k += n_threads) dst[k] = S.obs1[k];
   }
   if (C.obs2) {
     const int nf = C.n_valid * d2, n4 = nf >> 2;
     float* dst = C.obs2 + (size_t)C.arena0 * d2;
+    HH_NO_UNROLL
     for (int k = t; k < n4; k += n_threads) reinterpret_cast<float4*>(dst)[k] = reinterpret_cast<const float4*>(S.obs2)[k];
+    HH_NO_UNROLL
     for (int k = (n4 << 2) + t; k < nf; k += n_threads) dst[k] = S.obs2[k];
   }
 }

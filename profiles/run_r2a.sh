@@ -13,8 +13,8 @@ if grep -q "rows not found [1-9]\|did not complete" gpurun_out/r2a_tcgen05_probe
   echo "== tcgen05 probe, descriptor offsets swapped"
   timeout 120 build/tcgen05_probe swap 2>&1 | tee gpurun_out/r2a_tcgen05_probe_swap.txt
 fi
-echo "== step kernel: default vs S2 instruction-cache warm-up variant (build/lib_v4warm.so)"
-for lib in "" "$PWD/build/lib_v4warm.so"; do
+echo "== step kernel: default vs the instruction-footprint variants (profiles/build_variants.sh)"
+for lib in "" "$PWD/build/lib_v4warm.so" "$PWD/build/lib_v4rolled.so" "$PWD/build/lib_v4rolled_warm.so"; do
   for n in 8192 131072; do
     HH_LIB_PATH=$lib timeout 200 python bench.py --arenas $n --steps 200 --warmup 20 --no-cpu-baseline --no-rollout --no-hier --no-l5 2>/dev/null | tail -1 | \
       python -c "import json,sys; d=json.load(sys.stdin); print('${lib:-default}', d['config']['arenas_per_gpu'], round(d['value']/1e6,1), 'M env-steps/s', round(d['ms_per_step']*1000,2), 'us')"
