@@ -10,6 +10,8 @@
 //      activation tile can serve as the "hi" operand of the 3xTF32 split;
 //   4. the accuracy of the 3xTF32 product (A_hi B_hi + A_lo B_hi + A_hi B_lo) against fp64;
 //   5. the issue rate of back-to-back M = 64 / M = 128, N = 256 TF32 MMAs from shared memory on all SMs.
+//   6. two chained layers on one CTA (accumulator -> tcgen05.ld -> tanh -> rewritten A tile -> next MMAs): the ordering
+//      (tcgen05.wait::ld, fence.proxy.async, tcgen05 fences around the CTA barrier) the fused kernel relies on.
 // Build + run (one GPU, under a timeout -- every wait in the kernel is bounded, a wrong descriptor cannot hang it):
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o build/tcgen05_probe profiles/tcgen05_probe.cu
 //   timeout 120 build/tcgen05_probe            (add `swap` to exchange the descriptor's two byte-offset fields)
@@ -156,6 +158,76 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ A,
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kN));
 }
 
+// Two chained layers on one CTA, M = 128 (the mechanics the fused policy kernel needs): D1 = A B in TMEM; every thread reads
+// ITS row of D1 (lane = row for M = 128), applies tanh and writes the first kK columns back INTO the A tile in the canonical
+// layout; then D2 = tanh(D1[:, :kK]) B overwrites the accumulator.  Exercises tcgen05.ld -> generic-proxy smem store ->
+// fence.proxy.async -> tcgen05.mma ordering and the second phase of the completion barrier.
+__global__ void __launch_bounds__(128) chain_kernel(const float* __restrict__ A, const float* __restrict__ Bt,
+                                                    float* __restrict__ tmem_dump, int* __restrict__ status) {
+  constexpr int M = 128;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* sA = reinterpret_cast<float*>(smem);
+  float* sB = sA + M * kK;
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < M * kK; i += 128) sA[canon(i / kK, i % kK, M)] = A[i];
+  for (int i = tid; i < kN * kK; i += 128) sB[canon(i / kK, i % kK, kN)] = Bt[i];
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(kN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t idesc = instr_desc_tf32(M, kN), lboA = M * 16, lboB = kN * 16, sbo = 128;
+  uint32_t ok = 1;
+  for (int layer = 0; layer < 2 && ok; ++layer) {
+    if (warp == 1 && lane == 0) {
+#pragma unroll
+      for (int ks = 0; ks < kK / 8; ++ks)
+        umma_tf32(tmem, smem_desc(smem_u32(sA) + ks * 2 * lboA, lboA, sbo), smem_desc(smem_u32(sB) + ks * 2 * lboB, lboB, sbo), idesc,
+                  ks ? 1u : 0u);
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    }
+    ok = 0;
+    for (long long spin = 0; spin < (1ll << 24) && !ok; ++spin)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                   : "=r"(ok)
+                   : "r"(smem_u32(&bar)), "r"((uint32_t)layer)
+                   : "memory");
+    if (!ok) {
+      if (tid == 0) atomicExch(status, 1 + layer);
+      break;
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int ncols = layer == 0 ? kK : kN;          // layer 0: only the columns that feed layer 1
+    for (int c = 0; c < ncols; c += 8) {
+      uint32_t r[8];
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c;
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                   : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      for (int j = 0; j < 8; ++j) {
+        if (layer == 0) sA[canon(tid, c + j, M)] = tanhf(__uint_as_float(r[j]));     // row = lane = tid for M = 128
+        else tmem_dump[(size_t)tid * kN + c + j] = __uint_as_float(r[j]);
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the rewritten A tile -> visible to the tensor core
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kN));
+}
+
 static float h_trunc(float v) { uint32_t u; memcpy(&u, &v, 4); u &= 0xFFFFE000u; memcpy(&v, &u, 4); return v; }
 static float h_rn(float v) { uint32_t u; memcpy(&u, &v, 4); u = (u + 0x1000u) & 0xFFFFE000u; memcpy(&v, &u, 4); return v; }
 
@@ -269,6 +341,37 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(dA, A.data(), A.size() * sizeof(float), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dB, Bt.data(), Bt.size() * sizeof(float), cudaMemcpyHostToDevice));
   if (run<128>(A, Bt, dA, dB, dD, dS, swap)) return 1;
+  {   // two chained layers (only meaningful once the single product above is right)
+    const size_t smem = (size_t)((128 + kN) * kK) * sizeof(float);
+    CK(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaMemset(dD, 0, 128 * kN * sizeof(float)));
+    CK(cudaMemset(dS, 0, sizeof(int)));
+    chain_kernel<<<1, 128, smem>>>(dA, dB, dD, dS);
+    CK(cudaDeviceSynchronize());
+    int st = 0;
+    std::vector<float> D(128 * kN);
+    CK(cudaMemcpy(&st, dS, sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(D.data(), dD, D.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    if (st) printf("chain: layer %d never completed\n", st);
+    else {
+      double worst = 0, scale = 0;
+      for (int r = 0; r < 128; ++r) {
+        double h[kK];
+        for (int c = 0; c < kK; ++c) {
+          double acc = 0;
+          for (int k = 0; k < kK; ++k) acc += (double)h_trunc(A[r * kK + k]) * h_trunc(Bt[c * kK + k]);
+          h[c] = std::tanh(acc);
+        }
+        for (int n = 0; n < kN; ++n) {
+          double acc = 0;
+          for (int k = 0; k < kK; ++k) acc += h[k] * (double)h_trunc(Bt[n * kK + k]);
+          worst = std::fmax(worst, std::fabs(acc - D[(size_t)r * kN + n]));
+          scale = std::fmax(scale, std::fabs(acc));
+        }
+      }
+      printf("chain (M=128): D2 = tanh(D1[:, :%d]) B, max |D2 - ref| = %.3e (max |ref| %.2f; TF32 operands -> expect ~1e-2)\n", kK, worst, scale);
+    }
+  }
   if (run<64>(A, Bt, dA, dB, dD, dS, swap)) return 1;
   return 0;
 }
