@@ -1,6 +1,8 @@
 """profiles/code_by_stage.py <lib.so> [report.ncu-rep] -- static code size (and, with an ncu capture, executed warp instructions
 and stall samples) of step_kernel_v4<3,0> per call site in v4::step_body, i.e. per stage / role, and per out-of-line routine.
-Uses `cuobjdump -xelf` + `nvdisasm -gi` (the library is built with -lineinfo) and `ncu --page source --csv`."""
+Uses `cuobjdump -xelf` + `nvdisasm -gi` (the library is built with -lineinfo) and `ncu --page source --csv`.
+The library must be the build the capture was taken from (instructions are joined by their offset in the kernel); the
+sanity check is that the `executed` column sums to the capture's warp-instruction count."""
 import collections
 import csv
 import os
