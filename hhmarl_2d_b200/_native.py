@@ -12,8 +12,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("HH_LIB_PATH") or os.path.join(CSRC, "libhhmarl_b200.so")
-SOURCES = ["hh_api.cu", "hh_hier.cu", "hh_policy.cu"]
-HEADERS = ["hh_quad.cuh", "hh_cta.cuh", "hh_v4.cuh", "hh_state_pack.h", "hh_core.cuh", "hh_geodesic.cuh", os.path.join("..", "..", "include", "hhmarl_b200.h")]
+SOURCES = ["hh_api.cu", "hh_hier.cu", "hh_policy.cu", "hh_policy_tc.cu"]
+HEADERS = ["hh_policy_tc.h", "hh_quad.cuh", "hh_cta.cuh", "hh_v4.cuh", "hh_state_pack.h", "hh_core.cuh", "hh_geodesic.cuh", os.path.join("..", "..", "include", "hhmarl_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared"]
@@ -67,7 +67,8 @@ class HHPolicyChain(ctypes.Structure):
 class HHPolicyChainEx(ctypes.Structure):
     _fields_ = ([(n, VP) for n in ("x", "w1", "b1", "watt", "batt", "ws", "bs", "wh", "bh", "out", "rows", "range_dev", "act_out")]
                 + [(n, I32) for n in ("n_rows", "ldx", "d_in", "k1_pad", "att_lo", "att_n", "att_pad", "n_out", "ld_out", "n_heads")]
-                + [("head", I32 * 4), ("ld_act", I32)])
+                + [("head", I32 * 4), ("ld_act", I32)]
+                + [(n, VP) for n in ("img_w1", "img_att", "img_ws", "img_wh", "us_w1", "us_att", "us_ws", "us_wh")])
 
 
 class HHStateView(ctypes.Structure):
@@ -174,6 +175,10 @@ def bind(L: ctypes.CDLL, partial: bool = False) -> ctypes.CDLL:
     L.hh_policy_forward.restype = ctypes.c_int
     L.hh_policy_forward_ex.argtypes = [I32, P(HHPolicyChainEx), I32, VP]
     L.hh_policy_forward_ex.restype = ctypes.c_int
+    L.hh_policy_pack.argtypes = [VP, I32, I32, I32, I32, I32, I32, VP, VP, VP]
+    L.hh_policy_pack.restype = ctypes.c_int
+    L.hh_policy_image_bytes.argtypes = [I32, I32]
+    L.hh_policy_image_bytes.restype = ctypes.c_int64
     L.hh_policy_rows_by_key.argtypes = [I32, VP, I32, P(I32), VP, VP, VP]
     L.hh_policy_rows_by_key.restype = ctypes.c_int
     L.hh_policy_last_error.restype = ctypes.c_char_p
@@ -205,7 +210,7 @@ def bind(L: ctypes.CDLL, partial: bool = False) -> ctypes.CDLL:
 
 
 EXPORTS = ["hh_create", "hh_destroy", "hh_n_arenas", "hh_obs_dim", "hh_reset", "hh_step", "hh_step_begin", "hh_step_finish", "hh_reset_host",
-           "hh_step_host", "hh_step_host_begin", "hh_step_host_end", "hh_host_buffers", "hh_set_host_mode", "hh_get_state", "hh_set_state", "hh_launch_count", "hh_gae", "hh_gae_agents", "hh_sample_actions", "hh_pack_central", "hh_debug_geodesic", "hh_last_error", "hh_version", "hh_policy_forward", "hh_policy_forward_ex", "hh_policy_rows_by_key", "hh_policy_last_error",
+           "hh_step_host", "hh_step_host_begin", "hh_step_host_end", "hh_host_buffers", "hh_set_host_mode", "hh_get_state", "hh_set_state", "hh_launch_count", "hh_gae", "hh_gae_agents", "hh_sample_actions", "hh_pack_central", "hh_debug_geodesic", "hh_last_error", "hh_version", "hh_policy_forward", "hh_policy_forward_ex", "hh_policy_pack", "hh_policy_image_bytes", "hh_policy_rows_by_key", "hh_policy_last_error",
            "hh_hier_create", "hh_hier_destroy", "hh_hier_reset", "hh_hier_begin", "hh_hier_agents", "hh_hier_tick",
            "hh_hier_end", "hh_hier_eval_info", "hh_hier_get_state", "hh_hier_set_state", "hh_hier_launch_count", "hh_hier_last_error"]
 

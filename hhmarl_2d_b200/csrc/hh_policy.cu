@@ -22,6 +22,7 @@
 #include <string>
 
 #include "../../include/hhmarl_b200.h"
+#include "hh_policy_tc.h"
 
 namespace hh {
 namespace pf {
@@ -360,11 +361,12 @@ static int launch_policy(const hh::pf::Args& a, int n_chains, int max_rows, int 
   return 0;
 }
 
-static bool chain_ok(const hh_policy_chain_ex& s) {
-  if (!s.x || !s.w1 || !s.b1 || !s.ws || !s.bs || !s.wh || !s.bh || (!s.out && !s.act_out)) return false;
+static bool chain_ok(const hh_policy_chain_ex& s, bool tc) {
+  if (!s.x || !s.b1 || !s.bs || !s.bh || (!s.out && !s.act_out)) return false;
+  if (!tc && (!s.w1 || !s.ws || !s.wh)) return false;
   if (s.n_rows < 0 || s.d_in <= 0 || s.d_in > 72 || s.k1_pad % 8 || s.k1_pad < s.d_in || s.k1_pad > 72) return false;
   if (s.n_out <= 0 || s.n_out > 32) return false;
-  if (s.att_n > 0 && (!s.watt || !s.batt || s.att_pad % 8 || s.att_pad < s.att_n || s.att_lo + s.att_n != 500 || s.att_pad > 152))
+  if (s.att_n > 0 && ((!tc && !s.watt) || !s.batt || s.att_pad % 8 || s.att_pad < s.att_n || s.att_lo + s.att_n != 500 || s.att_pad > 152))
     return false;
   if (s.act_out) {
     if (s.n_heads < 1 || s.n_heads > 4) return false;
@@ -380,15 +382,27 @@ static bool chain_ok(const hh_policy_chain_ex& s) {
 
 extern "C" int hh_policy_forward_ex(int32_t n_chains, const hh_policy_chain_ex* chains, int32_t precision, void* stream) {
   using namespace hh::pf;
-  if (n_chains <= 0 || n_chains > kMaxChains || !chains || (precision != 0 && precision != 1)) {
+  if (n_chains <= 0 || n_chains > kMaxChains || !chains || precision < 0 || precision > 2) {
     g_pf_error = "hh_policy_forward_ex: bad argument";
     return -1;
+  }
+  if (precision == 2) {   // tcgen05 / TMEM path (hh_policy_tc.cu)
+    int rows = 0;
+    for (int i = 0; i < n_chains; ++i) {
+      if (!chain_ok(chains[i], true)) {
+        g_pf_error = "hh_policy_forward_ex: inconsistent chain description";
+        return -1;
+      }
+      if (chains[i].n_rows > rows) rows = chains[i].n_rows;
+    }
+    if (rows == 0) return 0;
+    return hh_pf_tc_launch(chains, n_chains, rows, stream, g_pf_error);
   }
   Args a;
   int max_rows = 0;
   for (int i = 0; i < n_chains; ++i) {
     const hh_policy_chain_ex& s = chains[i];
-    if (!chain_ok(s)) {
+    if (!chain_ok(s, false)) {
       g_pf_error = "hh_policy_forward_ex: inconsistent chain description";
       return -1;
     }
@@ -441,4 +455,9 @@ extern "C" int hh_policy_rows_by_key(int32_t n, const uint8_t* key_dev, int32_t 
     return -2;
   }
   return 0;
+}
+
+extern "C" int hh_policy_pack(const float* w_dev, int32_t k_rows, int32_t ldw, int32_t n_total, int32_t n_chunk, int32_t row_shift,
+                              int32_t ksteps, void* image_dev, float* unscale_dev, void* stream) {
+  return hh_pf_tc_pack(w_dev, k_rows, ldw, n_total, n_chunk, row_shift, ksteps, image_dev, unscale_dev, stream, g_pf_error);
 }

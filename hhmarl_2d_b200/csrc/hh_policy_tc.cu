@@ -1,0 +1,547 @@
+// hh_policy_tc.cu -- the policy forward (models/ac_models_hetero.py:86-103, 256-291, 368-404; same chains as hh_policy.cu) on
+// Blackwell's 5th-generation tensor cores: tcgen05.mma with the accumulators in tensor memory, operands in shared memory,
+// weights streamed by the TMA engine's bulk copies.  precision = 2 of hh_policy_forward_ex; fp32-equivalent results.
+//
+// Arithmetic ("H3").  kind::f16 MMAs run at twice the kind::tf32 rate and their operands take half the shared memory, so
+// every fp32 operand v is carried as TWO halves of a power-of-two multiple:  hi = rn_f16(2^s v),  lo = rn_f16(2^s v - hi)
+// (hi + lo = 2^s v to 2^-22 relative; the prescale keeps lo in fp16's normal range), and a product is three MMAs into
+// one fp32 accumulator:  A_lo B_hi + A_hi B_lo + A_hi B_hi.  Activations use s = 12 (|v| <= 1 after tanh / L2
+// normalisation; observations are in [0, 1]); each weight matrix gets the s that puts max |w| in [2^13, 2^14)
+// (hh_policy_pack, on the device).  The epilogue multiplies by 2^-(12 + s).  Measured (profiles/r2b_tcgen05_probe2.txt):
+// max error 3.7e-7 on sums of magnitude 1 (a sequential fp32 fma loop: 2.4e-7); 349 TFLOP/s fp32-equivalent at M = 64.
+//
+// One CTA = 64 rows of one chain (a 128-row tile of hi + lo activations would need 258 KB; measured in r2a: an M = 64 MMA takes
+// the same time as an M = 128 one, which is why the 2x of kind::f16 matters).  Shared memory: activation tile hi | lo as
+// [64 x 512] halves in the K-major no-swizzle canonical layout (8-row x 16-byte core matrices: element (r, k) at
+// (k / 8) * 1024 + r * 16 + (k % 8) * 2), input tile [64 x 80] the same way, a 4-slot ring of 16 KB weight stages.
+// Warp roles: warp 0 streams the weight images (cp.async.bulk -> mbarrier), one thread of warp 1 issues every MMA, warps
+// 2..9 are the epilogue (tcgen05.ld, bias, tanh / attention residual + L2 normalisation / head, hi + lo split, store back
+// into the activation tile for the next layer).  A 500-wide layer is two N = 256 halves in two TMEM regions, so that
+// the first half's epilogue overlaps the second half's MMAs and the next layer starts on the first half's columns.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/hhmarl_b200.h"
+#include "hh_policy_tc.h"
+
+namespace hh {
+namespace tc {
+
+constexpr int TM = 64;                     // rows per CTA
+constexpr int KA = 512;                    // K extent of the activation tile (500 padded)
+constexpr int KX = 80;                     // K extent of the input tile (<= 72 inputs, padded to a multiple of 16)
+constexpr uint32_t ACT_BYTES = TM * KA * 2;
+constexpr uint32_t X_BYTES = TM * KX * 2;
+constexpr uint32_t STAGE_BYTES = 16384;
+constexpr int NSTAGE = 4;
+constexpr uint32_t OFF_ACT_HI = 0, OFF_ACT_LO = ACT_BYTES, OFF_X_HI = 2 * ACT_BYTES, OFF_X_LO = OFF_X_HI + X_BYTES;
+constexpr uint32_t OFF_RING = OFF_X_LO + X_BYTES;
+constexpr uint32_t SMEM_BYTES = OFF_RING + NSTAGE * STAGE_BYTES;      // 217 088
+constexpr int kThreads = 320;
+constexpr int kEpiThreads = 256;
+constexpr float ACT_SCALE = 4096.0f, ACT_UNSCALE = 1.0f / 4096.0f;   // 2^12
+constexpr float ACT_CLAMP = 15.99f;        // |2^12 v| must stay below fp16's 65504
+constexpr uint32_t LBO_A = TM * 16, SBO = 128;
+constexpr int kTmemCols = 512;
+
+constexpr int kMaxSeg = 8;
+struct Seg {                 // one run of MMAs over consecutive K steps into one accumulator region
+  const uint8_t* w;          // packed weight image of this run (global)
+  uint16_t n;                // MMA N
+  uint16_t ksteps;           // K = 16 steps
+  uint16_t kps;              // K steps per ring stage (stage bytes = kps * n * 64)
+  uint16_t tmem_col;         // first accumulator column
+  uint16_t a_off16;          // start of the A operand inside its tile, in 16-byte units
+  uint8_t a_src;             // 0 = input tile, 1 = activation tile
+  uint8_t first;             // the first MMA overwrites the accumulator
+  uint8_t wait_act;          // activation barrier to wait for before the first MMA (0xff = none)
+  uint8_t commit_acc;        // accumulator barrier to commit to after the last MMA (0xff = none)
+};
+struct Chain {
+  const float *x, *b1, *batt, *bs, *bh, *us_w1, *us_att, *us_ws, *us_wh;
+  float* out;
+  const int* rows;
+  const int* range_dev;
+  int* act_out;
+  int n_rows, ldx, d_in, att_lo, att_n, att_pad, n_out, ld_out, n_heads, head[4], ld_act, n_seg;
+  Seg seg[kMaxSeg];
+};
+struct Args {
+  Chain c[8];
+};
+
+// barrier slots
+constexpr int B_FULL = 0, B_EMPTY = NSTAGE, B_ACC = 2 * NSTAGE, B_ACT = 2 * NSTAGE + 6, B_COUNT = 2 * NSTAGE + 6 + 5;
+// accumulator barriers: 0 L1 half 0, 1 L1 half 1, 2 attention, 3 shared half 0, 4 shared half 1, 5 head
+// activation barriers:  0 H[:, :256] ready, 1 H[:, 256:], 2 attention block rewritten, 3 Z[:, :256], 4 Z[:, 256:]
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;        // descriptor version of sm_100; no swizzle, base offset 0
+  return d;
+}
+// kind::f16 instruction descriptor: D = F32, A = B = F16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__device__ __forceinline__ uint32_t instr_desc_f16(uint32_t M, uint32_t N) { return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24); }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_tc_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_tc_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Every wait is bounded: a protocol error traps (the launch fails with an error) instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t spin = 0; !ok; ++spin) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    if (!ok && spin > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_16x256b_x1(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// byte offset of element (row, k) inside a 64-row operand tile
+__device__ __forceinline__ uint32_t canon(int row, int k) { return (uint32_t)((k >> 3) * (TM * 16) + row * 16 + (k & 7) * 2); }
+
+// store the pair (v0, v1) = elements (row, k), (row, k + 1), k even, as hi / lo halves of 2^12 v
+__device__ __forceinline__ void store_pair(uint8_t* hi_tile, uint8_t* lo_tile, int row, int k, float v0, float v1) {
+  const float s0 = v0 * ACT_SCALE, s1 = v1 * ACT_SCALE;
+  const __half2 h = __floats2half2_rn(s0, s1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
+  const uint32_t o = canon(row, k);
+  *reinterpret_cast<__half2*>(hi_tile + o) = h;
+  *reinterpret_cast<__half2*>(lo_tile + o) = l;
+}
+__device__ __forceinline__ float2 load_pair(const uint8_t* hi_tile, const uint8_t* lo_tile, int row, int k) {
+  const uint32_t o = canon(row, k);
+  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(hi_tile + o));
+  const float2 l = __half22float2(*reinterpret_cast<const __half2*>(lo_tile + o));
+  return make_float2((h.x + l.x) * ACT_UNSCALE, (h.y + l.y) * ACT_UNSCALE);
+}
+
+// epilogue of one 256-column half of a 500-wide layer: act[:, k0 + c] = tanh(acc * us + bias[k0 + c]); this warp owns
+// the 16 rows of its lane quadrant and 128 of the 256 columns
+__device__ __forceinline__ void epi_tanh_half(uint8_t* smem, uint32_t tmem, int tmem_col, int k0, const float* __restrict__ bias,
+                                              float us, int q, int part, int lane) {
+  const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(tmem_col + part * 128);
+  const int rlo = 16 * q + (lane >> 2), cpair = 2 * (lane & 3);
+  uint8_t *hi = smem + OFF_ACT_HI, *lo = smem + OFF_ACT_LO;
+#pragma unroll 1
+  for (int c = 0; c < 128; c += 32) {
+    uint32_t r[16];
+    tmem_ld_16x256b_x4(taddr + c, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = k0 + part * 128 + c + 8 * i + cpair;
+      const float2 b = __ldg(reinterpret_cast<const float2*>(bias + k));
+      store_pair(hi, lo, rlo, k, tanhf(fmaf(__uint_as_float(r[4 * i]), us, b.x)), tanhf(fmaf(__uint_as_float(r[4 * i + 1]), us, b.y)));
+      store_pair(hi, lo, rlo + 8, k, tanhf(fmaf(__uint_as_float(r[4 * i + 2]), us, b.x)),
+                 tanhf(fmaf(__uint_as_float(r[4 * i + 3]), us, b.y)));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) policy_forward_tc_kernel(const __grid_constant__ Args args) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bars[B_COUNT];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int rowmap[TM];
+  const Chain& C = args.c[blockIdx.y];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int beg = 0, cnt = C.n_rows;
+  if (C.range_dev) {
+    beg = C.range_dev[0];
+    cnt = C.range_dev[1];
+  }
+  const int row0 = blockIdx.x * TM;
+  if (row0 >= cnt) return;              // CTA-uniform
+  if (tid < TM) {
+    const int lr = row0 + tid;
+    rowmap[tid] = lr < cnt ? (C.rows ? C.rows[beg + lr] : beg + lr) : -1;
+  }
+  const uint32_t bar0 = smem_u32(bars);
+  if (tid == 0) {
+    for (int i = 0; i < 2 * NSTAGE + 6; ++i) mbar_init(bar0 + 8 * i, 1);
+    for (int i = 0; i < 5; ++i) mbar_init(bar0 + 8 * (B_ACT + i), i == 2 ? kEpiThreads / 2 : kEpiThreads);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  fence_tc_before();
+  __syncthreads();
+  fence_tc_after();
+  const uint32_t tmem = tmem_base_s;
+
+  // input rows -> hi / lo halves of 2^12 x in the canonical layout (zero beyond d_in and beyond the row list)
+  for (int i = tid; i < TM * (KX / 2); i += kThreads) {
+    const int r = i / (KX / 2), c = 2 * (i - r * (KX / 2));
+    const int gr = rowmap[r];
+    float v0 = 0.0f, v1 = 0.0f;
+    if (gr >= 0) {
+      const float* xr = C.x + (size_t)gr * C.ldx;
+      if (c < C.d_in) v0 = fminf(fmaxf(__ldg(xr + c), -ACT_CLAMP), ACT_CLAMP);
+      if (c + 1 < C.d_in) v1 = fminf(fmaxf(__ldg(xr + c + 1), -ACT_CLAMP), ACT_CLAMP);
+    }
+    store_pair(smem + OFF_X_HI, smem + OFF_X_LO, r, c, v0, v1);
+  }
+  fence_async_smem();
+  __syncthreads();
+
+  if (warp == 0) {
+    if (lane == 0) {   // ---- weight stream: the stages of every segment, in the order the MMAs consume them
+      uint32_t slot = 0, phase = 0;
+      for (int s = 0; s < C.n_seg; ++s) {
+        const Seg& g = C.seg[s];
+        const uint32_t bytes = (uint32_t)g.kps * g.n * 64u;
+        const uint8_t* src = g.w;
+        for (int k = 0; k < g.ksteps; k += g.kps) {
+          mbar_wait(bar0 + 8 * (B_EMPTY + slot), phase ^ 1);
+          mbar_expect_tx(bar0 + 8 * (B_FULL + slot), bytes);
+          bulk_g2s(smem_u32(smem + OFF_RING + slot * STAGE_BYTES), src, bytes, bar0 + 8 * (B_FULL + slot));
+          src += bytes;
+          if (++slot == NSTAGE) {
+            slot = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {   // ---- MMA issue
+      uint32_t slot = 0, phase = 0;
+      for (int s = 0; s < C.n_seg; ++s) {
+        const Seg& g = C.seg[s];
+        if (g.wait_act != 0xff) mbar_wait(bar0 + 8 * (B_ACT + g.wait_act), 0);
+        fence_tc_after();
+        const uint32_t idesc = instr_desc_f16(TM, g.n);
+        const uint32_t a_hi = smem_u32(smem + (g.a_src ? OFF_ACT_HI : OFF_X_HI)) + 16u * g.a_off16;
+        const uint32_t a_lo = a_hi + (g.a_src ? ACT_BYTES : X_BYTES);
+        const uint32_t lbo_b = 16u * g.n, blk = 64u * g.n;
+        const uint32_t d = tmem + g.tmem_col;
+        uint32_t kdone = 0;
+        for (int k = 0; k < g.ksteps; k += g.kps) {
+          mbar_wait(bar0 + 8 * (B_FULL + slot), phase);
+          fence_tc_after();
+          const uint32_t sb = smem_u32(smem + OFF_RING + slot * STAGE_BYTES);
+          for (int j = 0; j < g.kps; ++j, ++kdone) {
+            const uint32_t oa = kdone * 2 * LBO_A;
+            const uint64_t dah = smem_desc(a_hi + oa, LBO_A, SBO), dal = smem_desc(a_lo + oa, LBO_A, SBO);
+            const uint64_t dbh = smem_desc(sb + j * blk, lbo_b, SBO), dbl = smem_desc(sb + j * blk + blk / 2, lbo_b, SBO);
+            umma_f16(d, dal, dbh, idesc, (g.first && kdone == 0) ? 0u : 1u);   // small terms first
+            umma_f16(d, dah, dbl, idesc, 1u);
+            umma_f16(d, dah, dbh, idesc, 1u);
+          }
+          umma_commit(bar0 + 8 * (B_EMPTY + slot));       // the slot is free once these MMAs have read it
+          if (++slot == NSTAGE) {
+            slot = 0;
+            phase ^= 1;
+          }
+        }
+        if (g.commit_acc != 0xff) umma_commit(bar0 + 8 * (B_ACC + g.commit_acc));
+      }
+    }
+  } else {
+    // ---- epilogue warps 2..9: lane quadrant q = warp % 4 (the TMEM lanes a warp can read), column part (warp - 2) / 4
+    const int q = warp & 3, part = (warp - 2) >> 2;
+    const int rlo = 16 * q + (lane >> 2), cpair = 2 * (lane & 3);
+    uint8_t *hi = smem + OFF_ACT_HI, *lo = smem + OFF_ACT_LO;
+    {  // H = tanh(x W1 + b1)
+      const float us = __ldg(C.us_w1);
+      for (int h = 0; h < 2; ++h) {
+        mbar_wait(bar0 + 8 * (B_ACC + h), 0);
+        fence_tc_after();
+        epi_tanh_half(smem, tmem, 256 * h, 256 * h, C.b1, us, q, part, lane);
+        fence_async_smem();
+        fence_tc_before();
+        mbar_arrive(bar0 + 8 * (B_ACT + h));
+      }
+    }
+    if (C.att_n > 0 && part == 0) {   // single-token attention: r = full + (full Wa + ba), then L2-normalise the block
+      const float us = __ldg(C.us_att);
+      mbar_wait(bar0 + 8 * (B_ACC + 2), 0);
+      fence_tc_after();
+      const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16);
+      const int ngroups = C.att_pad >> 3;
+      float ss0 = 0.0f, ss1 = 0.0f;
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        float inv0 = 0.0f, inv1 = 0.0f;
+        if (pass) {
+          ss0 += __shfl_xor_sync(0xffffffffu, ss0, 1);
+          ss0 += __shfl_xor_sync(0xffffffffu, ss0, 2);
+          ss1 += __shfl_xor_sync(0xffffffffu, ss1, 1);
+          ss1 += __shfl_xor_sync(0xffffffffu, ss1, 2);
+          inv0 = 1.0f / fmaxf(sqrtf(ss0), 1e-12f);       // F.normalize: x / max(||x||_2, 1e-12)
+          inv1 = 1.0f / fmaxf(sqrtf(ss1), 1e-12f);
+        }
+#pragma unroll 1
+        for (int gidx = 0; gidx < ngroups; ++gidx) {
+          uint32_t r[4];
+          tmem_ld_16x256b_x1(taddr + 8 * gidx, r);
+          tmem_ld_wait();
+          const int col = 8 * gidx + cpair;
+          if (col < C.att_n) {                            // att_n is even: a pair is valid or invalid as a whole
+            const float2 b = __ldg(reinterpret_cast<const float2*>(C.batt + col));
+            const float2 p0 = load_pair(hi, lo, rlo, C.att_lo + col), p1 = load_pair(hi, lo, rlo + 8, C.att_lo + col);
+            const float v00 = fmaf(__uint_as_float(r[0]), us, b.x) + p0.x, v01 = fmaf(__uint_as_float(r[1]), us, b.y) + p0.y;
+            const float v10 = fmaf(__uint_as_float(r[2]), us, b.x) + p1.x, v11 = fmaf(__uint_as_float(r[3]), us, b.y) + p1.y;
+            if (!pass) {
+              ss0 += v00 * v00 + v01 * v01;
+              ss1 += v10 * v10 + v11 * v11;
+            } else {
+              store_pair(hi, lo, rlo, C.att_lo + col, v00 * inv0, v01 * inv0);
+              store_pair(hi, lo, rlo + 8, C.att_lo + col, v10 * inv1, v11 * inv1);
+            }
+          }
+        }
+      }
+      fence_async_smem();
+      fence_tc_before();
+      mbar_arrive(bar0 + 8 * (B_ACT + 2));
+    }
+    {  // Z = tanh(in Ws + bs), in place: no column may be rewritten before BOTH halves' MMAs have read the tile
+      const float us = __ldg(C.us_ws);
+      mbar_wait(bar0 + 8 * (B_ACC + 4), 0);
+      fence_tc_after();
+      for (int h = 0; h < 2; ++h) {
+        epi_tanh_half(smem, tmem, 256 * h, 256 * h, C.bs, us, q, part, lane);
+        fence_async_smem();
+        fence_tc_before();
+        mbar_arrive(bar0 + 8 * (B_ACT + 3 + h));
+      }
+    }
+    if (part == 0) {  // head: logits or value (+ optional per-head argmax, env_base.py:373-382)
+      const float us = __ldg(C.us_wh);
+      mbar_wait(bar0 + 8 * (B_ACC + 5), 0);
+      fence_tc_after();
+      float* lg = reinterpret_cast<float*>(smem + OFF_X_HI);       // [TM][33]; the input tile is dead by now
+      uint32_t r[16];
+      tmem_ld_16x256b_x4(tmem + ((uint32_t)(32 * q) << 16), r);
+      tmem_ld_wait();
+      const int g0 = rowmap[rlo], g1 = rowmap[rlo + 8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int col = 8 * i + cpair + j;
+          if (col < C.n_out) {
+            const float b = __ldg(C.bh + col);
+            const float v0 = fmaf(__uint_as_float(r[4 * i + j]), us, b), v1 = fmaf(__uint_as_float(r[4 * i + 2 + j]), us, b);
+            if (C.out) {
+              if (g0 >= 0) C.out[(size_t)g0 * C.ld_out + col] = v0;
+              if (g1 >= 0) C.out[(size_t)g1 * C.ld_out + col] = v1;
+            }
+            lg[rlo * 33 + col] = v0;
+            lg[(rlo + 8) * 33 + col] = v1;
+          }
+        }
+      if (C.act_out) {
+        __syncwarp();
+        const int row = 16 * q + lane;
+        if (lane < 16 && rowmap[row] >= 0) {
+          const float* lr = lg + row * 33;
+          int4 a = make_int4(0, 0, 0, 0);
+          int o = 0;
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            if (h < C.n_heads) {
+              int best = 0;
+              float bv = lr[o];
+              for (int k = 1; k < C.head[h]; ++k)
+                if (lr[o + k] > bv) { bv = lr[o + k]; best = k; }      // first maximum, like torch.argmax
+              (h == 0 ? a.x : h == 1 ? a.y : h == 2 ? a.z : a.w) = best;
+              o += C.head[h];
+            }
+          }
+          reinterpret_cast<int4*>(C.act_out)[(size_t)rowmap[row] * C.ld_act] = a;
+        }
+      }
+    }
+  }
+  fence_tc_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
+  }
+}
+
+// ---- operand images -----------------------------------------------------------------------------------------------
+// us[0] = 2^-(12 + s), us[1] = 2^s with s such that max |2^s w| lies in [2^13, 2^14)
+__global__ void pack_scale_kernel(const float* __restrict__ w, int k_rows, int ldw, int n_total, float* __restrict__ us) {
+  __shared__ float red[32];
+  float m = 0.0f;
+  for (int i = threadIdx.x; i < k_rows * n_total; i += blockDim.x) m = fmaxf(m, fabsf(w[(size_t)(i / n_total) * ldw + i % n_total]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, red[i]);
+    int s = 0;
+    if (m > 0.0f && isfinite(m)) s = 13 - ilogbf(m);
+    s = max(-60, min(60, s));
+    us[0] = ldexpf(1.0f, -(12 + s));
+    us[1] = ldexpf(1.0f, s);
+  }
+}
+// image = [chunk][kstep]{ hi [2 k-halves][n_chunk][8], lo [2][n_chunk][8] } halves; image row k' = kstep * 16 + half * 8 + kk
+// holds w row k' - row_shift (zero outside [0, k_rows)), image column c of chunk j holds w column j * n_chunk + c
+__global__ void pack_image_kernel(const float* __restrict__ w, int k_rows, int ldw, int n_total, int n_chunk, int row_shift,
+                                  int ksteps, const float* __restrict__ us, __half* __restrict__ img) {
+  const int total = ksteps * 16 * n_total;
+  const float scale = us[1];
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    int t = e;
+    const int kk = t & 7; t >>= 3;
+    const int c = t % n_chunk; t /= n_chunk;
+    const int h = t & 1; t >>= 1;
+    const int ks = t % ksteps;
+    const int chunk = t / ksteps;
+    const int row = ks * 16 + h * 8 + kk - row_shift, col = chunk * n_chunk + c;
+    const float v = (row >= 0 && row < k_rows) ? w[(size_t)row * ldw + col] * scale : 0.0f;
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
+    const size_t base = (size_t)(chunk * ksteps + ks) * n_chunk * 32 + (size_t)(h * n_chunk + c) * 8 + kk;
+    img[base] = hi;
+    img[base + (size_t)n_chunk * 16] = lo;
+  }
+}
+
+}  // namespace tc
+}  // namespace hh
+
+extern "C" int64_t hh_policy_image_bytes(int32_t ksteps, int32_t n_total) { return (int64_t)ksteps * n_total * 64; }
+
+int hh_pf_tc_pack(const float* w_dev, int k_rows, int ldw, int n_total, int n_chunk, int row_shift, int ksteps, void* image_dev,
+                  float* unscale_dev, void* stream, std::string& err) {
+  using namespace hh::tc;
+  if (!w_dev || !image_dev || !unscale_dev || k_rows <= 0 || ldw < n_total || n_total <= 0 || n_chunk <= 0 || n_total % n_chunk ||
+      n_chunk % 8 || n_chunk > 256 || ksteps <= 0 || row_shift < 0 || (uint32_t)n_chunk * 64u > STAGE_BYTES) {
+    err = "hh_policy_pack: bad argument";
+    return -1;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  pack_scale_kernel<<<1, 1024, 0, st>>>(w_dev, k_rows, ldw, n_total, unscale_dev);
+  const int total = ksteps * 16 * n_total;
+  pack_image_kernel<<<(total + 255) / 256, 256, 0, st>>>(w_dev, k_rows, ldw, n_total, n_chunk, row_shift, ksteps, unscale_dev,
+                                                         static_cast<__half*>(image_dev));
+  const cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) {
+    err = std::string("hh_policy_pack launch: ") + cudaGetErrorString(ce);
+    return -2;
+  }
+  return 0;
+}
+
+int hh_pf_tc_launch(const hh_policy_chain_ex* chains, int n_chains, int max_rows, void* stream, std::string& err) {
+  using namespace hh::tc;
+  Args a;
+  for (int i = 0; i < n_chains; ++i) {
+    const hh_policy_chain_ex& s = chains[i];
+    if (!s.img_w1 || !s.img_ws || !s.img_wh || !s.us_w1 || !s.us_ws || !s.us_wh || (s.att_n > 0 && (!s.img_att || !s.us_att))) {
+      err = "hh_policy_forward_ex(precision = 2): the chain carries no packed operand images (hh_policy_pack)";
+      return -1;
+    }
+    if (s.d_in > KX || (s.att_n & 1) || (s.att_lo & 1) || s.att_pad > 256 || (s.att_n > 0 && s.att_lo + s.att_n > 504)) {
+      err = "hh_policy_forward_ex(precision = 2): unsupported chain shape";
+      return -1;
+    }
+    Chain& c = a.c[i];
+    c.x = s.x; c.b1 = s.b1; c.batt = s.batt; c.bs = s.bs; c.bh = s.bh;
+    c.us_w1 = s.us_w1; c.us_att = s.us_att; c.us_ws = s.us_ws; c.us_wh = s.us_wh;
+    c.out = s.out; c.rows = s.rows; c.range_dev = s.range_dev; c.act_out = s.act_out;
+    c.n_rows = s.n_rows; c.ldx = s.ldx; c.d_in = s.d_in; c.att_lo = s.att_lo; c.att_n = s.att_n; c.att_pad = s.att_pad;
+    c.n_out = s.n_out; c.ld_out = s.ld_out; c.n_heads = s.n_heads;
+    for (int h = 0; h < 4; ++h) c.head[h] = s.head[h];
+    c.ld_act = s.ld_act > 0 ? s.ld_act : 1;
+    const int k1s = (s.d_in + 15) / 16;
+    int n = 0;
+    auto seg = [&](const void* w, size_t off, int nn, int ksteps, int kps, int col, int a_src, int a_k0, int first, int wait, int commit) {
+      Seg& g = c.seg[n++];
+      g.w = static_cast<const uint8_t*>(w) + off;
+      g.n = (uint16_t)nn; g.ksteps = (uint16_t)ksteps; g.kps = (uint16_t)kps; g.tmem_col = (uint16_t)col;
+      g.a_off16 = (uint16_t)((a_k0 / 8) * (TM * 16) / 16);
+      g.a_src = (uint8_t)a_src; g.first = (uint8_t)first; g.wait_act = (uint8_t)wait; g.commit_acc = (uint8_t)commit;
+    };
+    seg(s.img_w1, 0, 256, k1s, 1, 0, 0, 0, 1, 0xff, 0);
+    seg(s.img_w1, (size_t)k1s * 256 * 64, 256, k1s, 1, 256, 0, 0, 1, 0xff, 1);
+    int act_ready = 1;
+    if (s.att_n > 0) {
+      const int k0 = s.att_lo & ~7, ks = (s.att_lo + s.att_n - k0 + 15) / 16;
+      seg(s.img_att, 0, s.att_pad, ks, 1, 0, 1, k0, 1, 1, 2);
+      act_ready = 2;
+    }
+    seg(s.img_ws, 0, 256, KA / 16, 1, 0, 1, 0, 1, act_ready, 3);
+    seg(s.img_ws, (size_t)(KA / 16) * 256 * 64, 256, KA / 16, 1, 256, 1, 0, 1, 0xff, 4);
+    seg(s.img_wh, 0, 32, 16, 8, 0, 1, 0, 1, 3, 0xff);
+    seg(s.img_wh, (size_t)16 * 32 * 64, 32, 16, 8, 0, 1, 256, 0, 4, 5);
+    c.n_seg = n;
+  }
+  static bool opted_dev[64] = {};
+  int dev = 0;
+  cudaError_t ce = cudaGetDevice(&dev);
+  if (ce != cudaSuccess || dev < 0 || dev >= 64) {
+    err = "hh_policy_forward_ex: cudaGetDevice failed";
+    return -2;
+  }
+  if (!opted_dev[dev]) {
+    ce = cudaFuncSetAttribute(policy_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (ce != cudaSuccess) {
+      err = std::string("cudaFuncSetAttribute(policy_forward_tc_kernel): ") + cudaGetErrorString(ce);
+      return -2;
+    }
+    opted_dev[dev] = true;
+  }
+  const dim3 grid((max_rows + TM - 1) / TM, n_chains);
+  policy_forward_tc_kernel<<<grid, kThreads, SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(a);
+  ce = cudaGetLastError();
+  if (ce != cudaSuccess) {
+    err = std::string("policy_forward_tc_kernel launch: ") + cudaGetErrorString(ce);
+    return -2;
+  }
+  return 0;
+}

@@ -33,6 +33,10 @@ class PackedPolicyPair:
     _LISTS = ("W1", "b1", "Watt", "batt", "Wact", "bact", "Wval", "bval")
 
     def __init__(self, model1, model2):
+        # one SHARED_LAYER per process (ac_models_hetero.py:22-27): the packed forward applies model1's to all four chains
+        if model1.shared_layer is not model2.shared_layer:
+            raise ValueError("PackedPolicyPair needs two policies that share ONE shared_layer module "
+                             "(models.build_policy_pair); these were built separately")
         self.m = (model1, model2)
         self.fight = isinstance(model1, M.Fight1)
         self._pack()
@@ -134,11 +138,36 @@ class PackedPolicyPair:
         return l1, v1, l2, v2
 
 
+def _pack_image(w_rm: torch.Tensor, n_total: int, n_chunk: int, row_shift: int, ksteps: int, img=None, us=None):
+    """Operand image of a zero-padded row-major [K, ld] fp32 weight matrix for the tcgen05 path (hh_policy_pack):
+    fp16 hi / lo halves of 2^s w in the K-major canonical shared-memory layout, one 16 KB ring stage after the other in
+    the order the kernel consumes them.  -> (image uint8 tensor, scale pair float[2]); re-packs IN PLACE when given."""
+    L = nat.lib()
+    dev = w_rm.device
+    if img is None:
+        img = torch.empty(int(L.hh_policy_image_bytes(ksteps, n_total)), dtype=torch.uint8, device=dev)
+        us = torch.zeros(2, dtype=torch.float32, device=dev)
+    assert w_rm.is_contiguous() and w_rm.dtype == torch.float32 and w_rm.is_cuda
+    st = torch.cuda.current_stream(dev).cuda_stream
+    nat.check(L.hh_policy_pack(w_rm.data_ptr(), w_rm.shape[0], w_rm.stride(0), n_total, n_chunk, row_shift, ksteps,
+                               img.data_ptr(), us.data_ptr(), st), "hh_policy_pack")
+    return img, us
+
+
+def _att_image_geometry(att_lo: int, att_n: int):
+    """The attention block reads activation columns [att_lo, att_lo + att_n); the MMA's A operand has to start on a core
+    matrix (8 columns), so the image's K range starts at floor8(att_lo) and its first rows are zero."""
+    k0 = att_lo & ~7
+    return att_lo - k0, (att_lo + att_n - k0 + 15) // 16          # (row_shift, ksteps)
+
+
 class FusedPolicyPair:
     """The same forward as PackedPolicyPair.forward in ONE launch of the hand-written kernel csrc/hh_policy.cu
     (C ABI hh_policy_forward): per 64-row tile and chain the activations stay in shared memory, every GEMM runs on
-    the tensor cores as 3xTF32 (fp32-equivalent, precision=0) or plain TF32 (precision=1).  Weights are re-packed
-    into the zero-padded layouts the kernel expects; `refresh()` re-packs in place (CUDA-graph safe)."""
+    the tensor cores as 3xTF32 (fp32-equivalent, precision=0) or plain TF32 (precision=1), both on the legacy mma.sync
+    path, or -- precision=2, csrc/hh_policy_tc.cu -- on tcgen05 with TMEM accumulators (fp16 hi / lo operand split,
+    fp32-equivalent).  Weights are re-packed into the layouts the kernels expect; `refresh()` re-packs in place
+    (CUDA-graph safe)."""
 
     NP, NW, NH = 504, 512, 32     # K extent / N extent (row stride) of the 500-wide layers, head width
 
@@ -181,6 +210,30 @@ class FusedPolicyPair:
                 if self.fight:
                     self._to_fragments(self.watt[p][k], self._rm["watt"][p][k])
         self._to_fragments(self.ws, self._rm["ws"])
+        if self.precision == 2:
+            self._pack_images()
+
+    def _pack_images(self):
+        """tcgen05 path: operand images of every weight matrix (in place after the first call)."""
+        first = not hasattr(self, "img")
+        if first:
+            self.img = {}
+        rm = self._rm
+
+        def put(key, w, n_total, n_chunk, shift, ksteps):
+            old = self.img.get(key, (None, None))
+            self.img[key] = _pack_image(w, n_total, n_chunk, shift, ksteps, *old)
+
+        for p in range(2):
+            k1s = (self.packed.W1[p].shape[0] + 15) // 16
+            for k in range(2):
+                put(("w1", p, k), rm["w1"][p][k], 512, 256, 0, k1s)
+                put(("wh", p, k), rm["wh"][p][k], 32, 32, 0, 32)
+                if self.fight:
+                    lo, n, pad = self.att[k]
+                    shift, ks = _att_image_geometry(lo, n)
+                    put(("watt", p, k), rm["watt"][p][k], pad, pad, shift, ks)
+        put(("ws",), rm["ws"], 512, 256, 0, 32)
 
     @torch.no_grad()
     def _fill_row_major(self):
@@ -225,6 +278,8 @@ class FusedPolicyPair:
                 self._out = (torch.empty((B, n_act[0]), device=self.dev), torch.empty((B,), device=self.dev),
                              torch.empty((B, n_act[1]), device=self.dev), torch.empty((B,), device=self.dev))
             out = self._out
+        if self.precision == 2:
+            return self._forward_tc(flat1, flat2, out, n_act)
         chains = (nat.HHPolicyChain * 4)()
         for p, x in enumerate((flat1, flat2)):
             assert x.is_contiguous() and x.dtype == torch.float32 and x.is_cuda
@@ -243,6 +298,30 @@ class FusedPolicyPair:
         st = torch.cuda.current_stream(self.dev).cuda_stream
         nat.check(nat.lib().hh_policy_forward(B, chains, self.ws.data_ptr(), self.bs.data_ptr(), self.precision, st),
                   "hh_policy_forward")
+        return out
+
+
+    def _forward_tc(self, flat1, flat2, out, n_act):
+        chains = (nat.HHPolicyChainEx * 4)()
+        B = flat1.shape[0]
+        for p, x in enumerate((flat1, flat2)):
+            assert x.dtype == torch.float32 and x.is_cuda and x.stride(1) == 1
+            for k in range(2):
+                c = chains[2 * p + k]
+                c.x, c.ldx, c.d_in, c.k1_pad = x.data_ptr(), x.stride(0), x.shape[1], self.k1_pad[p]
+                c.b1, c.bs, c.bh = self.b1[p][k].data_ptr(), self.bs.data_ptr(), self.bh[p][k].data_ptr()
+                c.img_w1, c.us_w1 = (t.data_ptr() for t in self.img[("w1", p, k)])
+                c.img_ws, c.us_ws = (t.data_ptr() for t in self.img[("ws",)])
+                c.img_wh, c.us_wh = (t.data_ptr() for t in self.img[("wh", p, k)])
+                if self.fight:
+                    c.batt = self.batt[p][k].data_ptr()
+                    c.att_lo, c.att_n, c.att_pad = self.att[k]
+                    c.img_att, c.us_att = (t.data_ptr() for t in self.img[("watt", p, k)])
+                o = out[2 * p + k]
+                c.out, c.ld_out, c.n_out = o.data_ptr(), o.stride(0), (n_act[p] if k == 0 else 1)
+                c.n_rows = B
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        nat.check(nat.lib().hh_policy_forward_ex(4, chains, 2, st), "hh_policy_forward_ex")
         return out
 
 
@@ -284,6 +363,8 @@ class FusedActor:
             W[r0:r1, c0:c1] = w.t()
             self.b1[c0:c1] = b
         FusedPolicyPair._to_fragments(self.w1, W)
+        img = getattr(self, "img", {})
+        img["w1"] = _pack_image(W, 512, 256, 0, (own + 15) // 16, *img.get("w1", (None, None)))
         if self.fight:
             mha = m.att_act
             e = mha.embed_dim
@@ -294,16 +375,21 @@ class FusedActor:
             self.batt.zero_()
             self.batt[:100] = Wo @ bv + bo
             FusedPolicyPair._to_fragments(self.watt, Wa)
+            shift, ks = _att_image_geometry(400, 100)
+            img["watt"] = _pack_image(Wa, 104, 104, shift, ks, *img.get("watt", (None, None)))
         ws, bs = _lin(m.shared_layer)
         Wsp = torch.zeros((self.NP, self.NW), device=self.dev)
         Wsp[:500, :500] = ws.t()
         FusedPolicyPair._to_fragments(self.ws, Wsp)
+        img["ws"] = _pack_image(Wsp, 512, 256, 0, 32, *img.get("ws", (None, None)))
         self.bs.zero_()
         self.bs[:500] = bs
         wa, ba = _lin(m.act_out)
         Wh = torch.zeros((self.NP, self.NH), device=self.dev)
         Wh[:500, :self.n_out] = wa.t()
         FusedPolicyPair._to_fragments(self.wh, Wh)
+        img["wh"] = _pack_image(Wh, 32, 32, 0, 32, *img.get("wh", (None, None)))
+        self.img = img
         self.bh.zero_()
         self.bh[:self.n_out] = ba
 
@@ -317,6 +403,11 @@ class FusedActor:
         else:
             c.watt, c.batt, c.att_lo, c.att_n, c.att_pad = None, None, 0, 0, 0
         c.ws, c.bs, c.wh, c.bh = self.ws.data_ptr(), self.bs.data_ptr(), self.wh.data_ptr(), self.bh.data_ptr()
+        c.img_w1, c.us_w1 = (t.data_ptr() for t in self.img["w1"])
+        c.img_ws, c.us_ws = (t.data_ptr() for t in self.img["ws"])
+        c.img_wh, c.us_wh = (t.data_ptr() for t in self.img["wh"])
+        if self.fight:
+            c.img_att, c.us_att = (t.data_ptr() for t in self.img["watt"])
         c.out = out.data_ptr() if out is not None else None
         c.ld_out = out.stride(0) if out is not None else 0
         c.act_out = act_ptr if act_ptr is not None else (act_out.data_ptr() if act_out is not None else None)

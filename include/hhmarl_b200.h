@@ -177,8 +177,23 @@ typedef struct {
   int32_t* act_out;
   int32_t n_rows, ldx, d_in, k1_pad, att_lo, att_n, att_pad, n_out, ld_out, n_heads, head[4];
   int32_t ld_act;   /* row stride of act_out in units of 4 int32 (0 or 1: dense [.., 4]) */
+  /* precision = 2 (tcgen05 path): operand images of the four weight matrices and their scale pairs, written by
+   * hh_policy_pack; w1 / watt / ws / wh are not read then */
+  const void *img_w1, *img_att, *img_ws, *img_wh;
+  const float *us_w1, *us_att, *us_ws, *us_wh;
 } hh_policy_chain_ex;
+/* precision: 0 = 3xTF32 on mma.sync (fp32-equivalent), 1 = TF32 on mma.sync, 2 = tcgen05 / TMEM path: every fp32 operand as
+ * two fp16 halves of a power-of-two multiple, three kind::f16 MMAs per product, fp32 accumulation in tensor memory
+ * (fp32-equivalent; inputs x are expected in [-15.99, 15.99] -- observations are Box(0, 1), env_hetero.py:28-36). */
 int hh_policy_forward_ex(int32_t n_chains, const hh_policy_chain_ex* chains, int32_t precision, void* stream);
+/* Operand image of one weight matrix for precision = 2.  w_dev: fp32 row-major [k_rows][ldw] (K x N, zero-padded), columns
+ * [0, n_total) are packed in chunks of n_chunk columns (the MMA N: 256 for the 500-wide layers -> n_total 512; the padded
+ * width itself for the attention block and the head), image row k' = w row k' - row_shift (zero outside), ksteps * 16 image
+ * rows.  image_dev: hh_policy_image_bytes(ksteps, n_total) bytes; unscale_dev: float[2] = {2^-(12 + s), 2^s}.  Runs on
+ * `stream`, no host synchronisation (call it again after the weights changed). */
+int64_t hh_policy_image_bytes(int32_t ksteps, int32_t n_total);
+int hh_policy_pack(const float* w_dev, int32_t k_rows, int32_t ldw, int32_t n_total, int32_t n_chunk, int32_t row_shift,
+                   int32_t ksteps, void* image_dev, float* unscale_dev, void* stream);
 /* Row lists per key, built on the device: rows_dev int32 [n_keys][n], ranges_dev int32 [n_keys][2] = {k n, count_k} for the
  * arenas i with key_dev[i] == keys_host[k] (n_keys <= 4).  Level 5 draws the opponents' policy set per arena and episode
  * (env_hetero.py:55-59); the lists feed hh_policy_chain_ex.rows / range_dev without a host synchronisation. */

@@ -30,9 +30,14 @@ def timeit(fn, n=30):
 
 
 flops = 2 * B * 2 * (57 * 1000 + 100 * 100 + 150 * 150 + 2 * 500 * 500 + 500 * 27)
-for prec, name in ((0, "fused 3xTF32"), (1, "fused TF32")):
+for prec, name in ((2, "tcgen05 H3"), (0, "fused 3xTF32"), (1, "fused TF32")):
     fu = FusedPolicyPair(m1, m2, precision=prec)
     us = timeit(lambda: fu.forward(f1, f2))
+    if prec == 2:
+        with torch.no_grad():
+            ref = m1.forward_flat(f1)
+        out = fu.forward(f1, f2)
+        print("tcgen05 H3 max |logits - torch fp32|", (out[0] - ref[0]).abs().max().item(), "value", (out[1] - ref[1]).abs().max().item())
     print(f"{name:14s} {us:8.1f} us  ({flops / us / 1e6:6.1f} TFLOP/s useful)")
 pk = PackedPolicyPair(m1, m2)
 for tf32 in (False, True):

@@ -157,7 +157,7 @@ def test_fused_policy_forward_matches_torch(mode):
         pk = PackedPolicyPair(m1, m2).forward(f1, f2)
         for a, b in zip(pk, ref):
             assert torch.allclose(a, b, atol=2e-5, rtol=1e-5)
-        for prec, atol in ((0, 3e-5), (1, 2e-2)):
+        for prec, atol in ((2, 3e-5), (0, 3e-5), (1, 2e-2)):     # 2: tcgen05 / TMEM path (csrc/hh_policy_tc.cu)
             fu = FusedPolicyPair(m1, m2, precision=prec)
             out = [o.clone() for o in fu.forward(f1, f2)]
             for name, a, b in zip(("logits1", "value1", "logits2", "value2"), out, ref):
@@ -180,7 +180,29 @@ def test_fused_policy_forward_matches_torch(mode):
         torch.backends.cuda.matmul.allow_tf32 = prev
 
 
-def test_fused_actor_chains_gather_range_and_argmax():
+def test_policy_pack_image_layout():
+    """hh_policy_pack: fp16 hi / lo halves of 2^s w in the K-major canonical layout, stage after stage (csrc/hh_policy_tc.cu)."""
+    from hhmarl_2d_b200.fused_forward import _pack_image
+    torch.manual_seed(0)
+    for (K, ld, n_total, n_chunk, shift, ksteps) in ((72, 512, 512, 256, 0, 5), (152, 152, 152, 152, 6, 10), (504, 32, 32, 32, 0, 32)):
+        w = (torch.randn(K, ld, device="cuda") * 0.05).contiguous()
+        w[3, 5] = 0.0
+        img, us = _pack_image(w, n_total, n_chunk, shift, ksteps)
+        torch.cuda.synchronize()
+        unscale, scale = us.tolist()
+        assert 8192 <= w[:, :n_total].abs().max().item() * scale < 16384 and abs(unscale * scale * 4096 - 1) < 1e-12
+        h = img.view(torch.float16).view(n_total // n_chunk, ksteps, 2, 2, n_chunk, 8).float()   # [chunk][kstep][hi|lo][khalf][c][kk]
+        rec = (h[:, :, 0] + h[:, :, 1]) / scale                                                   # [chunk][kstep][khalf][c][kk]
+        rec = rec.permute(1, 2, 4, 0, 3).reshape(ksteps * 16, n_total)                            # [k'][col]
+        want = torch.zeros(ksteps * 16, n_total, device="cuda")
+        rows = min(K, ksteps * 16 - shift)
+        want[shift:shift + rows] = w[:rows, :n_total]
+        assert (rec - want).abs().max().item() <= 2.0 ** -21 * w.abs().max().item()
+        assert (h[:, :, 1].abs() <= h[:, :, 0].abs() * 2.0 ** -10 + 1e-30).all()                   # lo is the rounding residue of hi
+
+
+@pytest.mark.parametrize("precision", [2, 0])
+def test_fused_actor_chains_gather_range_and_argmax(precision):
     """hh_policy_forward_ex: the four frozen-actor kinds (Fight1/2, Esc1/2 .actor) as chains of one launch, with a
     row gather, a device-side {begin, count} range and the per-head argmax epilogue, against the torch modules."""
     from hhmarl_2d_b200 import models as M
@@ -212,7 +234,7 @@ def test_fused_actor_chains_gather_range_and_argmax():
                 fills.append(lambda c, fa=fa, rows=rows, j=j: fa.fill_chain(c, x, rows.numel(), out=outs[j], act_out=acts, rows=rows))
             else:
                 fills.append(lambda c, fa=fa, j=j: fa.fill_chain(c, x, n, out=outs[j], act_out=acts, rows=perm, range_dev=ranges[j]))
-        run_chains(fills, torch.device("cuda"), 0)
+        run_chains(fills, torch.device("cuda"), precision)
         n_checked = 0
         for j, (m, fa) in enumerate(zip(models, fas)):
             rows = perm[cuts[j]:cuts[j + 1]].long()
