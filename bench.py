@@ -309,7 +309,7 @@ def run_b200(args):
         from hhmarl_2d_b200 import models as M
         rollout = {}
         Tf = 20
-        for tag, kw in (("fused_3xtf32", dict(fused="3xtf32")), ("fused_tf32", dict(fused="tf32")),
+        for tag, kw in (("fused_tc", dict(fused="tc")), ("fused_3xtf32", dict(fused="3xtf32")), ("fused_tf32", dict(fused="tf32")),
                         ("fp32", dict(allow_tf32=False, fused=None)), ("tf32", dict(allow_tf32=True, fused=None)),
                         ("fp32_unpacked", dict(allow_tf32=False, packed=False, fused=None))):
             torch.manual_seed(rank)
@@ -345,8 +345,9 @@ def run_b200(args):
             except Exception as ex:  # noqa: BLE001
                 rollout["cpu_sampler_equivalent"] = {"error": repr(ex)}
         rollout["note"] = ("both policies' actor + central critic + Gumbel-max sampling + env step + GAE + action "
-                           "write-back, one CUDA graph per 20-tick fragment; random-init weights.  'fused_3xtf32' (the "
-                           "sampler's default) / 'fused_tf32': the hand-written forward kernel csrc/hh_policy.cu (one launch "
+                           "write-back, one CUDA graph per 20-tick fragment; random-init weights.  'fused_tc' (the sampler's "
+                           "default): csrc/hh_policy_tc.cu, tcgen05 / TMEM forward, fp32-equivalent (fp16 hi/lo operand split); "
+                           "'fused_3xtf32' / 'fused_tf32': the mma.sync forward kernel csrc/hh_policy.cu (one launch "
                            "per tick, 3xTF32 = fp32-equivalent / plain TF32 tensor-core products); 'fp32' / 'tf32': packed "
                            "cuBLAS GEMMs (fused_forward.PackedPolicyPair); 'fp32_unpacked': per-layer forward of models.py")
     except Exception as ex:  # noqa: BLE001
@@ -412,7 +413,8 @@ def run_b200(args):
             raise RuntimeError("skipped (--no-l5)")
         l5 = {}
         for tag, fused in (("fused_actors", True), ("torch_actors", False)):
-            env5 = VecLowLevelEnv(n, make_args(level=5), device=local, seed=3, arena_base=rank * n, autoreset=True)
+            env5 = VecLowLevelEnv(n, make_args(level=5), device=local, seed=3, arena_base=rank * n, autoreset=True,
+                                  allow_standin_opponents=True)   # random-init frozen actors: no trained weights exist here
             env5.fused_opponents = fused
             env5.reset()
             for w in range(5):

@@ -36,6 +36,11 @@ def main():
     ap.add_argument("--policy_dir", default="policies")
     ap.add_argument("--export_every", type=int, default=0)
     ap.add_argument("--tf32", action="store_true")
+    ap.add_argument("--restore", action="store_true",
+                    help="warm-start from the exported policies of level-1 (the reference restores L{level-1}, config.py:60-75) "
+                         "and, if present, resume this level's training state")
+    ap.add_argument("--standin_opponents", action="store_true",
+                    help="levels 4/5 without trained opponent files: seeded random-weight stand-ins (benchmarks only)")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank, local = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
@@ -48,16 +53,21 @@ def main():
     m1.to(dev); m2.to(dev)
     args = make_args(level=a.level, agent_mode=a.agent_mode, glob_frac=a.glob_frac, rew_scale=a.rew_scale)
     opp = None
-    if a.level >= 4 and os.path.isdir(a.policy_dir):
-        try:
-            opp = checkpoint.load_opponent_policies(a.policy_dir, a.level, a.agent_mode, dev)
-        except FileNotFoundError:
-            opp = None                         # seeded stand-ins (no trained weights available)
-    env = VecLowLevelEnv(a.arenas, args, device=local, seed=0, arena_base=rank * a.arenas, opponent_policies=opp)
+    if a.level >= 4 and not a.standin_opponents:
+        # like env_base._get_policies: missing L3 / L4 policy files are an error, not a silent fallback
+        opp = checkpoint.load_opponent_policies(a.policy_dir, a.level, a.agent_mode, dev)
+    if a.restore and a.level > 1:
+        prev1, prev2 = checkpoint.load_pair(a.policy_dir, a.level - 1, a.agent_mode, dev)
+        m1.load_state_dict(prev1.state_dict()); m2.load_state_dict(prev2.state_dict())
+    env = VecLowLevelEnv(a.arenas, args, device=local, seed=0, arena_base=rank * a.arenas, opponent_policies=opp,
+                         allow_standin_opponents=a.standin_opponents)
     smp = VecSampler(env, TorchPolicy(m1, 1), TorchPolicy(m2, 2), fragment_len=a.fragment,
                      use_cuda_graph=a.level <= 4, allow_tf32=a.tf32)
     learner = PPOLearner(m1, m2, num_sgd_iter=a.num_sgd_iter, sgd_minibatch_size=a.mini_batch_size)
-    for ep in range(a.epochs):
+    start = 0
+    if a.restore and os.path.exists(checkpoint.training_state_path(a.policy_dir, a.level, a.agent_mode)):
+        start = checkpoint.load_training_state(a.policy_dir, a.level, a.agent_mode, learner, smp)
+    for ep in range(start, a.epochs):
         t0 = time.time()
         batch = smp.collect()
         torch.cuda.synchronize()
@@ -74,6 +84,7 @@ def main():
                   f"learn {t2 - t1:.2f} s", flush=True)
         if a.export_every and (ep + 1) % a.export_every == 0 and rank == 0 and a.level >= 3:
             checkpoint.save_policies(a.policy_dir, a.level, a.agent_mode, m1, m2)
+            checkpoint.save_training_state(a.policy_dir, a.level, a.agent_mode, learner, smp)
     if world > 1:
         dist.destroy_process_group()
 

@@ -26,12 +26,42 @@ def save_policies(policy_dir: str, level: int, mode: str, model1, model2):
 
 
 def load_pair(policy_dir: str, level: int, mode: str, device="cpu"):
+    """Both policies of one level.  They share ONE shared_layer module (ac_models_hetero.py:22-27), so the two files must
+    carry the same shared-layer tensors; files from different runs are refused instead of silently letting AC2's copy
+    overwrite AC1's."""
     m1, m2 = M.build_policy_pair("fight" if mode == "fight" else "escape")
-    for ac, m in ((1, m1), (2, m2)):
-        blob = torch.load(policy_path(policy_dir, level, ac, mode), map_location=device)
+    blobs = [torch.load(policy_path(policy_dir, level, ac, mode), map_location=device) for ac in (1, 2)]
+    for k in blobs[0]["state_dict"]:
+        if k.startswith("shared_layer.") and not torch.equal(blobs[0]["state_dict"][k], blobs[1]["state_dict"][k]):
+            raise ValueError(f"{policy_path(policy_dir, level, 1, mode)} and ..._AC2_...: different {k}; the two policies of a "
+                             "level share one SHARED_LAYER and must come from the same training run")
+    for m, blob in zip((m1, m2), blobs):
         m.load_state_dict(blob["state_dict"])
         m.to(device).eval()
     return m1, m2
+
+
+def training_state_path(policy_dir: str, level: int, mode: str) -> str:
+    return os.path.join(policy_dir, f"L{level}_{mode}_training_state.pt")
+
+
+def save_training_state(policy_dir: str, level: int, mode: str, learner, sampler=None):
+    """What the reference's algo.save() keeps beyond the exported policies (train_hetero.py:281-288): optimiser moments,
+    the adaptive KL coefficients, the epoch counter, the learner's shuffling RNG and the sampler's action-RNG counters."""
+    os.makedirs(policy_dir, exist_ok=True)
+    blob = {"learner": learner.state_dict()}
+    if sampler is not None:
+        blob["sampler_ctr"] = sampler.ctr.detach().cpu()
+    torch.save(blob, training_state_path(policy_dir, level, mode))
+
+
+def load_training_state(policy_dir: str, level: int, mode: str, learner, sampler=None):
+    blob = torch.load(training_state_path(policy_dir, level, mode), map_location=learner.flat.device)
+    learner.load_state_dict(blob["learner"])
+    if sampler is not None and "sampler_ctr" in blob:
+        sampler.ctr.copy_(blob["sampler_ctr"].to(sampler.ctr.device))
+        sampler.refresh_policy()
+    return learner.epoch
 
 
 def load_opponent_policies(policy_dir: str, level: int, agent_mode: str, device="cpu"):

@@ -21,6 +21,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <string>
 
@@ -71,12 +72,13 @@ struct Chain {
 };
 struct Args {
   Chain c[8];
+  unsigned long long* prof;   // optional clock64() stamps, 32 per CTA (hh_policy_tc_profile; null = off)
 };
 
 // barrier slots
-constexpr int B_FULL = 0, B_EMPTY = NSTAGE, B_ACC = 2 * NSTAGE, B_ACT = 2 * NSTAGE + 6, B_COUNT = 2 * NSTAGE + 6 + 5;
+constexpr int B_FULL = 0, B_EMPTY = NSTAGE, B_ACC = 2 * NSTAGE, B_ACT = 2 * NSTAGE + 6, B_COUNT = 2 * NSTAGE + 6 + 6;
 // accumulator barriers: 0 L1 half 0, 1 L1 half 1, 2 attention, 3 shared half 0, 4 shared half 1, 5 head
-// activation barriers:  0 H[:, :256] ready, 1 H[:, 256:], 2 attention block rewritten, 3 Z[:, :256], 4 Z[:, 256:]
+// activation barriers:  0 H[:, :256] ready, 1 H[:, 256:], 2 attention block rewritten, 3 Z[:, :256], 4 Z[:, 256:], 5 input tile
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -126,6 +128,24 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "r"(bytes), "r"(bar)
                : "memory");
 }
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -160,34 +180,81 @@ __device__ __forceinline__ float2 load_pair(const uint8_t* hi_tile, const uint8_
   return make_float2((h.x + l.x) * ACT_UNSCALE, (h.y + l.y) * ACT_UNSCALE);
 }
 
+// tanh(x) from a = 2 log2(e) x:  1 - 2 / (2^a + 1), two SFU operations (abs error < 4e-7; saturates correctly at +-inf).
+// -DHH_TC_EXACT_TANH selects libdevice's tanhf (about four times the instructions; the epilogue is issue-bound).
+constexpr float kTwoLog2e = 2.8853900817779268f;
+__device__ __forceinline__ float tanh_from_scaled(float a) {
+#ifdef HH_TC_EXACT_TANH
+  return tanhf(a * (1.0f / kTwoLog2e));
+#else
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+  return fmaf(-2.0f, r, 1.0f);
+#endif
+}
+__device__ __forceinline__ void split_pair(float v0, float v1, __half2& h, __half2& l) {
+  const float s0 = v0 * ACT_SCALE, s1 = v1 * ACT_SCALE;
+  h = __floats2half2_rn(s0, s1);
+  const float2 hf = __half22float2(h);
+  l = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
+}
+
 // epilogue of one 256-column half of a 500-wide layer: act[:, k0 + c] = tanh(acc * us + bias[k0 + c]); this warp owns
-// the 16 rows of its lane quadrant and 128 of the 256 columns
+// the 16 rows of its lane quadrant and 128 of the 256 columns (64 values per thread).  With hold_bar != 0 the values are
+// computed first and stored only once that barrier has completed (the layer is rewritten in place: nothing may be
+// stored before every MMA that reads the old tile has finished).
+template <bool HOLD>
 __device__ __forceinline__ void epi_tanh_half(uint8_t* smem, uint32_t tmem, int tmem_col, int k0, const float* __restrict__ bias,
-                                              float us, int q, int part, int lane) {
+                                              float us, int q, int part, int lane, uint32_t hold_bar) {
   const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(tmem_col + part * 128);
   const int rlo = 16 * q + (lane >> 2), cpair = 2 * (lane & 3);
   uint8_t *hi = smem + OFF_ACT_HI, *lo = smem + OFF_ACT_LO;
-#pragma unroll 1
-  for (int c = 0; c < 128; c += 32) {
-    uint32_t r[16];
-    tmem_ld_16x256b_x4(taddr + c, r);
+  const float us2 = us * kTwoLog2e;
+  __half2 hh[32], ll[32];
+  uint32_t r[2][16];
+  tmem_ld_16x256b_x4(taddr, r[0]);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
     tmem_ld_wait();
+    if (c < 3) tmem_ld_16x256b_x4(taddr + 32 * (c + 1), r[(c + 1) & 1]);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int k = k0 + part * 128 + c + 8 * i + cpair;
-      const float2 b = __ldg(reinterpret_cast<const float2*>(bias + k));
-      store_pair(hi, lo, rlo, k, tanhf(fmaf(__uint_as_float(r[4 * i]), us, b.x)), tanhf(fmaf(__uint_as_float(r[4 * i + 1]), us, b.y)));
-      store_pair(hi, lo, rlo + 8, k, tanhf(fmaf(__uint_as_float(r[4 * i + 2]), us, b.x)),
-                 tanhf(fmaf(__uint_as_float(r[4 * i + 3]), us, b.y)));
+      const int k = k0 + part * 128 + 32 * c + 8 * i + cpair;
+      float2 b = __ldg(reinterpret_cast<const float2*>(bias + k));
+      b.x *= kTwoLog2e;
+      b.y *= kTwoLog2e;
+      const uint32_t* rr = r[c & 1] + 4 * i;
+      split_pair(tanh_from_scaled(fmaf(__uint_as_float(rr[0]), us2, b.x)), tanh_from_scaled(fmaf(__uint_as_float(rr[1]), us2, b.y)),
+                 hh[8 * c + 2 * i], ll[8 * c + 2 * i]);
+      split_pair(tanh_from_scaled(fmaf(__uint_as_float(rr[2]), us2, b.x)), tanh_from_scaled(fmaf(__uint_as_float(rr[3]), us2, b.y)),
+                 hh[8 * c + 2 * i + 1], ll[8 * c + 2 * i + 1]);
     }
   }
+  if (HOLD) mbar_wait(hold_bar, 0);
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = k0 + part * 128 + 32 * c + 8 * i + cpair;
+      const uint32_t o = canon(rlo, k);
+      *reinterpret_cast<__half2*>(hi + o) = hh[8 * c + 2 * i];
+      *reinterpret_cast<__half2*>(lo + o) = ll[8 * c + 2 * i];
+      *reinterpret_cast<__half2*>(hi + o + 128) = hh[8 * c + 2 * i + 1];     // row + 8
+      *reinterpret_cast<__half2*>(lo + o + 128) = ll[8 * c + 2 * i + 1];
+    }
 }
 
+// CS = CTAs per cluster: the CS row tiles of a cluster belong to the same chain and consume the same weight stream, so
+// each CTA fetches 1 / CS of every stage and multicasts it into all of them (the L2 reads drop by CS; a slot is reused
+// once the MMAs of ALL CS CTAs have read it).
+template <int CS>
 __global__ void __launch_bounds__(kThreads, 1) policy_forward_tc_kernel(const __grid_constant__ Args args) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[B_COUNT];
   __shared__ uint32_t tmem_base_s;
   __shared__ int rowmap[TM];
+  __shared__ float ssum[2][TM];
   const Chain& C = args.c[blockIdx.y];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int beg = 0, cnt = C.n_rows;
@@ -196,15 +263,17 @@ __global__ void __launch_bounds__(kThreads, 1) policy_forward_tc_kernel(const __
     cnt = C.range_dev[1];
   }
   const int row0 = blockIdx.x * TM;
-  if (row0 >= cnt) return;              // CTA-uniform
+  if ((int)(blockIdx.x / CS) * CS * TM >= cnt) return;   // cluster-uniform: a CTA without rows still relays its share of the weights
+  unsigned long long* prof = args.prof ? args.prof + 32 * (size_t)(blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
+  constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1u);
   if (tid < TM) {
     const int lr = row0 + tid;
     rowmap[tid] = lr < cnt ? (C.rows ? C.rows[beg + lr] : beg + lr) : -1;
   }
   const uint32_t bar0 = smem_u32(bars);
   if (tid == 0) {
-    for (int i = 0; i < 2 * NSTAGE + 6; ++i) mbar_init(bar0 + 8 * i, 1);
-    for (int i = 0; i < 5; ++i) mbar_init(bar0 + 8 * (B_ACT + i), i == 2 ? kEpiThreads / 2 : kEpiThreads);
+    for (int i = 0; i < 2 * NSTAGE + 6; ++i) mbar_init(bar0 + 8 * i, (i >= B_EMPTY && i < B_EMPTY + NSTAGE) ? CS : 1);
+    for (int i = 0; i < 6; ++i) mbar_init(bar0 + 8 * (B_ACT + i), kEpiThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -214,34 +283,27 @@ __global__ void __launch_bounds__(kThreads, 1) policy_forward_tc_kernel(const __
   fence_tc_before();
   __syncthreads();
   fence_tc_after();
+  if (CS > 1) cluster_sync();           // every CTA's barriers are initialised before a peer can signal them
   const uint32_t tmem = tmem_base_s;
-
-  // input rows -> hi / lo halves of 2^12 x in the canonical layout (zero beyond d_in and beyond the row list)
-  for (int i = tid; i < TM * (KX / 2); i += kThreads) {
-    const int r = i / (KX / 2), c = 2 * (i - r * (KX / 2));
-    const int gr = rowmap[r];
-    float v0 = 0.0f, v1 = 0.0f;
-    if (gr >= 0) {
-      const float* xr = C.x + (size_t)gr * C.ldx;
-      if (c < C.d_in) v0 = fminf(fmaxf(__ldg(xr + c), -ACT_CLAMP), ACT_CLAMP);
-      if (c + 1 < C.d_in) v1 = fminf(fmaxf(__ldg(xr + c + 1), -ACT_CLAMP), ACT_CLAMP);
-    }
-    store_pair(smem + OFF_X_HI, smem + OFF_X_LO, r, c, v0, v1);
-  }
-  fence_async_smem();
-  __syncthreads();
 
   if (warp == 0) {
     if (lane == 0) {   // ---- weight stream: the stages of every segment, in the order the MMAs consume them
       uint32_t slot = 0, phase = 0;
+      const uint32_t rank = CS > 1 ? cluster_rank() : 0u;
+      const uint32_t ring = smem_u32(smem + OFF_RING);
+      long long stall = 0;
       for (int s = 0; s < C.n_seg; ++s) {
         const Seg& g = C.seg[s];
-        const uint32_t bytes = (uint32_t)g.kps * g.n * 64u;
-        const uint8_t* src = g.w;
-        for (int k = 0; k < g.ksteps; k += g.kps) {
+        const uint32_t bytes = (uint32_t)g.kps * g.n * 64u, part = bytes / CS;
+        const uint8_t* src = g.w + rank * part;
+        const int n_stage = g.ksteps / g.kps;
+        for (int k = 0; k < n_stage; ++k) {
+          const long long t0 = prof ? clock64() : 0;
           mbar_wait(bar0 + 8 * (B_EMPTY + slot), phase ^ 1);
+          if (prof) stall += clock64() - t0;
           mbar_expect_tx(bar0 + 8 * (B_FULL + slot), bytes);
-          bulk_g2s(smem_u32(smem + OFF_RING + slot * STAGE_BYTES), src, bytes, bar0 + 8 * (B_FULL + slot));
+          if (CS == 1) bulk_g2s(ring + slot * STAGE_BYTES, src, bytes, bar0 + 8 * (B_FULL + slot));
+          else bulk_g2s_mc(ring + slot * STAGE_BYTES + rank * part, src, part, bar0 + 8 * (B_FULL + slot), kMask);
           src += bytes;
           if (++slot == NSTAGE) {
             slot = 0;
@@ -249,92 +311,156 @@ __global__ void __launch_bounds__(kThreads, 1) policy_forward_tc_kernel(const __
           }
         }
       }
+      if (prof) {
+        prof[28] = (unsigned long long)stall;
+        prof[29] = (unsigned long long)clock64();
+      }
     }
   } else if (warp == 1) {
-    if (lane == 0) {   // ---- MMA issue
+    if (lane == 0) {   // ---- MMA issue.  Descriptors advance by adding to their 14-bit address field (16-byte units).
       uint32_t slot = 0, phase = 0;
+      long long stall = 0;
+      if (prof) prof[0] = (unsigned long long)clock64();
+      mbar_wait(bar0 + 8 * (B_ACT + 5), 0);           // the input tile is in shared memory
+      const uint64_t ring_desc = smem_desc(smem_u32(smem + OFF_RING), 0, SBO);
       for (int s = 0; s < C.n_seg; ++s) {
         const Seg& g = C.seg[s];
+        const uint32_t n = g.n, kps = g.kps, n_stage = g.ksteps / kps;
         if (g.wait_act != 0xff) mbar_wait(bar0 + 8 * (B_ACT + g.wait_act), 0);
+        if (prof) prof[1 + 2 * s] = (unsigned long long)clock64();
         fence_tc_after();
-        const uint32_t idesc = instr_desc_f16(TM, g.n);
+        const uint32_t idesc = instr_desc_f16(TM, n);
         const uint32_t a_hi = smem_u32(smem + (g.a_src ? OFF_ACT_HI : OFF_X_HI)) + 16u * g.a_off16;
-        const uint32_t a_lo = a_hi + (g.a_src ? ACT_BYTES : X_BYTES);
-        const uint32_t lbo_b = 16u * g.n, blk = 64u * g.n;
+        uint64_t da_hi = smem_desc(a_hi, LBO_A, SBO);
+        uint64_t da_lo = smem_desc(a_hi + (g.a_src ? ACT_BYTES : X_BYTES), LBO_A, SBO);
+        const uint64_t db_seg = ring_desc | ((uint64_t)n << 16);          // leading byte offset of B = 16 n bytes
+        const uint32_t lo_off = 2u * n, step_off = 4u * n;                // B lo block, next K step (16-byte units)
         const uint32_t d = tmem + g.tmem_col;
-        uint32_t kdone = 0;
-        for (int k = 0; k < g.ksteps; k += g.kps) {
+        uint32_t acc = g.first ? 0u : 1u;
+        for (uint32_t k = 0; k < n_stage; ++k) {
+          const long long t0 = prof ? clock64() : 0;
           mbar_wait(bar0 + 8 * (B_FULL + slot), phase);
+          if (prof) stall += clock64() - t0;
           fence_tc_after();
-          const uint32_t sb = smem_u32(smem + OFF_RING + slot * STAGE_BYTES);
-          for (int j = 0; j < g.kps; ++j, ++kdone) {
-            const uint32_t oa = kdone * 2 * LBO_A;
-            const uint64_t dah = smem_desc(a_hi + oa, LBO_A, SBO), dal = smem_desc(a_lo + oa, LBO_A, SBO);
-            const uint64_t dbh = smem_desc(sb + j * blk, lbo_b, SBO), dbl = smem_desc(sb + j * blk + blk / 2, lbo_b, SBO);
-            umma_f16(d, dal, dbh, idesc, (g.first && kdone == 0) ? 0u : 1u);   // small terms first
-            umma_f16(d, dah, dbl, idesc, 1u);
-            umma_f16(d, dah, dbh, idesc, 1u);
+          uint64_t db = db_seg + (uint64_t)(slot * (STAGE_BYTES >> 4));
+          for (uint32_t j = 0; j < kps; ++j) {
+            umma_f16(d, da_lo, db, idesc, acc);                // small terms first
+            umma_f16(d, da_hi, db + lo_off, idesc, 1u);
+            umma_f16(d, da_hi, db, idesc, 1u);
+            acc = 1u;
+            da_hi += (2 * LBO_A) >> 4;
+            da_lo += (2 * LBO_A) >> 4;
+            db += step_off;
           }
-          umma_commit(bar0 + 8 * (B_EMPTY + slot));       // the slot is free once these MMAs have read it
+          // the slot is free once these MMAs have read it -- in every CTA of the cluster
+          if (CS == 1) umma_commit(bar0 + 8 * (B_EMPTY + slot));
+          else umma_commit_mc(bar0 + 8 * (B_EMPTY + slot), kMask);
           if (++slot == NSTAGE) {
             slot = 0;
             phase ^= 1;
           }
         }
         if (g.commit_acc != 0xff) umma_commit(bar0 + 8 * (B_ACC + g.commit_acc));
+        if (prof) prof[2 + 2 * s] = (unsigned long long)clock64();
       }
+      if (prof) prof[15] = (unsigned long long)stall;
     }
   } else {
     // ---- epilogue warps 2..9: lane quadrant q = warp % 4 (the TMEM lanes a warp can read), column part (warp - 2) / 4
+    const int et = tid - 64;
     const int q = warp & 3, part = (warp - 2) >> 2;
     const int rlo = 16 * q + (lane >> 2), cpair = 2 * (lane & 3);
     uint8_t *hi = smem + OFF_ACT_HI, *lo = smem + OFF_ACT_LO;
+    // input rows -> hi / lo halves of 2^12 x in the canonical layout (zero beyond d_in and beyond the row list)
+    {
+      constexpr int kIter = TM * (KX / 2) / kEpiThreads;     // 10 pairs per thread: all loads in flight before the first use
+      float v0[kIter], v1[kIter];
+#pragma unroll
+      for (int it = 0; it < kIter; ++it) {
+        const int i = et + it * kEpiThreads, r = i / (KX / 2), c = 2 * (i - r * (KX / 2));
+        const int gr = rowmap[r];
+        const float* xr = C.x + (size_t)(gr >= 0 ? gr : 0) * C.ldx;
+        v0[it] = (gr >= 0 && c < C.d_in) ? __ldg(xr + c) : 0.0f;
+        v1[it] = (gr >= 0 && c + 1 < C.d_in) ? __ldg(xr + c + 1) : 0.0f;
+      }
+#pragma unroll
+      for (int it = 0; it < kIter; ++it) {
+        const int i = et + it * kEpiThreads, r = i / (KX / 2), c = 2 * (i - r * (KX / 2));
+        store_pair(smem + OFF_X_HI, smem + OFF_X_LO, r, c, fminf(fmaxf(v0[it], -ACT_CLAMP), ACT_CLAMP),
+                   fminf(fmaxf(v1[it], -ACT_CLAMP), ACT_CLAMP));
+      }
+    }
+    fence_async_smem();
+    mbar_arrive(bar0 + 8 * (B_ACT + 5));
     {  // H = tanh(x W1 + b1)
       const float us = __ldg(C.us_w1);
       for (int h = 0; h < 2; ++h) {
         mbar_wait(bar0 + 8 * (B_ACC + h), 0);
+        if (prof && et == 0) prof[16 + 2 * h] = (unsigned long long)clock64();
         fence_tc_after();
-        epi_tanh_half(smem, tmem, 256 * h, 256 * h, C.b1, us, q, part, lane);
+        epi_tanh_half<false>(smem, tmem, 256 * h, 256 * h, C.b1, us, q, part, lane, 0u);
         fence_async_smem();
         fence_tc_before();
         mbar_arrive(bar0 + 8 * (B_ACT + h));
+        if (prof && et == 0) prof[17 + 2 * h] = (unsigned long long)clock64();
       }
     }
-    if (C.att_n > 0 && part == 0) {   // single-token attention: r = full + (full Wa + ba), then L2-normalise the block
+    if (C.att_n > 0) {   // single-token attention: r = full + (full Wa + ba), then L2-normalise the block
       const float us = __ldg(C.us_att);
       mbar_wait(bar0 + 8 * (B_ACC + 2), 0);
+      if (prof && et == 0) prof[20] = (unsigned long long)clock64();
       fence_tc_after();
       const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16);
-      const int ngroups = C.att_pad >> 3;
+      const int n_chunk = (C.att_pad + 31) >> 5, c_mid = (n_chunk + 1) >> 1;       // 32-column chunks: part 0 the first half
+      const int c_beg = part ? c_mid : 0, c_end = part ? n_chunk : c_mid;
+      float v[3][16];
       float ss0 = 0.0f, ss1 = 0.0f;
-#pragma unroll 1
-      for (int pass = 0; pass < 2; ++pass) {
-        float inv0 = 0.0f, inv1 = 0.0f;
-        if (pass) {
-          ss0 += __shfl_xor_sync(0xffffffffu, ss0, 1);
-          ss0 += __shfl_xor_sync(0xffffffffu, ss0, 2);
-          ss1 += __shfl_xor_sync(0xffffffffu, ss1, 1);
-          ss1 += __shfl_xor_sync(0xffffffffu, ss1, 2);
-          inv0 = 1.0f / fmaxf(sqrtf(ss0), 1e-12f);       // F.normalize: x / max(||x||_2, 1e-12)
-          inv1 = 1.0f / fmaxf(sqrtf(ss1), 1e-12f);
-        }
-#pragma unroll 1
-        for (int gidx = 0; gidx < ngroups; ++gidx) {
-          uint32_t r[4];
-          tmem_ld_16x256b_x1(taddr + 8 * gidx, r);
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        const int chunk = c_beg + ci;
+        if (chunk < c_end) {                                // warp-uniform
+          uint32_t r[16];
+          tmem_ld_16x256b_x4(taddr + 32 * chunk, r);
           tmem_ld_wait();
-          const int col = 8 * gidx + cpair;
-          if (col < C.att_n) {                            // att_n is even: a pair is valid or invalid as a whole
-            const float2 b = __ldg(reinterpret_cast<const float2*>(C.batt + col));
-            const float2 p0 = load_pair(hi, lo, rlo, C.att_lo + col), p1 = load_pair(hi, lo, rlo + 8, C.att_lo + col);
-            const float v00 = fmaf(__uint_as_float(r[0]), us, b.x) + p0.x, v01 = fmaf(__uint_as_float(r[1]), us, b.y) + p0.y;
-            const float v10 = fmaf(__uint_as_float(r[2]), us, b.x) + p1.x, v11 = fmaf(__uint_as_float(r[3]), us, b.y) + p1.y;
-            if (!pass) {
-              ss0 += v00 * v00 + v01 * v01;
-              ss1 += v10 * v10 + v11 * v11;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int col = 32 * chunk + 8 * i + cpair;
+            if (col < C.att_n) {                            // att_n is even: a pair is valid or invalid as a whole
+              const float2 b = __ldg(reinterpret_cast<const float2*>(C.batt + col));
+              const float2 p0 = load_pair(hi, lo, rlo, C.att_lo + col), p1 = load_pair(hi, lo, rlo + 8, C.att_lo + col);
+              v[ci][4 * i] = fmaf(__uint_as_float(r[4 * i]), us, b.x) + p0.x;
+              v[ci][4 * i + 1] = fmaf(__uint_as_float(r[4 * i + 1]), us, b.y) + p0.y;
+              v[ci][4 * i + 2] = fmaf(__uint_as_float(r[4 * i + 2]), us, b.x) + p1.x;
+              v[ci][4 * i + 3] = fmaf(__uint_as_float(r[4 * i + 3]), us, b.y) + p1.y;
             } else {
-              store_pair(hi, lo, rlo, C.att_lo + col, v00 * inv0, v01 * inv0);
-              store_pair(hi, lo, rlo + 8, C.att_lo + col, v10 * inv1, v11 * inv1);
+              v[ci][4 * i] = v[ci][4 * i + 1] = v[ci][4 * i + 2] = v[ci][4 * i + 3] = 0.0f;
+            }
+            ss0 += v[ci][4 * i] * v[ci][4 * i] + v[ci][4 * i + 1] * v[ci][4 * i + 1];
+            ss1 += v[ci][4 * i + 2] * v[ci][4 * i + 2] + v[ci][4 * i + 3] * v[ci][4 * i + 3];
+          }
+        }
+      }
+      ss0 += __shfl_xor_sync(0xffffffffu, ss0, 1);
+      ss0 += __shfl_xor_sync(0xffffffffu, ss0, 2);
+      ss1 += __shfl_xor_sync(0xffffffffu, ss1, 1);
+      ss1 += __shfl_xor_sync(0xffffffffu, ss1, 2);
+      if ((lane & 3) == 0) {
+        ssum[part][rlo] = ss0;
+        ssum[part][rlo + 8] = ss1;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");       // the eight epilogue warps
+      const float inv0 = 1.0f / fmaxf(sqrtf(ssum[0][rlo] + ssum[1][rlo]), 1e-12f);          // F.normalize: x / max(||x||_2, 1e-12)
+      const float inv1 = 1.0f / fmaxf(sqrtf(ssum[0][rlo + 8] + ssum[1][rlo + 8]), 1e-12f);
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        const int chunk = c_beg + ci;
+        if (chunk < c_end) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int col = 32 * chunk + 8 * i + cpair;
+            if (col < C.att_n) {
+              store_pair(hi, lo, rlo, C.att_lo + col, v[ci][4 * i] * inv0, v[ci][4 * i + 1] * inv0);
+              store_pair(hi, lo, rlo + 8, C.att_lo + col, v[ci][4 * i + 2] * inv1, v[ci][4 * i + 3] * inv1);
             }
           }
         }
@@ -342,21 +468,30 @@ __global__ void __launch_bounds__(kThreads, 1) policy_forward_tc_kernel(const __
       fence_async_smem();
       fence_tc_before();
       mbar_arrive(bar0 + 8 * (B_ACT + 2));
+      if (prof && et == 0) prof[21] = (unsigned long long)clock64();
     }
-    {  // Z = tanh(in Ws + bs), in place: no column may be rewritten before BOTH halves' MMAs have read the tile
+    {  // Z = tanh(in Ws + bs), in place: the first half is computed while the second half's MMAs run and stored once they
+       // have all read the tile
       const float us = __ldg(C.us_ws);
-      mbar_wait(bar0 + 8 * (B_ACC + 4), 0);
+      mbar_wait(bar0 + 8 * (B_ACC + 3), 0);
+      if (prof && et == 0) prof[22] = (unsigned long long)clock64();
       fence_tc_after();
-      for (int h = 0; h < 2; ++h) {
-        epi_tanh_half(smem, tmem, 256 * h, 256 * h, C.bs, us, q, part, lane);
-        fence_async_smem();
-        fence_tc_before();
-        mbar_arrive(bar0 + 8 * (B_ACT + 3 + h));
-      }
+      epi_tanh_half<true>(smem, tmem, 0, 0, C.bs, us, q, part, lane, bar0 + 8 * (B_ACC + 4));
+      fence_async_smem();
+      fence_tc_before();
+      mbar_arrive(bar0 + 8 * (B_ACT + 3));
+      if (prof && et == 0) prof[23] = (unsigned long long)clock64();
+      fence_tc_after();
+      epi_tanh_half<false>(smem, tmem, 256, 256, C.bs, us, q, part, lane, 0u);
+      fence_async_smem();
+      fence_tc_before();
+      mbar_arrive(bar0 + 8 * (B_ACT + 4));
+      if (prof && et == 0) prof[24] = (unsigned long long)clock64();
     }
     if (part == 0) {  // head: logits or value (+ optional per-head argmax, env_base.py:373-382)
       const float us = __ldg(C.us_wh);
       mbar_wait(bar0 + 8 * (B_ACC + 5), 0);
+      if (prof && et == 0) prof[25] = (unsigned long long)clock64();
       fence_tc_after();
       float* lg = reinterpret_cast<float*>(smem + OFF_X_HI);       // [TM][33]; the input tile is dead by now
       uint32_t r[16];
@@ -401,9 +536,11 @@ __global__ void __launch_bounds__(kThreads, 1) policy_forward_tc_kernel(const __
         }
       }
     }
+    if (prof && et == 0) prof[26] = (unsigned long long)clock64();
   }
   fence_tc_before();
   __syncthreads();
+  if (CS > 1) cluster_sync();           // no CTA leaves while a peer may still write into its shared memory
   if (warp == 1) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
@@ -453,6 +590,23 @@ __global__ void pack_image_kernel(const float* __restrict__ w, int k_rows, int l
 
 }  // namespace tc
 }  // namespace hh
+
+// tuning / profiling knobs of the tcgen05 path (tests and profiles/ only)
+static unsigned long long* g_prof = nullptr;
+static int g_cluster = [] {
+  const char* e = getenv("HH_TC_CLUSTER");
+  const int v = e ? atoi(e) : 2;
+  return (v == 1 || v == 2 || v == 4) ? v : 2;
+}();
+extern "C" int hh_policy_tc_profile(unsigned long long* stamps_dev) {   // 32 clock64() stamps per CTA, null = off
+  g_prof = stamps_dev;
+  return 0;
+}
+extern "C" int hh_policy_tc_cluster(int32_t ctas) {                     // 1, 2 or 4 CTAs share a weight stream (multicast)
+  if (ctas != 1 && ctas != 2 && ctas != 4) return -1;
+  g_cluster = ctas;
+  return 0;
+}
 
 extern "C" int64_t hh_policy_image_bytes(int32_t ksteps, int32_t n_total) { return (int64_t)ksteps * n_total * 64; }
 
@@ -521,6 +675,7 @@ int hh_pf_tc_launch(const hh_policy_chain_ex* chains, int n_chains, int max_rows
     seg(s.img_wh, (size_t)16 * 32 * 64, 32, 16, 8, 0, 1, 256, 0, 4, 5);
     c.n_seg = n;
   }
+  a.prof = g_prof;
   static bool opted_dev[64] = {};
   int dev = 0;
   cudaError_t ce = cudaGetDevice(&dev);
@@ -529,16 +684,34 @@ int hh_pf_tc_launch(const hh_policy_chain_ex* chains, int n_chains, int max_rows
     return -2;
   }
   if (!opted_dev[dev]) {
-    ce = cudaFuncSetAttribute(policy_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    ce = cudaFuncSetAttribute(policy_forward_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(policy_forward_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(policy_forward_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (ce != cudaSuccess) {
       err = std::string("cudaFuncSetAttribute(policy_forward_tc_kernel): ") + cudaGetErrorString(ce);
       return -2;
     }
     opted_dev[dev] = true;
   }
-  const dim3 grid((max_rows + TM - 1) / TM, n_chains);
-  policy_forward_tc_kernel<<<grid, kThreads, SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(a);
-  ce = cudaGetLastError();
+  const int tiles = (max_rows + TM - 1) / TM;
+  int cs = g_cluster;                    // CTAs per cluster (weight multicast); a launch of one tile needs none
+  if (tiles < 2) cs = 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)((tiles + cs - 1) / cs * cs), (unsigned)n_chains);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = cs > 1 ? 1 : 0;
+  ce = cs == 4   ? cudaLaunchKernelEx(&cfg, policy_forward_tc_kernel<4>, a)
+       : cs == 2 ? cudaLaunchKernelEx(&cfg, policy_forward_tc_kernel<2>, a)
+                 : cudaLaunchKernelEx(&cfg, policy_forward_tc_kernel<1>, a);
+  if (ce == cudaSuccess) ce = cudaGetLastError();
   if (ce != cudaSuccess) {
     err = std::string("policy_forward_tc_kernel launch: ") + cudaGetErrorString(ce);
     return -2;

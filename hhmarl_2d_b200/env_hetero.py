@@ -46,7 +46,9 @@ class LowLevelEnv(_Base):
         arena_id = int(env_config.get("arena_id", env_config.get("worker_index", 0)
                                       if hasattr(env_config, "get") else 0))
         self._vec = VecLowLevelEnv(1, self.args, device=int(env_config.get("device", 0)), seed=seed,
-                                   arena_base=arena_id, autoreset=False)
+                                   arena_base=arena_id, autoreset=False,
+                                   opponent_policies=env_config.get("opponent_policies"),
+                                   allow_standin_opponents=bool(env_config.get("allow_standin_opponents", False)))
         self._alive_at_step_start = np.array([1, 1])
         super().__init__()
 

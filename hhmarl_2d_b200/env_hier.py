@@ -83,7 +83,7 @@ class VecHighLevelEnv:
         self.tick_hook = None   # callable(sub_step) run after every hh_hier_tick (trace.HierTraceRecorder); None = no cost
         self.trace = None   # set to a list to record (phase, ll_obs, ll_info, ll_act) per sub-step (tests)
         self.fused_policies = True   # the frozen low-level actors through csrc/hh_policy.cu (False: torch forward)
-        self.policy_precision = 0    # 0: 3xTF32 (fp32-equivalent logits before the argmax), 1: plain TF32 (~2x faster forward)
+        self.policy_precision = 2    # 2: tcgen05 path (fp32-equivalent logits before the argmax), 0: 3xTF32 on mma.sync, 1: plain TF32
         self._fused = None
 
     def _stream(self):

@@ -52,6 +52,11 @@ class OpponentPolicies:
         self.device = torch.device(device)
         self.policies = policies if policies is not None else default_policies(level, agent_mode, seed, self.device)
         self.per_set = level == 5 and agent_mode == "fight"
+        # user-supplied policies (checkpoint.load_opponent_policies defaults to the CPU) move to the env's device: the
+        # fused kernel is handed their data_ptr()s
+        for d in (self.policies.values() if self.per_set else (self.policies,)):
+            for m in d.values():
+                m.to(self.device).eval()
 
     def _models_for(self, k):
         """(model for opponent id 3 / AC1, model for opponent id 4 / AC2, mode) for policy set k."""
@@ -75,7 +80,7 @@ class OpponentPolicies:
         self._fa_n = n
 
     @torch.no_grad()
-    def act_fused(self, opp_obs3, opp_obs4, policy_set=None, precision: int = 0):
+    def act_fused(self, opp_obs3, opp_obs4, policy_set=None, precision: int = 2):
         """Same result as act() (per-head argmax of the frozen actors) in three launches and without host
         synchronisation: hh_policy_rows_by_key lists the arenas of every policy set on the device, then all
         (set, opponent) actors run as chains of ONE hh_policy_forward_ex launch that writes the actions in place."""

@@ -8,8 +8,8 @@ this environment, so these semantics are restated, not pinned ("parity unpinned"
 Deviations (deliberate, documented in DESIGN.md): one Adam over the union of both policies' parameters with
 loss = loss_ac1 + loss_ac2 (RLlib keeps one optimiser per policy, each containing the process-wide SHARED_LAYER);
 rollouts are fixed-length fragments cut every `max_seq_len` ticks rather than per-episode sequences.
-Multi-GPU: arenas are sharded, gradients are averaged with ONE all-reduce per minibatch over a flat bucket that
-holds both policies' gradients; advantage statistics and the KL statistic are all-reduced.
+Multi-GPU: arenas are sharded, gradients are averaged with ONE all-reduce per minibatch over the flat gradient buffer
+of both policies; advantage statistics and the KL statistic are all-reduced.
 """
 from __future__ import annotations
 
@@ -27,6 +27,11 @@ def _seq_major(x, L):
 
 
 class PPOLearner:
+    """Device-resident learner: parameters and gradients of both policies live in ONE flat buffer each (the modules'
+    tensors are views into them), so the gradient exchange is a single all-reduce on the flat gradient with no
+    pack / unpack, the optimiser is one fused Adam over one tensor, shuffling is a device randperm and the statistics
+    stay on the device until the end of update() (one host synchronisation per update)."""
+
     def __init__(self, model1, model2, lr=1e-4, clip_param=0.25, kl_target=0.025, kl_coeff=0.2, vf_clip_param=10.0,
                  vf_loss_coeff=1.0, entropy_coeff=0.0, num_sgd_iter=30, sgd_minibatch_size=256, max_seq_len=20,
                  seed=0):
@@ -39,34 +44,37 @@ class PPOLearner:
                     seen.add(id(p))
                     params.append(p)
         self.params = params
-        self.opt = torch.optim.Adam(params, lr=lr)
+        dev = params[0].device
+        n_tot = sum(p.numel() for p in params)
+        self.flat = torch.zeros(n_tot, device=dev, requires_grad=True)       # the leaf the optimiser owns
+        self.flat.grad = torch.zeros(n_tot, device=dev)
+        o = 0
+        with torch.no_grad():
+            for p in params:
+                n = p.numel()
+                self.flat[o:o + n].copy_(p.reshape(-1))
+                p.data = self.flat.data[o:o + n].view_as(p)                  # the module now reads the flat buffer
+                p.grad = self.flat.grad[o:o + n].view_as(p)                  # autograd accumulates into the flat gradient
+                o += n
+        self.grad_bytes = 4 * n_tot
+        try:
+            self.opt = torch.optim.Adam([self.flat], lr=lr, fused=dev.type == "cuda")
+        except (TypeError, RuntimeError):
+            self.opt = torch.optim.Adam([self.flat], lr=lr)
         self.clip, self.kl_target, self.kl_coeff = clip_param, kl_target, [kl_coeff, kl_coeff]
         self.vf_clip, self.vf_coeff, self.ent_coeff = vf_clip_param, vf_loss_coeff, entropy_coeff
         self.num_sgd_iter, self.mb, self.L = num_sgd_iter, sgd_minibatch_size, max_seq_len
-        self.gen = torch.Generator(device="cpu")
+        self.gen = torch.Generator(device=dev)
         self.gen.manual_seed(seed)
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        self._flat = None
+        self.epoch = 0
 
-    # ------------------------------------------------------------------ gradient exchange (one bucket)
+    # ------------------------------------------------------------------ gradient exchange (one bucket, no copies)
     def _allreduce_grads(self):
         if self.world == 1:
             return
-        if self._flat is None:
-            self._flat = torch.zeros(sum(p.numel() for p in self.params), device=self.params[0].device)
-        o = 0
-        for p in self.params:
-            n = p.numel()
-            self._flat[o:o + n] = p.grad.reshape(-1) if p.grad is not None else 0
-            o += n
-        dist.all_reduce(self._flat)
-        self._flat /= self.world
-        o = 0
-        for p in self.params:
-            n = p.numel()
-            if p.grad is not None:
-                p.grad.copy_(self._flat[o:o + n].view_as(p.grad))
-            o += n
+        dist.all_reduce(self.flat.grad)          # the ONE collective of the data path (NCCL over NVLink)
+        self.flat.grad.div_(self.world)
 
     def _global_mean_std(self, x):
         s = torch.stack([x.sum(), (x * x).sum(), torch.tensor(float(x.numel()), device=x.device)])
@@ -99,43 +107,59 @@ class PPOLearner:
                              logits=_seq_major(batch["logits1" if i == 0 else "logits2"], L),
                              logp=_seq_major(batch["logp"][:, :, i], L),
                              adv=(adv - mean) / std.clamp_min(1e-4), vtarg=_seq_major(batch["vtarg"][:, :, i], L)))
+        dev = data[0]["flat"].device
         n_seq = data[0]["flat"].shape[0] // L
-        seq_per_mb = max(1, self.mb // L)
+        seq_per_mb = max(1, min(n_seq, self.mb // L))     # a batch smaller than one minibatch is ONE (smaller) minibatch
         iters = self.num_sgd_iter if num_sgd_iter is None else num_sgd_iter
-        stats = {"loss": 0.0, "kl": [0.0, 0.0], "vf_loss": [0.0, 0.0], "entropy": [0.0, 0.0], "minibatches": 0}
-        ar = torch.arange(L, device=data[0]["flat"].device)
+        acc = torch.zeros(7, device=dev)                  # loss, kl x2, vf_loss x2, entropy x2: summed on the device
+        n_mb = 0
+        ar = torch.arange(L, device=dev)
         for _ in range(iters):
-            perm = torch.randperm(n_seq, generator=self.gen).to(ar.device)
-            for s in range(0, n_seq - seq_per_mb + 1, seq_per_mb):
-                rows = (perm[s:s + seq_per_mb, None] * L + ar[None, :]).reshape(-1)
-                seq_lens = torch.full((seq_per_mb,), L, dtype=torch.int32)
+            perm = torch.randperm(n_seq, generator=self.gen, device=dev)
+            for s in range(0, n_seq, seq_per_mb):         # the last minibatch holds the remainder
+                sel = perm[s:s + seq_per_mb]
+                rows = (sel[:, None] * L + ar[None, :]).reshape(-1)
+                seq_lens = [L] * int(sel.shape[0])
                 total = 0.0
+                parts = []
                 for i in range(2):
                     d = data[i]
                     loss, kl, vfl, ent = self._loss(i, d["flat"][rows], d["actions"][rows], d["logits"][rows],
                                                     d["logp"][rows], d["adv"][rows], d["vtarg"][rows], seq_lens)
                     total = total + loss
-                    stats["kl"][i] += float(kl)
-                    stats["vf_loss"][i] += float(vfl)
-                    stats["entropy"][i] += float(ent)
-                self.opt.zero_grad(set_to_none=False)
+                    parts += [kl, vfl, ent]
+                self.flat.grad.zero_()
                 total.backward()
                 self._allreduce_grads()
                 self.opt.step()
-                stats["loss"] += float(total.detach())
-                stats["minibatches"] += 1
-        m = max(1, stats["minibatches"])
-        for k in ("kl", "vf_loss", "entropy"):
-            stats[k] = [v / m for v in stats[k]]
-        stats["loss"] /= m
-        for i in range(2):   # RLlib's adaptive KL coefficient (update_kl)
-            kl = torch.tensor(stats["kl"][i], device=ar.device)
-            if self.world > 1:
-                dist.all_reduce(kl)
-                kl /= self.world
-            if float(kl) > 2.0 * self.kl_target:
-                self.kl_coeff[i] *= 1.5
-            elif float(kl) < 0.5 * self.kl_target:
-                self.kl_coeff[i] *= 0.5
+                acc += torch.stack([total.detach(), parts[0], parts[3], parts[1], parts[4], parts[2], parts[5]])
+                n_mb += 1
+        if self.world > 1 and n_mb:
+            kl_sum = acc[1:3].clone()
+            dist.all_reduce(kl_sum)
+            acc[1:3] = kl_sum / self.world
+        vals = (acc / max(1, n_mb)).tolist()              # the one host synchronisation of the update
+        stats = {"loss": vals[0], "kl": vals[1:3], "vf_loss": vals[3:5], "entropy": vals[5:7], "minibatches": n_mb}
+        if n_mb:                                          # RLlib's adaptive KL coefficient (update_kl)
+            for i in range(2):
+                if stats["kl"][i] > 2.0 * self.kl_target:
+                    self.kl_coeff[i] *= 1.5
+                elif stats["kl"][i] < 0.5 * self.kl_target:
+                    self.kl_coeff[i] *= 0.5
         stats["kl_coeff"] = list(self.kl_coeff)
+        self.epoch += 1
         return stats
+
+    # ------------------------------------------------------------------ training state (resume): what algo.save() keeps
+    # beyond the policy weights -- optimiser moments, adaptive KL coefficients, epoch counter, shuffling RNG
+    def state_dict(self):
+        return {"flat": self.flat.detach().clone(), "opt": self.opt.state_dict(), "kl_coeff": list(self.kl_coeff),
+                "epoch": self.epoch, "gen": self.gen.get_state()}
+
+    def load_state_dict(self, sd):
+        with torch.no_grad():
+            self.flat.copy_(sd["flat"].to(self.flat.device))
+        self.opt.load_state_dict(sd["opt"])
+        self.kl_coeff = list(sd["kl_coeff"])
+        self.epoch = int(sd["epoch"])
+        self.gen.set_state(sd["gen"].cpu() if self.gen.device.type == "cpu" else sd["gen"])

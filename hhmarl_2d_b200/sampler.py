@@ -76,17 +76,18 @@ class VecSampler:
 
     def __init__(self, env, policy1: TorchPolicy, policy2: TorchPolicy, fragment_len: int = 64,
                  gamma: float = 0.99, lam: float = 0.95, use_cuda_graph: bool = True, packed: bool = True,
-                 allow_tf32: bool = False, fused: str | None = "3xtf32"):
-        """`fused`: "3xtf32" (default: csrc/hh_policy.cu, fp32-equivalent tensor-core forward in one launch per
-        tick), "tf32" (same kernel, plain TF32 products) or None (cuBLAS: `packed` / per-layer torch forward)."""
+                 allow_tf32: bool = False, fused: str | None = "tc"):
+        """`fused`: "tc" (default: csrc/hh_policy_tc.cu, tcgen05 / TMEM forward, fp32-equivalent, one launch per tick),
+        "3xtf32" / "tf32" (csrc/hh_policy.cu on mma.sync: fp32-equivalent / plain TF32 products) or None (cuBLAS:
+        `packed` / per-layer torch forward)."""
         self.env, self.p1, self.p2, self.T = env, policy1, policy2, fragment_len
         self.allow_tf32 = allow_tf32
         self.packed = None
         if fused is not None:
-            if fused not in ("3xtf32", "tf32"):
-                raise ValueError("fused must be '3xtf32', 'tf32' or None")
+            if fused not in ("tc", "3xtf32", "tf32"):
+                raise ValueError("fused must be 'tc', '3xtf32', 'tf32' or None")
             from .fused_forward import FusedPolicyPair
-            self.packed = FusedPolicyPair(policy1.model, policy2.model, precision=0 if fused == "3xtf32" else 1)
+            self.packed = FusedPolicyPair(policy1.model, policy2.model, precision={"tc": 2, "3xtf32": 0, "tf32": 1}[fused])
         elif packed:
             from .fused_forward import PackedPolicyPair
             self.packed = PackedPolicyPair(policy1.model, policy2.model)

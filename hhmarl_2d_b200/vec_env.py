@@ -32,11 +32,19 @@ class VecLowLevelEnv:
     """
 
     def __init__(self, n_arenas: int, args=None, device: int = 0, seed: int = 0, arena_base: int = 0,
-                 autoreset: bool = True, opponent_policies=None):
+                 autoreset: bool = True, opponent_policies=None, allow_standin_opponents: bool = False):
+        """opponent_policies (levels 4/5): the frozen self-play policies of `_get_policies("LowLevel")`
+        (env_base.py:312-331; checkpoint.load_opponent_policies).  Like the reference, which fails when the policy files
+        are missing, a level-4/5 env without them is an error -- unless `allow_standin_opponents` asks for seeded
+        random-weight stand-ins (tests and benchmarks: there are no trained weights in the repository)."""
         self.args = args if args is not None else make_args()
         a = self.args
         if a.num_agents != 2 or a.num_opps != 2:
             raise ValueError("VecLowLevelEnv implements the 2-vs-2 low-level scenario")
+        if a.level >= 4 and opponent_policies is None and not allow_standin_opponents:
+            raise ValueError(f"level {a.level} needs the frozen opponent policies (opponent_policies=..., see "
+                             "checkpoint.load_opponent_policies); pass allow_standin_opponents=True for seeded "
+                             "random-weight stand-ins")
         self.n_arenas = int(n_arenas)
         self.device_index = int(device)
         cfg = nat.HHConfig(level=a.level, agent_mode=0 if a.agent_mode == "fight" else 1, horizon=a.horizon,
@@ -58,8 +66,11 @@ class VecLowLevelEnv:
         self._bufs = None
         self._opp = None
         self._opp_policies_arg = opponent_policies
+        # optional override of the opponents' controller at levels 4/5: fn(dict(obs3 [N,30], obs4 [N,29], pset [N] u8)) ->
+        # int32 [N,2,4] CUDA tensor (the golden-replay tests inject the reference's recorded actions through it)
+        self.opponent_action_fn = None
         self.fused_opponents = True     # levels 4/5: frozen actors through csrc/hh_policy.cu (False: per-layer torch forward)
-        self.opponent_precision = 0     # 0: 3xTF32 (fp32-equivalent logits before the argmax), 1: plain TF32
+        self.opponent_precision = 2     # 2: tcgen05 path (fp32-equivalent logits before the argmax), 0: 3xTF32 on mma.sync, 1: plain TF32
         self.level = int(a.level)
 
     # ------------------------------------------------------------------ device (torch) API
@@ -113,26 +124,36 @@ class VecLowLevelEnv:
         return b["obs1"], b["obs2"], b["rew"], b["done"]
 
     # ------------------------------------------------------------------ levels 4/5: frozen-policy opponents
-    def _ensure_opponents(self):
-        if self._opp is None:
-            from .opponents import OpponentPolicies
+    def _ensure_opp_bufs(self):
+        if getattr(self, "_opp_bufs", None) is None:
             t = self._torch
             dev = t.device("cuda", self.device_index)
             n = self.n_arenas
-            self._opp = OpponentPolicies(self.level, self.args.agent_mode, self._opp_policies_arg, seed=0, device=dev)
             self._opp_bufs = dict(obs3=t.empty((n, 30), dtype=t.float32, device=dev),
                                   obs4=t.empty((n, 29), dtype=t.float32, device=dev),
                                   pset=t.empty((n,), dtype=t.uint8, device=dev))
+
+    def _ensure_opponents(self):
+        if self._opp is None:
+            from .opponents import OpponentPolicies
+            dev = self._torch.device("cuda", self.device_index)
+            self._opp = OpponentPolicies(self.level, self.args.agent_mode, self._opp_policies_arg, seed=0, device=dev)
+            self._ensure_opp_bufs()
         return self._opp
 
     def opponent_actions(self, actions):
         """First half of a level-4/5 step (hh_step_begin) + the batched opponent networks.
         Returns the opponents' int32 [N,2,4] actions; leaves the env mid-step until hh_step_finish."""
-        opp = self._ensure_opponents()
+        if self.opponent_action_fn is None:
+            opp = self._ensure_opponents()
+        else:
+            self._ensure_opp_bufs()
         ob = self._opp_bufs
         nat.check(nat.lib().hh_step_begin(self._h, actions.data_ptr(), ob["obs3"].data_ptr(), ob["obs4"].data_ptr(),
                                           ob["pset"].data_ptr(), self._stream()), "hh_step_begin")
-        if self.fused_opponents and ob["obs3"].is_cuda:
+        if self.opponent_action_fn is not None:
+            self.last_opp_actions = self.opponent_action_fn(ob).contiguous()
+        elif self.fused_opponents and ob["obs3"].is_cuda:
             self.last_opp_actions = opp.act_fused(ob["obs3"], ob["obs4"], ob["pset"], self.opponent_precision).contiguous()
         else:
             self.last_opp_actions = opp.act(ob["obs3"], ob["obs4"], ob["pset"]).contiguous()

@@ -148,7 +148,7 @@ def make_namespace(level=1, agent_mode="fight", horizon=None, map_size=0.3, rew_
     return Namespace(level=level, horizon=horizon, agent_mode=agent_mode, num_agents=2, num_opps=2,
                      total_num=4, map_size=map_size, rew_scale=rew_scale, glob_frac=glob_frac,
                      esc_dist_rew=esc_dist_rew, friendly_kill=friendly_kill,
-                     friendly_punish=friendly_punish, eval_info=False, eval_hl=False,
+                     friendly_punish=friendly_punish, eval_info=False, eval_hl=True,   # config.py:50 default
                      eval_level_ag=5, eval_level_opp=4, hier_opp_fight_ratio=75,
                      hier_action_assess=True)
 
@@ -156,7 +156,12 @@ def make_namespace(level=1, agent_mode="fight", horizon=None, map_size=0.3, rew_
 class ReferenceEnv:
     """The reference's LowLevelEnv driven under the RNG contract for one (seed, arena_id)."""
 
-    def __init__(self, args: Namespace, seed: int, arena_id: int, policies=None):
+    def __init__(self, args: Namespace, seed: int, arena_id: int, policy_fn=None):
+        """`policy_fn(unit_id, ac_type, mode, policy_set, obs) -> action` (levels 4/5; mode 0 fight / 1 escape; policy_set =
+        k of env_hetero.py:57 at level-5 fight, else 0) stands in for the pickled RLlib policies, which are not in the
+        repository (env_base.py:312-347): it is called at the point where the reference calls
+        self.policy[...](input_dict=..., state=..., seq_lens=...) (env_base.py:392-396) and its answer comes back as
+        logits whose per-head argmax (env_base.py:373-382) is that action."""
         install()
         import envs.env_base as env_base
         from envs.env_hetero import LowLevelEnv
@@ -164,23 +169,52 @@ class ReferenceEnv:
         self.args = args
         self.g = orc.PhiloxStream(seed, arena_id, 0)
         self.c = orc.PhiloxStream(seed, arena_id, 1)
-        self._policies = policies
         if args.level >= 4:
-            # the reference torch.load()s pickled RLlib models that are not in the repo
-            # (env_base.py:312-347); install ray-free restatements instead.
-            orig = env_base.HHMARLBaseEnv._get_policies
+            if policy_fn is None:
+                raise ValueError("levels 4/5 need a policy_fn")
+            import torch
+            outer = self
 
-            def _get(this, mode):
+            class _Pol:
+                def __init__(self, mode, ac_type, pset):
+                    self.mode, self.ac_type, self.pset = mode, ac_type, pset
+
+                def __call__(self, input_dict=None, state=None, seq_lens=None):
+                    o = input_dict["obs"]
+                    assert set(o) == {"obs_1_own", "obs_2", "act_1_own", "act_2"}
+                    assert not o["obs_2"].any() and not o["act_1_own"].any() and not o["act_2"].any()
+                    obs = o["obs_1_own"][0].numpy()
+                    act = policy_fn(outer._cur_unit, self.ac_type, self.mode, self.pset, obs)
+                    heads = (13, 9, 2, 2) if self.ac_type == 1 else (13, 9, 2)
+                    logits = torch.full((1, sum(heads)), -10.0)
+                    k = 0
+                    for h, a in zip(heads, act):
+                        logits[0, k + int(a)] = 10.0
+                        k += h
+                    return logits, []
+
+            def _get(this, mode):      # the key structure of env_base.py:318-331
+                assert mode == "LowLevel"
                 this.policy = {}
-                this.policies = policies if args.level == 5 and args.agent_mode == "fight" else None
-                if this.policies is None:
-                    this.policy = policies
+                if args.agent_mode == "fight" and args.level == 5:
+                    this.policies = {k: ({"fight_1": _Pol(0, 1, k), "fight_2": _Pol(0, 2, k)} if k <= 4 else
+                                         {"escape_1": _Pol(1, 1, k), "escape_2": _Pol(1, 2, k)}) for k in (3, 4, 5)}
+                elif args.agent_mode == "fight" or args.level == 5:
+                    this.policy = {"fight_1": _Pol(0, 1, 0), "fight_2": _Pol(0, 2, 0)}
+
+            orig = env_base.HHMARLBaseEnv._get_policies
+            orig_pa = env_base.HHMARLBaseEnv._policy_actions
+
+            def _pa(this, policy_type, agent_id, unit):
+                outer._cur_unit = agent_id
+                return orig_pa(this, policy_type, agent_id, unit)
 
             env_base.HHMARLBaseEnv._get_policies = _get
             try:
                 self.env = LowLevelEnv({"args": args})
             finally:
                 env_base.HHMARLBaseEnv._get_policies = orig
+            self.env._policy_actions = types.MethodType(_pa, self.env)
         else:
             self.env = LowLevelEnv({"args": args})
 

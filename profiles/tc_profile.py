@@ -1,0 +1,51 @@
+"""profiles/tc_profile.py -- per-role clock64() stamps of the tcgen05 policy forward (csrc/hh_policy_tc.cu): where a CTA's time
+goes (MMA issue per segment, waits for the weight stream, the epilogue phases).  python profiles/tc_profile.py [rows] [cluster]"""
+import ctypes
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from hhmarl_2d_b200 import _native as nat  # noqa: E402
+from hhmarl_2d_b200 import models as M  # noqa: E402
+from hhmarl_2d_b200.fused_forward import FusedPolicyPair  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+cluster = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+L = nat.lib()
+L.hh_policy_tc_profile.argtypes = [ctypes.c_void_p]
+L.hh_policy_tc_cluster.argtypes = [ctypes.c_int32]
+assert L.hh_policy_tc_cluster(cluster) == 0
+torch.manual_seed(0)
+m1, m2 = M.build_policy_pair("fight")
+m1.cuda(); m2.cuda()
+f1 = torch.rand(B, 57, device="cuda"); f2 = torch.rand(B, 57, device="cuda")
+fu = FusedPolicyPair(m1, m2, precision=2)
+for _ in range(3):
+    fu.forward(f1, f2)
+tiles = (B + 63) // 64
+tiles = (tiles + cluster - 1) // cluster * cluster
+buf = torch.zeros(4 * tiles * 32, dtype=torch.int64, device="cuda")
+L.hh_policy_tc_profile(buf.data_ptr())
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+fu.forward(f1, f2)
+e1.record()
+torch.cuda.synchronize()
+L.hh_policy_tc_profile(None)
+s = buf.view(4, tiles, 32).cpu().double()
+t0 = s[:, :, 0:1]
+rel = s - t0
+names = {1: "seg0 L1h0 start", 2: "seg0 end", 3: "seg1 L1h1 start", 4: "seg1 end", 5: "seg2 ATT start", 6: "seg2 end",
+         7: "seg3 SHh0 start", 8: "seg3 end", 9: "seg4 SHh1 start", 10: "seg4 end", 11: "seg5 HEADa start", 12: "seg5 end",
+         13: "seg6 HEADb start", 14: "seg6 end", 16: "epi L1h0 begin", 17: "epi L1h0 end", 18: "epi L1h1 begin", 19: "epi L1h1 end",
+         20: "epi ATT begin", 21: "epi ATT end", 22: "epi SH begin", 23: "epi SHh0 end", 24: "epi SHh1 end", 25: "epi HEAD begin",
+         26: "epi done", 29: "producer done"}
+print(f"rows {B}, cluster {cluster}: launch {e0.elapsed_time(e1) * 1e3:.1f} us (with stamps); cycles relative to the MMA thread's start, "
+      f"median over {4 * tiles} CTAs [actor chain 0 | critic chain 1]")
+for k in sorted(names):
+    a, c = rel[0, :, k].median().item(), rel[1, :, k].median().item()
+    print(f"  {names[k]:18s} {a:9.0f} {c:9.0f}")
+print(f"  MMA thread waiting for weight stages (sum): {s[0, :, 15].median().item():9.0f} {s[1, :, 15].median().item():9.0f}")
+print(f"  producer waiting for free slots (sum):      {s[0, :, 28].median().item():9.0f} {s[1, :, 28].median().item():9.0f}")

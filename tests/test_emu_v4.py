@@ -16,7 +16,7 @@ import test_gpu_parity as tgp  # noqa: E402
 pytestmark = pytest.mark.skipif(emu_env.cuda_include() is None, reason="needs cuda_runtime.h for the vector types")
 
 
-@pytest.mark.parametrize("path", gu.golden_files(), ids=lambda p: p.split("lowlevel_")[-1][:-4])
+@pytest.mark.parametrize("path", gu.golden_files(policy_levels=False), ids=lambda p: p.split("lowlevel_")[-1][:-4])
 def test_v4_schedule_replays_reference_golden(path):
     with emu_env.emulated():
         tgp.test_cuda_replays_reference_golden(path)

@@ -21,7 +21,7 @@ F64_FIELDS = ("lat", "lon", "heading", "speed", "new_heading", "new_speed")
 def _vec(n, level, mode, seed, arena_base=0, autoreset=True, **kw):
     from hhmarl_2d_b200 import VecLowLevelEnv, make_args
     return VecLowLevelEnv(n, make_args(level=level, agent_mode=mode, **kw), device=0, seed=seed,
-                          arena_base=arena_base, autoreset=autoreset)
+                          arena_base=arena_base, autoreset=autoreset, allow_standin_opponents=True)
 
 
 def _close(a, b, what):
@@ -35,6 +35,27 @@ def _close(a, b, what):
 def test_cuda_replays_reference_golden(path):
     g, seed, arena, level, mode, kw = gu.load(path)
     env = _vec(1, level, mode, seed, arena_base=arena, autoreset=False, **kw)
+    if level >= 4:
+        # levels 4/5 (hh_step_begin / hh_step_finish): the opponents' mid-step observations and policy set must equal the
+        # reference's recorded policy queries; the reference's recorded answers are injected as the opponents' actions
+        import torch
+        cur = {"t": 0}
+
+        def inject(ob):
+            t = cur["t"]
+            obs = {3: ob["obs3"][0].cpu().numpy(), 4: ob["obs4"][0].cpu().numpy()}
+            pset = int(ob["pset"][0])
+            act = np.zeros((1, 2, 4), np.int32)
+            for k in range(int(g["n_calls"][t])):
+                u, ty, m, ps = (int(g[f][t][k]) for f in ("c_unit", "c_type", "c_mode", "c_pset"))
+                assert ps == pset and ty == (1 if u == 3 else 2), (t, u)
+                width = ((26, 24) if m == 0 else (30, 29))[ty - 1]
+                _close(obs[u][:width], g["c_obs"][t][k][:width], f"t={t} opponent {u} policy-query obs")
+                assert not obs[u][width:].any() and not g["c_obs"][t][k][width:].any()
+                act[0, u - 3] = g["c_act"][t][k]
+            return torch.from_numpy(act).cuda()
+
+        env.opponent_action_fn = inject
     o1, o2 = env.reset_host()
     ep = 0
     _close(o1[0], g["reset_obs1"][0], "reset obs1")
@@ -43,6 +64,8 @@ def test_cuda_replays_reference_golden(path):
     worst = 0.0
     for t in range(len(g["done"])):
         act = g["actions"][t].astype(np.int32)[None]
+        if level >= 4:
+            cur["t"] = t
         o1, o2, rew, done = env.step_host(act)
         st = env.get_state()
         assert int(st["error"][0]) == 0

@@ -12,14 +12,19 @@ import oracle as orc
 @pytest.mark.parametrize("path", gu.golden_files(), ids=lambda p: p.split("lowlevel_")[-1][:-4])
 def test_oracle_replays_golden(path):
     g, seed, arena, level, mode, kw = gu.load(path)
-    env = orc.OracleEnv(orc.make_args(level=level, agent_mode=mode, **kw), seed, arena)
+    pol = gu.GoldenPolicy(g) if level >= 4 else None     # levels 4/5: queries checked, recorded answers fed back
+    env = orc.OracleEnv(orc.make_args(level=level, agent_mode=mode, **kw), seed, arena, policy_fn=pol.fn if pol else None)
     o1, o2 = env.reset()
     ep = 0
     np.testing.assert_allclose(o1, g["reset_obs1"][0], atol=1e-7)
     np.testing.assert_allclose(o2, g["reset_obs2"][0], atol=1e-7)
     n_kill_steps = 0
     for t in range(len(g["done"])):
+        if pol:
+            pol.begin_step(t)
         o1, o2, rew, present, done = env.step(g["actions"][t])
+        if pol:
+            pol.end_step()
         st = env.state()
         assert st.error == 0
         assert done == bool(g["done"][t]), t
@@ -42,3 +47,5 @@ def test_oracle_replays_golden(path):
             np.testing.assert_allclose(o1, g["reset_obs1"][ep], atol=1e-7)
             np.testing.assert_allclose(o2, g["reset_obs2"][ep], atol=1e-7)
     assert ep == len(g["reset_obs1"]) - 1 and n_kill_steps > 0
+    if level == 5 and mode == "fight":
+        assert set(g["c_pset"][g["c_unit"] > 0].tolist()) == {3, 4, 5}      # L3-fight, L4-fight and L3-escape opponent sets

@@ -127,3 +127,49 @@ def test_policy_files_round_trip_with_reference_naming(tmp_path):
     checkpoint.save_policies(d, 5, "escape", e51, e52)
     with torch.no_grad():
         assert torch.equal(checkpoint.load_highlevel_policies(d, 4)["escape_1"].actor(xe), e51.actor(xe))
+
+
+def test_training_state_resumes_and_small_batches_still_learn(tmp_path):
+    """checkpoint.save_training_state / load_training_state (what algo.save() keeps beyond the exported weights: Adam
+    moments, adaptive KL coefficients, epoch, shuffling RNG): a resumed learner continues bit-identically.  Also: a
+    batch smaller than sgd_minibatch_size is ONE minibatch (not zero), the remainder minibatch is used, and two
+    policies built separately (two shared layers) are refused by the packed forward."""
+    from hhmarl_2d_b200 import checkpoint
+    from hhmarl_2d_b200.fused_forward import PackedPolicyPair
+    torch.manual_seed(0)
+
+    def fresh():
+        torch.manual_seed(1)
+        m1, m2 = M.build_policy_pair("fight")
+        return m1, m2, PPOLearner(m1, m2, num_sgd_iter=1, sgd_minibatch_size=8192, lr=1e-3)
+
+    b1, b2 = _fake_batch(20, 5, seed=1), _fake_batch(20, 5, seed=2)
+    m1, m2, la = fresh()
+    st = la.update(b1)
+    assert st["minibatches"] == 1                      # 5 sequences < 8192 / 20: one (smaller) minibatch, weights move
+    checkpoint.save_training_state(str(tmp_path), 3, "fight", la)
+    la.update(b2)
+    want = la.flat.detach().clone()
+    n1, n2, lb = fresh()
+    assert checkpoint.load_training_state(str(tmp_path), 3, "fight", lb) == 1
+    assert torch.equal(n1.act_out._model[0].weight, lb.params[[id(p) for p in lb.params].index(id(n1.act_out._model[0].weight))])
+    lb.update(b2)
+    assert torch.equal(lb.flat.detach(), want) and lb.kl_coeff == la.kl_coeff and lb.epoch == 2
+    # remainder minibatch: 5 sequences, 2 per minibatch -> 3 minibatches
+    _, _, lc = fresh()
+    lc.mb = 40
+    assert lc.update(b1)["minibatches"] == 3
+    # separately built policies do not share a shared layer
+    with pytest.raises(ValueError):
+        PackedPolicyPair(M.Fight1(), M.Fight2())
+    # policy files of one level must agree on the shared layer
+    checkpoint.save_policies(str(tmp_path), 3, "fight", m1, m2)
+    checkpoint.load_pair(str(tmp_path), 3, "fight")
+    o1, o2 = M.build_policy_pair("fight")
+    with torch.no_grad():
+        o2.shared_layer._model[0].weight.add_(1.0)
+    blob = torch.load(checkpoint.policy_path(str(tmp_path), 3, 2, "fight"))
+    blob["state_dict"] = o2.state_dict()
+    torch.save(blob, checkpoint.policy_path(str(tmp_path), 3, 2, "fight"))
+    with pytest.raises(ValueError):
+        checkpoint.load_pair(str(tmp_path), 3, "fight")
