@@ -69,13 +69,16 @@ def test_policy_forward_validates_arguments_without_a_gpu():
     from hhmarl_2d_b200 import _native as nat
     L = nat.lib()
     assert ctypes.sizeof(nat.HHPolicyChain) == 8 * 8 + 8 * 4
-    assert ctypes.sizeof(nat.HHPolicyChainEx) == 13 * 8 + 16 * 4          # 15 int32 + padding
+    assert ctypes.sizeof(nat.HHPolicyChainEx) == 13 * 8 + 16 * 4 + 8 * 8  # 15 int32 + padding, then the precision-2 images
     one = (nat.HHPolicyChainEx * 1)()
     assert L.hh_policy_forward_ex(0, one, 0, None) == -1            # no chains
     assert L.hh_policy_forward_ex(9, one, 0, None) == -1            # more than 8
-    assert L.hh_policy_forward_ex(1, one, 2, None) == -1            # unknown precision
+    assert L.hh_policy_forward_ex(1, one, 3, None) == -1            # unknown precision
     assert L.hh_policy_forward_ex(1, one, 0, None) == -1            # null pointers
     assert b"chain" in L.hh_policy_last_error()
+    assert L.hh_policy_forward_ex(1, one, 2, None) == -1            # tcgen05 path: same checks before any CUDA call
+    assert L.hh_policy_image_bytes(32, 512) == 32 * 512 * 64        # one K = 16 step of n columns: hi + lo halves
+    assert L.hh_policy_pack(None, 504, 512, 512, 256, 0, 32, None, None, None) == -1
     four = (nat.HHPolicyChain * 4)()
     assert L.hh_policy_forward(0, four, None, None, 0, None) == -1
     assert L.hh_step_host_begin(None, None) == -1 and L.hh_step_host_end(None, None, None, None, None) == -1
