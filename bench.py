@@ -55,6 +55,13 @@ def parse():
     ap.add_argument("--no-rollout", action="store_true")
     ap.add_argument("--no-hier", action="store_true")
     ap.add_argument("--no-l5", action="store_true")
+    ap.add_argument("--no-ppo", action="store_true")
+    ap.add_argument("--leg", default="step", choices=["step", "rollout"],
+                    help="what `value` measures: 'step' = the fused env-step kernel with pre-generated actions (default; the "
+                         "kernel the roofline is about), 'rollout' = the whole on-device sampler loop (policy forward + "
+                         "sampling + env step + GAE); both arms accept it, and the default line carries both")
+    ap.add_argument("--l5-arenas", type=int, default=0, help="arenas per GPU of the level-5 leg (0: 32 768 on one GPU = "
+                    "BASELINE config 3, 8 192 per GPU under torchrun = config 4)")
     return ap.parse_args()
 
 
@@ -117,6 +124,22 @@ def cpu_sampler_equivalent(level: int, seconds: float = 4.0):
         torch.set_num_threads(prev)
 
 
+def _sampler_worker(args):
+    level, seconds = args
+    return cpu_sampler_equivalent(level, seconds)
+
+
+def cpu_sampler_all_cores(level: int, seconds: float, workers: int):
+    """The reference's sampler layout (train_hetero.py:212: one rollout worker per core): `workers` processes, each one
+    reference-style worker (cpu_sampler_equivalent) for `seconds`.  Returns aggregate env-steps/s."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(workers) as pool:
+        pool.map(_sampler_worker, [(level, 0.2)] * workers)          # imports + warm-up outside the timed sample
+        rates = pool.map(_sampler_worker, [(level, seconds)] * workers)
+    return float(sum(rates)), rates
+
+
 def best_thread_count(level: int):
     """Host boxes may expose more logical CPUs than the cgroup lets us use: probe a few thread
     counts on a small sample and keep the fastest."""
@@ -149,21 +172,47 @@ def run_reference(args):
     value = n_total / t_total
     sample = (f"{cores} host threads (best of a thread-count probe; box reports {os.cpu_count()} logical CPUs) x "
               f"{per_step} env-steps of the L{args.level} scenario per bench step, random actions")
+    # the sampler leg of the reference arm: one reference-style rollout worker per usable core (env step + batch-1 torch
+    # forward of both policies + sampling), bounded sample
+    workers = max(1, min(cores, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else cores))
+    roll = None
+    try:
+        secs = 6.0 if args.leg == "rollout" else 3.0
+        rv, rates = cpu_sampler_all_cores(args.level, secs, workers)
+        roll = {"value": rv, "unit": UNIT, "cores": workers, "kind": "port",
+                "sample": f"{workers} worker processes x {secs:.0f} s: C-oracle env step + batch-1 torch-CPU forward of both policies "
+                          "(actor + central critic) + MultiCategorical sampling per env step, 1 torch thread each (the reference: one "
+                          "Ray rollout worker per core, train_hetero.py:212, with the slower Python env)",
+                "per_worker_min_max": [min(rates), max(rates)]}
+    except Exception as ex:  # noqa: BLE001
+        roll = {"error": repr(ex)}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(args, cores_note=True),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "rollout": roll, "leg": args.leg, "gpu_launches": 0}
+    if args.leg == "rollout" and roll and "value" in roll:
+        line.update(value=roll["value"], ms_per_step=None, cpu_baseline=dict(roll), step_kernel_leg={"value": value, "unit": UNIT, "cores": cores},
+                    e2e={"value": roll["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+        line["config"] = workload_config(args, leg="rollout")
     print(json.dumps(line))
 
 
-def workload_config(args, cores_note=False):
+def workload_config(args, cores_note=False, leg=None):
+    leg = leg or "step"
+    if leg == "rollout":
+        return {"workload": f"{args.arenas} arenas/GPU, 2-vs-2 level-{args.level} scripted-opponent fight, horizon "
+                            f"{({1: 150, 2: 200, 3: 300}).get(args.level)}: the sampler loop -- Fight1 / Fight2 actor + central critic "
+                            "forward, MultiCategorical sampling, env step, rollout buffers, GAE, action write-back (BASELINE configs[1])",
+                "arenas_per_gpu": args.arenas, "level": args.level, "agent_mode": "fight", "leg": "rollout",
+                "cache": "inputs larger than L2: every tick reads / writes its own slice of the ~130 MB rollout buffers, the env state "
+                         "and the 5 MB of packed weights"}
     return {"workload": f"{args.arenas} arenas/GPU, 2-vs-2 level-{args.level} scripted-opponent fight, "
                         f"horizon {({1: 150, 2: 200, 3: 300}).get(args.level)}, uniform random MultiDiscrete actions, "
                         "auto-reset",
-            "arenas_per_gpu": args.arenas, "level": args.level, "agent_mode": "fight",
+            "arenas_per_gpu": args.arenas, "level": args.level, "agent_mode": "fight", "leg": "step",
             "cache": "L2 flushed (256 MiB write) between timed steps"}
 
 
@@ -220,6 +269,39 @@ class ClockSampler:
                 "samples": len(rows), "scope": scope, "power_w_max": max((r[3] for r in rows), default=None)}
 
 
+def pin_rank_to_local_cores(local: int, world: int):
+    """N > 1: each rank (its Python launch loop and the host side of the e2e leg) gets its own slice of the cores NVML
+    reports as local to its GPU (NUMA node / PCIe root); ranks whose GPUs share a node split that node's cores evenly."""
+    if world <= 1 or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        avail = sorted(os.sched_getaffinity(0))
+        pools = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            nw = (max(avail) // 64) + 1
+            pools = []
+            for g in range(world):
+                words = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(g), nw)
+                pools.append(tuple(c for c in avail if (words[c // 64] >> (c % 64)) & 1))
+            if not all(pools):
+                pools = None
+        except Exception:  # noqa: BLE001
+            pools = None
+        numa = pools is not None
+        if pools is None:
+            pools = [tuple(avail)] * world
+        sharers = [g for g in range(world) if pools[g] == pools[local]]
+        per = max(1, len(pools[local]) // len(sharers))
+        k = sharers.index(local) * per
+        mine = list(pools[local][k:k + per]) or list(pools[local])
+        os.sched_setaffinity(0, mine)
+        return {"cores": len(mine), "first": mine[0], "numa_local": numa}
+    except Exception as ex:  # noqa: BLE001
+        return {"error": repr(ex)}
+
+
 # ------------------------------------------------------------------------------------ GPU arm
 def run_b200(args):
     import numpy as np
@@ -235,6 +317,7 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     n, K, W = args.arenas, args.steps, args.warmup
+    affinity = pin_rank_to_local_cores(local, world)
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -272,6 +355,10 @@ def run_b200(args):
     barrier()
     t0 = time.perf_counter()
     launches_before = env.launch_count
+    # The GPU first spins for ~10 ms so that the host loop below runs AHEAD of it for the whole timed region: every event
+    # bracket then holds exactly one kernel with its launch already queued (no host launch lag inside a bracket, which at
+    # N = 8 -- 8 Python loops on one host -- used to leak into the max-over-ranks).
+    torch.cuda._sleep(20_000_000)
     for k in range(K):
         flush.fill_(k & 0xFF)          # evict the arena state from L2 (outside the event bracket)
         ev0[k].record()
@@ -281,13 +368,20 @@ def run_b200(args):
     t1 = time.perf_counter()
     gpu_launches = env.launch_count - launches_before
     clocks = sampler.summary(t0, t1) if sampler else None
-    step_ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
+    step_ms = sorted(a.elapsed_time(b) for a, b in zip(ev0, ev1))
     total_ms = float(sum(step_ms))
-    tot = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    mine = torch.tensor([total_ms, step_ms[0], step_ms[len(step_ms) // 2], step_ms[-1]], dtype=torch.float64, device=dev)
+    per_rank = [mine.clone() for _ in range(world)]
     if world > 1:
-        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-    total_ms = float(tot.item())
+        dist.all_gather(per_rank, mine)
+    else:
+        per_rank = [mine]
+    per_rank = [[float(v) for v in t.tolist()] for t in per_rank]
+    total_ms = max(r[0] for r in per_rank)
     value = world * n * K / (total_ms * 1e-3)
+    step_stats = {"per_rank_us": [{"mean": 1e3 * r[0] / K, "min": 1e3 * r[1], "median": 1e3 * r[2], "max": 1e3 * r[3]} for r in per_rank],
+                  "note": "CUDA-event bracket of every step kernel launch; the host loop runs ahead of the GPU (a 10 ms device-side spin "
+                          "precedes the timed region), `value` uses the slowest rank's sum"}
 
     # ---- back-to-back (no flush; state stays in L2), one event pair around K launches
     barrier()
@@ -332,6 +426,73 @@ def run_b200(args):
                 dist.all_reduce(rt, op=dist.ReduceOp.MAX)
             rollout[tag] = {"value": world * n * Tf * R / (float(rt.item()) * 1e-3), "unit": UNIT,
                             "ms_per_tick": float(rt.item()) / (R * Tf)}
+            if tag == "fused_tc":
+                rollout["fragment_bytes"] = int(sum(v.numel() * v.element_size() for v in smp.buf.values()))
+                # (i) the same loop end to end: every fragment's batch is copied to pinned host memory inside the timed region
+                #     (what a host-side learner / RLlib's train batch would read); the sampler has no host INPUT
+                host = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in smp.buf.items()}
+                barrier()
+                th0 = time.perf_counter()
+                for _ in range(R):
+                    bb = smp.collect()
+                    for k, v in bb.items():
+                        host[k].copy_(v, non_blocking=True)
+                torch.cuda.synchronize()
+                th1 = time.perf_counter()
+                et = torch.tensor([th1 - th0], dtype=torch.float64, device=dev)
+                if world > 1:
+                    dist.all_reduce(et, op=dist.ReduceOp.MAX)
+                rollout["e2e"] = {"value": world * n * Tf * R / float(et.item()), "unit": UNIT, "h2d_bytes_per_step": 0,
+                                  "d2h_bytes_per_step": rollout["fragment_bytes"] // Tf,
+                                  "api": "VecSampler.collect() + D2H of the whole fragment batch into pinned host memory"}
+                del host
+                # (ii) the dominant kernel alone: the tcgen05 policy forward on the recorded central observations of the
+                #      fragment (a different tick's rows every launch), CUDA events around R2 launches
+                fu, bufs = smp.packed, smp.buf
+                outs = (torch.empty((n, 26), device=dev), torch.empty((n,), device=dev), torch.empty((n, 24), device=dev),
+                        torch.empty((n,), device=dev))
+                for t in range(3):
+                    fu.forward(bufs["flat1"][t], bufs["flat2"][t], out=outs)
+                R2 = 40
+                k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                barrier()
+                k0.record()
+                for t in range(R2):
+                    fu.forward(bufs["flat1"][t % Tf], bufs["flat2"][t % Tf], out=outs)
+                k1.record()
+                torch.cuda.synchronize()
+                kern_us = k0.elapsed_time(k1) * 1e3 / R2
+                macs_useful = macs_issued = 0
+                for p_ in range(2):
+                    for kk in range(2):
+                        w1 = fu._rm["w1"][p_][kk]
+                        att_n = fu.att[kk][1] if fu.fight else 0
+                        n_out = fu.packed.Wact[p_].shape[1] if kk == 0 else 1
+                        macs_useful += int((w1 != 0).sum()) + att_n * att_n + 500 * 500 + 500 * n_out
+                        k1s = (fu.packed.W1[p_].shape[0] + 15) // 16
+                        att_iss = 0
+                        if fu.fight:
+                            lo_, n_, pad_ = fu.att[kk]
+                            att_iss = ((lo_ + n_ - (lo_ & ~7) + 15) // 16) * 16 * pad_
+                        macs_issued += k1s * 16 * 512 + att_iss + 512 * 512 + 512 * 32
+                rows_pad = (n + 63) // 64 * 64
+                peak_tf, peak_src2 = 1590.0, "fallback (B200_PROFILING.md)"
+                try:
+                    peak_tf = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+                    peak_src2 = "measured (MEASURED_PEAKS.json bf16_tflops, cuBLAS burst; kind::f16 and bf16 MMAs run at the same rate)"
+                except Exception:  # noqa: BLE001
+                    pass
+                issued = 3 * 2 * macs_issued * rows_pad / (kern_us * 1e-6) / 1e12
+                rollout["roofline"] = {
+                    "bound": "tensor", "achieved": issued, "peak": peak_tf, "unit": "TFLOP/s", "frac": issued / peak_tf,
+                    "traffic": None, "peak_source": peak_src2, "kernel": "hh::tc::policy_forward_tc_kernel", "kernel_us": kern_us,
+                    "useful_tflops": 2 * macs_useful * n / (kern_us * 1e-6) / 1e12,
+                    "useful_flop_per_launch": 2 * macs_useful * n, "issued_flop_per_launch": 3 * 2 * macs_issued * rows_pad,
+                    "share_of_rollout_tick": kern_us * 1e-3 / rollout[tag]["ms_per_tick"],
+                    "note": "fp32-equivalent forward = 3 kind::f16 MMAs per product on zero-padded tiles (K to 16, N to 256 / 104 / "
+                            "152 / 32): `achieved` counts the MMA work issued, `useful_tflops` the reference's own multiply-adds.  "
+                            "An M = 64 tile runs the tensor pipe at half the M = 128 rate (profiles/r2a_tcgen05_probe.txt), and the "
+                            "kernel is bound by the weight stream from L2 (profiles/README.md, round 2)"}
             del smp, env_r
         rollout["fragment_len"] = Tf
         if cpu_base is not None:   # N = 1, rank 0: the reference-style rollout worker on one host core, bounded sample
@@ -412,31 +573,93 @@ def run_b200(args):
         if args.no_l5:
             raise RuntimeError("skipped (--no-l5)")
         l5 = {}
+        # BASELINE config 3 = 32 768 arenas on ONE GPU; config 4 = 8 192 per GPU on 8 (65 536 in total)
+        n5 = args.l5_arenas or (32768 if world == 1 else 8192)
+        g5 = torch.Generator(device=dev)
+        g5.manual_seed(4321 + rank)
+        acts5 = torch.stack([torch.randint(0, 13, (4, n5, 2), device=dev, generator=g5), torch.randint(0, 9, (4, n5, 2), device=dev, generator=g5),
+                             torch.randint(0, 2, (4, n5, 2), device=dev, generator=g5), torch.randint(0, 2, (4, n5, 2), device=dev, generator=g5)],
+                            dim=-1).to(torch.int32).contiguous()
         for tag, fused in (("fused_actors", True), ("torch_actors", False)):
-            env5 = VecLowLevelEnv(n, make_args(level=5), device=local, seed=3, arena_base=rank * n, autoreset=True,
+            env5 = VecLowLevelEnv(n5, make_args(level=5), device=local, seed=3, arena_base=rank * n5, autoreset=True,
                                   allow_standin_opponents=True)   # random-init frozen actors: no trained weights exist here
             env5.fused_opponents = fused
             env5.reset()
             for w in range(5):
-                env5.step(acts[w % n_act])
+                env5.step(acts5[w % 4])
             barrier()
             q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            S5 = 40
+            S5 = 40 if fused else 8
             q0.record()
             for k in range(S5):
-                env5.step(acts[k % n_act])
+                env5.step(acts5[k % 4])
             q1.record()
             barrier()
             qt = torch.tensor([q0.elapsed_time(q1)], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(qt, op=dist.ReduceOp.MAX)
-            l5[tag] = {"value": world * n * S5 / (float(qt.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(qt.item()) / S5}
+            l5[tag] = {"value": world * n5 * S5 / (float(qt.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(qt.item()) / S5}
             del env5
+        l5["arenas_per_gpu"] = n5
+        l5["config"] = "BASELINE configs[2]: 32 768 arenas, level 5, 1 GPU" if world == 1 and n5 == 32768 else \
+            f"BASELINE configs[3] layout: {n5} arenas per GPU x {world} GPUs, level 5"
         l5["note"] = ("level 5 (horizon 400): split step around the opponents' frozen actors (3 policy sets x 2 aircraft types); "
-                      "'fused_actors' = csrc/hh_policy.cu chains (one launch, 3xTF32, argmax in the epilogue), 'torch_actors' = "
-                      "per-set gather + per-layer cuBLAS forward")
+                      "'fused_actors' = csrc/hh_policy_tc.cu chains (one tcgen05 launch, fp32-equivalent, argmax in the epilogue), "
+                      "'torch_actors' = per-set gather + per-layer cuBLAS forward")
+        del acts5
     except Exception as ex:  # noqa: BLE001
         l5 = {"error": repr(ex)}
+
+    # ---- BASELINE config 4 (and its 1-GPU slice): level-5 rollout fragment -> PPO update with the gradient all-reduce over
+    #      NCCL (the ONE collective of the path), 8 192 arenas per GPU
+    ppo = None
+    try:
+        if args.no_ppo:
+            raise RuntimeError("skipped (--no-ppo)")
+        from hhmarl_2d_b200 import VecSampler, TorchPolicy, PPOLearner
+        from hhmarl_2d_b200 import models as M
+        torch.manual_seed(0)                       # identical initial weights on every rank
+        m1, m2 = M.build_policy_pair("fight")
+        m1.to(dev); m2.to(dev)
+        envp = VecLowLevelEnv(n, make_args(level=5), device=local, seed=5, arena_base=rank * n, autoreset=True,
+                              allow_standin_opponents=True)
+        Tp = 20
+        smp = VecSampler(envp, TorchPolicy(m1, 1), TorchPolicy(m2, 2), fragment_len=Tp, use_cuda_graph=True)
+        learner = PPOLearner(m1, m2, num_sgd_iter=1, sgd_minibatch_size=8192)
+        learner.time_allreduce = True
+        for _ in range(2):
+            learner.update(smp.collect())
+            smp.refresh_policy()
+        IT = 3
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * IT + 1)]
+        barrier()
+        ev[0].record()
+        for it in range(IT):
+            batch = smp.collect()
+            ev[2 * it + 1].record()
+            st = learner.update(batch)
+            smp.refresh_policy()
+            ev[2 * it + 2].record()
+        barrier()
+        t_s = sum(ev[2 * it].elapsed_time(ev[2 * it + 1]) for it in range(IT))
+        t_l = sum(ev[2 * it + 1].elapsed_time(ev[2 * it + 2]) for it in range(IT))
+        tt = torch.tensor([t_s, t_l, t_s + t_l], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_s, t_l, t_all = (float(v) for v in tt.tolist())
+        ar = learner.allreduce_us()
+        ppo = {"sample_and_learn": {"value": world * n * Tp * IT / (t_all * 1e-3), "unit": UNIT},
+               "rollout": {"value": world * n * Tp * IT / (t_s * 1e-3), "unit": UNIT, "ms_per_fragment": t_s / IT},
+               "learner_ms_per_update": t_l / IT, "minibatches_per_update": st["minibatches"], "sgd_minibatch_size": 8192,
+               "num_sgd_iter": 1, "fragment_len": Tp, "arenas_per_gpu": n, "level": 5,
+               "allreduce": {"bytes": learner.grad_bytes, "us_per_minibatch": ar, "backend": "nccl" if world > 1 else None,
+                             "world": world},
+               "note": "level-5 self-play rollout (frozen stand-in opponents) + PPOLearner.update (both policies, flat "
+                       "parameter / gradient buffers, fused Adam), one all-reduce of the flat gradient per minibatch; "
+                       "num_sgd_iter 1 here to bound the bench (train_hetero.py uses the RLlib default 30)"}
+        del smp, envp, learner
+    except Exception as ex:  # noqa: BLE001
+        ppo = {"error": repr(ex)}
 
     # ---- end to end through the host entry point of the C ABI
     acts_host = acts.cpu().numpy()
@@ -551,6 +774,10 @@ def run_b200(args):
                 "rollout": rollout,
                 "hier": hier,
                 "level5": l5,
+                "ppo": ppo,
+                "step_time": step_stats,
+                "cpu_affinity": affinity,
+                "leg": args.leg,
                 "gpu_launches": int(gpu_launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -562,6 +789,16 @@ def run_b200(args):
                 "clocks": clocks}
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
+        if args.leg == "rollout" and isinstance(rollout, dict) and "fused_tc" in rollout:
+            # `value` = the whole sampler loop (north_star's "rollout loop"); the step-kernel numbers move to step_kernel_leg
+            line["step_kernel_leg"] = {k: line[k] for k in ("value", "ms_per_step", "e2e", "roofline", "gpu_launches", "config")}
+            r = rollout["fused_tc"]
+            line.update(value=r["value"], ms_per_step=r["ms_per_tick"], config=workload_config(args, leg="rollout"),
+                        dtype="f64 env + fp32-equivalent policy (fp16 hi/lo split on tcgen05)",
+                        e2e=rollout.get("e2e"), roofline=rollout.get("roofline"), gpu_launches=4 * rollout["fragment_len"] * max(2, K // 20))
+            if cpu_base is not None and isinstance(rollout.get("cpu_sampler_equivalent"), dict) and "value_per_worker" in rollout["cpu_sampler_equivalent"]:
+                c = rollout["cpu_sampler_equivalent"]
+                line["cpu_baseline"] = {"value": c["value_per_worker"], "unit": UNIT, "cores": 1, "kind": "port", "sample": c["sample"]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

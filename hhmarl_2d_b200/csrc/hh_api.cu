@@ -558,7 +558,10 @@ step_begin_kernel(StatePtrs S, Params P, const int32_t* __restrict__ actions, fl
   if (u >= 2) {
     float* row = u == 2 ? s3 + al * kOppD3 : s4 + al * kOppD4;
     const int len = obs_len(u, L.opp_mode), stride = u == 2 ? kOppD3 : kOppD4;
-    L.ota = unit_observation(L, W, g, u, L.opp_mode, row);
+    // only an opponent that still exists queries its policy (env_hetero.py:160-182), and only that query rewrites its
+    // opp_to_attack (lowlevel_state, env_hetero.py:89-96): a destroyed opponent keeps its last value
+    const int o_new = unit_observation(L, W, g, u, L.opp_mode, row);
+    if (L.alive) L.ota = o_new;
     for (int k = len; k < stride; ++k) row[k] = 0.0f;
   }
   cta_sync();

@@ -301,13 +301,29 @@ class FusedPolicyPair:
         return out
 
 
+    @torch.no_grad()
+    def forward_one(self, p: int, flat, out=None):
+        """Actor + central critic of ONE policy (p = 0: ac1_policy, 1: ac2_policy) on its flattened central observation:
+        what RLlib's Policy.compute_actions evaluates for one policy's batch.  -> (logits [B, 26|24], value [B])"""
+        assert self.precision == 2, "forward_one runs on the tcgen05 path (precision=2)"
+        B = flat.shape[0]
+        n_act = self.packed.Wact[p].shape[1]
+        if out is None:
+            out = (torch.empty((B, n_act), device=self.dev), torch.empty((B,), device=self.dev))
+        self._launch_tc([(p, flat, out)], [n_act if q == p else None for q in range(2)])
+        return out
+
     def _forward_tc(self, flat1, flat2, out, n_act):
-        chains = (nat.HHPolicyChainEx * 4)()
-        B = flat1.shape[0]
-        for p, x in enumerate((flat1, flat2)):
+        self._launch_tc([(0, flat1, out[0:2]), (1, flat2, out[2:4])], n_act)
+        return out
+
+    def _launch_tc(self, jobs, n_act):
+        chains = (nat.HHPolicyChainEx * (2 * len(jobs)))()
+        for j, (p, x, o2) in enumerate(jobs):
+            B = x.shape[0]
             assert x.dtype == torch.float32 and x.is_cuda and x.stride(1) == 1
             for k in range(2):
-                c = chains[2 * p + k]
+                c = chains[2 * j + k]
                 c.x, c.ldx, c.d_in, c.k1_pad = x.data_ptr(), x.stride(0), x.shape[1], self.k1_pad[p]
                 c.b1, c.bs, c.bh = self.b1[p][k].data_ptr(), self.bs.data_ptr(), self.bh[p][k].data_ptr()
                 c.img_w1, c.us_w1 = (t.data_ptr() for t in self.img[("w1", p, k)])
@@ -317,12 +333,11 @@ class FusedPolicyPair:
                     c.batt = self.batt[p][k].data_ptr()
                     c.att_lo, c.att_n, c.att_pad = self.att[k]
                     c.img_att, c.us_att = (t.data_ptr() for t in self.img[("watt", p, k)])
-                o = out[2 * p + k]
+                o = o2[k]
                 c.out, c.ld_out, c.n_out = o.data_ptr(), o.stride(0), (n_act[p] if k == 0 else 1)
                 c.n_rows = B
         st = torch.cuda.current_stream(self.dev).cuda_stream
-        nat.check(nat.lib().hh_policy_forward_ex(4, chains, 2, st), "hh_policy_forward_ex")
-        return out
+        nat.check(nat.lib().hh_policy_forward_ex(len(chains), chains, 2, st), "hh_policy_forward_ex")
 
 
 class FusedActor:

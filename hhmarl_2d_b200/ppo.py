@@ -68,13 +68,32 @@ class PPOLearner:
         self.gen.manual_seed(seed)
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.epoch = 0
+        self._ar_events = []
 
     # ------------------------------------------------------------------ gradient exchange (one bucket, no copies)
     def _allreduce_grads(self):
         if self.world == 1:
             return
+        timed = getattr(self, "time_allreduce", False) and self.flat.is_cuda
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         dist.all_reduce(self.flat.grad)          # the ONE collective of the data path (NCCL over NVLink)
+        if timed:
+            e1.record()
+            self._ar_events.append((e0, e1))
         self.flat.grad.div_(self.world)
+
+    _ar_events: list = []
+
+    def allreduce_us(self):
+        """Mean device time of the gradient all-reduce per minibatch since the last call (time_allreduce = True), or None."""
+        if not self._ar_events:
+            return None
+        torch.cuda.synchronize()
+        v = [a.elapsed_time(b) * 1e3 for a, b in self._ar_events]
+        self._ar_events = []
+        return sum(v) / len(v)
 
     def _global_mean_std(self, x):
         s = torch.stack([x.sum(), (x * x).sum(), torch.tensor(float(x.numel()), device=x.device)])

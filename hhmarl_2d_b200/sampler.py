@@ -57,11 +57,24 @@ class TorchPolicy:
     def __init__(self, model: torch.nn.Module, ac_type: int):
         self.model, self.ac_type = model, ac_type
         self.splits = M.ACTION_SPLITS[ac_type]
+        self._fused = None           # (FusedPolicyPair, index): set by VecSampler / attach_fused
+
+    def attach_fused(self, pair, index: int):
+        """Route compute_actions through the fused tcgen05 forward of `pair` (fused_forward.FusedPolicyPair, precision 2)
+        instead of the eager torch modules; `index` 0 = ac1_policy, 1 = ac2_policy."""
+        self._fused = (pair, index)
 
     @torch.no_grad()
     def compute_actions(self, obs_batch, state_batches=None, prev_action_batch=None, prev_reward_batch=None,
                         explore=True, **kw):
-        logits, vf = self.model.forward_flat(obs_batch)
+        """RLlib's Policy.compute_actions contract (train_hetero.py:200-205, 242): obs_batch = the flattened central
+        observation [B, 57|66] -> (actions [B, heads], state_out = [], {action_logp, action_dist_inputs, vf_preds})."""
+        if self._fused is not None and obs_batch.is_cuda:
+            pair, idx = self._fused
+            logits, vf = pair.forward_one(idx, obs_batch.contiguous())
+            logits, vf = logits.clone(), vf.clone()
+        else:
+            logits, vf = self.model.forward_flat(obs_batch)
         actions, logp = multicategorical_sample(logits, self.splits, explore)
         return actions, [], {"action_logp": logp, "action_dist_inputs": logits, "vf_preds": vf}
 
@@ -88,6 +101,9 @@ class VecSampler:
                 raise ValueError("fused must be 'tc', '3xtf32', 'tf32' or None")
             from .fused_forward import FusedPolicyPair
             self.packed = FusedPolicyPair(policy1.model, policy2.model, precision={"tc": 2, "3xtf32": 0, "tf32": 1}[fused])
+            if fused == "tc":          # the policies' own compute_actions run the same kernel
+                policy1.attach_fused(self.packed, 0)
+                policy2.attach_fused(self.packed, 1)
         elif packed:
             from .fused_forward import PackedPolicyPair
             self.packed = PackedPolicyPair(policy1.model, policy2.model)
@@ -109,8 +125,10 @@ class VecSampler:
         self.cur1 = torch.zeros((n, 7 + d1 + d2), **f32)   # [act_1_own(4) | act_2(3) | obs_1_own | obs_2], actions 0
         self.cur2 = torch.zeros((n, 7 + d1 + d2), **f32)   # [act_1_own(3) | act_2(4) | obs_1_own | obs_2]
         self.d1, self.d2 = d1, d2
-        self.native_glue = (d1, d2) == (26, 24)        # hh_sample_actions is written for the fight-mode head layout
-        self.direct = self.native_glue and fused is not None and env.level <= 3   # kernels write into the buffers themselves
+        # hh_sample_actions depends on the LOGITS layout (26 / 24 in both agent modes), hh_pack_central takes d1, d2:
+        # the native glue serves fight (26 / 24) and escape (30 / 29) observations alike
+        self.native_glue = True
+        self.direct = self.native_glue and fused is not None   # kernels write into the buffers themselves (all levels)
         self.ctr = torch.zeros((n, 2), dtype=torch.int32, device=dev)
         self.seed = int(getattr(env, "_cfg").seed) + 0x5A17
         self.scale = ACT_SCALE.to(dev)

@@ -37,26 +37,33 @@ def test_gae_kernel_matches_numpy():
     np.testing.assert_allclose(vt.cpu().numpy(), ev, rtol=2e-4, atol=2e-4)
 
 
-@pytest.mark.parametrize("use_graph", [False, True])
-def test_sampler_fragment_is_consistent(use_graph):
+@pytest.mark.parametrize("use_graph,mode,level", [(False, "fight", 3), (True, "fight", 3), (True, "escape", 3), (False, "escape", 5),
+                                                  (True, "fight", 5)])
+def test_sampler_fragment_is_consistent(use_graph, mode, level):
+    """Fight (26 / 24 observations) and escape (30 / 29; env_base.py:137-164, 223-233) rollouts, scripted (3) and frozen-policy
+    (5) opponents: buffers, central-observation layout, action write-back, log-probs and GAE of recorded fragments."""
     from hhmarl_2d_b200 import VecLowLevelEnv, make_args, VecSampler, TorchPolicy
     from hhmarl_2d_b200 import models as M
     from hhmarl_2d_b200.sampler import multicategorical_logp_entropy_kl
     torch.manual_seed(0)
     n, T = 512, 40
-    env = VecLowLevelEnv(n, make_args(level=3), device=0, seed=11)
-    m1, m2 = M.build_policy_pair("fight")
+    mk = lambda: VecLowLevelEnv(n, make_args(level=level, agent_mode=mode), device=0, seed=11, allow_standin_opponents=True)  # noqa: E731
+    env = mk()
+    d1, d2 = env.obs_dim
+    assert (d1, d2) == ((26, 24) if mode == "fight" else (30, 29))
+    m1, m2 = M.build_policy_pair(mode)
     m1.cuda(); m2.cuda()
     smp = VecSampler(env, TorchPolicy(m1, 1), TorchPolicy(m2, 2), fragment_len=T, use_cuda_graph=use_graph)
+    assert smp.direct and smp.native_glue
     frags = [{k: v.clone() for k, v in smp.collect().items()} for _ in range(3)]
     # independent replay of the recorded actions on a fresh env with the same seed
-    env2 = VecLowLevelEnv(n, make_args(level=3), device=0, seed=11)
+    env2 = mk()
     o1, o2 = env2.reset()
     for b in frags:
         for t in range(T):
             # observation columns of the flattened central obs (train_hetero.py:162-181, sorted-key order)
-            assert torch.equal(b["flat1"][t][:, 7:33], o1) and torch.equal(b["flat1"][t][:, 33:], o2)
-            assert torch.equal(b["flat2"][t][:, 7:31], o2) and torch.equal(b["flat2"][t][:, 31:], o1)
+            assert torch.equal(b["flat1"][t][:, 7:7 + d1], o1) and torch.equal(b["flat1"][t][:, 7 + d1:], o2)
+            assert torch.equal(b["flat2"][t][:, 7:7 + d2], o2) and torch.equal(b["flat2"][t][:, 7 + d2:], o1)
             o1, o2, r, d = env2.step(b["actions"][t].contiguous())
             assert torch.equal(r, b["rew"][t]) and torch.equal(d, b["done"][t])
         # action write-back of on_postprocess_trajectory (train_hetero.py:140-160)
@@ -73,6 +80,130 @@ def test_sampler_fragment_is_consistent(use_graph):
         ea, ev = _gae_numpy(b["rew"].cpu().numpy(), b["vf"].cpu().numpy(), b["last_vf"].cpu().numpy(), b["done"].cpu().numpy(), 0.99, 0.95)
         np.testing.assert_allclose(b["adv"].cpu().numpy(), ea, rtol=1e-3, atol=1e-3)
     assert sum(int(b["done"].sum()) for b in frags) > 0
+
+
+def test_compute_actions_contract_on_the_fused_path():
+    """TorchPolicy.compute_actions = RLlib's Policy.compute_actions (train_hetero.py:200-205, 242): (actions, [], {action_logp,
+    action_dist_inputs, vf_preds}); once a sampler exists it runs the SAME fused tcgen05 forward as the rollout, checked
+    here against the eager torch modules."""
+    from hhmarl_2d_b200 import VecLowLevelEnv, make_args, VecSampler, TorchPolicy
+    from hhmarl_2d_b200 import models as M
+    from hhmarl_2d_b200.sampler import multicategorical_logp_entropy_kl
+    torch.manual_seed(2)
+    for mode in ("fight", "escape"):
+        m1, m2 = M.build_policy_pair(mode)
+        m1.cuda(); m2.cuda()
+        p1, p2 = TorchPolicy(m1, 1), TorchPolicy(m2, 2)
+        eager = p1.compute_actions(torch.rand(7, m1.central_dim, device="cuda"))           # before attach: torch forward
+        assert eager[0].shape == (7, 4) and eager[1] == []
+        env = VecLowLevelEnv(64, make_args(level=3, agent_mode=mode), device=0, seed=1)
+        VecSampler(env, p1, p2, fragment_len=20, use_cuda_graph=False)
+        assert p1._fused is not None and p2._fused is not None
+        for pol, m, heads in ((p1, m1, (13, 9, 2, 2)), (p2, m2, (13, 9, 2))):
+            B = 777
+            obs = torch.rand(B, m.central_dim, device="cuda")
+            obs[:, :7] = 0
+            act, state, extra = pol.compute_actions(obs, explore=True)
+            assert state == [] and set(extra) == {"action_logp", "action_dist_inputs", "vf_preds"}
+            assert act.shape == (B, len(heads)) and extra["action_dist_inputs"].shape == (B, sum(heads))
+            assert extra["action_logp"].shape == (B,) and extra["vf_preds"].shape == (B,)
+            with torch.no_grad():
+                lg, vf = m.forward_flat(obs)
+            assert (extra["action_dist_inputs"] - lg).abs().max().item() < 3e-5 and (extra["vf_preds"] - vf).abs().max().item() < 3e-5
+            lp, _, _ = multicategorical_logp_entropy_kl(extra["action_dist_inputs"], act, heads)
+            assert torch.allclose(lp, extra["action_logp"], atol=1e-5)
+            for h, w in enumerate(heads):
+                assert int(act[:, h].min()) >= 0 and int(act[:, h].max()) < w
+            det, _, x2 = pol.compute_actions(obs, explore=False)
+            assert torch.equal(det, M.deterministic_actions(x2["action_dist_inputs"], pol.ac_type))
+            a1, _, x1 = pol.compute_single_action(obs[3], explore=False)
+            assert torch.equal(a1, det[3]) and x1["vf_preds"].shape == ()
+
+
+@pytest.mark.parametrize("level,mode", [(3, "escape"), (5, "escape")])
+def test_escape_mode_training_iterations(level, mode):
+    """the escape-mode path that PRODUCES the escape policies levels 5 / hier consume -- sample with the fused
+    forward (30 / 29 observations, ammunition penalties env_base.py:223-233) and learn for three PPO iterations."""
+    from hhmarl_2d_b200 import VecLowLevelEnv, make_args, VecSampler, TorchPolicy, PPOLearner
+    from hhmarl_2d_b200 import models as M
+    torch.manual_seed(0)
+    env = VecLowLevelEnv(256, make_args(level=level, agent_mode=mode, esc_dist_rew=True), device=0, seed=5, allow_standin_opponents=True)
+    m1, m2 = M.build_policy_pair(mode)
+    m1.cuda(); m2.cuda()
+    smp = VecSampler(env, TorchPolicy(m1, 1), TorchPolicy(m2, 2), fragment_len=20, use_cuda_graph=True)
+    learner = PPOLearner(m1, m2, num_sgd_iter=2, sgd_minibatch_size=2560)
+    w0 = m1.inp2._model[0].weight.clone()
+    for it in range(3):
+        b = smp.collect()
+        assert b["flat1"].shape[-1] == 7 + 30 + 29 and torch.isfinite(b["adv"]).all()
+        st = learner.update(b)
+        smp.refresh_policy()
+        assert st["minibatches"] == 4 and np.isfinite(st["loss"])
+    assert not torch.equal(w0, m1.inp2._model[0].weight)
+    with torch.no_grad():      # the sampler's packed weights follow the learner (refresh_policy)
+        b = smp.collect()
+        f1 = b["flat1"][3].clone(); f1[:, :7] = 0
+        lg, _ = m1.forward_flat(f1)
+    assert (b["logits1"][3] - lg).abs().max().item() < 5e-5
+
+
+def test_learner_improves_the_level1_reward():
+    """Wiring check of sampler -> GAE -> action write-back -> learner (train_hetero.py:120-160, 212-217): at level 1 (static
+    opponents) the mean fragment reward of a PPO-trained pair must rise clearly above that of the initial random policy."""
+    from hhmarl_2d_b200 import VecLowLevelEnv, make_args, VecSampler, TorchPolicy, PPOLearner
+    from hhmarl_2d_b200 import models as M
+    torch.manual_seed(0)
+    n, T = 2048, 40
+    env = VecLowLevelEnv(n, make_args(level=1), device=0, seed=21)
+    m1, m2 = M.build_policy_pair("fight")
+    m1.cuda(); m2.cuda()
+    smp = VecSampler(env, TorchPolicy(m1, 1), TorchPolicy(m2, 2), fragment_len=T, use_cuda_graph=True)
+    learner = PPOLearner(m1, m2, lr=3e-4, num_sgd_iter=4, sgd_minibatch_size=8192)
+    hist = []
+    for it in range(30):
+        b = smp.collect()
+        hist.append(float(b["rew"].sum(0).mean()))          # mean reward per arena and fragment, both agents
+        learner.update(b)
+        smp.refresh_policy()
+    first, last = np.mean(hist[:4]), np.mean(hist[-4:])
+    print("level-1 fragment reward: first 4 iterations %.3f, last 4 %.3f" % (first, last), hist)
+    assert last > first + 0.15, (first, last)
+
+
+def _nccl_worker(rank, world, port, out_dir):
+    import os
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from hhmarl_2d_b200 import VecLowLevelEnv, make_args, VecSampler, TorchPolicy, PPOLearner
+    from hhmarl_2d_b200 import models as M
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    torch.manual_seed(0)                                      # identical initial weights
+    m1, m2 = M.build_policy_pair("fight")
+    m1.cuda(rank); m2.cuda(rank)
+    n = 256
+    env = VecLowLevelEnv(n, make_args(level=3), device=rank, seed=9, arena_base=rank * n)    # different arenas per rank
+    smp = VecSampler(env, TorchPolicy(m1, 1), TorchPolicy(m2, 2), fragment_len=20, use_cuda_graph=False)
+    learner = PPOLearner(m1, m2, num_sgd_iter=2, sgd_minibatch_size=1280)
+    for _ in range(2):
+        st = learner.update(smp.collect())
+        smp.refresh_policy()
+    torch.save({"flat": learner.flat.detach().cpu(), "rew": float(smp.buf["rew"].sum()), "mb": st["minibatches"]},
+               os.path.join(out_dir, f"rank{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_nccl_ranks_end_an_update_with_identical_weights(tmp_path):
+    """arenas sharded over ranks, ONE NCCL all-reduce of the flat gradient per minibatch.  Two ranks with
+    different arenas (different rollouts) must hold bit-identical weights after the updates."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run by profiles/run_r2_multi.sh under gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    mp.spawn(_nccl_worker, args=(2, 29621, str(tmp_path)), nprocs=2, join=True)
+    a, b = (torch.load(tmp_path / f"rank{r}.pt") for r in (0, 1))
+    assert a["mb"] == b["mb"] == 8 and a["rew"] != b["rew"]      # different data ...
+    assert torch.equal(a["flat"], b["flat"])                     # ... same weights
 
 
 def test_ppo_update_on_gpu():
