@@ -457,7 +457,7 @@ extern "C" int hh_policy_rows_by_key(int32_t n, const uint8_t* key_dev, int32_t 
   return 0;
 }
 
-extern "C" int hh_policy_pack(const float* w_dev, int32_t k_rows, int32_t ldw, int32_t n_total, int32_t n_chunk, int32_t row_shift,
-                              int32_t ksteps, void* image_dev, float* unscale_dev, void* stream) {
-  return hh_pf_tc_pack(w_dev, k_rows, ldw, n_total, n_chunk, row_shift, ksteps, image_dev, unscale_dev, stream, g_pf_error);
+extern "C" int hh_policy_pack(const float* w_dev, int32_t k_rows, int32_t n_cols, int32_t ldw, int32_t n_total, int32_t n_chunk,
+                              int32_t row_shift, int32_t ksteps, int32_t kps, void* image_dev, float* unscale_dev, void* stream) {
+  return hh_pf_tc_pack(w_dev, k_rows, n_cols, ldw, n_total, n_chunk, row_shift, ksteps, kps, image_dev, unscale_dev, stream, g_pf_error);
 }

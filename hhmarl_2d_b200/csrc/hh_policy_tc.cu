@@ -73,6 +73,7 @@ struct Chain {
 struct Args {
   Chain c[8];
   unsigned long long* prof;   // optional clock64() stamps, 32 per CTA (hh_policy_tc_profile; null = off)
+  int debug;                  // timing experiments only (results are garbage): 1 = no weight copies, 2 = no MMAs
 };
 
 // barrier slots
@@ -96,6 +97,21 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// The issuing WARP runs converged and one elected lane issues (elect.sync inside the asm): with warp-uniform operands the
+// compiler keeps the descriptors in uniform registers.  (Issuing from `if (lane == 0)` made it wrap every UTCHMMA in an
+// ELECT + 7x R2UR.BROADCAST waterfall loop -- ~130 cycles of the issuing thread per MMA, profiles/README.md round 2.)
+__device__ __forceinline__ void umma_f16_elect(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+               "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(bar)
+               : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -121,6 +137,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
                  : "r"(bar), "r"(parity)
                  : "memory");
     if (!ok && spin > (1u << 24)) __trap();
+  }
+}
+// Busy poll (test_wait never suspends the thread): for the single-lane roles whose barriers are signalled from the peer
+// CTA / the tensor cores, where the wake-up of a suspended try_wait is what the stage round trip waits for.
+__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t spin = 0; !ok; ++spin) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    if (!ok && spin > (1u << 28)) __trap();
   }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -317,17 +345,17 @@ __global__ void __launch_bounds__(kThreads, 1) policy_forward_tc_kernel(const __
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {   // ---- MMA issue.  Descriptors advance by adding to their 14-bit address field (16-byte units).
+    {   // ---- MMA issue by the converged warp (one elected lane inside the asm).  Descriptors advance by adding to their 14-bit address field (16-byte units).
       uint32_t slot = 0, phase = 0;
       long long stall = 0;
-      if (prof) prof[0] = (unsigned long long)clock64();
+      if (prof && lane == 0) prof[0] = (unsigned long long)clock64();
       mbar_wait(bar0 + 8 * (B_ACT + 5), 0);           // the input tile is in shared memory
       const uint64_t ring_desc = smem_desc(smem_u32(smem + OFF_RING), 0, SBO);
       for (int s = 0; s < C.n_seg; ++s) {
         const Seg& g = C.seg[s];
         const uint32_t n = g.n, kps = g.kps, n_stage = g.ksteps / kps;
         if (g.wait_act != 0xff) mbar_wait(bar0 + 8 * (B_ACT + g.wait_act), 0);
-        if (prof) prof[1 + 2 * s] = (unsigned long long)clock64();
+        if (prof && lane == 0) prof[1 + 2 * s] = (unsigned long long)clock64();
         fence_tc_after();
         const uint32_t idesc = instr_desc_f16(TM, n);
         const uint32_t a_hi = smem_u32(smem + (g.a_src ? OFF_ACT_HI : OFF_X_HI)) + 16u * g.a_off16;
@@ -344,26 +372,26 @@ __global__ void __launch_bounds__(kThreads, 1) policy_forward_tc_kernel(const __
           fence_tc_after();
           uint64_t db = db_seg + (uint64_t)(slot * (STAGE_BYTES >> 4));
           for (uint32_t j = 0; j < kps; ++j) {
-            umma_f16(d, da_lo, db, idesc, acc);                // small terms first
-            umma_f16(d, da_hi, db + lo_off, idesc, 1u);
-            umma_f16(d, da_hi, db, idesc, 1u);
+            umma_f16_elect(d, da_lo, db, idesc, acc);                // small terms first
+            umma_f16_elect(d, da_hi, db + lo_off, idesc, 1u);
+            umma_f16_elect(d, da_hi, db, idesc, 1u);
             acc = 1u;
             da_hi += (2 * LBO_A) >> 4;
             da_lo += (2 * LBO_A) >> 4;
             db += step_off;
           }
           // the slot is free once these MMAs have read it -- in every CTA of the cluster
-          if (CS == 1) umma_commit(bar0 + 8 * (B_EMPTY + slot));
+          if (CS == 1) umma_commit_elect(bar0 + 8 * (B_EMPTY + slot));
           else umma_commit_mc(bar0 + 8 * (B_EMPTY + slot), kMask);
           if (++slot == NSTAGE) {
             slot = 0;
             phase ^= 1;
           }
         }
-        if (g.commit_acc != 0xff) umma_commit(bar0 + 8 * (B_ACC + g.commit_acc));
-        if (prof) prof[2 + 2 * s] = (unsigned long long)clock64();
+        if (g.commit_acc != 0xff) umma_commit_elect(bar0 + 8 * (B_ACC + g.commit_acc));
+        if (prof && lane == 0) prof[2 + 2 * s] = (unsigned long long)clock64();
       }
-      if (prof) prof[15] = (unsigned long long)stall;
+      if (prof && lane == 0) prof[15] = (unsigned long long)stall;
     }
   } else {
     // ---- epilogue warps 2..9: lane quadrant q = warp % 4 (the TMEM lanes a warp can read), column part (warp - 2) / 4
@@ -547,12 +575,460 @@ __global__ void __launch_bounds__(kThreads, 1) policy_forward_tc_kernel(const __
   }
 }
 
+// =====================================================================================================================
+// CTA-PAIR form (default): two CTAs of a cluster = two 64-row tiles of the same chain share ONE weight stream.  Every
+// MMA is a tcgen05.mma.cta_group::2 of M = 128 issued by the pair's CTA 0: each CTA supplies its own 64 activation rows
+// and HALF of the weight columns of the step (its ring holds 8 KB per K step instead of 16), so the bytes an SM pulls
+// from L2 per row halve -- the single-CTA kernel above is bound by exactly that stream -- and the pair's tensor cores run
+// at the M = 128 rate (profiles/r2i_tcgen05_probe3.txt: 2.0x the M = 64 rate).  Accumulator of an N-wide step in each CTA's
+// tensor memory: its row m in lane m for columns [0, N/2) and in lane 64 + m for columns [N/2, N) (N/2 TMEM columns).
+// Protocol: each CTA streams its own half into its own ring; CTA 1 relays "stage landed" to CTA 0's full barrier (a bulk
+// copy cannot complete on a remote barrier, probe3); CTA 0's commits are multicast to both CTAs' empty / accumulator
+// barriers; both CTAs' epilogue warps arrive (one lane per warp) on CTA 0's activation barriers.
+constexpr int NSTAGE2 = 8;
+constexpr uint32_t STAGE2_BYTES = 8192;
+static_assert(NSTAGE2 * STAGE2_BYTES == NSTAGE * STAGE_BYTES, "same ring footprint");
+constexpr int P_FULL = 0, P_EMPTY = NSTAGE2, P_ACC = 2 * NSTAGE2, P_ACT = 2 * NSTAGE2 + 6, P_COUNT = 2 * NSTAGE2 + 12;
+constexpr int kEpiWarps = kEpiThreads / 32;
+
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_f16_elect(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_both_elect(uint32_t bar) {
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+               "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}\n" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void umma2_commit_both(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// the relay's arrive carries no data of its own (the stage was written by the TMA engine and is read by the tensor
+// cores): no cluster-scope release fence on the signalling thread
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait that also acquires what a peer CTA released (its epilogue's shared-memory writes, its relay)
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t spin = 0; !ok; ++spin) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    if (!ok && spin > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+// this warp's part of a phase is done: its shared-memory writes are visible to the tensor cores, its TMEM reads are
+// complete; one lane tells CTA 0
+__device__ __forceinline__ void warp_arrive_leader(uint32_t leader_bar, int lane) {
+  fence_async_smem();
+  fence_tc_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive_cluster(leader_bar);
+}
+
+// epilogue of one N = 256 step of a 500-wide layer in the pair layout: the thread owns row 32 (q & 1) + lane and 64
+// consecutive activation columns k0 + 128 (q >> 1) + 64 part + [0, 64)
+template <bool HOLD>
+__device__ __forceinline__ void epi2_tanh_half(uint8_t* smem, uint32_t tmem, int tmem_col, int k0, const float* __restrict__ bias,
+                                               float us, int q, int part, int lane, uint32_t hold_bar) {
+  const int row = 32 * (q & 1) + lane;
+  const int kb = k0 + 128 * (q >> 1) + 64 * part;
+  const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(tmem_col + 64 * part);
+  const float us2 = us * kTwoLog2e;
+  uint4 hh[8], ll[8];
+  uint32_t r[2][16];
+  tmem_ld_32x32b_x16(taddr, r[0]);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    tmem_ld_wait();
+    if (c < 3) tmem_ld_32x32b_x16(taddr + 16 * (c + 1), r[(c + 1) & 1]);
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const int k = kb + 16 * c + 8 * g;
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + k)), b1 = __ldg(reinterpret_cast<const float4*>(bias + k + 4));
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      __half2 h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float v0 = tanh_from_scaled(fmaf(__uint_as_float(r[c & 1][8 * g + 2 * j]), us2, bb[2 * j] * kTwoLog2e));
+        const float v1 = tanh_from_scaled(fmaf(__uint_as_float(r[c & 1][8 * g + 2 * j + 1]), us2, bb[2 * j + 1] * kTwoLog2e));
+        split_pair(v0, v1, h[j], l[j]);
+      }
+      hh[2 * c + g] = make_uint4(*reinterpret_cast<uint32_t*>(&h[0]), *reinterpret_cast<uint32_t*>(&h[1]),
+                                 *reinterpret_cast<uint32_t*>(&h[2]), *reinterpret_cast<uint32_t*>(&h[3]));
+      ll[2 * c + g] = make_uint4(*reinterpret_cast<uint32_t*>(&l[0]), *reinterpret_cast<uint32_t*>(&l[1]),
+                                 *reinterpret_cast<uint32_t*>(&l[2]), *reinterpret_cast<uint32_t*>(&l[3]));
+    }
+  }
+  if (HOLD) mbar_wait(hold_bar, 0);
+  uint8_t *hi = smem + OFF_ACT_HI, *lo = smem + OFF_ACT_LO;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t o = (uint32_t)(((kb >> 3) + i) * (TM * 16) + row * 16);       // one core-matrix row = 8 columns = 16 bytes
+    *reinterpret_cast<uint4*>(hi + o) = hh[i];
+    *reinterpret_cast<uint4*>(lo + o) = ll[i];
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) policy_forward_pair_kernel(const __grid_constant__ Args args) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bars[P_COUNT];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int rowmap[TM];
+  __shared__ float ssum[4][TM];
+  const Chain& C = args.c[blockIdx.y];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int beg = 0, cnt = C.n_rows;
+  if (C.range_dev) {
+    beg = C.range_dev[0];
+    cnt = C.range_dev[1];
+  }
+  const int row0 = blockIdx.x * TM;
+  if ((int)(blockIdx.x >> 1) * 2 * TM >= cnt) return;   // pair-uniform: a CTA without rows still supplies its half of the weights
+  unsigned long long* prof = args.prof ? args.prof + 32 * (size_t)(blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
+  const uint32_t rank = cluster_rank();
+  if (tid < TM) {
+    const int lr = row0 + tid;
+    rowmap[tid] = lr < cnt ? (C.rows ? C.rows[beg + lr] : beg + lr) : -1;
+  }
+  const uint32_t bar0 = smem_u32(bars);
+  if (tid == 0) {
+    for (int i = 0; i < NSTAGE2; ++i) {
+      mbar_init(bar0 + 8 * (P_FULL + i), rank == 0 ? 2 : 1);     // CTA 0: its own copy + CTA 1's relay
+      mbar_init(bar0 + 8 * (P_EMPTY + i), 1);
+    }
+    for (int i = 0; i < 6; ++i) {
+      mbar_init(bar0 + 8 * (P_ACC + i), 1);
+      mbar_init(bar0 + 8 * (P_ACT + i), 2 * kEpiWarps);          // one arrival per epilogue warp of both CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  fence_tc_before();
+  __syncthreads();
+  cluster_sync();                       // both CTAs' barriers and allocations exist before anyone signals a peer
+  fence_tc_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t ring = smem_u32(smem + OFF_RING);
+
+  if (warp == 0) {
+    if (lane == 0) {   // ---- this CTA's half of the weight stream
+      uint32_t slot = 0, phase = 0;
+      long long stall = 0;
+      for (int s = 0; s < C.n_seg; ++s) {
+        const Seg& g = C.seg[s];
+        const uint32_t bytes = (uint32_t)g.kps * g.n * 32u;                 // per CTA and stage
+        const uint8_t* src = g.w + rank * bytes;
+        const int n_stage = g.ksteps / g.kps;
+        for (int k = 0; k < n_stage; ++k) {
+          const long long t0 = prof ? clock64() : 0;
+          mbar_spin(bar0 + 8 * (P_EMPTY + slot), phase ^ 1);
+          if (prof) stall += clock64() - t0;
+          if (args.debug & 1) {
+            mbar_arrive(bar0 + 8 * (P_FULL + slot));
+          } else {
+            mbar_expect_tx(bar0 + 8 * (P_FULL + slot), bytes);
+            bulk_g2s(ring + slot * STAGE2_BYTES, src, bytes, bar0 + 8 * (P_FULL + slot));
+          }
+          src += 2 * bytes;
+          if (++slot == NSTAGE2) {
+            slot = 0;
+            phase ^= 1;
+          }
+        }
+      }
+      if (prof) {
+        prof[28] = (unsigned long long)stall;
+        prof[29] = (unsigned long long)clock64();
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 1) {
+     if (lane == 0) {   // ---- relay: "my half of stage k has landed" -> CTA 0's full barrier
+      uint32_t slot = 0, phase = 0;
+      long long stall = 0;
+      const uint32_t leader_full = map_to_cta(bar0 + 8 * P_FULL, 0);
+      if (prof) prof[0] = (unsigned long long)clock64();
+      for (int s = 0; s < C.n_seg; ++s) {
+        const int n_stage = C.seg[s].ksteps / C.seg[s].kps;
+        if (prof) prof[1 + 2 * s] = (unsigned long long)clock64();
+        for (int k = 0; k < n_stage; ++k) {
+          const long long t0 = prof ? clock64() : 0;
+          mbar_spin(bar0 + 8 * (P_FULL + slot), phase);
+          if (prof) stall += clock64() - t0;
+          mbar_arrive_cluster_relaxed(leader_full + 8 * slot);
+          if (++slot == NSTAGE2) {
+            slot = 0;
+            phase ^= 1;
+          }
+        }
+        if (prof) prof[2 + 2 * s] = (unsigned long long)clock64();
+      }
+      if (prof) prof[15] = (unsigned long long)stall;
+     }
+    } else {   // ---- MMA issue for the pair (CTA 0): the converged warp, one elected lane inside the asm
+      uint32_t slot = 0, phase = 0;
+      long long stall = 0, t_mma = 0, t_commit = 0;
+      if (prof && lane == 0) prof[0] = (unsigned long long)clock64();
+      mbar_wait_cluster(bar0 + 8 * (P_ACT + 5), 0);           // both input tiles are in shared memory
+      const uint64_t ring_desc = smem_desc(ring, 0, SBO);
+      for (int s = 0; s < C.n_seg; ++s) {
+        const Seg& g = C.seg[s];
+        const uint32_t n = g.n, kps = g.kps, n_stage = g.ksteps / kps;
+        if (g.wait_act != 0xff) mbar_wait_cluster(bar0 + 8 * (P_ACT + g.wait_act), 0);
+        if (prof && lane == 0) prof[1 + 2 * s] = (unsigned long long)clock64();
+        fence_tc_after();
+        const uint32_t idesc = instr_desc_f16(2 * TM, n);
+        const uint32_t a_hi = smem_u32(smem + (g.a_src ? OFF_ACT_HI : OFF_X_HI)) + 16u * g.a_off16;
+        uint64_t da_hi = smem_desc(a_hi, LBO_A, SBO);
+        uint64_t da_lo = smem_desc(a_hi + (g.a_src ? ACT_BYTES : X_BYTES), LBO_A, SBO);
+        const uint64_t db_seg = ring_desc | ((uint64_t)(n >> 1) << 16);   // a CTA holds n / 2 weight columns: LBO = 16 (n / 2) bytes
+        const uint32_t lo_off = n, step_off = 2u * n;                     // B lo block, next K step (16-byte units)
+        const uint32_t d = tmem + g.tmem_col;
+        uint32_t acc = g.first ? 0u : 1u;
+        for (uint32_t k = 0; k < n_stage; ++k) {
+          const long long t0 = prof ? clock64() : 0;
+          mbar_spin(bar0 + 8 * (P_FULL + slot), phase);     // the tensor cores read the stage (async proxy): no thread-level acquire needed
+          if (prof) stall += clock64() - t0;
+          fence_tc_after();
+          uint64_t db = db_seg + (uint64_t)(slot * (STAGE2_BYTES >> 4));
+          const long long t1 = prof ? clock64() : 0;
+          for (uint32_t j = 0; j < kps && !(args.debug & 2); ++j) {
+            umma2_f16_elect(d, da_lo, db, idesc, acc);                // small terms first
+            umma2_f16_elect(d, da_hi, db + lo_off, idesc, 1u);
+            umma2_f16_elect(d, da_hi, db, idesc, 1u);
+            acc = 1u;
+            da_hi += (2 * LBO_A) >> 4;
+            da_lo += (2 * LBO_A) >> 4;
+            db += step_off;
+          }
+          const long long t2 = prof ? clock64() : 0;
+          // both rings' slots are free once these MMAs have read them; slots are released two at a time (a commit after
+          // every stage was measured to slow the MMA stream down)
+          if ((k & 1u) || k + 1 == n_stage) {
+            if (k & 1u) umma2_commit_both_elect(bar0 + 8 * (P_EMPTY + (slot == 0 ? NSTAGE2 - 1 : slot - 1)));
+            umma2_commit_both_elect(bar0 + 8 * (P_EMPTY + slot));
+          }
+          if (prof) {
+            t_mma += t2 - t1;
+            t_commit += clock64() - t2;
+          }
+          if (++slot == NSTAGE2) {
+            slot = 0;
+            phase ^= 1;
+          }
+        }
+        if (g.commit_acc != 0xff) umma2_commit_both_elect(bar0 + 8 * (P_ACC + g.commit_acc));
+        if (prof && lane == 0) prof[2 + 2 * s] = (unsigned long long)clock64();
+      }
+      if (prof && lane == 0) {
+        prof[15] = (unsigned long long)stall;
+        prof[30] = (unsigned long long)t_mma;
+        prof[31] = (unsigned long long)t_commit;
+      }
+    }
+  } else {
+    // ---- epilogue warps 2..9: TMEM lane quadrant q = warp % 4 -> rows 32 (q & 1) + lane, column half q >> 1; part (warp - 2) / 4
+    const int et = tid - 64;
+    const int q = warp & 3, part = (warp - 2) >> 2;
+    const int row = 32 * (q & 1) + lane;
+    uint8_t *hi = smem + OFF_ACT_HI, *lo = smem + OFF_ACT_LO;
+    const uint32_t act0 = map_to_cta(bar0 + 8 * P_ACT, 0);     // CTA 0's activation barriers
+    {
+      constexpr int kIter = TM * (KX / 2) / kEpiThreads;
+      float v0[kIter], v1[kIter];
+#pragma unroll
+      for (int it = 0; it < kIter; ++it) {
+        const int i = et + it * kEpiThreads, r = i / (KX / 2), c = 2 * (i - r * (KX / 2));
+        const int gr = rowmap[r];
+        const float* xr = C.x + (size_t)(gr >= 0 ? gr : 0) * C.ldx;
+        v0[it] = (gr >= 0 && c < C.d_in) ? __ldg(xr + c) : 0.0f;
+        v1[it] = (gr >= 0 && c + 1 < C.d_in) ? __ldg(xr + c + 1) : 0.0f;
+      }
+#pragma unroll
+      for (int it = 0; it < kIter; ++it) {
+        const int i = et + it * kEpiThreads, r = i / (KX / 2), c = 2 * (i - r * (KX / 2));
+        store_pair(smem + OFF_X_HI, smem + OFF_X_LO, r, c, fminf(fmaxf(v0[it], -ACT_CLAMP), ACT_CLAMP),
+                   fminf(fmaxf(v1[it], -ACT_CLAMP), ACT_CLAMP));
+      }
+    }
+    warp_arrive_leader(act0 + 8 * 5, lane);
+    {  // H = tanh(x W1 + b1)
+      const float us = __ldg(C.us_w1);
+      for (int h = 0; h < 2; ++h) {
+        mbar_wait(bar0 + 8 * (P_ACC + h), 0);
+        if (prof && et == 0) prof[16 + 2 * h] = (unsigned long long)clock64();
+        fence_tc_after();
+        epi2_tanh_half<false>(smem, tmem, 128 * h, 256 * h, C.b1, us, q, part, lane, 0u);
+        warp_arrive_leader(act0 + 8 * h, lane);
+        if (prof && et == 0) prof[17 + 2 * h] = (unsigned long long)clock64();
+      }
+    }
+    if (C.att_n > 0) {   // single-token attention: r = full + (full Wa + ba), then L2-normalise the block
+      const float us = __ldg(C.us_att);
+      mbar_wait(bar0 + 8 * (P_ACC + 2), 0);
+      if (prof && et == 0) prof[20] = (unsigned long long)clock64();
+      fence_tc_after();
+      const int n_sub = C.att_pad >> 1;                                   // this lane half's columns: D column n_sub (q >> 1) + t
+      const int t_mid = (((n_sub >> 3) + 1) >> 1) << 3;                    // part 0: TMEM columns [0, t_mid), part 1: [t_mid, n_sub)
+      const int t_beg = part ? t_mid : 0, t_end = part ? n_sub : t_mid;
+      const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + 256u;
+      float v[5][8];
+      float ss = 0.0f;
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        const int t0 = t_beg + 8 * u;
+        if (t0 < t_end) {                                                  // warp-uniform
+          uint32_t r[8];
+          tmem_ld_32x32b_x8(taddr + t0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int col = n_sub * (q >> 1) + t0 + j;
+            float x = 0.0f;
+            if (col < C.att_n) {
+              const uint32_t o = canon(row, C.att_lo + col);
+              const float res = (__half2float(*reinterpret_cast<const __half*>(hi + o)) + __half2float(*reinterpret_cast<const __half*>(lo + o))) *
+                                ACT_UNSCALE;
+              x = fmaf(__uint_as_float(r[j]), us, __ldg(C.batt + col)) + res;
+            }
+            v[u][j] = x;
+            ss += x * x;
+          }
+        }
+      }
+      ssum[2 * (q >> 1) + part][row] = ss;
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");       // the eight epilogue warps
+      const float inv = 1.0f / fmaxf(sqrtf(ssum[0][row] + ssum[1][row] + ssum[2][row] + ssum[3][row]), 1e-12f);   // F.normalize
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        const int t0 = t_beg + 8 * u;
+        if (t0 < t_end) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int col = n_sub * (q >> 1) + t0 + j;
+            if (col < C.att_n) {
+              const float sv = v[u][j] * inv * ACT_SCALE;
+              const __half h = __float2half_rn(sv);
+              const uint32_t o = canon(row, C.att_lo + col);
+              *reinterpret_cast<__half*>(hi + o) = h;
+              *reinterpret_cast<__half*>(lo + o) = __float2half_rn(sv - __half2float(h));
+            }
+          }
+        }
+      }
+      warp_arrive_leader(act0 + 8 * 2, lane);
+      if (prof && et == 0) prof[21] = (unsigned long long)clock64();
+    }
+    {  // Z = tanh(in Ws + bs), in place: the first half is computed while the second half's MMAs run and stored once they
+       // have all read the tile
+      const float us = __ldg(C.us_ws);
+      mbar_wait(bar0 + 8 * (P_ACC + 3), 0);
+      if (prof && et == 0) prof[22] = (unsigned long long)clock64();
+      fence_tc_after();
+      epi2_tanh_half<true>(smem, tmem, 0, 0, C.bs, us, q, part, lane, bar0 + 8 * (P_ACC + 4));
+      warp_arrive_leader(act0 + 8 * 3, lane);
+      if (prof && et == 0) prof[23] = (unsigned long long)clock64();
+      fence_tc_after();
+      epi2_tanh_half<false>(smem, tmem, 128, 256, C.bs, us, q, part, lane, 0u);
+      warp_arrive_leader(act0 + 8 * 4, lane);
+      if (prof && et == 0) prof[24] = (unsigned long long)clock64();
+    }
+    if (part == 0) {  // head: logits or value (+ optional per-head argmax, env_base.py:373-382); N = 32: 16 columns per lane half
+      const float us = __ldg(C.us_wh);
+      mbar_wait(bar0 + 8 * (P_ACC + 5), 0);
+      if (prof && et == 0) prof[25] = (unsigned long long)clock64();
+      fence_tc_after();
+      float* lg = reinterpret_cast<float*>(smem + OFF_X_HI);       // [TM][33]; the input tile is dead by now
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(tmem + ((uint32_t)(32 * q) << 16) + 384u, r);
+      tmem_ld_wait();
+      const int gr = rowmap[row];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int col = 16 * (q >> 1) + j;
+        if (col < C.n_out) {
+          const float x = fmaf(__uint_as_float(r[j]), us, __ldg(C.bh + col));
+          if (C.out && gr >= 0) C.out[(size_t)gr * C.ld_out + col] = x;
+          lg[row * 33 + col] = x;
+        }
+      }
+      if (C.act_out) {
+        asm volatile("bar.sync 2, 128;" ::: "memory");             // the four part-0 warps hold a row's 32 columns between them
+        if (q < 2 && gr >= 0) {
+          const float* lr = lg + row * 33;
+          int4 a = make_int4(0, 0, 0, 0);
+          int o = 0;
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            if (h < C.n_heads) {
+              int best = 0;
+              float bv = lr[o];
+              for (int k = 1; k < C.head[h]; ++k)
+                if (lr[o + k] > bv) { bv = lr[o + k]; best = k; }      // first maximum, like torch.argmax
+              (h == 0 ? a.x : h == 1 ? a.y : h == 2 ? a.z : a.w) = best;
+              o += C.head[h];
+            }
+          }
+          reinterpret_cast<int4*>(C.act_out)[(size_t)gr * C.ld_act] = a;
+        }
+      }
+    }
+    if (prof && et == 0) prof[26] = (unsigned long long)clock64();
+  }
+  fence_tc_before();
+  __syncthreads();
+  cluster_sync();                       // neither CTA leaves (or frees tensor memory) while the pair's MMAs may still run
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
+  }
+}
+
 // ---- operand images -----------------------------------------------------------------------------------------------
 // us[0] = 2^-(12 + s), us[1] = 2^s with s such that max |2^s w| lies in [2^13, 2^14)
-__global__ void pack_scale_kernel(const float* __restrict__ w, int k_rows, int ldw, int n_total, float* __restrict__ us) {
+__global__ void pack_scale_kernel(const float* __restrict__ w, int k_rows, int ldw, int n_cols, float* __restrict__ us) {
   __shared__ float red[32];
   float m = 0.0f;
-  for (int i = threadIdx.x; i < k_rows * n_total; i += blockDim.x) m = fmaxf(m, fabsf(w[(size_t)(i / n_total) * ldw + i % n_total]));
+  for (int i = threadIdx.x; i < k_rows * n_cols; i += blockDim.x) m = fmaxf(m, fabsf(w[(size_t)(i / n_cols) * ldw + i % n_cols]));
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
   __syncthreads();
@@ -565,12 +1041,15 @@ __global__ void pack_scale_kernel(const float* __restrict__ w, int k_rows, int l
     us[1] = ldexpf(1.0f, s);
   }
 }
-// image = [chunk][kstep]{ hi [2 k-halves][n_chunk][8], lo [2][n_chunk][8] } halves; image row k' = kstep * 16 + half * 8 + kk
-// holds w row k' - row_shift (zero outside [0, k_rows)), image column c of chunk j holds w column j * n_chunk + c
-__global__ void pack_image_kernel(const float* __restrict__ w, int k_rows, int ldw, int n_total, int n_chunk, int row_shift,
-                                  int ksteps, const float* __restrict__ us, __half* __restrict__ img) {
+// image = [chunk][stage][cta r < split][kstep j < kps]{ hi [2 k-halves][n_sub][8], lo [2][n_sub][8] } halves, n_sub = n_chunk / split:
+// every (stage, CTA) part is contiguous = one bulk copy.  Image row k' = kstep * 16 + half * 8 + kk holds w row k' - row_shift
+// (zero outside [0, k_rows)); column c of chunk ch holds w column ch * n_chunk + c (zero from n_cols on); CTA r of a pair
+// owns the columns [r n_sub, (r + 1) n_sub) of the chunk.
+__global__ void pack_image_kernel(const float* __restrict__ w, int k_rows, int n_cols, int ldw, int n_total, int n_chunk, int row_shift,
+                                  int ksteps, int kps, int split, const float* __restrict__ us, __half* __restrict__ img) {
   const int total = ksteps * 16 * n_total;
   const float scale = us[1];
+  const int n_sub = n_chunk / split, n_stage = ksteps / kps;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     int t = e;
     const int kk = t & 7; t >>= 3;
@@ -579,12 +1058,14 @@ __global__ void pack_image_kernel(const float* __restrict__ w, int k_rows, int l
     const int ks = t % ksteps;
     const int chunk = t / ksteps;
     const int row = ks * 16 + h * 8 + kk - row_shift, col = chunk * n_chunk + c;
-    const float v = (row >= 0 && row < k_rows) ? w[(size_t)row * ldw + col] * scale : 0.0f;
+    const float v = (row >= 0 && row < k_rows && col < n_cols) ? w[(size_t)row * ldw + col] * scale : 0.0f;
     const __half hi = __float2half_rn(v);
     const __half lo = __float2half_rn(v - __half2float(hi));
-    const size_t base = (size_t)(chunk * ksteps + ks) * n_chunk * 32 + (size_t)(h * n_chunk + c) * 8 + kk;
+    const int r = c / n_sub, cs = c - r * n_sub, stage = ks / kps, j = ks - stage * kps;
+    const size_t blk = (((size_t)(chunk * n_stage + stage) * split + r) * kps + j) * ((size_t)n_sub * 32);
+    const size_t base = blk + (size_t)(h * n_sub + cs) * 8 + kk;
     img[base] = hi;
-    img[base + (size_t)n_chunk * 16] = lo;
+    img[base + (size_t)n_sub * 16] = lo;
   }
 }
 
@@ -593,36 +1074,38 @@ __global__ void pack_image_kernel(const float* __restrict__ w, int k_rows, int l
 
 // tuning / profiling knobs of the tcgen05 path (tests and profiles/ only)
 static unsigned long long* g_prof = nullptr;
-static int g_cluster = [] {
-  const char* e = getenv("HH_TC_CLUSTER");
-  const int v = e ? atoi(e) : 2;
-  return (v == 1 || v == 2 || v == 4) ? v : 2;
+static int g_pair = [] {            // 1 (default): CTA-pair kernel (cta_group::2); 0: one CTA per tile (HH_TC_PAIR=0)
+  const char* e = getenv("HH_TC_PAIR");
+  return (e && atoi(e) == 0) ? 0 : 1;
 }();
 extern "C" int hh_policy_tc_profile(unsigned long long* stamps_dev) {   // 32 clock64() stamps per CTA, null = off
   g_prof = stamps_dev;
   return 0;
 }
-extern "C" int hh_policy_tc_cluster(int32_t ctas) {                     // 1, 2 or 4 CTAs share a weight stream (multicast)
-  if (ctas != 1 && ctas != 2 && ctas != 4) return -1;
-  g_cluster = ctas;
+static int g_debug = 0;
+extern "C" int hh_policy_tc_debug(int32_t flags) {   // timing experiments (profiles/tc_profile.py): results are garbage
+  g_debug = flags;
   return 0;
 }
+extern "C" int32_t hh_policy_tc_pair(void) { return g_pair; }           // the layout hh_policy_pack must produce: split = 1 + pair
 
 extern "C" int64_t hh_policy_image_bytes(int32_t ksteps, int32_t n_total) { return (int64_t)ksteps * n_total * 64; }
 
-int hh_pf_tc_pack(const float* w_dev, int k_rows, int ldw, int n_total, int n_chunk, int row_shift, int ksteps, void* image_dev,
-                  float* unscale_dev, void* stream, std::string& err) {
+int hh_pf_tc_pack(const float* w_dev, int k_rows, int n_cols, int ldw, int n_total, int n_chunk, int row_shift, int ksteps, int kps,
+                  void* image_dev, float* unscale_dev, void* stream, std::string& err) {
   using namespace hh::tc;
-  if (!w_dev || !image_dev || !unscale_dev || k_rows <= 0 || ldw < n_total || n_total <= 0 || n_chunk <= 0 || n_total % n_chunk ||
-      n_chunk % 8 || n_chunk > 256 || ksteps <= 0 || row_shift < 0 || (uint32_t)n_chunk * 64u > STAGE_BYTES) {
+  const int split = 1 + g_pair;
+  if (!w_dev || !image_dev || !unscale_dev || k_rows <= 0 || n_cols <= 0 || ldw < n_cols || n_total < n_cols || n_chunk <= 0 ||
+      n_total % n_chunk || n_chunk % (8 * split) || (g_pair && n_chunk % 16) || n_chunk > 256 || ksteps <= 0 || kps <= 0 || ksteps % kps ||
+      row_shift < 0 || (uint32_t)kps * n_chunk * 64u > STAGE_BYTES) {
     err = "hh_policy_pack: bad argument";
     return -1;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  pack_scale_kernel<<<1, 1024, 0, st>>>(w_dev, k_rows, ldw, n_total, unscale_dev);
+  pack_scale_kernel<<<1, 1024, 0, st>>>(w_dev, k_rows, ldw, n_cols, unscale_dev);
   const int total = ksteps * 16 * n_total;
-  pack_image_kernel<<<(total + 255) / 256, 256, 0, st>>>(w_dev, k_rows, ldw, n_total, n_chunk, row_shift, ksteps, unscale_dev,
-                                                         static_cast<__half*>(image_dev));
+  pack_image_kernel<<<(total + 255) / 256, 256, 0, st>>>(w_dev, k_rows, n_cols, ldw, n_total, n_chunk, row_shift, ksteps, kps, split,
+                                                         unscale_dev, static_cast<__half*>(image_dev));
   const cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) {
     err = std::string("hh_policy_pack launch: ") + cudaGetErrorString(ce);
@@ -634,6 +1117,7 @@ int hh_pf_tc_pack(const float* w_dev, int k_rows, int ldw, int n_total, int n_ch
 int hh_pf_tc_launch(const hh_policy_chain_ex* chains, int n_chains, int max_rows, void* stream, std::string& err) {
   using namespace hh::tc;
   Args a;
+  const int pair = g_pair;
   for (int i = 0; i < n_chains; ++i) {
     const hh_policy_chain_ex& s = chains[i];
     if (!s.img_w1 || !s.img_ws || !s.img_wh || !s.us_w1 || !s.us_ws || !s.us_wh || (s.att_n > 0 && (!s.img_att || !s.us_att))) {
@@ -648,7 +1132,10 @@ int hh_pf_tc_launch(const hh_policy_chain_ex* chains, int n_chains, int max_rows
     c.x = s.x; c.b1 = s.b1; c.batt = s.batt; c.bs = s.bs; c.bh = s.bh;
     c.us_w1 = s.us_w1; c.us_att = s.us_att; c.us_ws = s.us_ws; c.us_wh = s.us_wh;
     c.out = s.out; c.rows = s.rows; c.range_dev = s.range_dev; c.act_out = s.act_out;
-    c.n_rows = s.n_rows; c.ldx = s.ldx; c.d_in = s.d_in; c.att_lo = s.att_lo; c.att_n = s.att_n; c.att_pad = s.att_pad;
+    c.n_rows = s.n_rows; c.ldx = s.ldx; c.d_in = s.d_in; c.att_lo = s.att_lo; c.att_n = s.att_n;
+    // the attention step's N: the block padded to the MMA's granularity (8 columns; 16 for the pair form)
+    const int att_nn = s.att_n > 0 ? (pair ? (s.att_n + 15) / 16 * 16 : (s.att_n + 7) / 8 * 8) : 0;
+    c.att_pad = att_nn;
     c.n_out = s.n_out; c.ld_out = s.ld_out; c.n_heads = s.n_heads;
     for (int h = 0; h < 4; ++h) c.head[h] = s.head[h];
     c.ld_act = s.ld_act > 0 ? s.ld_act : 1;
@@ -661,21 +1148,25 @@ int hh_pf_tc_launch(const hh_policy_chain_ex* chains, int n_chains, int max_rows
       g.a_off16 = (uint16_t)((a_k0 / 8) * (TM * 16) / 16);
       g.a_src = (uint8_t)a_src; g.first = (uint8_t)first; g.wait_act = (uint8_t)wait; g.commit_acc = (uint8_t)commit;
     };
+    // accumulator regions (TMEM columns): single-CTA form 0 / 256 (an N = 256 step takes 256 columns), pair form 0 / 128 /
+    // 256 (attention) / 384 (head) (N / 2 columns per step)
+    const int colB = pair ? 128 : 256, colAtt = pair ? 256 : 0, colHead = pair ? 384 : 0;
     seg(s.img_w1, 0, 256, k1s, 1, 0, 0, 0, 1, 0xff, 0);
-    seg(s.img_w1, (size_t)k1s * 256 * 64, 256, k1s, 1, 256, 0, 0, 1, 0xff, 1);
+    seg(s.img_w1, (size_t)k1s * 256 * 64, 256, k1s, 1, colB, 0, 0, 1, 0xff, 1);
     int act_ready = 1;
     if (s.att_n > 0) {
       const int k0 = s.att_lo & ~7, ks = (s.att_lo + s.att_n - k0 + 15) / 16;
-      seg(s.img_att, 0, s.att_pad, ks, 1, 0, 1, k0, 1, 1, 2);
+      seg(s.img_att, 0, att_nn, ks, 1, colAtt, 1, k0, 1, 1, 2);
       act_ready = 2;
     }
     seg(s.img_ws, 0, 256, KA / 16, 1, 0, 1, 0, 1, act_ready, 3);
-    seg(s.img_ws, (size_t)(KA / 16) * 256 * 64, 256, KA / 16, 1, 256, 1, 0, 1, 0xff, 4);
-    seg(s.img_wh, 0, 32, 16, 8, 0, 1, 0, 1, 3, 0xff);
-    seg(s.img_wh, (size_t)16 * 32 * 64, 32, 16, 8, 0, 1, 256, 0, 4, 5);
+    seg(s.img_ws, (size_t)(KA / 16) * 256 * 64, 256, KA / 16, 1, colB, 1, 0, 1, 0xff, 4);
+    seg(s.img_wh, 0, 32, 16, 8, colHead, 1, 0, 1, 3, 0xff);
+    seg(s.img_wh, (size_t)16 * 32 * 64, 32, 16, 8, colHead, 1, 256, 0, 4, 5);
     c.n_seg = n;
   }
   a.prof = g_prof;
+  a.debug = g_debug;
   static bool opted_dev[64] = {};
   int dev = 0;
   cudaError_t ce = cudaGetDevice(&dev);
@@ -685,35 +1176,20 @@ int hh_pf_tc_launch(const hh_policy_chain_ex* chains, int n_chains, int max_rows
   }
   if (!opted_dev[dev]) {
     ce = cudaFuncSetAttribute(policy_forward_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(policy_forward_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(policy_forward_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(policy_forward_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (ce != cudaSuccess) {
-      err = std::string("cudaFuncSetAttribute(policy_forward_tc_kernel): ") + cudaGetErrorString(ce);
+      err = std::string("cudaFuncSetAttribute(policy_forward kernels): ") + cudaGetErrorString(ce);
       return -2;
     }
     opted_dev[dev] = true;
   }
   const int tiles = (max_rows + TM - 1) / TM;
-  int cs = g_cluster;                    // CTAs per cluster (weight multicast); a launch of one tile needs none
-  if (tiles < 2) cs = 1;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)((tiles + cs - 1) / cs * cs), (unsigned)n_chains);
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = SMEM_BYTES;
-  cfg.stream = static_cast<cudaStream_t>(stream);
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)cs;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = cs > 1 ? 1 : 0;
-  ce = cs == 4   ? cudaLaunchKernelEx(&cfg, policy_forward_tc_kernel<4>, a)
-       : cs == 2 ? cudaLaunchKernelEx(&cfg, policy_forward_tc_kernel<2>, a)
-                 : cudaLaunchKernelEx(&cfg, policy_forward_tc_kernel<1>, a);
-  if (ce == cudaSuccess) ce = cudaGetLastError();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (pair) policy_forward_pair_kernel<<<dim3((unsigned)((tiles + 1) / 2 * 2), (unsigned)n_chains), kThreads, SMEM_BYTES, st>>>(a);
+  else policy_forward_tc_kernel<1><<<dim3((unsigned)tiles, (unsigned)n_chains), kThreads, SMEM_BYTES, st>>>(a);
+  ce = cudaGetLastError();
   if (ce != cudaSuccess) {
-    err = std::string("policy_forward_tc_kernel launch: ") + cudaGetErrorString(ce);
+    err = std::string("policy_forward (tcgen05) launch: ") + cudaGetErrorString(ce);
     return -2;
   }
   return 0;

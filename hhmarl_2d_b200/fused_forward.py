@@ -138,10 +138,12 @@ class PackedPolicyPair:
         return l1, v1, l2, v2
 
 
-def _pack_image(w_rm: torch.Tensor, n_total: int, n_chunk: int, row_shift: int, ksteps: int, img=None, us=None):
+def _pack_image(w_rm: torch.Tensor, n_cols: int, n_total: int, n_chunk: int, row_shift: int, ksteps: int, kps: int = 1,
+                img=None, us=None):
     """Operand image of a zero-padded row-major [K, ld] fp32 weight matrix for the tcgen05 path (hh_policy_pack):
-    fp16 hi / lo halves of 2^s w in the K-major canonical shared-memory layout, one 16 KB ring stage after the other in
-    the order the kernel consumes them.  -> (image uint8 tensor, scale pair float[2]); re-packs IN PLACE when given."""
+    fp16 hi / lo halves of 2^s w in the K-major canonical shared-memory layout, one ring stage after the other in
+    the order the kernel consumes them (for the CTA-pair kernel each stage is split into the two CTAs' column halves).
+    -> (image uint8 tensor, scale pair float[2]); re-packs IN PLACE when given."""
     L = nat.lib()
     dev = w_rm.device
     if img is None:
@@ -149,16 +151,18 @@ def _pack_image(w_rm: torch.Tensor, n_total: int, n_chunk: int, row_shift: int, 
         us = torch.zeros(2, dtype=torch.float32, device=dev)
     assert w_rm.is_contiguous() and w_rm.dtype == torch.float32 and w_rm.is_cuda
     st = torch.cuda.current_stream(dev).cuda_stream
-    nat.check(L.hh_policy_pack(w_rm.data_ptr(), w_rm.shape[0], w_rm.stride(0), n_total, n_chunk, row_shift, ksteps,
-                               img.data_ptr(), us.data_ptr(), st), "hh_policy_pack")
+    nat.check(L.hh_policy_pack(w_rm.data_ptr(), w_rm.shape[0], min(n_cols, w_rm.shape[1]), w_rm.stride(0), n_total, n_chunk, row_shift,
+                               ksteps, kps, img.data_ptr(), us.data_ptr(), st), "hh_policy_pack")
     return img, us
 
 
 def _att_image_geometry(att_lo: int, att_n: int):
     """The attention block reads activation columns [att_lo, att_lo + att_n); the MMA's A operand has to start on a core
-    matrix (8 columns), so the image's K range starts at floor8(att_lo) and its first rows are zero."""
+    matrix (8 columns), so the image's K range starts at floor8(att_lo) and its first rows are zero; its N is the block
+    padded to the MMA's N granularity (16 columns for the CTA-pair kernel, 8 otherwise)."""
     k0 = att_lo & ~7
-    return att_lo - k0, (att_lo + att_n - k0 + 15) // 16          # (row_shift, ksteps)
+    g = 16 if nat.lib().hh_policy_tc_pair() else 8
+    return att_lo - k0, (att_lo + att_n - k0 + 15) // 16, (att_n + g - 1) // g * g          # (row_shift, ksteps, N)
 
 
 class FusedPolicyPair:
@@ -220,20 +224,20 @@ class FusedPolicyPair:
             self.img = {}
         rm = self._rm
 
-        def put(key, w, n_total, n_chunk, shift, ksteps):
+        def put(key, w, n_cols, n_total, n_chunk, shift, ksteps, kps=1):
             old = self.img.get(key, (None, None))
-            self.img[key] = _pack_image(w, n_total, n_chunk, shift, ksteps, *old)
+            self.img[key] = _pack_image(w, n_cols, n_total, n_chunk, shift, ksteps, kps, *old)
 
         for p in range(2):
             k1s = (self.packed.W1[p].shape[0] + 15) // 16
             for k in range(2):
-                put(("w1", p, k), rm["w1"][p][k], 512, 256, 0, k1s)
-                put(("wh", p, k), rm["wh"][p][k], 32, 32, 0, 32)
+                put(("w1", p, k), rm["w1"][p][k], 512, 512, 256, 0, k1s)
+                put(("wh", p, k), rm["wh"][p][k], 32, 32, 32, 0, 32, 8)
                 if self.fight:
                     lo, n, pad = self.att[k]
-                    shift, ks = _att_image_geometry(lo, n)
-                    put(("watt", p, k), rm["watt"][p][k], pad, pad, shift, ks)
-        put(("ws",), rm["ws"], 512, 256, 0, 32)
+                    shift, ks, nn = _att_image_geometry(lo, n)
+                    put(("watt", p, k), rm["watt"][p][k], n, nn, nn, shift, ks)
+        put(("ws",), rm["ws"], 512, 512, 256, 0, 32)
 
     @torch.no_grad()
     def _fill_row_major(self):
@@ -379,7 +383,7 @@ class FusedActor:
             self.b1[c0:c1] = b
         FusedPolicyPair._to_fragments(self.w1, W)
         img = getattr(self, "img", {})
-        img["w1"] = _pack_image(W, 512, 256, 0, (own + 15) // 16, *img.get("w1", (None, None)))
+        img["w1"] = _pack_image(W, 512, 512, 256, 0, (own + 15) // 16, 1, *img.get("w1", (None, None)))
         if self.fight:
             mha = m.att_act
             e = mha.embed_dim
@@ -390,20 +394,20 @@ class FusedActor:
             self.batt.zero_()
             self.batt[:100] = Wo @ bv + bo
             FusedPolicyPair._to_fragments(self.watt, Wa)
-            shift, ks = _att_image_geometry(400, 100)
-            img["watt"] = _pack_image(Wa, 104, 104, shift, ks, *img.get("watt", (None, None)))
+            shift, ks, nn = _att_image_geometry(400, 100)
+            img["watt"] = _pack_image(Wa, 100, nn, nn, shift, ks, 1, *img.get("watt", (None, None)))
         ws, bs = _lin(m.shared_layer)
         Wsp = torch.zeros((self.NP, self.NW), device=self.dev)
         Wsp[:500, :500] = ws.t()
         FusedPolicyPair._to_fragments(self.ws, Wsp)
-        img["ws"] = _pack_image(Wsp, 512, 256, 0, 32, *img.get("ws", (None, None)))
+        img["ws"] = _pack_image(Wsp, 512, 512, 256, 0, 32, 1, *img.get("ws", (None, None)))
         self.bs.zero_()
         self.bs[:500] = bs
         wa, ba = _lin(m.act_out)
         Wh = torch.zeros((self.NP, self.NH), device=self.dev)
         Wh[:500, :self.n_out] = wa.t()
         FusedPolicyPair._to_fragments(self.wh, Wh)
-        img["wh"] = _pack_image(Wh, 32, 32, 0, 32, *img.get("wh", (None, None)))
+        img["wh"] = _pack_image(Wh, 32, 32, 32, 0, 32, 8, *img.get("wh", (None, None)))
         self.img = img
         self.bh.zero_()
         self.bh[:self.n_out] = ba

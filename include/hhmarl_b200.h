@@ -186,14 +186,17 @@ typedef struct {
  * two fp16 halves of a power-of-two multiple, three kind::f16 MMAs per product, fp32 accumulation in tensor memory
  * (fp32-equivalent; inputs x are expected in [-15.99, 15.99] -- observations are Box(0, 1), env_hetero.py:28-36). */
 int hh_policy_forward_ex(int32_t n_chains, const hh_policy_chain_ex* chains, int32_t precision, void* stream);
-/* Operand image of one weight matrix for precision = 2.  w_dev: fp32 row-major [k_rows][ldw] (K x N, zero-padded), columns
- * [0, n_total) are packed in chunks of n_chunk columns (the MMA N: 256 for the 500-wide layers -> n_total 512; the padded
- * width itself for the attention block and the head), image row k' = w row k' - row_shift (zero outside), ksteps * 16 image
- * rows.  image_dev: hh_policy_image_bytes(ksteps, n_total) bytes; unscale_dev: float[2] = {2^-(12 + s), 2^s}.  Runs on
- * `stream`, no host synchronisation (call it again after the weights changed). */
+/* Operand image of one weight matrix for precision = 2.  w_dev: fp32 row-major [k_rows][ldw] (K x N), of which the first
+ * n_cols columns are packed (zero beyond, up to n_total) in chunks of n_chunk columns (the MMA N: 256 for the 500-wide layers
+ * -> n_total 512; the padded width itself for the attention block -- a multiple of 16 -- and 32 for the head), image row
+ * k' = w row k' - row_shift (zero outside), ksteps * 16 image rows, kps K steps per 16 KB ring stage (1; 8 for the head).
+ * The image is laid out for the kernel hh_policy_tc_pair() selects (1: CTA pairs, each CTA streams half of a chunk's columns).
+ * image_dev: hh_policy_image_bytes(ksteps, n_total) bytes; unscale_dev: float[2] = {2^-(12 + s), 2^s}.  Runs on `stream`, no
+ * host synchronisation (call it again after the weights changed). */
 int64_t hh_policy_image_bytes(int32_t ksteps, int32_t n_total);
-int hh_policy_pack(const float* w_dev, int32_t k_rows, int32_t ldw, int32_t n_total, int32_t n_chunk, int32_t row_shift,
-                   int32_t ksteps, void* image_dev, float* unscale_dev, void* stream);
+int hh_policy_pack(const float* w_dev, int32_t k_rows, int32_t n_cols, int32_t ldw, int32_t n_total, int32_t n_chunk,
+                   int32_t row_shift, int32_t ksteps, int32_t kps, void* image_dev, float* unscale_dev, void* stream);
+int32_t hh_policy_tc_pair(void);
 /* Row lists per key, built on the device: rows_dev int32 [n_keys][n], ranges_dev int32 [n_keys][2] = {k n, count_k} for the
  * arenas i with key_dev[i] == keys_host[k] (n_keys <= 4).  Level 5 draws the opponents' policy set per arena and episode
  * (env_hetero.py:55-59); the lists feed hh_policy_chain_ex.rows / range_dev without a host synchronisation. */

@@ -30,14 +30,6 @@ def timeit(fn, n=30):
 
 
 flops = 2 * B * 2 * (57 * 1000 + 100 * 100 + 150 * 150 + 2 * 500 * 500 + 500 * 27)
-import ctypes  # noqa: E402
-from hhmarl_2d_b200 import _native as nat  # noqa: E402
-for cs in (1, 2, 4):
-    nat.lib().hh_policy_tc_cluster(ctypes.c_int32(cs))
-    fu = FusedPolicyPair(m1, m2, precision=2)
-    us = timeit(lambda: fu.forward(f1, f2))
-    print(f"tcgen05 H3, {cs} CTA(s) per weight stream: {us:8.1f} us  ({flops / us / 1e6:6.1f} TFLOP/s useful)")
-nat.lib().hh_policy_tc_cluster(ctypes.c_int32(2))
 for prec, name in ((2, "tcgen05 H3"), (0, "fused 3xTF32"), (1, "fused TF32")):
     fu = FusedPolicyPair(m1, m2, precision=prec)
     us = timeit(lambda: fu.forward(f1, f2))

@@ -12,11 +12,9 @@ from hhmarl_2d_b200 import models as M  # noqa: E402
 from hhmarl_2d_b200.fused_forward import FusedPolicyPair  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
-cluster = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 L = nat.lib()
 L.hh_policy_tc_profile.argtypes = [ctypes.c_void_p]
-L.hh_policy_tc_cluster.argtypes = [ctypes.c_int32]
-assert L.hh_policy_tc_cluster(cluster) == 0
+cluster = 2 if L.hh_policy_tc_pair() else 1
 torch.manual_seed(0)
 m1, m2 = M.build_policy_pair("fight")
 m1.cuda(); m2.cuda()
@@ -26,26 +24,37 @@ for _ in range(3):
     fu.forward(f1, f2)
 tiles = (B + 63) // 64
 tiles = (tiles + cluster - 1) // cluster * cluster
-buf = torch.zeros(4 * tiles * 32, dtype=torch.int64, device="cuda")
-L.hh_policy_tc_profile(buf.data_ptr())
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-fu.forward(f1, f2)
-e1.record()
-torch.cuda.synchronize()
-L.hh_policy_tc_profile(None)
-s = buf.view(4, tiles, 32).cpu().double()
-t0 = s[:, :, 0:1]
-rel = s - t0
 names = {1: "seg0 L1h0 start", 2: "seg0 end", 3: "seg1 L1h1 start", 4: "seg1 end", 5: "seg2 ATT start", 6: "seg2 end",
          7: "seg3 SHh0 start", 8: "seg3 end", 9: "seg4 SHh1 start", 10: "seg4 end", 11: "seg5 HEADa start", 12: "seg5 end",
          13: "seg6 HEADb start", 14: "seg6 end", 16: "epi L1h0 begin", 17: "epi L1h0 end", 18: "epi L1h1 begin", 19: "epi L1h1 end",
          20: "epi ATT begin", 21: "epi ATT end", 22: "epi SH begin", 23: "epi SHh0 end", 24: "epi SHh1 end", 25: "epi HEAD begin",
          26: "epi done", 29: "producer done"}
-print(f"rows {B}, cluster {cluster}: launch {e0.elapsed_time(e1) * 1e3:.1f} us (with stamps); cycles relative to the MMA thread's start, "
-      f"median over {4 * tiles} CTAs [actor chain 0 | critic chain 1]")
-for k in sorted(names):
-    a, c = rel[0, :, k].median().item(), rel[1, :, k].median().item()
-    print(f"  {names[k]:18s} {a:9.0f} {c:9.0f}")
-print(f"  MMA thread waiting for weight stages (sum): {s[0, :, 15].median().item():9.0f} {s[1, :, 15].median().item():9.0f}")
-print(f"  producer waiting for free slots (sum):      {s[0, :, 28].median().item():9.0f} {s[1, :, 28].median().item():9.0f}")
+L.hh_policy_tc_debug.argtypes = [ctypes.c_int32]
+modes = [(0, "normal")] + ([(1, "DEBUG no weight copies (timing only)"), (2, "DEBUG no MMAs (timing only)")] if len(sys.argv) > 2 else [])
+for flags, label in modes:
+    L.hh_policy_tc_debug(flags)
+    buf = torch.zeros(4 * tiles * 32, dtype=torch.int64, device="cuda")
+    L.hh_policy_tc_profile(buf.data_ptr())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fu.forward(f1, f2)
+    e1.record()
+    torch.cuda.synchronize()
+    L.hh_policy_tc_profile(None)
+    L.hh_policy_tc_debug(0)
+    s = buf.view(4, tiles, 32).cpu().double()
+    print(f"== {label}: rows {B}, {'CTA pairs (cta_group::2)' if cluster == 2 else 'one CTA per tile'}: launch {e0.elapsed_time(e1) * 1e3:.1f} us "
+          f"(with stamps); cycles relative to the start stamp of warp 1 of the same CTA, median over the CTAs of [actor chain 0 | critic chain 1]")
+    for rank in range(cluster):
+        sr = s[:, rank::cluster, :]
+        rel = sr - sr[:, :, 0:1]
+        if cluster == 2:
+            print(f" CTA rank {rank} of the pair ({'MMA issue' if rank == 0 else 'relay: segment stamps = its waits for its own stages'})")
+        for k in sorted(names):
+            if flags and not (7 <= k <= 10):
+                continue
+            a, c = rel[0, :, k].median().item(), rel[1, :, k].median().item()
+            print(f"  {names[k]:18s} {a:9.0f} {c:9.0f}")
+        print(f"  warp 1 waiting for weight stages (sum):     {sr[0, :, 15].median().item():9.0f} {sr[1, :, 15].median().item():9.0f}")
+        print(f"  producer waiting for free slots (sum):      {sr[0, :, 28].median().item():9.0f} {sr[1, :, 28].median().item():9.0f}")
+        print(f"  warp 1 cycles in MMA issue / in commits:    {sr[0, :, 30].median().item():9.0f} {sr[0, :, 31].median().item():9.0f}")

@@ -78,7 +78,8 @@ def test_policy_forward_validates_arguments_without_a_gpu():
     assert b"chain" in L.hh_policy_last_error()
     assert L.hh_policy_forward_ex(1, one, 2, None) == -1            # tcgen05 path: same checks before any CUDA call
     assert L.hh_policy_image_bytes(32, 512) == 32 * 512 * 64        # one K = 16 step of n columns: hi + lo halves
-    assert L.hh_policy_pack(None, 504, 512, 512, 256, 0, 32, None, None, None) == -1
+    assert L.hh_policy_pack(None, 504, 512, 512, 512, 256, 0, 32, 1, None, None, None) == -1
+    assert L.hh_policy_tc_pair() in (0, 1)
     four = (nat.HHPolicyChain * 4)()
     assert L.hh_policy_forward(0, four, None, None, 0, None) == -1
     assert L.hh_step_host_begin(None, None) == -1 and L.hh_step_host_end(None, None, None, None, None) == -1

@@ -312,24 +312,30 @@ def test_fused_policy_forward_matches_torch(mode):
 
 
 def test_policy_pack_image_layout():
-    """hh_policy_pack: fp16 hi / lo halves of 2^s w in the K-major canonical layout, stage after stage (csrc/hh_policy_tc.cu)."""
+    """hh_policy_pack: fp16 hi / lo halves of 2^s w in the K-major canonical layout, ring stage after ring stage; for the
+    CTA-pair kernel every stage is split into the two CTAs' column halves (csrc/hh_policy_tc.cu)."""
+    from hhmarl_2d_b200 import _native as nat
     from hhmarl_2d_b200.fused_forward import _pack_image
     torch.manual_seed(0)
-    for (K, ld, n_total, n_chunk, shift, ksteps) in ((72, 512, 512, 256, 0, 5), (152, 152, 152, 152, 6, 10), (504, 32, 32, 32, 0, 32)):
+    split = 1 + nat.lib().hh_policy_tc_pair()
+    for (K, ld, n_cols, n_total, n_chunk, shift, ksteps, kps) in ((72, 512, 512, 512, 256, 0, 5, 1), (152, 152, 150, 160, 160, 6, 10, 1),
+                                                                  (504, 32, 32, 32, 32, 0, 32, 8)):
         w = (torch.randn(K, ld, device="cuda") * 0.05).contiguous()
         w[3, 5] = 0.0
-        img, us = _pack_image(w, n_total, n_chunk, shift, ksteps)
+        img, us = _pack_image(w, n_cols, n_total, n_chunk, shift, ksteps, kps)
         torch.cuda.synchronize()
         unscale, scale = us.tolist()
-        assert 8192 <= w[:, :n_total].abs().max().item() * scale < 16384 and abs(unscale * scale * 4096 - 1) < 1e-12
-        h = img.view(torch.float16).view(n_total // n_chunk, ksteps, 2, 2, n_chunk, 8).float()   # [chunk][kstep][hi|lo][khalf][c][kk]
-        rec = (h[:, :, 0] + h[:, :, 1]) / scale                                                   # [chunk][kstep][khalf][c][kk]
-        rec = rec.permute(1, 2, 4, 0, 3).reshape(ksteps * 16, n_total)                            # [k'][col]
+        assert 8192 <= w[:, :n_cols].abs().max().item() * scale < 16384 and abs(unscale * scale * 4096 - 1) < 1e-12
+        n_sub, n_stage = n_chunk // split, ksteps // kps
+        # [chunk][stage][cta][kstep in stage][hi|lo][khalf][column of the CTA's half][kk]
+        h = img.view(torch.float16).view(n_total // n_chunk, n_stage, split, kps, 2, 2, n_sub, 8).float()
+        rec = (h[:, :, :, :, 0] + h[:, :, :, :, 1]) / scale                      # [chunk][stage][cta][j][khalf][cs][kk]
+        rec = rec.permute(1, 3, 4, 6, 0, 2, 5).reshape(ksteps * 16, n_total)    # [(stage, j, khalf, kk)][(chunk, cta, cs)]
         want = torch.zeros(ksteps * 16, n_total, device="cuda")
         rows = min(K, ksteps * 16 - shift)
-        want[shift:shift + rows] = w[:rows, :n_total]
+        want[shift:shift + rows, :n_cols] = w[:rows, :n_cols]
         assert (rec - want).abs().max().item() <= 2.0 ** -21 * w.abs().max().item()
-        assert (h[:, :, 1].abs() <= h[:, :, 0].abs() * 2.0 ** -10 + 1e-30).all()                   # lo is the rounding residue of hi
+        assert (h[:, :, :, :, 1].abs() <= h[:, :, :, :, 0].abs() * 2.0 ** -10 + 1e-30).all()     # lo is the rounding residue of hi
 
 
 @pytest.mark.parametrize("precision", [2, 0])
