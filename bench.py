@@ -483,16 +483,22 @@ def run_b200(args):
                 except Exception:  # noqa: BLE001
                     pass
                 issued = 3 * 2 * macs_issued * rows_pad / (kern_us * 1e-6) / 1e12
+                ptraffic, ptensor = None, None
+                try:
+                    pj = json.load(open(os.path.join(ROOT, "profiles", "policy_kernel_traffic.json")))
+                    ptraffic, ptensor = pj.get("dram_bytes_per_launch"), pj.get("tensor_pipe_active_pct")
+                except Exception:  # noqa: BLE001
+                    pass
                 rollout["roofline"] = {
                     "bound": "tensor", "achieved": issued, "peak": peak_tf, "unit": "TFLOP/s", "frac": issued / peak_tf,
-                    "traffic": None, "peak_source": peak_src2, "kernel": "hh::tc::policy_forward_tc_kernel", "kernel_us": kern_us,
+                    "traffic": ptraffic, "tensor_pipe_active_pct_ncu": ptensor, "peak_source": peak_src2, "kernel": "hh::tc::policy_forward_tc_kernel", "kernel_us": kern_us,
                     "useful_tflops": 2 * macs_useful * n / (kern_us * 1e-6) / 1e12,
                     "useful_flop_per_launch": 2 * macs_useful * n, "issued_flop_per_launch": 3 * 2 * macs_issued * rows_pad,
                     "share_of_rollout_tick": kern_us * 1e-3 / rollout[tag]["ms_per_tick"],
                     "note": "fp32-equivalent forward = 3 kind::f16 MMAs per product on zero-padded tiles (K to 16, N to 256 / 104 / "
                             "152 / 32): `achieved` counts the MMA work issued, `useful_tflops` the reference's own multiply-adds.  "
-                            "An M = 64 tile runs the tensor pipe at half the M = 128 rate (profiles/r2a_tcgen05_probe.txt), and the "
-                            "kernel is bound by the weight stream from L2 (profiles/README.md, round 2)"}
+                            "An M = 64 tile runs the tensor pipe at half the M = 128 rate (profiles/r2a_tcgen05_probe.txt), so 0.5 is the "
+                            "ceiling of `frac` for this tile shape; ncu: tensor pipe active 48 % of the cycles (profiles/r2q_policy_forward_ncu.md)"}
             del smp, env_r
         rollout["fragment_len"] = Tf
         if cpu_base is not None:   # N = 1, rank 0: the reference-style rollout worker on one host core, bounded sample
@@ -753,11 +759,24 @@ def run_b200(args):
                 pass
         kern_ms = total_ms / K                      # one kernel per step: event bracket == the launch
         achieved = ALGO_BYTES_PER_ENV_STEP * n / (kern_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, attainable = None, None
         tp = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                tj = json.load(open(tp))
+                traffic = tj.get("dram_bytes_per_launch")
+                if tj.get("issue_active_pct") and n == 8192:
+                    # the bound this kernel can actually approach: its 4.44 M warp instructions on 148 x 4 issue slots
+                    w = float(tj["warp_instructions_per_launch"])
+                    attainable = {"bound": "issue slots", "achieved_pct_of_peak": tj["issue_active_pct"],
+                                  "fp64_pipe_active_pct": tj.get("fp64_pipe_active_pct"),
+                                  "warp_instructions_per_launch": w,
+                                  "floor_us_at_full_issue": w / (148 * 4) / 1.965e3,
+                                  "stall_no_instruction_per_issue": tj.get("stall_no_instruction_per_issue"),
+                                  "source": tj.get("counters_source"),
+                                  "note": "measured ncu counters: the step is a chain of ten barrier-separated stages with one or two "
+                                          "warps per scheduler; instruction fetch (no_instruction) and fixed FP64 latencies (wait) leave "
+                                          "three of four issue slots empty -- it is latency-bound, neither DRAM- nor FP64-throughput-bound"}
             except Exception:  # noqa: BLE001
                 pass
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -784,7 +803,7 @@ def run_b200(args):
                              "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * n,
                              "kernel": {"quad": "hh::step_kernel<3,0>", "cta": "hh::step_kernel_cta<3,0>"}.get(
                                  os.environ.get("HH_STEP_IMPL", "v4"), "hh::step_kernel_v4<3,0>"),
-                             "kernel_ms": kern_ms,
+                             "kernel_ms": kern_ms, "attainable": attainable,
                              "note": "bound by the dependent FP64 instruction chain of one CTA's step phases, not by DRAM: see DESIGN.md section 4"},
                 "clocks": clocks}
         if cpu_base is not None:

@@ -113,6 +113,78 @@ __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
                "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(bar)
                : "memory");
 }
+// lean forms for the issue loops: descriptors as (low word, constant high word); only the low word (address, LBO) changes
+constexpr uint32_t kDescHi = (SBO >> 4) | (1u << 14);       // stride byte offset 128, descriptor version 1, no swizzle
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16); }
+template <int GROUP, bool ACC1>
+__device__ __forceinline__ void umma_lean(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  if (GROUP == 2) {
+    if (ACC1)
+      asm volatile("{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\telect.sync _|q, 0xffffffff;\n\t"
+                   "setp.eq.u32 p, 0, 0;\n\t@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(tmem_d),
+                   "r"(a_lo), "r"(b_lo), "r"(kDescHi), "r"(idesc)
+                   : "memory");
+    else
+      asm volatile("{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\telect.sync _|q, 0xffffffff;\n\t"
+                   "setp.ne.b32 p, %5, 0;\n\t@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(tmem_d),
+                   "r"(a_lo), "r"(b_lo), "r"(kDescHi), "r"(idesc), "r"(accumulate)
+                   : "memory");
+  } else {
+    if (ACC1)
+      asm volatile("{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\telect.sync _|q, 0xffffffff;\n\t"
+                   "setp.eq.u32 p, 0, 0;\n\t@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(tmem_d),
+                   "r"(a_lo), "r"(b_lo), "r"(kDescHi), "r"(idesc)
+                   : "memory");
+    else
+      asm volatile("{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\telect.sync _|q, 0xffffffff;\n\t"
+                   "setp.ne.b32 p, %5, 0;\n\t@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(tmem_d),
+                   "r"(a_lo), "r"(b_lo), "r"(kDescHi), "r"(idesc), "r"(accumulate)
+                   : "memory");
+  }
+}
+// One K = 16 step of the split product in ONE asm block: A_lo B_hi (accumulate flag), A_hi B_lo, A_hi B_hi.  The five
+// descriptor words enter once (each vector -> uniform register move costs the issuing warp ~10 cycles; as three separate
+// blocks that was ~100 cycles per MMA -- more than a cta_group::2 MMA takes to execute).
+template <int GROUP>
+__device__ __forceinline__ void umma3_lean(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_hi, uint32_t b_lo, uint32_t idesc,
+                                           uint32_t accumulate) {
+  if (GROUP == 2)
+    asm volatile(
+        "{\n\t.reg .pred p, t, q;\n\t.reg .b32 hi;\n\t.reg .b64 dal, dah, dbh, dbl;\n\t"
+        "mov.u32 hi, 0x4008;\n\t"
+        "mov.b64 dal, {%1, hi};\n\tmov.b64 dah, {%2, hi};\n\tmov.b64 dbh, {%3, hi};\n\tmov.b64 dbl, {%4, hi};\n\t"
+        "elect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %6, 0;\n\tsetp.eq.u32 t, 0, 0;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], dal, dbh, %5, p;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], dah, dbl, %5, t;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], dah, dbh, %5, t;\n\t}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_hi), "r"(b_lo), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p, t, q;\n\t.reg .b32 hi;\n\t.reg .b64 dal, dah, dbh, dbl;\n\t"
+        "mov.u32 hi, 0x4008;\n\t"
+        "mov.b64 dal, {%1, hi};\n\tmov.b64 dah, {%2, hi};\n\tmov.b64 dbh, {%3, hi};\n\tmov.b64 dbl, {%4, hi};\n\t"
+        "elect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %6, 0;\n\tsetp.eq.u32 t, 0, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], dal, dbh, %5, p;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], dah, dbl, %5, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], dah, dbh, %5, t;\n\t}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_hi), "r"(b_lo), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+static_assert(kDescHi == 0x4008u, "the descriptor's constant high word is spelled out in umma3_lean");
+// warp-uniform wait: every lane polls, the loop condition is a vote -> control flow (and everything computed under it) stays
+// warp-uniform for the compiler
+__device__ __forceinline__ void mbar_wait_uniform(uint32_t bar, uint32_t parity) {
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    if (__all_sync(0xffffffffu, ok)) break;
+    if (spin > (1u << 28)) __trap();
+  }
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -349,36 +421,32 @@ __global__ void __launch_bounds__(kThreads, 1) policy_forward_tc_kernel(const __
       uint32_t slot = 0, phase = 0;
       long long stall = 0;
       if (prof && lane == 0) prof[0] = (unsigned long long)clock64();
-      mbar_wait(bar0 + 8 * (B_ACT + 5), 0);           // the input tile is in shared memory
-      const uint64_t ring_desc = smem_desc(smem_u32(smem + OFF_RING), 0, SBO);
+      mbar_wait_uniform(bar0 + 8 * (B_ACT + 5), 0);   // the input tile is in shared memory
       for (int s = 0; s < C.n_seg; ++s) {
         const Seg& g = C.seg[s];
         const uint32_t n = g.n, kps = g.kps, n_stage = g.ksteps / kps;
-        if (g.wait_act != 0xff) mbar_wait(bar0 + 8 * (B_ACT + g.wait_act), 0);
+        if (g.wait_act != 0xff) mbar_wait_uniform(bar0 + 8 * (B_ACT + g.wait_act), 0);
         if (prof && lane == 0) prof[1 + 2 * s] = (unsigned long long)clock64();
         fence_tc_after();
         const uint32_t idesc = instr_desc_f16(TM, n);
-        const uint32_t a_hi = smem_u32(smem + (g.a_src ? OFF_ACT_HI : OFF_X_HI)) + 16u * g.a_off16;
-        uint64_t da_hi = smem_desc(a_hi, LBO_A, SBO);
-        uint64_t da_lo = smem_desc(a_hi + (g.a_src ? ACT_BYTES : X_BYTES), LBO_A, SBO);
-        const uint64_t db_seg = ring_desc | ((uint64_t)n << 16);          // leading byte offset of B = 16 n bytes
+        const uint32_t a_addr = smem_u32(smem + (g.a_src ? OFF_ACT_HI : OFF_X_HI)) + 16u * g.a_off16;
+        uint32_t a_hi = desc_lo(a_addr, LBO_A), a_lo = desc_lo(a_addr + (g.a_src ? ACT_BYTES : X_BYTES), LBO_A);
+        const uint32_t b_seg = desc_lo(smem_u32(smem + OFF_RING), 16u * n);   // leading byte offset of B = 16 n bytes
         const uint32_t lo_off = 2u * n, step_off = 4u * n;                // B lo block, next K step (16-byte units)
         const uint32_t d = tmem + g.tmem_col;
         uint32_t acc = g.first ? 0u : 1u;
         for (uint32_t k = 0; k < n_stage; ++k) {
           const long long t0 = prof ? clock64() : 0;
-          mbar_wait(bar0 + 8 * (B_FULL + slot), phase);
+          mbar_wait_uniform(bar0 + 8 * (B_FULL + slot), phase);
           if (prof) stall += clock64() - t0;
           fence_tc_after();
-          uint64_t db = db_seg + (uint64_t)(slot * (STAGE_BYTES >> 4));
+          uint32_t b = b_seg + slot * (STAGE_BYTES >> 4);
           for (uint32_t j = 0; j < kps; ++j) {
-            umma_f16_elect(d, da_lo, db, idesc, acc);                // small terms first
-            umma_f16_elect(d, da_hi, db + lo_off, idesc, 1u);
-            umma_f16_elect(d, da_hi, db, idesc, 1u);
+            umma3_lean<1>(d, a_lo, a_hi, b, b + lo_off, idesc, acc);   // small terms first
             acc = 1u;
-            da_hi += (2 * LBO_A) >> 4;
-            da_lo += (2 * LBO_A) >> 4;
-            db += step_off;
+            a_hi += (2 * LBO_A) >> 4;
+            a_lo += (2 * LBO_A) >> 4;
+            b += step_off;
           }
           // the slot is free once these MMAs have read it -- in every CTA of the cluster
           if (CS == 1) umma_commit_elect(bar0 + 8 * (B_EMPTY + slot));
@@ -576,7 +644,7 @@ __global__ void __launch_bounds__(kThreads, 1) policy_forward_tc_kernel(const __
 }
 
 // =====================================================================================================================
-// CTA-PAIR form (default): two CTAs of a cluster = two 64-row tiles of the same chain share ONE weight stream.  Every
+// CTA-PAIR form (HH_TC_PAIR=1; see g_pair below for why it is not the default): two CTAs of a cluster = two 64-row tiles of the same chain share ONE weight stream.  Every
 // MMA is a tcgen05.mma.cta_group::2 of M = 128 issued by the pair's CTA 0: each CTA supplies its own 64 activation rows
 // and HALF of the weight columns of the step (its ring holds 8 KB per K step instead of 16), so the bytes an SM pulls
 // from L2 per row halve -- the single-CTA kernel above is bound by exactly that stream -- and the pair's tensor cores run
@@ -760,7 +828,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) policy_
         const int n_stage = g.ksteps / g.kps;
         for (int k = 0; k < n_stage; ++k) {
           const long long t0 = prof ? clock64() : 0;
-          mbar_spin(bar0 + 8 * (P_EMPTY + slot), phase ^ 1);
+          if (!(slot & 1u)) mbar_spin(bar0 + 8 * (P_EMPTY + slot + 1), phase ^ 1);   // slots are released in pairs (odd slot's barrier)
           if (prof) stall += clock64() - t0;
           if (args.debug & 1) {
             mbar_arrive(bar0 + 8 * (P_FULL + slot));
@@ -809,7 +877,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) policy_
       long long stall = 0, t_mma = 0, t_commit = 0;
       if (prof && lane == 0) prof[0] = (unsigned long long)clock64();
       mbar_wait_cluster(bar0 + 8 * (P_ACT + 5), 0);           // both input tiles are in shared memory
-      const uint64_t ring_desc = smem_desc(ring, 0, SBO);
       for (int s = 0; s < C.n_seg; ++s) {
         const Seg& g = C.seg[s];
         const uint32_t n = g.n, kps = g.kps, n_stage = g.ksteps / kps;
@@ -817,36 +884,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) policy_
         if (prof && lane == 0) prof[1 + 2 * s] = (unsigned long long)clock64();
         fence_tc_after();
         const uint32_t idesc = instr_desc_f16(2 * TM, n);
-        const uint32_t a_hi = smem_u32(smem + (g.a_src ? OFF_ACT_HI : OFF_X_HI)) + 16u * g.a_off16;
-        uint64_t da_hi = smem_desc(a_hi, LBO_A, SBO);
-        uint64_t da_lo = smem_desc(a_hi + (g.a_src ? ACT_BYTES : X_BYTES), LBO_A, SBO);
-        const uint64_t db_seg = ring_desc | ((uint64_t)(n >> 1) << 16);   // a CTA holds n / 2 weight columns: LBO = 16 (n / 2) bytes
+        const uint32_t a_addr = smem_u32(smem + (g.a_src ? OFF_ACT_HI : OFF_X_HI)) + 16u * g.a_off16;
+        uint32_t a_hi = desc_lo(a_addr, LBO_A), a_lo = desc_lo(a_addr + (g.a_src ? ACT_BYTES : X_BYTES), LBO_A);
+        const uint32_t b_seg = desc_lo(ring, 8u * n);                     // a CTA holds n / 2 weight columns: LBO = 16 (n / 2) bytes
         const uint32_t lo_off = n, step_off = 2u * n;                     // B lo block, next K step (16-byte units)
         const uint32_t d = tmem + g.tmem_col;
         uint32_t acc = g.first ? 0u : 1u;
         for (uint32_t k = 0; k < n_stage; ++k) {
           const long long t0 = prof ? clock64() : 0;
-          mbar_spin(bar0 + 8 * (P_FULL + slot), phase);     // the tensor cores read the stage (async proxy): no thread-level acquire needed
+          mbar_wait_uniform(bar0 + 8 * (P_FULL + slot), phase);   // the tensor cores read the stage (async proxy): no thread-level acquire
           if (prof) stall += clock64() - t0;
           fence_tc_after();
-          uint64_t db = db_seg + (uint64_t)(slot * (STAGE2_BYTES >> 4));
+          uint32_t b = b_seg + slot * (STAGE2_BYTES >> 4);
           const long long t1 = prof ? clock64() : 0;
           for (uint32_t j = 0; j < kps && !(args.debug & 2); ++j) {
-            umma2_f16_elect(d, da_lo, db, idesc, acc);                // small terms first
-            umma2_f16_elect(d, da_hi, db + lo_off, idesc, 1u);
-            umma2_f16_elect(d, da_hi, db, idesc, 1u);
+            umma3_lean<2>(d, a_lo, a_hi, b, b + lo_off, idesc, acc);   // small terms first
             acc = 1u;
-            da_hi += (2 * LBO_A) >> 4;
-            da_lo += (2 * LBO_A) >> 4;
-            db += step_off;
+            a_hi += (2 * LBO_A) >> 4;
+            a_lo += (2 * LBO_A) >> 4;
+            b += step_off;
           }
           const long long t2 = prof ? clock64() : 0;
-          // both rings' slots are free once these MMAs have read them; slots are released two at a time (a commit after
-          // every stage was measured to slow the MMA stream down)
-          if ((k & 1u) || k + 1 == n_stage) {
-            if (k & 1u) umma2_commit_both_elect(bar0 + 8 * (P_EMPTY + (slot == 0 ? NSTAGE2 - 1 : slot - 1)));
-            umma2_commit_both_elect(bar0 + 8 * (P_EMPTY + slot));
-          }
+          // both rings' slots are free once these MMAs have read them.  Slots are released in PAIRS (one multicast commit
+          // per two stages, on the odd slot's barrier, which the producers wait for before refilling the even slot)
+          if (slot & 1u) umma2_commit_both_elect(bar0 + 8 * (P_EMPTY + slot));
           if (prof) {
             t_mma += t2 - t1;
             t_commit += clock64() - t2;
@@ -1074,9 +1135,14 @@ __global__ void pack_image_kernel(const float* __restrict__ w, int k_rows, int n
 
 // tuning / profiling knobs of the tcgen05 path (tests and profiles/ only)
 static unsigned long long* g_prof = nullptr;
-static int g_pair = [] {            // 1 (default): CTA-pair kernel (cta_group::2); 0: one CTA per tile (HH_TC_PAIR=0)
+// 0 (default): one CTA per 64-row tile; 1 (HH_TC_PAIR=1): the CTA-pair kernel (cta_group::2).  Measured at 8 192 rows x 4 chains
+// (profiles/README.md, round 2): 143 us against 185 us -- the pair form halves the weight bytes per SM and its MMAs run at
+// twice the rate, but every MMA costs the issuing warp ~100 cycles (seven vector -> uniform register moves per UTCHMMA), more
+// than a cta_group::2 MMA takes to execute, and the pair's extra signalling (relay, multicast commits) is on the critical
+// path; it stays in the library as a tested variant.
+static int g_pair = [] {
   const char* e = getenv("HH_TC_PAIR");
-  return (e && atoi(e) == 0) ? 0 : 1;
+  return (e && atoi(e) == 1) ? 1 : 0;
 }();
 extern "C" int hh_policy_tc_profile(unsigned long long* stamps_dev) {   // 32 clock64() stamps per CTA, null = off
   g_prof = stamps_dev;

@@ -311,6 +311,45 @@ def test_fused_policy_forward_matches_torch(mode):
         torch.backends.cuda.matmul.allow_tf32 = prev
 
 
+def test_pair_kernel_variant_matches_torch():
+    """HH_TC_PAIR=1: the CTA-pair form of the tcgen05 forward (cta_group::2 MMAs, each CTA streams half of the weight columns,
+    relay + multicast commits) -- not the default (profiles/README.md, round 2), kept as a tested variant.  Runs in a
+    subprocess because the layout of the packed images is fixed when the library is loaded."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import torch\n"
+        "from hhmarl_2d_b200 import _native as nat, models as M\n"
+        "from hhmarl_2d_b200.fused_forward import FusedPolicyPair, FusedActor, run_chains\n"
+        "assert nat.lib().hh_policy_tc_pair() == 1\n"
+        "torch.manual_seed(1)\n"
+        "worst = 0.0\n"
+        "for mode in ('fight', 'escape'):\n"
+        "    m1, m2 = M.build_policy_pair(mode); m1.cuda(); m2.cuda()\n"
+        "    for m in (m1, m2):\n"
+        "        for p in m.parameters():\n"
+        "            if p.dim() == 1: torch.nn.init.normal_(p, std=0.1)\n"
+        "    for B in (1037, 64, 1):\n"
+        "        f1 = torch.rand(B, m1.central_dim, device='cuda'); f2 = torch.rand(B, m1.central_dim, device='cuda')\n"
+        "        with torch.no_grad():\n"
+        "            ref = (*m1.forward_flat(f1), *m2.forward_flat(f2))\n"
+        "        out = FusedPolicyPair(m1, m2, precision=2).forward(f1, f2)\n"
+        "        worst = max(worst, max((a - b).abs().max().item() for a, b in zip(out, ref)))\n"
+        "    fa = FusedActor(m1)\n"
+        "    x = torch.rand(300, 30, device='cuda'); o = torch.empty(300, fa.n_out, device='cuda')\n"
+        "    run_chains([lambda c: fa.fill_chain(c, x, 300, out=o)], torch.device('cuda'), 2)\n"
+        "    with torch.no_grad():\n"
+        "        worst = max(worst, (o - m1.actor(x[:, :fa.d_in])).abs().max().item())\n"
+        "print('WORST', worst)\n"
+        "assert worst < 3e-5\n")
+    env = dict(os.environ, HH_TC_PAIR="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "WORST" in r.stdout
+
+
 def test_policy_pack_image_layout():
     """hh_policy_pack: fp16 hi / lo halves of 2^s w in the K-major canonical layout, ring stage after ring stage; for the
     CTA-pair kernel every stage is split into the two CTAs' column halves (csrc/hh_policy_tc.cu)."""
