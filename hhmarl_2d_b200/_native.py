@@ -197,6 +197,8 @@ def bind(L: ctypes.CDLL, partial: bool = False) -> ctypes.CDLL:
         getattr(L, fn).restype = ctypes.c_int
     L.hh_hier_end.argtypes = [VP, VP, VP, VP, VP, VP]
     L.hh_hier_end.restype = ctypes.c_int
+    L.hh_hier_policy_rows.argtypes = [VP, VP, VP, VP, VP]
+    L.hh_hier_policy_rows.restype = ctypes.c_int
     L.hh_hier_eval_info.argtypes = [VP, VP, VP]
     L.hh_hier_eval_info.restype = ctypes.c_int
     L.hh_hier_get_state.argtypes = [VP, VP]
@@ -214,7 +216,7 @@ def bind(L: ctypes.CDLL, partial: bool = False) -> ctypes.CDLL:
 EXPORTS = ["hh_create", "hh_destroy", "hh_n_arenas", "hh_obs_dim", "hh_reset", "hh_step", "hh_step_begin", "hh_step_finish", "hh_reset_host",
            "hh_step_host", "hh_step_host_begin", "hh_step_host_end", "hh_host_buffers", "hh_set_host_mode", "hh_get_state", "hh_set_state", "hh_launch_count", "hh_gae", "hh_gae_agents", "hh_sample_actions", "hh_pack_central", "hh_debug_geodesic", "hh_last_error", "hh_version", "hh_policy_forward", "hh_policy_forward_ex", "hh_policy_pack", "hh_policy_image_bytes", "hh_policy_tc_pair", "hh_policy_rows_by_key", "hh_policy_last_error",
            "hh_hier_create", "hh_hier_destroy", "hh_hier_reset", "hh_hier_begin", "hh_hier_agents", "hh_hier_tick",
-           "hh_hier_end", "hh_hier_eval_info", "hh_hier_get_state", "hh_hier_set_state", "hh_hier_launch_count", "hh_hier_last_error"]
+           "hh_hier_end", "hh_hier_policy_rows", "hh_hier_eval_info", "hh_hier_get_state", "hh_hier_set_state", "hh_hier_launch_count", "hh_hier_last_error"]
 
 
 def check(rc: int, what: str):

@@ -142,7 +142,7 @@ __device__ int lowlevel_obs(Arena& A, const Geom& g, int i, float* out) {
   if (A.ca[i] != 0) {  // fight_state_values (env_base.py:111-135) against the commander's choice
     int idx = A.ca[i] - 1;
     if (idx < 0) idx += A.ota_n[i];
-    if (idx < 0 || idx >= A.ota_n[i]) { A.err |= 128; idx = 0; }
+    if (idx < 0 || idx >= A.ota_n[i]) { atomicOr(&A.err, 128); idx = 0; }
     const int o = A.ota_id[i][idx];
     const double dn = A.ota_dn[i][idx];  // stale distance of the commander step
     out[n++] = (float)focus_norm_from_deg(fdeg(A, i, o));
@@ -174,6 +174,18 @@ __device__ int lowlevel_obs(Arena& A, const Geom& g, int i, float* out) {
   n += 5;
   for (int k = n; k < LL_STRIDE; ++k) out[k] = 0.0f;
   return n;
+}
+
+__device__ void write_ll_unit(Arena& A, const Geom& g, int i, float* row, uint8_t* info_out) {
+  // bits 1-2 (policy kind) are constant for the whole commander step, bit 0 = the unit queries its policy now
+  uint8_t info = (A.ca[i] == 0 ? 2 : 0) | (A.actype[i] == 2 ? 4 : 0);
+  if (A.active && A.alive[i]) {
+    lowlevel_obs(A, g, i, row);
+    info |= 1;
+  } else {
+    for (int k = 0; k < LL_STRIDE; ++k) row[k] = 0.0f;
+  }
+  *info_out = info;
 }
 
 __device__ void write_ll(Arena& A, const Geom& g, int first, float* ll_obs, uint8_t* ll_info) {
@@ -361,6 +373,120 @@ __device__ void do_tick(Arena& A, const Rng& rng, const HParams& P, Events& ev) 
   }
 }
 
+// ---- the same tick, split for the staged kernels (tick_kernel below): every unit's rate limits and its one-tick move are
+// independent of the other units (a shooter's cannon test reads only POSITIONS of the others and its OWN heading), so they run
+// unit-parallel ahead of the id-ordered pass, which commits the positions in id order (targets with a lower id are seen at
+// their new position, higher ids at their old one, the shooter itself at its old one: cmano_simulator.py:142, ac1.py:81-133).
+struct TickTmp {
+  double nlat[NU], nlon[NU];   // aircraft positions after this tick's move
+  uint8_t alive0[NU], ralive0[NU], rmove[NU];
+};
+
+__device__ void tick_unit_prepare(Arena& A, const HParams& P, int i, TickTmp& T) {   // one thread per (arena, unit)
+  T.alive0[i] = A.alive[i];
+  T.ralive0[i] = A.ralive[i];
+  T.rmove[i] = 0;
+  if (!A.alive[i]) return;
+  const bool ac1 = A.actype[i] == 1;
+  const double max_deg = ac1 ? 5.0 : 3.5, max_kn = ac1 ? 35.0 : 28.0;
+  if (A.hdg[i] != A.nhdg[i]) {
+    const double d = signed_heading_diff(A.hdg[i], A.nhdg[i]);
+    A.hdg[i] = fabs(d) <= max_deg ? A.nhdg[i] : pymod(A.hdg[i] + (d >= 0.0 ? max_deg : -max_deg), 360.0);
+  }
+  if (A.spd[i] != A.nspd[i]) {
+    const double d = A.nspd[i] - A.spd[i];
+    A.spd[i] = fabs(d) <= max_kn ? A.nspd[i] : A.spd[i] + (d >= 0.0 ? max_kn : -max_kn);
+  }
+  T.nlat[i] = A.lat[i];
+  T.nlon[i] = A.lon[i];
+  if (A.spd[i] > 0.0) {
+    const double2 q = P.short_moves ? geo::direct_tick(A.lat[i], A.lon[i], A.hdg[i], A.spd[i] * kKnotsToMs * 1.0)
+                                   : geo::direct(A.lat[i], A.lon[i], A.hdg[i], A.spd[i] * kKnotsToMs * 1.0);
+    T.nlat[i] = q.x;
+    T.nlon[i] = q.y;
+  }
+}
+
+__device__ void tick_resolve(Arena& A, const Rng& rng, const HParams& P, TickTmp& T, Events& ev) {   // one thread per arena
+  ev.n = 0;
+  for (int i = 0; i < NU; ++i) {
+    if (!T.alive0[i]) continue;
+    const bool ac1 = A.actype[i] == 1;
+    if (A.burst[i] > 0) {
+      A.burst[i] -= 1;
+      A.crem[i] = A.crem[i] > 0 ? A.crem[i] - 1 : 0;
+      const double range = ac1 ? 2.0 : 4.5, half_w = (ac1 ? 10.0 : 7.0) / 2.0;
+      const double p_hit = ac1 ? 0.75 / (5.0 / 1.0) : 0.9 / (3.0 / 1.0);
+      uint8_t snap[NU];
+      for (int j = 0; j < NU; ++j) snap[j] = A.alive[j];  // list(sim.active_units.values()) at this moment
+      for (int j = 0; j < NU; ++j) {
+        if (j == i || !snap[j]) continue;
+        if (!(P.friendly_kill || ((i < NA) != (j < NA)))) continue;
+        if (unit_in_cannon_range(A.lat[i], A.lon[i], A.hdg[i], A.lat[j], A.lon[j], range, half_w)) {
+          if (c_random_at(rng, A.dc++) < p_hit) {
+            A.alive[j] = 0;
+            ev.killer[ev.n] = i;
+            ev.victim[ev.n] = j;
+            ev.n += 1;
+          }
+        }
+      }
+    }
+    if (ac1 && A.hasm[i]) {
+      if (!A.ralive[i]) A.hasm[i] = 0;
+      else A.rnhdg[i] = clip(__dmul_rn(A.rhdg[i], uniform_from(0.95, 1.05, g_next(rng, A))), 0.0, 359.0);
+    }
+    A.lat[i] = T.nlat[i];
+    A.lon[i] = T.nlon[i];
+  }
+  // rockets in launch order: proximity kills and lifetime here, the surviving rockets' moves unit-parallel afterwards
+  for (;;) {
+    int s = -1;
+    for (int k = 0; k < NU; ++k)
+      if (T.ralive0[k] && (s < 0 || A.rid[k] < A.rid[s])) s = k;
+    if (s < 0) break;
+    T.ralive0[s] = 0;
+    const int t = A.rtgt[s];
+    if (within_1km(A.rlat[s], A.rlon[s], A.lat[t], A.lon[t]) && A.alive[t]) {
+      A.ralive[s] = 0;
+      A.alive[t] = 0;
+      ev.killer[ev.n] = s;
+      ev.victim[ev.n] = t;
+      ev.n += 1;
+      continue;
+    }
+    if (P.friendly_kill) {
+      const int f = (s + 1) == 2 ? 0 : 1;  // friendly_id = 1 if source.id == 2 else 2 (rocket_unit.py:46)
+      if (A.alive[f] && within_1km(A.rlat[s], A.rlon[s], A.lat[f], A.lon[f])) {
+        A.ralive[s] = 0;
+        A.alive[f] = 0;
+        ev.killer[ev.n] = s;
+        ev.victim[ev.n] = f;
+        ev.n += 1;
+        continue;
+      }
+    }
+    if (A.rage[s] > 10) {
+      A.ralive[s] = 0;
+      continue;
+    }
+    T.rmove[s] = 1;
+  }
+}
+
+__device__ void tick_rocket_move(Arena& A, const HParams& P, int s, const TickTmp& T) {   // one thread per (arena, rocket slot)
+  if (!T.rmove[s]) return;
+  if (A.rhdg[s] != A.rnhdg[s]) {
+    const double d = signed_heading_diff(A.rhdg[s], A.rnhdg[s]);
+    A.rhdg[s] = fabs(d) <= 10.0 ? A.rnhdg[s] : A.rhdg[s] + (d >= 0.0 ? 10.0 : -10.0);
+  }
+  const double2 q = P.short_moves ? geo::direct_tick(A.rlat[s], A.rlon[s], A.rhdg[s], rocket_speed(A.rage[s]) * kKnotsToMs * 1.0)
+                                 : geo::direct(A.rlat[s], A.rlon[s], A.rhdg[s], rocket_speed(A.rage[s]) * kKnotsToMs * 1.0);
+  A.rlat[s] = q.x;
+  A.rlon[s] = q.y;
+  A.rage[s] += 1;
+}
+
 // _combat_rewards(mode="HighLevel") (env_base.py:240-310) + HighLevelEnv._get_rewards (env_hier.py:210-224)
 __device__ bool get_rewards(Arena& A, const Geom& g, const HParams& P, const Events& ev) {
   const double s = P.rew_scale;
@@ -514,43 +640,147 @@ __global__ void __launch_bounds__(64) reset_kernel(Arena* arenas, HParams P, con
   commander_state(A, g, obs + (size_t)a * NA * OBS_HL);
 }
 
-__global__ void __launch_bounds__(64) begin_kernel(Arena* arenas, HParams P, const int32_t* cmd, float* ll_obs, uint8_t* ll_info) {
-  HH_HIER_PROLOGUE
-  action_assess(A, rng, P, cmd + (size_t)a * NA);
-  A.sub = 0;
-  A.kill_event = A.situation_event = 0;
-  A.active = 1;
-  write_ll(A, g, 0, ll_obs + (size_t)a * NU * LL_STRIDE, ll_info + (size_t)a * NU);
-  for (int i = NA; i < NU; ++i)   // opponents' policy kinds are known already (their observations come later)
-    ll_info[(size_t)a * NU + i] = (A.ca[i] == 0 ? 2 : 0) | (A.actype[i] == 2 ? 4 : 0);
-  // bit 3 (this call only): alive at the start of the commander step -- a unit that is dead now makes no policy query
-  // in any of the step's sub-steps, so the host leaves it out of the batched forwards
-  for (int i = 0; i < NU; ++i)
-    if (A.alive[i]) ll_info[(size_t)a * NU + i] |= 8;
-}
+// ---- staged kernels of the sub-step loop.  A CTA owns kAr arenas whose records are staged in shared memory (coalesced
+// load / store of the ~0.9 KB array-of-structs records); the id-ordered parts run one thread per arena, the per-unit parts
+// (rate limits + one-tick geodesic moves, rocket moves, the low-level observations) one thread per (arena, unit).
+constexpr int kAr = 32, kHT = kAr * NU;   // 192 threads
+static_assert(sizeof(Arena) % 8 == 0, "records are copied in 8-byte words");
 
-__global__ void __launch_bounds__(64) agents_kernel(Arena* arenas, HParams P, const int32_t* act, float* ll_obs, uint8_t* ll_info) {
-  HH_HIER_PROLOGUE
-  if (A.active)
-    for (int i = 0; i < NA; ++i)
-      if (A.alive[i]) base_action_hl(A, rng, i, act + ((size_t)a * NU + i) * 4);
-  write_ll(A, g, NA, ll_obs + (size_t)a * NU * LL_STRIDE, ll_info + (size_t)a * NU);
-}
+struct HStage {
+  Arena rec[kAr];
+  float rows[kAr][NA][LL_STRIDE];
+  TickTmp tmp[kAr];
+  uint8_t info[kAr][NA];
+};
 
-__global__ void __launch_bounds__(64) tick_kernel(Arena* arenas, HParams P, const int32_t* act, float* ll_obs, uint8_t* ll_info) {
-  HH_HIER_PROLOGUE
-  if (A.active) {
-    for (int i = NA; i < NU; ++i)
-      if (A.alive[i]) base_action_hl(A, rng, i, act + ((size_t)a * NU + i) * 4);
-    Events ev;
-    do_tick(A, rng, P, ev);
-    A.kill_event = get_rewards(A, g, P, ev) ? 1 : 0;
-    if (A.sub > 10) A.situation_event = surrounding_event(A) ? 1 : 0;   // min_sub_steps = 10 (env_hier.py:120,133)
-    A.sub += 1;
-    A.steps += 1;
-    A.active = (A.sub <= 15 && !A.kill_event && !A.situation_event) ? 1 : 0;   // n_sub_steps = 15 (env_hier.py:33,125)
+__device__ __forceinline__ int stage_load(HStage& S, const Arena* arenas, int n_arenas) {
+  const int arena0 = blockIdx.x * kAr;
+  const int n_valid = min(kAr, n_arenas - arena0);
+  const unsigned long long* src = reinterpret_cast<const unsigned long long*>(arenas + arena0);
+  unsigned long long* dst = reinterpret_cast<unsigned long long*>(S.rec);
+  const int words = n_valid * (int)(sizeof(Arena) / 8);
+  for (int k = threadIdx.x; k < words; k += kHT) dst[k] = src[k];
+  __syncthreads();
+  return n_valid;
+}
+// writes the records back and the three staged observation rows / info bytes of every arena (units first .. first + 2)
+__device__ __forceinline__ void stage_store(HStage& S, Arena* arenas, int n_valid, int first, float* ll_obs, uint8_t* ll_info) {
+  __syncthreads();
+  const int arena0 = blockIdx.x * kAr;
+  unsigned long long* dst = reinterpret_cast<unsigned long long*>(arenas + arena0);
+  const unsigned long long* src = reinterpret_cast<const unsigned long long*>(S.rec);
+  const int words = n_valid * (int)(sizeof(Arena) / 8);
+  for (int k = threadIdx.x; k < words; k += kHT) dst[k] = src[k];
+  for (int k = threadIdx.x; k < n_valid * NA * LL_STRIDE; k += kHT) {
+    const int al = k / (NA * LL_STRIDE), r = k - al * (NA * LL_STRIDE);
+    ll_obs[((size_t)(arena0 + al) * NU + first) * LL_STRIDE + r] = (&S.rows[al][0][0])[r];
   }
-  write_ll(A, g, 0, ll_obs + (size_t)a * NU * LL_STRIDE, ll_info + (size_t)a * NU);
+  for (int k = threadIdx.x; k < n_valid * NA; k += kHT) {
+    const int al = k / NA, u = k - al * NA;
+    ll_info[(size_t)(arena0 + al) * NU + first + u] = S.info[al][u];
+  }
+}
+__device__ __forceinline__ void stage_write_ll(HStage& S, const Geom& g, int n_valid, int first) {
+  const int t = threadIdx.x;
+  if (t < kAr * NA) {
+    const int al = t / NA, u = t - al * NA;
+    if (al < n_valid) write_ll_unit(S.rec[al], g, first + u, S.rows[al][u], &S.info[al][u]);
+  }
+}
+
+__global__ void __launch_bounds__(kHT) begin_kernel(Arena* arenas, HParams P, const int32_t* cmd, float* ll_obs, uint8_t* ll_info) {
+  extern __shared__ __align__(16) unsigned char hsm[];
+  HStage& S = *reinterpret_cast<HStage*>(hsm);
+  const int n_valid = stage_load(S, arenas, P.n_arenas);
+  const int arena0 = blockIdx.x * kAr, t = threadIdx.x;
+  const Geom g = make_geom(P.map_size);
+  if (t < n_valid) {
+    Arena& A = S.rec[t];
+    const int a = arena0 + t;
+    const Rng rng{P.seed_lo, P.seed_hi, P.arena_base + (uint32_t)a};
+    action_assess(A, rng, P, cmd + (size_t)a * NA);
+    A.sub = 0;
+    A.kill_event = A.situation_event = 0;
+    A.active = 1;
+  }
+  __syncthreads();
+  stage_write_ll(S, g, n_valid, 0);
+  stage_store(S, arenas, n_valid, 0, ll_obs, ll_info);
+  if (t < n_valid) {
+    const Arena& A = S.rec[t];
+    const size_t a = (size_t)(arena0 + t);
+    for (int i = NA; i < NU; ++i)   // opponents' policy kinds are known already (their observations come later)
+      ll_info[a * NU + i] = (A.ca[i] == 0 ? 2 : 0) | (A.actype[i] == 2 ? 4 : 0);
+  }
+  __syncthreads();                  // the agents' info bytes above were written by other threads of this CTA
+  if (t < n_valid) {
+    // bit 3 (this call only): alive at the start of the commander step -- a unit that is dead now makes no policy query
+    // in any of the step's sub-steps, so the host leaves it out of the batched forwards
+    const Arena& A = S.rec[t];
+    const size_t a = (size_t)(arena0 + t);
+    for (int i = 0; i < NU; ++i)
+      if (A.alive[i]) ll_info[a * NU + i] |= 8;
+  }
+}
+
+__global__ void __launch_bounds__(kHT) agents_kernel(Arena* arenas, HParams P, const int32_t* act, float* ll_obs, uint8_t* ll_info) {
+  extern __shared__ __align__(16) unsigned char hsm[];
+  HStage& S = *reinterpret_cast<HStage*>(hsm);
+  const int n_valid = stage_load(S, arenas, P.n_arenas);
+  const int arena0 = blockIdx.x * kAr, t = threadIdx.x;
+  const Geom g = make_geom(P.map_size);
+  if (t < n_valid) {
+    Arena& A = S.rec[t];
+    const int a = arena0 + t;
+    const Rng rng{P.seed_lo, P.seed_hi, P.arena_base + (uint32_t)a};
+    if (A.active)
+      for (int i = 0; i < NA; ++i)
+        if (A.alive[i]) base_action_hl(A, rng, i, act + ((size_t)a * NU + i) * 4);
+  }
+  __syncthreads();
+  stage_write_ll(S, g, n_valid, NA);
+  stage_store(S, arenas, n_valid, NA, ll_obs, ll_info);
+}
+
+__global__ void __launch_bounds__(kHT) tick_kernel(Arena* arenas, HParams P, const int32_t* act, float* ll_obs, uint8_t* ll_info) {
+  extern __shared__ __align__(16) unsigned char hsm[];
+  HStage& S = *reinterpret_cast<HStage*>(hsm);
+  __shared__ Events evs[kAr];
+  const int n_valid = stage_load(S, arenas, P.n_arenas);
+  const int arena0 = blockIdx.x * kAr, t = threadIdx.x;
+  const Geom g = make_geom(P.map_size);
+  const int ual = t / NU, uu = t - ual * NU;      // (arena, unit) of the unit-parallel stages
+  if (t < n_valid) {                              // opponents' _take_base_action (id order)
+    Arena& A = S.rec[t];
+    const int a = arena0 + t;
+    const Rng rng{P.seed_lo, P.seed_hi, P.arena_base + (uint32_t)a};
+    if (A.active)
+      for (int i = NA; i < NU; ++i)
+        if (A.alive[i]) base_action_hl(A, rng, i, act + ((size_t)a * NU + i) * 4);
+  }
+  __syncthreads();
+  if (ual < n_valid && S.rec[ual].active) tick_unit_prepare(S.rec[ual], P, uu, S.tmp[ual]);
+  __syncthreads();
+  if (t < n_valid && S.rec[t].active) {
+    const Rng rng{P.seed_lo, P.seed_hi, P.arena_base + (uint32_t)(arena0 + t)};
+    tick_resolve(S.rec[t], rng, P, S.tmp[t], evs[t]);
+  }
+  __syncthreads();
+  if (ual < n_valid && S.rec[ual].active) tick_rocket_move(S.rec[ual], P, uu, S.tmp[ual]);
+  __syncthreads();
+  if (t < n_valid) {
+    Arena& A = S.rec[t];
+    if (A.active) {
+      A.kill_event = get_rewards(A, g, P, evs[t]) ? 1 : 0;
+      if (A.sub > 10) A.situation_event = surrounding_event(A) ? 1 : 0;   // min_sub_steps = 10 (env_hier.py:120,133)
+      A.sub += 1;
+      A.steps += 1;
+      A.active = (A.sub <= 15 && !A.kill_event && !A.situation_event) ? 1 : 0;   // n_sub_steps = 15 (env_hier.py:33,125)
+    }
+  }
+  __syncthreads();
+  stage_write_ll(S, g, n_valid, 0);
+  stage_store(S, arenas, n_valid, 0, ll_obs, ll_info);
 }
 
 // HHMARLBaseEnv.step with args.eval_info (env_base.py:91-107): the step's `info` dict as int32[12] per arena =
@@ -599,6 +829,29 @@ __global__ void __launch_bounds__(64) end_kernel(Arena* arenas, HParams P, float
   A.active = 0;
   if (d && P.autoreset) reset_arena(A, rng, P);
   commander_state(A, g, obs + (size_t)a * NA * OBS_HL);
+}
+
+// Row lists of the frozen low-level policies for one commander step, built on the device (no host synchronisation): which
+// network a unit queries (fight / escape x aircraft type) is fixed by hh_hier_begin's info bytes.  List 2 k + h holds the
+// flat unit indices (arena * 6 + unit) of policy kind k (0 fight AC1, 1 fight AC2, 2 escape AC1, 3 escape AC2) among the
+// agents (h = 0, units 0-2) or the opponents (h = 1, units 3-5) that were alive at the start of the step.
+__global__ void policy_rows_init_kernel(int cap, int32_t* __restrict__ ranges) {
+  const int k = threadIdx.x;
+  if (k < 8) {
+    ranges[2 * k] = k * cap;
+    ranges[2 * k + 1] = 0;
+  }
+}
+__global__ void policy_rows_fill_kernel(int n_units, int cap, const uint8_t* __restrict__ ll_info, int32_t* __restrict__ rows,
+                                        int32_t* __restrict__ ranges) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_units) return;
+  const int v = ll_info[i];
+  if (!(v & 8)) return;                                 // not alive at the start of the commander step: never queries
+  const int bits = v & 6, kind = bits == 0 ? 0 : bits == 4 ? 1 : bits == 2 ? 2 : 3;
+  const int list = 2 * kind + ((i % NU) >= NA ? 1 : 0);
+  const int pos = atomicAdd(&ranges[2 * list + 1], 1);
+  rows[(size_t)list * cap + pos] = i;
 }
 
 }  // namespace hier
@@ -686,6 +939,21 @@ extern "C" void hh_hier_destroy(hh_hier_env* e) {
     HHH_CUDA(cudaGetLastError());                                                                     \
     e->launches += 1;                                                                                 \
   } while (0)
+// the staged kernels of the sub-step loop: kAr arenas per CTA, records in (dynamic) shared memory
+#define HIER_LAUNCH_STAGED(kern, ...)                                                                 \
+  do {                                                                                                \
+    static bool opted[64] = {};                                                                       \
+    if (e->device >= 0 && e->device < 64 && !opted[e->device]) {                                      \
+      HHH_CUDA(cudaFuncSetAttribute(hh::hier::kern, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                    (int)sizeof(hh::hier::HStage)));                                  \
+      opted[e->device] = true;                                                                        \
+    }                                                                                                 \
+    const int blocks = (e->P.n_arenas + hh::hier::kAr - 1) / hh::hier::kAr;                           \
+    hh::hier::kern<<<blocks, hh::hier::kHT, sizeof(hh::hier::HStage), static_cast<cudaStream_t>(stream)>>>( \
+        e->arenas, e->P, __VA_ARGS__);                                                                \
+    HHH_CUDA(cudaGetLastError());                                                                     \
+    e->launches += 1;                                                                                 \
+  } while (0)
 
 extern "C" int hh_hier_reset(hh_hier_env* e, const uint8_t* mask_dev, float* obs_dev, void* stream) {
   if (!e || !obs_dev) return hfail(-1, "hh_hier_reset: null argument");
@@ -696,22 +964,32 @@ extern "C" int hh_hier_reset(hh_hier_env* e, const uint8_t* mask_dev, float* obs
 extern "C" int hh_hier_begin(hh_hier_env* e, const int32_t* cmd_dev, float* ll_obs_dev, uint8_t* ll_info_dev, void* stream) {
   if (!e || !cmd_dev || !ll_obs_dev || !ll_info_dev) return hfail(-1, "hh_hier_begin: null argument");
   if (!e->initialised) return hfail(-4, "hh_hier_begin: call hh_hier_reset first");
-  HIER_LAUNCH(begin_kernel, cmd_dev, ll_obs_dev, ll_info_dev);
+  HIER_LAUNCH_STAGED(begin_kernel, cmd_dev, ll_obs_dev, ll_info_dev);
   return 0;
 }
 extern "C" int hh_hier_agents(hh_hier_env* e, const int32_t* act_dev, float* ll_obs_dev, uint8_t* ll_info_dev, void* stream) {
   if (!e || !act_dev || !ll_obs_dev || !ll_info_dev) return hfail(-1, "hh_hier_agents: null argument");
-  HIER_LAUNCH(agents_kernel, act_dev, ll_obs_dev, ll_info_dev);
+  HIER_LAUNCH_STAGED(agents_kernel, act_dev, ll_obs_dev, ll_info_dev);
   return 0;
 }
 extern "C" int hh_hier_tick(hh_hier_env* e, const int32_t* act_dev, float* ll_obs_dev, uint8_t* ll_info_dev, void* stream) {
   if (!e || !act_dev || !ll_obs_dev || !ll_info_dev) return hfail(-1, "hh_hier_tick: null argument");
-  HIER_LAUNCH(tick_kernel, act_dev, ll_obs_dev, ll_info_dev);
+  HIER_LAUNCH_STAGED(tick_kernel, act_dev, ll_obs_dev, ll_info_dev);
   return 0;
 }
 extern "C" int hh_hier_end(hh_hier_env* e, float* obs_dev, float* rew_dev, uint8_t* done_dev, int32_t* substeps_dev, void* stream) {
   if (!e || !obs_dev || !rew_dev || !done_dev) return hfail(-1, "hh_hier_end: null argument");
   HIER_LAUNCH(end_kernel, obs_dev, rew_dev, done_dev, substeps_dev);
+  return 0;
+}
+extern "C" int hh_hier_policy_rows(hh_hier_env* e, const uint8_t* ll_info_dev, int32_t* rows_dev, int32_t* ranges_dev, void* stream) {
+  if (!e || !ll_info_dev || !rows_dev || !ranges_dev) return hfail(-1, "hh_hier_policy_rows: null argument");
+  const int n_units = e->P.n_arenas * hh::hier::NU, cap = e->P.n_arenas * hh::hier::NA;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  hh::hier::policy_rows_init_kernel<<<1, 32, 0, st>>>(cap, ranges_dev);
+  hh::hier::policy_rows_fill_kernel<<<(n_units + 255) / 256, 256, 0, st>>>(n_units, cap, ll_info_dev, rows_dev, ranges_dev);
+  HHH_CUDA(cudaGetLastError());
+  e->launches += 2;
   return 0;
 }
 extern "C" int hh_hier_eval_info(hh_hier_env* e, int32_t* info_dev, void* stream) {

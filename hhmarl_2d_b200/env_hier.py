@@ -96,13 +96,22 @@ class VecHighLevelEnv:
 
     # frozen low-level policies, batched: env_base.py:349-398 (per-head argmax of the actor).  Which network a
     # unit uses (fight/escape x aircraft type) is fixed for the whole commander step, so the row lists are built
-    # once per step (4 host syncs) and reused by all 16 sub-steps; rows of units that do not query right now
+    # once per step (on the device: hh_hier_policy_rows) and reused by all 16 sub-steps; rows of units that do not query right now
     # (dead, or arena already out of its sub-step loop) are computed and ignored by the kernels.
     _KINDS = (("fight", 1, 0), ("fight", 2, 4), ("escape", 1, 2), ("escape", 2, 6))
     _DIMS = {("fight", 1): 26, ("fight", 2): 24, ("escape", 1): 30, ("escape", 2): 29}
 
     def _build_rows(self):
         t = self._torch
+        if self.fused_policies:
+            # device-built lists (hh_hier_policy_rows): no host synchronisation anywhere in the commander step
+            if getattr(self, "_rows_dev", None) is None:
+                self._rows_dev = t.zeros((8, self.n_arenas * 3), dtype=t.int32, device=self.dev)
+                self._ranges_dev = t.zeros((8, 2), dtype=t.int32, device=self.dev)
+            nat.check(nat.lib().hh_hier_policy_rows(self._h, self.ll_info.data_ptr(), self._rows_dev.data_ptr(),
+                                                    self._ranges_dev.data_ptr(), self._stream()), "hh_hier_policy_rows")
+            self._rows = [(mode, ac, first, 2 * k + (first // 3)) for k, (mode, ac, _) in enumerate(self._KINDS) for first in (0, 3)]
+            return
         kind = (self.ll_info & 6).reshape(-1)
         live = (self.ll_info & 8).reshape(-1) != 0     # alive at the start of this commander step (hh_hier_begin)
         self._rows = []
@@ -128,14 +137,16 @@ class VecHighLevelEnv:
             self._fused = {}
         obs_flat, act_flat = self.ll_obs.reshape(-1, 30), self.ll_act.reshape(-1, 4)
         fills = []
-        for mode, ac, f, idx in self._rows:
-            if f != first or idx.numel() == 0:
+        cap = self.n_arenas * 3
+        for mode, ac, f, lst in self._rows:
+            if f != first:
                 continue
             key = self._policy_key(mode, ac, first)
             if key not in self._fused:
                 self._fused[key] = FusedActor(self.policies[key])
             fa = self._fused[key]
-            fills.append(lambda c, fa=fa, idx=idx: fa.fill_chain(c, obs_flat, idx.numel(), act_out=act_flat, rows=idx))
+            fills.append(lambda c, fa=fa, lst=lst: fa.fill_chain(c, obs_flat, cap, act_out=act_flat, rows=self._rows_dev,
+                                                                 range_dev=self._ranges_dev[lst]))
         run_chains(fills, self.dev, self.policy_precision)
 
     def _infer(self, first: int):

@@ -273,6 +273,11 @@ int hh_hier_end(hh_hier_env* env, float* obs_dev, float* rew_dev, uint8_t* done_
  * opp_fight, opp_escape, agent_steps, opp_steps, opp1, opp2, opp3 of the commander step in flight.  Call it after
  * the last hh_hier_tick and BEFORE hh_hier_end (whose auto-reset replaces the finished episode). */
 #define HH_HIER_EVAL_INFO_LEN 12
+/* Row lists of the frozen low-level policies for the commander step that hh_hier_begin opened, built on the device (no host
+ * synchronisation): list 2 k + h (k: 0 fight AC1, 1 fight AC2, 2 escape AC1, 3 escape AC2; h: 0 agents = units 1-3, 1 opponents
+ * = units 4-6) holds the flat unit indices arena * 6 + unit of the units alive at the start of the step (ll_info bit 3).
+ * rows_dev int32 [8][3 N], ranges_dev int32 [8][2] = {list * 3 N, count}: feed hh_policy_chain_ex.rows / range_dev. */
+int hh_hier_policy_rows(hh_hier_env* env, const uint8_t* ll_info_dev, int32_t* rows_dev, int32_t* ranges_dev, void* stream);
 int hh_hier_eval_info(hh_hier_env* env, int32_t* info_dev, void* stream);
 int hh_hier_get_state(hh_hier_env* env, hh_hier_arena* out_host);
 int hh_hier_set_state(hh_hier_env* env, const hh_hier_arena* in_host);
