@@ -552,8 +552,9 @@ def run_b200(args):
         hier = {"commander_steps_per_s": world * n * HS / (float(ht.item()) * 1e-3),
                 "sim_ticks_per_s": float(tk.item()) / (float(ht.item()) * 1e-3), "commander_steps": HS,
                 "mean_substeps": float(tk.item()) / (world * n * HS), "arenas_per_gpu": n,
-                "note": "HighLevelEnv 3-vs-3, 16 masked sub-steps x (2 env launches + 2 launches of csrc/hh_policy.cu: the frozen "
-                        "fight / escape actors of all six aircraft as gathered chains, 3xTF32, argmax in the epilogue)"}
+                "note": "HighLevelEnv 3-vs-3, 16 masked sub-steps x (2 staged env launches + 2 launches of csrc/hh_policy_tc.cu: the frozen "
+                        "fight / escape actors of all six aircraft as gathered chains on tcgen05, fp32-equivalent, argmax in the epilogue; "
+                        "row lists built on the device, no host synchronisation inside a commander step)"}
         from hhmarl_2d_b200.env_hier import CommanderSampler
         from hhmarl_2d_b200 import models as MM
         cs = CommanderSampler(henv, MM.CommanderGru().to(dev), fragment_len=4)

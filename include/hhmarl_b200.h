@@ -155,7 +155,9 @@ int hh_pack_central(int32_t n_arenas, int32_t d1, int32_t d2, const float* obs1_
  * i.e. the (b0, b1) operand pair of mma.m16n8k8 of every lane, block by block.  Biases are plain vectors: b1 [512],
  * batt [att_pad], bs [512], bh [32]; att_n = 0 means no attention block (Esc1 / Esc2).
  * The four chains (policy 1 actor, policy 1 critic, policy 2 actor, policy 2 critic) run in ONE launch.
- * precision 0: 3xTF32 tensor-core products (fp32-equivalent results); 1: plain TF32. */
+ * precision 0: 3xTF32 tensor-core products on mma.sync (fp32-equivalent results); 1: plain TF32 (hh_policy.cu).  The
+ * tcgen05 / TMEM path (precision 2, hh_policy_tc.cu) is reached through hh_policy_forward_ex below with operand images
+ * built by hh_policy_pack; it does not read the fragment-ordered matrices. */
 typedef struct {
   const float *x, *w1, *b1, *watt, *batt, *wh, *bh;   /* device pointers */
   float* out;                                         /* [n_rows, ld_out], first n_out columns written */
