@@ -506,10 +506,11 @@ constexpr int kV4MinCtas = HH_V4_MIN_CTAS;
 template <int LEVEL, int MODE>
 __global__ void __launch_bounds__(v4::kThreads, kV4MinCtas)
 step_kernel_v4(StatePtrs S, Params P, const int32_t* __restrict__ actions, float* __restrict__ obs1,
-               float* __restrict__ obs2, float* __restrict__ rew_out, uint8_t* __restrict__ done_out) {
+               float* __restrict__ obs2, float* __restrict__ rew_out, uint8_t* __restrict__ done_out, int block0) {
+  // block0 > 0: a launch over a sub-range of the arenas (pipelined host mode; P.n_arenas is then the range's end)
   extern __shared__ __align__(16) unsigned char v4_smem[];
   v4::step_body<LEVEL, MODE>(*reinterpret_cast<v4::Smem*>(v4_smem), S, P, actions, obs1, obs2, rew_out, done_out,
-                             blockIdx.x);
+                             blockIdx.x + block0);
 }
 template <int LEVEL, int MODE>
 static cudaError_t v4_opt_in_smem() {
@@ -780,7 +781,10 @@ struct hh_env {
   void* pinned_dev = nullptr;   // device-side address of the pinned slab (zero-copy host mode)
   size_t pinned_bytes = 0;
   bool host_pending = false;    // a step enqueued by hh_step_host_begin has not been collected yet
-  int host_mode = 1;            // 0: staged (H2D, launch, D2H); 1: zero-copy (kernels read / write the pinned slab)
+  int host_mode = 1;            // 0: staged (H2D, launch, D2H); 1: zero-copy (kernels read / write the pinned slab);
+                                // 2: pipelined (two half-batch launches, the first half's D2H under the second half's kernel)
+  cudaStream_t cstream = nullptr;       // copy stream of the pipelined mode
+  cudaGraphExec_t pipe_graph = nullptr; // one graph launch per pipelined host step
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -954,7 +958,11 @@ extern "C" int hh_create(const hh_config* cfg, int32_t n_arenas, int32_t device,
       }
     }
     const char* hm = getenv("HH_HOST_MODE");
-    e->host_mode = (hm && std::string(hm) == "staged") ? 0 : 1;   // default: zero-copy (+23 % e2e, profiles/README.md)
+    // default: zero-copy (+23 % e2e over staged).  The pipelined mode (two half-batch launches, copy-engine D2H of the first half
+    // under the second half's kernel, one CUDA graph) is bit-identical but measured SLOWER at 8 192 arenas (74.6 M env-steps/s
+    // against 99.6 M): the graph's six nodes on two streams cost more in scheduling latency than the overlap returns
+    // (profiles/README.md, round 2); it stays selectable (HH_HOST_MODE=pipelined, hh_set_host_mode(2)).
+    e->host_mode = (hm && std::string(hm) == "staged") ? 0 : (hm && std::string(hm) == "pipelined") ? 2 : 1;
     e->step_impl = !impl ? 4 : (std::string(impl) == "quad" ? 2 : (std::string(impl) == "cta" ? 3 : 4));
   }
   *out = e;
@@ -965,6 +973,8 @@ extern "C" void hh_destroy(hh_env* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->hstream) cudaStreamSynchronize(e->hstream);   // a step sent with hh_step_host_begin may still be in flight
+  if (e->pipe_graph) cudaGraphExecDestroy(e->pipe_graph);
+  if (e->cstream) cudaStreamDestroy(e->cstream);
   if (e->slab) cudaFree(e->slab);
   if (e->d_slab) cudaFree(e->d_slab);
   if (e->rew_pre) cudaFree(e->rew_pre);
@@ -995,15 +1005,24 @@ extern "C" int hh_reset(hh_env* e, const uint8_t* mask_dev, float* obs1, float* 
   return 0;
 }
 
+// arenas [first, end) of the v4 step (first a multiple of v4::kArenas); the whole batch is first = 0, end = n
+template <int LEVEL>
+static void launch_step_v4_range(hh_env* e, int first, int end, const int32_t* actions, float* obs1, float* obs2, float* rew,
+                                 uint8_t* done, cudaStream_t st) {
+  Params P = e->P;
+  P.n_arenas = end;
+  const int block0 = first / v4::kArenas, vblocks = (end - first + v4::kArenas - 1) / v4::kArenas;
+  if (e->cfg.agent_mode == 0)
+    step_kernel_v4<LEVEL, 0><<<vblocks, v4::kThreads, sizeof(v4::Smem), st>>>(e->S, P, actions, obs1, obs2, rew, done, block0);
+  else
+    step_kernel_v4<LEVEL, 1><<<vblocks, v4::kThreads, sizeof(v4::Smem), st>>>(e->S, P, actions, obs1, obs2, rew, done, block0);
+}
+
 template <int LEVEL>
 static void launch_step(hh_env* e, const int32_t* actions, float* obs1, float* obs2, float* rew, uint8_t* done,
                         cudaStream_t st) {
   if (e->step_impl == 4) {
-    const int vblocks = (e->n + v4::kArenas - 1) / v4::kArenas;
-    if (e->cfg.agent_mode == 0)
-      step_kernel_v4<LEVEL, 0><<<vblocks, v4::kThreads, sizeof(v4::Smem), st>>>(e->S, e->P, actions, obs1, obs2, rew, done);
-    else
-      step_kernel_v4<LEVEL, 1><<<vblocks, v4::kThreads, sizeof(v4::Smem), st>>>(e->S, e->P, actions, obs1, obs2, rew, done);
+    launch_step_v4_range<LEVEL>(e, 0, e->n, actions, obs1, obs2, rew, done, st);
     return;
   }
   if (e->step_impl == 3) {
@@ -1142,7 +1161,7 @@ extern "C" int hh_host_buffers(hh_env* e, int32_t** actions, float** obs1, float
 
 extern "C" int hh_set_host_mode(hh_env* e, int32_t mode) {
   if (!e) return fail(-1, "hh_set_host_mode: null env");
-  if (mode != 0 && mode != 1) return fail(-1, "hh_set_host_mode: mode must be 0 (staged copies) or 1 (zero-copy)");
+  if (mode < 0 || mode > 2) return fail(-1, "hh_set_host_mode: mode must be 0 (staged copies), 1 (zero-copy) or 2 (pipelined)");
   e->host_mode = mode;
   return 0;
 }
@@ -1159,7 +1178,7 @@ extern "C" int hh_reset_host(hh_env* e, const uint8_t* mask_host, float* obs1_ho
     memcpy(pin + h.o_mask, mask_host, N);
     HH_CUDA(cudaMemcpyAsync(e->d_mask, pin + h.o_mask, N, cudaMemcpyHostToDevice, e->hstream));
   }
-  if (e->host_mode == 1) {
+  if (e->host_mode >= 1) {
     char* pd = static_cast<char*>(e->pinned_dev);
     rc = hh_reset(e, mask_host ? e->d_mask : nullptr, reinterpret_cast<float*>(pd + h.o_obs1),
                   reinterpret_cast<float*>(pd + h.o_obs2), e->hstream);
@@ -1173,6 +1192,59 @@ extern "C" int hh_reset_host(hh_env* e, const uint8_t* mask_host, float* obs1_ho
   HH_CUDA(cudaStreamSynchronize(e->hstream));
   if (obs1_host && obs1_host != reinterpret_cast<float*>(pin + h.o_obs1)) memcpy(obs1_host, pin + h.o_obs1, N * d1 * sizeof(float));
   if (obs2_host && obs2_host != reinterpret_cast<float*>(pin + h.o_obs2)) memcpy(obs2_host, pin + h.o_obs2, N * d2 * sizeof(float));
+  return 0;
+}
+
+// Pipelined host step (host mode 2).  A lone CTA of the step kernel needs ~14 us, two co-resident ones ~22 us, and the
+// 1.6 MB of observations need ~33 us over PCIe: so the batch is stepped as TWO half-batch launches back to back (one CTA per
+// SM each), and the first half's observations travel (copy engine, D2H) while the second half computes.  Actions are read
+// from, rewards / done flags written to, the pinned slab directly (small); the whole step is one CUDA-graph launch.
+static bool pipelined_applies(const hh_env* e) {
+  return e->cfg.level <= 3 && e->step_impl == 4 && e->n >= 2048 && e->initialised;
+}
+static int pipelined_step(hh_env* e) {
+  if (!e->pipe_graph) {
+    const HostLayout h = host_layout(e);
+    const size_t N = (size_t)e->n;
+    const int d1 = obs_dim(e->cfg, 1), d2 = obs_dim(e->cfg, 2);
+    const int half = (e->n / 2 + v4::kArenas - 1) / v4::kArenas * v4::kArenas;
+    char* pd = static_cast<char*>(e->pinned_dev);
+    char* pin = static_cast<char*>(e->pinned);
+    const int32_t* act = reinterpret_cast<const int32_t*>(pd + h.o_act);
+    float* rew = reinterpret_cast<float*>(pd + h.o_rew);
+    uint8_t* done = reinterpret_cast<uint8_t*>(pd + h.o_done);
+    if (!e->cstream) HH_CUDA(cudaStreamCreateWithFlags(&e->cstream, cudaStreamNonBlocking));
+    cudaEvent_t ev[3];
+    for (auto& x : ev) HH_CUDA(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+    cudaGraph_t graph = nullptr;
+    HH_CUDA(cudaStreamBeginCapture(e->hstream, cudaStreamCaptureModeThreadLocal));
+    const int bounds[3] = {0, half, e->n};
+    for (int c = 0; c < 2; ++c) {
+      switch (e->cfg.level) {
+        case 1: launch_step_v4_range<1>(e, bounds[c], bounds[c + 1], act, e->d_obs1, e->d_obs2, rew, done, e->hstream); break;
+        case 2: launch_step_v4_range<2>(e, bounds[c], bounds[c + 1], act, e->d_obs1, e->d_obs2, rew, done, e->hstream); break;
+        default: launch_step_v4_range<3>(e, bounds[c], bounds[c + 1], act, e->d_obs1, e->d_obs2, rew, done, e->hstream); break;
+      }
+      cudaEventRecord(ev[c], e->hstream);
+      cudaStreamWaitEvent(e->cstream, ev[c], 0);
+      const size_t a0 = (size_t)bounds[c], cnt = (size_t)(bounds[c + 1] - bounds[c]);
+      cudaMemcpyAsync(pin + h.o_obs1 + a0 * d1 * sizeof(float), e->d_obs1 + a0 * d1, cnt * d1 * sizeof(float), cudaMemcpyDeviceToHost,
+                      e->cstream);
+      cudaMemcpyAsync(pin + h.o_obs2 + a0 * d2 * sizeof(float), e->d_obs2 + a0 * d2, cnt * d2 * sizeof(float), cudaMemcpyDeviceToHost,
+                      e->cstream);
+    }
+    (void)N;
+    cudaEventRecord(ev[2], e->cstream);
+    cudaStreamWaitEvent(e->hstream, ev[2], 0);
+    cudaError_t ce = cudaStreamEndCapture(e->hstream, &graph);
+    for (auto& x : ev) cudaEventDestroy(x);
+    if (ce != cudaSuccess || !graph) return fail(-2, std::string("pipelined host step: stream capture failed: ") + cudaGetErrorString(ce));
+    ce = cudaGraphInstantiate(&e->pipe_graph, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) return fail(-2, std::string("pipelined host step: cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+  }
+  HH_CUDA(cudaGraphLaunch(e->pipe_graph, e->hstream));
+  e->launches += 2;
   return 0;
 }
 
@@ -1190,7 +1262,10 @@ extern "C" int hh_step_host_begin(hh_env* e, const int32_t* actions_host) {
   const HostLayout h = host_layout(e);
   char* pin = static_cast<char*>(e->pinned);
   if (reinterpret_cast<const char*>(actions_host) != pin + h.o_act) memcpy(pin + h.o_act, actions_host, N * 8 * sizeof(int32_t));
-  if (e->host_mode == 1) {
+  if (e->host_mode == 2 && pipelined_applies(e)) {
+    rc = pipelined_step(e);
+    if (rc) return rc;
+  } else if (e->host_mode >= 1) {
     // zero-copy: the step kernel loads the actions from, and stores observations / rewards / done flags to, the
     // pinned slab through its device-side mapping -- no staging copies, the PCIe traffic rides on the kernel
     char* pd = static_cast<char*>(e->pinned_dev);

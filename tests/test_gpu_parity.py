@@ -357,6 +357,35 @@ def test_zero_copy_host_mode_matches_staged_host_mode():
             assert np.array_equal(sa[k], sb[k]), k
 
 
+def test_pipelined_host_mode_matches_staged_host_mode():
+    """hh_set_host_mode(2) (optional; zero-copy is the default): the batch is stepped as two half-batch launches (sub-range launches of the v4 kernel) and
+    the first half's observations travel over PCIe while the second half computes, all in one CUDA-graph launch.  Same bits as
+    the staged path: ragged arena count (the halves are cut on a CTA boundary), both agent modes, 300 ticks with auto-reset."""
+    for mode, n in (("fight", 4096 + 77), ("escape", 2048)):
+        a = _vec(n, 3, mode, 19)
+        a.set_host_mode("staged")
+        b = _vec(n, 3, mode, 19)
+        b.set_host_mode("pipelined")
+        act_pin, o1, o2, r, d = b.host_buffers()
+        x = a.reset_host()
+        y = b.reset_host()
+        assert np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1])
+        rng = np.random.default_rng(6)
+        l0 = b.launch_count
+        for t in range(300):
+            act = np.stack([rng.integers(0, 13, (n, 2)), rng.integers(0, 9, (n, 2)), rng.integers(0, 2, (n, 2)),
+                            rng.integers(0, 2, (n, 2))], axis=-1).astype(np.int32)
+            x1, x2, xr, xd = a.step_host(act)
+            act_pin[...] = act
+            y1, y2, yr, yd = b.step_host(act_pin, out=(o1, o2, r, d))
+            assert np.array_equal(x1, y1) and np.array_equal(x2, y2) and np.array_equal(xr, yr) and np.array_equal(xd, yd), t
+        assert b.launch_count - l0 == 600          # two sub-range launches per step: the pipelined path did run
+        sa, sb = a.get_state(), b.get_state()
+        for k in sa:
+            assert np.array_equal(sa[k], sb[k]), k
+        assert int(sa["steps"].max()) < 300        # episodes ended and were reset inside the launches
+
+
 def test_send_poll_on_two_handles_matches_one_synchronous_env():
     """hh_step_host_begin / _end (send_actions / poll): two half-batch handles kept in flight together reproduce the
     synchronous full-batch env bit for bit (arena_base makes the halves the same arenas); misuse is an error."""
