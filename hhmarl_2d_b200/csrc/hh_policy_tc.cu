@@ -55,11 +55,12 @@ struct Seg {                 // one run of MMAs over consecutive K steps into on
   uint16_t ksteps;           // K = 16 steps
   uint16_t kps;              // K steps per ring stage (stage bytes = kps * n * 64)
   uint16_t tmem_col;         // first accumulator column
-  uint16_t a_off16;          // start of the A operand inside its tile, in 16-byte units
+  uint16_t a_k0;             // first K column of the A operand inside its tile (a multiple of 8; of 16 in the M = 128 form)
   uint8_t a_src;             // 0 = input tile, 1 = activation tile
   uint8_t first;             // the first MMA overwrites the accumulator
   uint8_t wait_act;          // activation barrier to wait for before the first MMA (0xff = none)
   uint8_t commit_acc;        // accumulator barrier to commit to after the last MMA (0xff = none)
+  uint8_t wait_free;         // M = 128 form: "accumulator drained" barrier to wait for before the first MMA (0xff = none)
 };
 struct Chain {
   const float *x, *b1, *batt, *bs, *bh, *us_w1, *us_att, *us_ws, *us_wh;
@@ -429,7 +430,7 @@ __global__ void __launch_bounds__(kThreads, 1) policy_forward_tc_kernel(const __
         if (prof && lane == 0) prof[1 + 2 * s] = (unsigned long long)clock64();
         fence_tc_after();
         const uint32_t idesc = instr_desc_f16(TM, n);
-        const uint32_t a_addr = smem_u32(smem + (g.a_src ? OFF_ACT_HI : OFF_X_HI)) + 16u * g.a_off16;
+        const uint32_t a_addr = smem_u32(smem + (g.a_src ? OFF_ACT_HI : OFF_X_HI)) + (uint32_t)(g.a_k0 >> 3) * (TM * 16);
         uint32_t a_hi = desc_lo(a_addr, LBO_A), a_lo = desc_lo(a_addr + (g.a_src ? ACT_BYTES : X_BYTES), LBO_A);
         const uint32_t b_seg = desc_lo(smem_u32(smem + OFF_RING), 16u * n);   // leading byte offset of B = 16 n bytes
         const uint32_t lo_off = 2u * n, step_off = 4u * n;                // B lo block, next K step (16-byte units)
@@ -884,7 +885,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) policy_
         if (prof && lane == 0) prof[1 + 2 * s] = (unsigned long long)clock64();
         fence_tc_after();
         const uint32_t idesc = instr_desc_f16(2 * TM, n);
-        const uint32_t a_addr = smem_u32(smem + (g.a_src ? OFF_ACT_HI : OFF_X_HI)) + 16u * g.a_off16;
+        const uint32_t a_addr = smem_u32(smem + (g.a_src ? OFF_ACT_HI : OFF_X_HI)) + (uint32_t)(g.a_k0 >> 3) * (TM * 16);
         uint32_t a_hi = desc_lo(a_addr, LBO_A), a_lo = desc_lo(a_addr + (g.a_src ? ACT_BYTES : X_BYTES), LBO_A);
         const uint32_t b_seg = desc_lo(ring, 8u * n);                     // a CTA holds n / 2 weight columns: LBO = 16 (n / 2) bytes
         const uint32_t lo_off = n, step_off = 2u * n;                     // B lo block, next K step (16-byte units)
@@ -1084,6 +1085,367 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) policy_
   }
 }
 
+// =====================================================================================================================
+// M = 128 form (default): one CTA = 128 rows of one chain, so every weight byte and every MMA serves twice the rows of the
+// 64-row form above (an M = 128 kind::f16 MMA takes the time of an M = 64 one, profiles/r2v_tcgen05_probe4.txt).  A 128-row
+// tile of hi + lo activations does not fit in shared memory; the hi halves live there ([128 x 512] halves, canonical layout with
+// 128 rows: LBO 2048, SBO 128) and the LO halves in TENSOR MEMORY, columns [256, 512): the A operand of the A_lo B_hi MMA is read
+// from TMEM (lane = row, 32-bit column c = elements k = 2 c, 2 c + 1), written there by the epilogue with tcgen05.st.  That leaves
+// ONE accumulator region, columns [0, 256): a 500-wide layer is two N = 256 halves through the same region, the epilogue
+// DRAINS it into registers (64 values per thread: thread = row, 16 epilogue warps = 4 lane quadrants x 4 column parts) and frees
+// it at once, so the next half's MMAs run under the tanh / split / store work; the shared layer's first half is held in
+// registers until the second half's MMAs have read the tile it overwrites.  The input tile's lo halves sit in TMEM columns
+// [472, 512) (the tail of the lo region, rewritten only by layer 1's LAST epilogue).  Weight images are those of the 64-row form.
+constexpr int TM2 = 128;
+constexpr uint32_t ACT2_BYTES = TM2 * KA * 2;              // 131 072: hi halves only
+constexpr uint32_t X2_BYTES = TM2 * KX * 2;                // 20 480
+constexpr uint32_t OFF2_ACT = 0, OFF2_X = ACT2_BYTES, OFF2_RING = ACT2_BYTES + X2_BYTES;
+constexpr uint32_t SMEM2_BYTES = OFF2_RING + NSTAGE * STAGE_BYTES;   // 217 088
+constexpr uint32_t LBO_A2 = TM2 * 16;
+constexpr int kEpiWarps2 = 16, kThreads2 = 64 + 32 * kEpiWarps2;     // 576
+constexpr uint32_t kAccCol = 0, kLoCol = 256, kXLoCol = 472;
+constexpr int Q_FULL = 0, Q_EMPTY = NSTAGE, Q_ACC = 2 * NSTAGE, Q_ACT = Q_ACC + 6, Q_FREE = Q_ACT + 6, Q_COUNT = Q_FREE + 6;
+
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+               "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+               "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x2(uint32_t taddr, uint32_t r0, uint32_t r1) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(r0), "r"(r1) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x2(uint32_t taddr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// one K = 16 step: A_lo (tensor memory) B_hi with the accumulate flag, then A_hi (shared memory) B_lo, A_hi B_hi
+__device__ __forceinline__ void umma3_m128(uint32_t tmem_d, uint32_t ta_lo, uint32_t a_hi, uint32_t b_hi, uint32_t b_lo, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, t, q;\n\t.reg .b32 hi;\n\t.reg .b64 dah, dbh, dbl;\n\t"
+      "mov.u32 hi, 0x4008;\n\t"
+      "mov.b64 dah, {%2, hi};\n\tmov.b64 dbh, {%3, hi};\n\tmov.b64 dbl, {%4, hi};\n\t"
+      "elect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %6, 0;\n\tsetp.eq.u32 t, 0, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], dbh, %5, p;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], dah, dbl, %5, t;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], dah, dbh, %5, t;\n\t}\n" ::"r"(tmem_d),
+      "r"(ta_lo), "r"(a_hi), "r"(b_hi), "r"(b_lo), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// a warp's part of a phase is done (its shared-memory and tensor-memory writes are visible to the tensor cores, its TMEM reads
+// complete): one lane arrives
+__device__ __forceinline__ void warp_arrive_local(uint32_t bar, int lane) {
+  fence_async_smem();
+  tmem_st_wait();
+  fence_tc_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+
+// epilogue of one N = 256 half: thread = row 32 q + lane, columns 64 part + [0, 64) of the half.  Drains the accumulator, frees
+// it (free_bar), computes tanh(acc * us + bias) and its hi / lo split, and -- once hold_bar (if any) has completed -- stores hi
+// into the activation tile and lo into tensor memory at activation columns k0 + 64 part + [0, 64).
+template <bool HOLD>
+__device__ __forceinline__ void epi128_tanh_half(uint8_t* smem, uint32_t tmem, int k0, const float* __restrict__ bias, float us, int q,
+                                                 int part, int lane, uint32_t free_bar, uint32_t hold_bar) {
+  const int row = 32 * q + lane, kb = k0 + 64 * part;
+  const uint32_t lane_base = tmem + ((uint32_t)(32 * q) << 16);
+  const float us2 = us * kTwoLog2e;
+  uint32_t raw[64];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x16(lane_base + kAccCol + 64 * part + 16 * c, *reinterpret_cast<uint32_t(*)[16]>(&raw[16 * c]));
+  tmem_ld_wait();
+  fence_tc_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(free_bar);         // the accumulator region can take the next MMAs
+  uint4 hh[8];
+  uint32_t ll[32];
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const int k = kb + 8 * g;
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + k)), b1 = __ldg(reinterpret_cast<const float4*>(bias + k + 4));
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    __half2 h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float v0 = tanh_from_scaled(fmaf(__uint_as_float(raw[8 * g + 2 * j]), us2, bb[2 * j] * kTwoLog2e));
+      const float v1 = tanh_from_scaled(fmaf(__uint_as_float(raw[8 * g + 2 * j + 1]), us2, bb[2 * j + 1] * kTwoLog2e));
+      split_pair(v0, v1, h[j], l[j]);
+      ll[4 * g + j] = *reinterpret_cast<uint32_t*>(&l[j]);
+    }
+    hh[g] = make_uint4(*reinterpret_cast<uint32_t*>(&h[0]), *reinterpret_cast<uint32_t*>(&h[1]), *reinterpret_cast<uint32_t*>(&h[2]),
+                       *reinterpret_cast<uint32_t*>(&h[3]));
+  }
+  if (HOLD) mbar_wait(hold_bar, 0);
+  uint8_t* hi = smem + OFF2_ACT;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(hi + (uint32_t)(((kb >> 3) + g) * (TM2 * 16) + row * 16)) = hh[g];
+  tmem_st_32x32b_x16(lane_base + kLoCol + (kb >> 1), *reinterpret_cast<uint32_t(*)[16]>(&ll[0]));
+  tmem_st_32x32b_x16(lane_base + kLoCol + (kb >> 1) + 16, *reinterpret_cast<uint32_t(*)[16]>(&ll[16]));
+}
+
+__global__ void __launch_bounds__(kThreads2, 1) policy_forward_m128_kernel(const __grid_constant__ Args args) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bars[Q_COUNT];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int rowmap[TM2];
+  __shared__ float ssum[4][TM2];
+  const Chain& C = args.c[blockIdx.y];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int beg = 0, cnt = C.n_rows;
+  if (C.range_dev) {
+    beg = C.range_dev[0];
+    cnt = C.range_dev[1];
+  }
+  const int row0 = blockIdx.x * TM2;
+  if (row0 >= cnt) return;              // CTA-uniform
+  unsigned long long* prof = args.prof ? args.prof + 32 * (size_t)(blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
+  if (tid < TM2) {
+    const int lr = row0 + tid;
+    rowmap[tid] = lr < cnt ? (C.rows ? C.rows[beg + lr] : beg + lr) : -1;
+  }
+  const uint32_t bar0 = smem_u32(bars);
+  if (tid == 0) {
+    for (int i = 0; i < 2 * NSTAGE + 6; ++i) mbar_init(bar0 + 8 * i, 1);
+    for (int i = 0; i < 12; ++i) mbar_init(bar0 + 8 * (Q_ACT + i), kEpiWarps2);   // activation + accumulator-free: one lane per warp
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  fence_tc_before();
+  __syncthreads();
+  fence_tc_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {   // ---- weight stream
+      uint32_t slot = 0, phase = 0;
+      const uint32_t ring = smem_u32(smem + OFF2_RING);
+      long long stall = 0;
+      for (int s = 0; s < C.n_seg; ++s) {
+        const Seg& g = C.seg[s];
+        const uint32_t bytes = (uint32_t)g.kps * g.n * 64u;
+        const uint8_t* src = g.w;
+        const int n_stage = g.ksteps / g.kps;
+        for (int k = 0; k < n_stage; ++k) {
+          const long long t0 = prof ? clock64() : 0;
+          mbar_wait(bar0 + 8 * (Q_EMPTY + slot), phase ^ 1);
+          if (prof) stall += clock64() - t0;
+          mbar_expect_tx(bar0 + 8 * (Q_FULL + slot), bytes);
+          bulk_g2s(ring + slot * STAGE_BYTES, src, bytes, bar0 + 8 * (Q_FULL + slot));
+          src += bytes;
+          if (++slot == NSTAGE) {
+            slot = 0;
+            phase ^= 1;
+          }
+        }
+      }
+      if (prof) {
+        prof[28] = (unsigned long long)stall;
+        prof[29] = (unsigned long long)clock64();
+      }
+    }
+  } else if (warp == 1) {
+    {   // ---- MMA issue by the converged warp (one elected lane inside the asm)
+      uint32_t slot = 0, phase = 0;
+      long long stall = 0;
+      if (prof && lane == 0) prof[0] = (unsigned long long)clock64();
+      mbar_wait_uniform(bar0 + 8 * (Q_ACT + 5), 0);   // the input tile is in shared / tensor memory
+      for (int s = 0; s < C.n_seg; ++s) {
+        const Seg& g = C.seg[s];
+        const uint32_t n = g.n, kps = g.kps, n_stage = g.ksteps / kps;
+        if (g.wait_act != 0xff) mbar_wait_uniform(bar0 + 8 * (Q_ACT + g.wait_act), 0);
+        if (g.wait_free != 0xff) mbar_wait_uniform(bar0 + 8 * (Q_FREE + g.wait_free), 0);
+        if (prof && lane == 0) prof[1 + 2 * s] = (unsigned long long)clock64();
+        fence_tc_after();
+        const uint32_t idesc = instr_desc_f16(TM2, n);
+        const uint32_t a_addr = smem_u32(smem + (g.a_src ? OFF2_ACT : OFF2_X)) + (uint32_t)(g.a_k0 >> 3) * (TM2 * 16);
+        uint32_t a_hi = desc_lo(a_addr, LBO_A2);
+        uint32_t ta_lo = tmem + (g.a_src ? kLoCol : kXLoCol) + (uint32_t)(g.a_k0 >> 1);
+        const uint32_t b_seg = desc_lo(smem_u32(smem + OFF2_RING), 16u * n);
+        const uint32_t lo_off = 2u * n, step_off = 4u * n;
+        const uint32_t d = tmem + kAccCol;
+        uint32_t acc = g.first ? 0u : 1u;
+        for (uint32_t k = 0; k < n_stage; ++k) {
+          const long long t0 = prof ? clock64() : 0;
+          mbar_wait_uniform(bar0 + 8 * (Q_FULL + slot), phase);
+          if (prof) stall += clock64() - t0;
+          fence_tc_after();
+          uint32_t b = b_seg + slot * (STAGE_BYTES >> 4);
+          for (uint32_t j = 0; j < kps; ++j) {
+            umma3_m128(d, ta_lo, a_hi, b, b + lo_off, idesc, acc);
+            acc = 1u;
+            a_hi += (2 * LBO_A2) >> 4;
+            ta_lo += 8;
+            b += step_off;
+          }
+          umma_commit_elect(bar0 + 8 * (Q_EMPTY + slot));
+          if (++slot == NSTAGE) {
+            slot = 0;
+            phase ^= 1;
+          }
+        }
+        if (g.commit_acc != 0xff) umma_commit_elect(bar0 + 8 * (Q_ACC + g.commit_acc));
+        if (prof && lane == 0) prof[2 + 2 * s] = (unsigned long long)clock64();
+      }
+      if (prof && lane == 0) prof[15] = (unsigned long long)stall;
+    }
+  } else {
+    // ---- epilogue warps 2..17: TMEM lane quadrant q = warp % 4 (rows 32 q + lane), column part (warp - 2) / 4
+    const int et = tid - 64;
+    const int q = warp & 3, part = (warp - 2) >> 2;
+    const int row = 32 * q + lane;
+    const uint32_t lane_base = tmem + ((uint32_t)(32 * q) << 16);
+    uint8_t* hi = smem + OFF2_ACT;
+    {  // input row -> hi halves (shared memory) and lo halves (tensor memory) of 2^12 x; part p: columns 20 p .. 20 p + 19
+      const int gr = rowmap[row];
+      const float* xr = C.x + (size_t)(gr >= 0 ? gr : 0) * C.ldx;
+      float v[20];
+#pragma unroll
+      for (int j = 0; j < 20; ++j) {
+        const int c = 20 * part + j;
+        v[j] = (gr >= 0 && c < C.d_in) ? fminf(fmaxf(__ldg(xr + c), -ACT_CLAMP), ACT_CLAMP) : 0.0f;
+      }
+      uint32_t lo_w[10];
+#pragma unroll
+      for (int j = 0; j < 10; ++j) {
+        __half2 h, l;
+        split_pair(v[2 * j], v[2 * j + 1], h, l);
+        const int c = 20 * part + 2 * j;
+        *reinterpret_cast<__half2*>(smem + OFF2_X + (uint32_t)((c >> 3) * (TM2 * 16) + row * 16 + (c & 7) * 2)) = h;
+        lo_w[j] = *reinterpret_cast<uint32_t*>(&l);
+      }
+#pragma unroll
+      for (int j = 0; j < 5; ++j) tmem_st_32x32b_x2(lane_base + kXLoCol + 10 * part + 2 * j, lo_w[2 * j], lo_w[2 * j + 1]);
+      warp_arrive_local(bar0 + 8 * (Q_ACT + 5), lane);
+    }
+    {  // H = tanh(x W1 + b1)
+      const float us = __ldg(C.us_w1);
+      for (int h = 0; h < 2; ++h) {
+        mbar_wait(bar0 + 8 * (Q_ACC + h), 0);
+        if (prof && et == 0) prof[16 + 2 * h] = (unsigned long long)clock64();
+        fence_tc_after();
+        epi128_tanh_half<false>(smem, tmem, 256 * h, C.b1, us, q, part, lane, bar0 + 8 * (Q_FREE + h), 0u);
+        warp_arrive_local(bar0 + 8 * (Q_ACT + h), lane);
+        if (prof && et == 0) prof[17 + 2 * h] = (unsigned long long)clock64();
+      }
+    }
+    if (C.att_n > 0) {   // single-token attention: r = full + (full Wa + ba), then L2-normalise the block
+      const float us = __ldg(C.us_att);
+      mbar_wait(bar0 + 8 * (Q_ACC + 2), 0);
+      if (prof && et == 0) prof[20] = (unsigned long long)clock64();
+      fence_tc_after();
+      // this warp's columns of the block: pairs [pp_beg, pp_end) of the att_pad / 2 column pairs, split evenly over the 4 parts
+      const int n_pairs = C.att_pad >> 1, per = (n_pairs + 3) >> 2;
+      const int pp_beg = part * per, pp_end = min(n_pairs, pp_beg + per);
+      float v[20][2];                       // at most 80 / 4 = 20 pairs per part
+      float ss = 0.0f;
+#pragma unroll
+      for (int u = 0; u < 20; ++u) {
+        const int pp = pp_beg + u;
+        v[u][0] = v[u][1] = 0.0f;
+        if (pp < pp_end) {                  // warp-uniform
+          uint32_t r0, r1, l0;
+          tmem_ld_32x32b_x2(lane_base + kAccCol + 2 * pp, r0, r1);
+          const int col = 2 * pp, k = C.att_lo + col;
+          // the lo pair of (k, k + 1) = ONE column (x1: a wider load would run past column 511 at the block's end)
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(l0) : "r"(lane_base + kLoCol + (uint32_t)min(k >> 1, 255)));
+          tmem_ld_wait();
+          if (col < C.att_n) {
+            const float2 b = __ldg(reinterpret_cast<const float2*>(C.batt + col));
+            const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(hi + (uint32_t)((k >> 3) * (TM2 * 16) + row * 16 + (k & 7) * 2)));
+            const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&l0));
+            v[u][0] = fmaf(__uint_as_float(r0), us, b.x) + (hf.x + lf.x) * ACT_UNSCALE;
+            v[u][1] = fmaf(__uint_as_float(r1), us, b.y) + (hf.y + lf.y) * ACT_UNSCALE;
+            ss += v[u][0] * v[u][0] + v[u][1] * v[u][1];
+          }
+        }
+      }
+      fence_tc_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar0 + 8 * (Q_FREE + 2));
+      ssum[part][row] = ss;
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps2) : "memory");       // the sixteen epilogue warps
+      const float inv = 1.0f / fmaxf(sqrtf(ssum[0][row] + ssum[1][row] + ssum[2][row] + ssum[3][row]), 1e-12f);   // F.normalize
+#pragma unroll
+      for (int u = 0; u < 20; ++u) {
+        const int pp = pp_beg + u, col = 2 * pp, k = C.att_lo + col;
+        if (pp < pp_end && col < C.att_n) {
+          __half2 h, l;
+          split_pair(v[u][0] * inv, v[u][1] * inv, h, l);
+          *reinterpret_cast<__half2*>(hi + (uint32_t)((k >> 3) * (TM2 * 16) + row * 16 + (k & 7) * 2)) = h;
+          // one 32-bit column of the lo operand = this pair (att_lo is even)
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(lane_base + kLoCol + (k >> 1)), "r"(*reinterpret_cast<uint32_t*>(&l))
+                       : "memory");
+        }
+      }
+      warp_arrive_local(bar0 + 8 * (Q_ACT + 2), lane);
+      if (prof && et == 0) prof[21] = (unsigned long long)clock64();
+    }
+    {  // Z = tanh(in Ws + bs), in place: the first half is drained and computed while the second half's MMAs run and stored
+       // once they have all read the tile
+      const float us = __ldg(C.us_ws);
+      mbar_wait(bar0 + 8 * (Q_ACC + 3), 0);
+      if (prof && et == 0) prof[22] = (unsigned long long)clock64();
+      fence_tc_after();
+      epi128_tanh_half<true>(smem, tmem, 0, C.bs, us, q, part, lane, bar0 + 8 * (Q_FREE + 3), bar0 + 8 * (Q_ACC + 4));
+      warp_arrive_local(bar0 + 8 * (Q_ACT + 3), lane);
+      if (prof && et == 0) prof[23] = (unsigned long long)clock64();
+      fence_tc_after();
+      epi128_tanh_half<false>(smem, tmem, 256, C.bs, us, q, part, lane, bar0 + 8 * (Q_FREE + 4), 0u);
+      warp_arrive_local(bar0 + 8 * (Q_ACT + 4), lane);
+      if (prof && et == 0) prof[24] = (unsigned long long)clock64();
+    }
+    if (part == 0) {  // head: logits or value (+ optional per-head argmax, env_base.py:373-382)
+      const float us = __ldg(C.us_wh);
+      mbar_wait(bar0 + 8 * (Q_ACC + 5), 0);
+      if (prof && et == 0) prof[25] = (unsigned long long)clock64();
+      fence_tc_after();
+      float* lg = reinterpret_cast<float*>(smem + OFF2_X);       // [TM2][33]; the input tile is dead by now
+      uint32_t r[32];
+      tmem_ld_32x32b_x16(lane_base + kAccCol, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+      tmem_ld_32x32b_x16(lane_base + kAccCol + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+      tmem_ld_wait();
+      const int gr = rowmap[row];
+#pragma unroll
+      for (int col = 0; col < 32; ++col) {
+        if (col < C.n_out) {
+          const float x = fmaf(__uint_as_float(r[col]), us, __ldg(C.bh + col));
+          if (C.out && gr >= 0) C.out[(size_t)gr * C.ld_out + col] = x;
+          lg[row * 33 + col] = x;
+        }
+      }
+      if (C.act_out && gr >= 0) {          // the thread holds its row's 32 columns: no exchange needed
+        const float* lr = lg + row * 33;
+        int4 a = make_int4(0, 0, 0, 0);
+        int o = 0;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          if (h < C.n_heads) {
+            int best = 0;
+            float bv = lr[o];
+            for (int k = 1; k < C.head[h]; ++k)
+              if (lr[o + k] > bv) { bv = lr[o + k]; best = k; }      // first maximum, like torch.argmax
+            (h == 0 ? a.x : h == 1 ? a.y : h == 2 ? a.z : a.w) = best;
+            o += C.head[h];
+          }
+        }
+        reinterpret_cast<int4*>(C.act_out)[(size_t)gr * C.ld_act] = a;
+      }
+    }
+    if (prof && et == 0) prof[26] = (unsigned long long)clock64();
+  }
+  fence_tc_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
+  }
+}
+
 // ---- operand images -----------------------------------------------------------------------------------------------
 // us[0] = 2^-(12 + s), us[1] = 2^s with s such that max |2^s w| lies in [2^13, 2^14)
 __global__ void pack_scale_kernel(const float* __restrict__ w, int k_rows, int ldw, int n_cols, float* __restrict__ us) {
@@ -1140,9 +1502,12 @@ static unsigned long long* g_prof = nullptr;
 // twice the rate, but every MMA costs the issuing warp ~100 cycles (seven vector -> uniform register moves per UTCHMMA), more
 // than a cta_group::2 MMA takes to execute, and the pair's extra signalling (relay, multicast commits) is on the critical
 // path; it stays in the library as a tested variant.
-static int g_pair = [] {
-  const char* e = getenv("HH_TC_PAIR");
-  return (e && atoi(e) == 1) ? 1 : 0;
+static int g_mode = [] {            // HH_TC_MODE = m128 (default) | m64 | pair   (HH_TC_PAIR=1 is the older spelling of pair)
+  const char* e = getenv("HH_TC_MODE");
+  const char* p = getenv("HH_TC_PAIR");
+  if (e && std::string(e) == "m64") return 0;
+  if ((e && std::string(e) == "pair") || (p && atoi(p) == 1)) return 1;
+  return 2;
 }();
 extern "C" int hh_policy_tc_profile(unsigned long long* stamps_dev) {   // 32 clock64() stamps per CTA, null = off
   g_prof = stamps_dev;
@@ -1153,13 +1518,17 @@ extern "C" int hh_policy_tc_debug(int32_t flags) {   // timing experiments (prof
   g_debug = flags;
   return 0;
 }
-extern "C" int32_t hh_policy_tc_pair(void) { return g_pair; }           // the layout hh_policy_pack must produce: split = 1 + pair
+// 0: 64-row tiles, one CTA each; 1: the CTA-pair form; 2 (default): 128-row tiles with the lo halves in tensor memory.  Decides the
+// layout hh_policy_pack produces (pair: every stage split into two column halves) and the attention block's geometry
+extern "C" int32_t hh_policy_tc_mode(void) { return g_mode; }
+extern "C" int32_t hh_policy_tc_pair(void) { return g_mode == 1; }
 
 extern "C" int64_t hh_policy_image_bytes(int32_t ksteps, int32_t n_total) { return (int64_t)ksteps * n_total * 64; }
 
 int hh_pf_tc_pack(const float* w_dev, int k_rows, int n_cols, int ldw, int n_total, int n_chunk, int row_shift, int ksteps, int kps,
                   void* image_dev, float* unscale_dev, void* stream, std::string& err) {
   using namespace hh::tc;
+  const int g_pair = g_mode == 1;
   const int split = 1 + g_pair;
   if (!w_dev || !image_dev || !unscale_dev || k_rows <= 0 || n_cols <= 0 || ldw < n_cols || n_total < n_cols || n_chunk <= 0 ||
       n_total % n_chunk || n_chunk % (8 * split) || (g_pair && n_chunk % 16) || n_chunk > 256 || ksteps <= 0 || kps <= 0 || ksteps % kps ||
@@ -1183,7 +1552,7 @@ int hh_pf_tc_pack(const float* w_dev, int k_rows, int n_cols, int ldw, int n_tot
 int hh_pf_tc_launch(const hh_policy_chain_ex* chains, int n_chains, int max_rows, void* stream, std::string& err) {
   using namespace hh::tc;
   Args a;
-  const int pair = g_pair;
+  const int pair = g_mode == 1, m128 = g_mode == 2;
   for (int i = 0; i < n_chains; ++i) {
     const hh_policy_chain_ex& s = chains[i];
     if (!s.img_w1 || !s.img_ws || !s.img_wh || !s.us_w1 || !s.us_ws || !s.us_wh || (s.att_n > 0 && (!s.img_att || !s.us_att))) {
@@ -1200,20 +1569,40 @@ int hh_pf_tc_launch(const hh_policy_chain_ex* chains, int n_chains, int max_rows
     c.out = s.out; c.rows = s.rows; c.range_dev = s.range_dev; c.act_out = s.act_out;
     c.n_rows = s.n_rows; c.ldx = s.ldx; c.d_in = s.d_in; c.att_lo = s.att_lo; c.att_n = s.att_n;
     // the attention step's N: the block padded to the MMA's granularity (8 columns; 16 for the pair form)
-    const int att_nn = s.att_n > 0 ? (pair ? (s.att_n + 15) / 16 * 16 : (s.att_n + 7) / 8 * 8) : 0;
+    const int att_nn = s.att_n > 0 ? ((pair || m128) ? (s.att_n + 15) / 16 * 16 : (s.att_n + 7) / 8 * 8) : 0;
     c.att_pad = att_nn;
     c.n_out = s.n_out; c.ld_out = s.ld_out; c.n_heads = s.n_heads;
     for (int h = 0; h < 4; ++h) c.head[h] = s.head[h];
     c.ld_act = s.ld_act > 0 ? s.ld_act : 1;
     const int k1s = (s.d_in + 15) / 16;
     int n = 0;
-    auto seg = [&](const void* w, size_t off, int nn, int ksteps, int kps, int col, int a_src, int a_k0, int first, int wait, int commit) {
+    auto seg = [&](const void* w, size_t off, int nn, int ksteps, int kps, int col, int a_src, int a_k0, int first, int wait, int commit,
+                   int wait_free = 0xff) {
       Seg& g = c.seg[n++];
       g.w = static_cast<const uint8_t*>(w) + off;
       g.n = (uint16_t)nn; g.ksteps = (uint16_t)ksteps; g.kps = (uint16_t)kps; g.tmem_col = (uint16_t)col;
-      g.a_off16 = (uint16_t)((a_k0 / 8) * (TM * 16) / 16);
+      g.a_k0 = (uint16_t)a_k0;
       g.a_src = (uint8_t)a_src; g.first = (uint8_t)first; g.wait_act = (uint8_t)wait; g.commit_acc = (uint8_t)commit;
+      g.wait_free = (uint8_t)wait_free;
     };
+    if (m128) {
+      // one accumulator region: every segment waits for the drain of the previous one (accumulator-free barriers 0 .. 4:
+      // after layer 1 half 0 / half 1, the attention block, the shared layer's half 0 / half 1)
+      seg(s.img_w1, 0, 256, k1s, 1, 0, 0, 0, 1, 0xff, 0);
+      seg(s.img_w1, (size_t)k1s * 256 * 64, 256, k1s, 1, 0, 0, 0, 1, 0xff, 1, 0);
+      int act_ready = 1, free_ready = 1;
+      if (s.att_n > 0) {
+        const int k0 = s.att_lo & ~15, ks = (s.att_lo + s.att_n - k0 + 15) / 16;
+        seg(s.img_att, 0, att_nn, ks, 1, 0, 1, k0, 1, 1, 2, 1);
+        act_ready = 2; free_ready = 2;
+      }
+      seg(s.img_ws, 0, 256, KA / 16, 1, 0, 1, 0, 1, act_ready, 3, free_ready);
+      seg(s.img_ws, (size_t)(KA / 16) * 256 * 64, 256, KA / 16, 1, 0, 1, 0, 1, 0xff, 4, 3);
+      seg(s.img_wh, 0, 32, 16, 8, 0, 1, 0, 1, 3, 0xff, 4);
+      seg(s.img_wh, (size_t)16 * 32 * 64, 32, 16, 8, 0, 1, 256, 0, 4, 5);
+      c.n_seg = n;
+      continue;
+    }
     // accumulator regions (TMEM columns): single-CTA form 0 / 256 (an N = 256 step takes 256 columns), pair form 0 / 128 /
     // 256 (attention) / 384 (head) (N / 2 columns per step)
     const int colB = pair ? 128 : 256, colAtt = pair ? 256 : 0, colHead = pair ? 384 : 0;
@@ -1243,6 +1632,7 @@ int hh_pf_tc_launch(const hh_policy_chain_ex* chains, int n_chains, int max_rows
   if (!opted_dev[dev]) {
     ce = cudaFuncSetAttribute(policy_forward_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(policy_forward_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(policy_forward_m128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM2_BYTES);
     if (ce != cudaSuccess) {
       err = std::string("cudaFuncSetAttribute(policy_forward kernels): ") + cudaGetErrorString(ce);
       return -2;
@@ -1251,7 +1641,8 @@ int hh_pf_tc_launch(const hh_policy_chain_ex* chains, int n_chains, int max_rows
   }
   const int tiles = (max_rows + TM - 1) / TM;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (pair) policy_forward_pair_kernel<<<dim3((unsigned)((tiles + 1) / 2 * 2), (unsigned)n_chains), kThreads, SMEM_BYTES, st>>>(a);
+  if (m128) policy_forward_m128_kernel<<<dim3((unsigned)((max_rows + TM2 - 1) / TM2), (unsigned)n_chains), kThreads2, SMEM2_BYTES, st>>>(a);
+  else if (pair) policy_forward_pair_kernel<<<dim3((unsigned)((tiles + 1) / 2 * 2), (unsigned)n_chains), kThreads, SMEM_BYTES, st>>>(a);
   else policy_forward_tc_kernel<1><<<dim3((unsigned)tiles, (unsigned)n_chains), kThreads, SMEM_BYTES, st>>>(a);
   ce = cudaGetLastError();
   if (ce != cudaSuccess) {

@@ -160,8 +160,9 @@ def _att_image_geometry(att_lo: int, att_n: int):
     """The attention block reads activation columns [att_lo, att_lo + att_n); the MMA's A operand has to start on a core
     matrix (8 columns), so the image's K range starts at floor8(att_lo) and its first rows are zero; its N is the block
     padded to the MMA's N granularity (16 columns for the CTA-pair kernel, 8 otherwise)."""
-    k0 = att_lo & ~7
-    g = 16 if nat.lib().hh_policy_tc_pair() else 8
+    mode = nat.lib().hh_policy_tc_mode()              # 0: 64-row tiles, 1: CTA pairs, 2: 128-row tiles (A_lo in tensor memory)
+    k0 = att_lo & ~15 if mode == 2 else att_lo & ~7   # the TMEM operand of the 128-row form starts on a K = 16 step
+    g = 16 if mode >= 1 else 8
     return att_lo - k0, (att_lo + att_n - k0 + 15) // 16, (att_n + g - 1) // g * g          # (row_shift, ksteps, N)
 
 

@@ -199,6 +199,7 @@ int64_t hh_policy_image_bytes(int32_t ksteps, int32_t n_total);
 int hh_policy_pack(const float* w_dev, int32_t k_rows, int32_t n_cols, int32_t ldw, int32_t n_total, int32_t n_chunk,
                    int32_t row_shift, int32_t ksteps, int32_t kps, void* image_dev, float* unscale_dev, void* stream);
 int32_t hh_policy_tc_pair(void);
+int32_t hh_policy_tc_mode(void);   /* 0: 64-row tiles, 1: CTA pairs, 2 (default): 128-row tiles, lo halves in tensor memory */
 /* Row lists per key, built on the device: rows_dev int32 [n_keys][n], ranges_dev int32 [n_keys][2] = {k n, count_k} for the
  * arenas i with key_dev[i] == keys_host[k] (n_keys <= 4).  Level 5 draws the opponents' policy set per arena and episode
  * (env_hetero.py:55-59); the lists feed hh_policy_chain_ex.rows / range_dev without a host synchronisation. */

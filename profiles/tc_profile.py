@@ -15,6 +15,8 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 L = nat.lib()
 L.hh_policy_tc_profile.argtypes = [ctypes.c_void_p]
 cluster = 2 if L.hh_policy_tc_pair() else 1
+L.hh_policy_tc_mode.restype = ctypes.c_int32
+TM = 128 if L.hh_policy_tc_mode() == 2 else 64
 torch.manual_seed(0)
 m1, m2 = M.build_policy_pair("fight")
 m1.cuda(); m2.cuda()
@@ -22,7 +24,7 @@ f1 = torch.rand(B, 57, device="cuda"); f2 = torch.rand(B, 57, device="cuda")
 fu = FusedPolicyPair(m1, m2, precision=2)
 for _ in range(3):
     fu.forward(f1, f2)
-tiles = (B + 63) // 64
+tiles = (B + TM - 1) // TM
 tiles = (tiles + cluster - 1) // cluster * cluster
 names = {1: "seg0 L1h0 start", 2: "seg0 end", 3: "seg1 L1h1 start", 4: "seg1 end", 5: "seg2 ATT start", 6: "seg2 end",
          7: "seg3 SHh0 start", 8: "seg3 end", 9: "seg4 SHh1 start", 10: "seg4 end", 11: "seg5 HEADa start", 12: "seg5 end",
@@ -43,7 +45,7 @@ for flags, label in modes:
     L.hh_policy_tc_profile(None)
     L.hh_policy_tc_debug(0)
     s = buf.view(4, tiles, 32).cpu().double()
-    print(f"== {label}: rows {B}, {'CTA pairs (cta_group::2)' if cluster == 2 else 'one CTA per tile'}: launch {e0.elapsed_time(e1) * 1e3:.1f} us "
+    print(f"== {label}: rows {B}, {'CTA pairs (cta_group::2)' if cluster == 2 else f'one CTA per {TM}-row tile'}: launch {e0.elapsed_time(e1) * 1e3:.1f} us "
           f"(with stamps); cycles relative to the start stamp of warp 1 of the same CTA, median over the CTAs of [actor chain 0 | critic chain 1]")
     for rank in range(cluster):
         sr = s[:, rank::cluster, :]

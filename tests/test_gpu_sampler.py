@@ -311,10 +311,12 @@ def test_fused_policy_forward_matches_torch(mode):
         torch.backends.cuda.matmul.allow_tf32 = prev
 
 
-def test_pair_kernel_variant_matches_torch():
-    """HH_TC_PAIR=1: the CTA-pair form of the tcgen05 forward (cta_group::2 MMAs, each CTA streams half of the weight columns,
-    relay + multicast commits) -- not the default (profiles/README.md, round 2), kept as a tested variant.  Runs in a
-    subprocess because the layout of the packed images is fixed when the library is loaded."""
+@pytest.mark.parametrize("variant,mode_id", [("pair", 1), ("m64", 0)])
+def test_tc_kernel_variants_match_torch(variant, mode_id):
+    """HH_TC_MODE=pair: the CTA-pair form of the tcgen05 forward (cta_group::2 MMAs, each CTA streams half of the weight
+    columns, relay + multicast commits); HH_TC_MODE=m64: 64-row tiles with hi and lo activations in shared memory.  Neither
+    is the default (128-row tiles, lo halves in tensor memory; profiles/README.md, round 2); both stay tested variants.  Runs
+    in a subprocess because the layout of the packed images is fixed when the library is loaded."""
     import os
     import subprocess
     import sys
@@ -322,7 +324,7 @@ def test_pair_kernel_variant_matches_torch():
         "import torch\n"
         "from hhmarl_2d_b200 import _native as nat, models as M\n"
         "from hhmarl_2d_b200.fused_forward import FusedPolicyPair, FusedActor, run_chains\n"
-        "assert nat.lib().hh_policy_tc_pair() == 1\n"
+        f"assert nat.lib().hh_policy_tc_mode() == {mode_id}\n"
         "torch.manual_seed(1)\n"
         "worst = 0.0\n"
         "for mode in ('fight', 'escape'):\n"
@@ -343,7 +345,7 @@ def test_pair_kernel_variant_matches_torch():
         "        worst = max(worst, (o - m1.actor(x[:, :fa.d_in])).abs().max().item())\n"
         "print('WORST', worst)\n"
         "assert worst < 3e-5\n")
-    env = dict(os.environ, HH_TC_PAIR="1")
+    env = dict(os.environ, HH_TC_MODE=variant)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
