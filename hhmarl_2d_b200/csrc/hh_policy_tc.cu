@@ -294,6 +294,17 @@ __device__ __forceinline__ float tanh_from_scaled(float a) {
   return fmaf(-2.0f, r, 1.0f);
 #endif
 }
+// 2^12 tanh(x) from a = 2 log2(e) x in one fma after the two SFU operations (the activation prescale folded in)
+__device__ __forceinline__ float tanh_scaled_4096(float a) {
+#ifdef HH_TC_EXACT_TANH
+  return ACT_SCALE * tanhf(a * (1.0f / kTwoLog2e));
+#else
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+  return fmaf(-2.0f * ACT_SCALE, r, ACT_SCALE);
+#endif
+}
 __device__ __forceinline__ void split_pair(float v0, float v1, __half2& h, __half2& l) {
   const float s0 = v0 * ACT_SCALE, s1 = v1 * ACT_SCALE;
   h = __floats2half2_rn(s0, s1);
@@ -1148,7 +1159,8 @@ __device__ __forceinline__ void warp_arrive_local(uint32_t bar, int lane) {
 // into the activation tile and lo into tensor memory at activation columns k0 + 64 part + [0, 64).
 template <bool HOLD>
 __device__ __forceinline__ void epi128_tanh_half(uint8_t* smem, uint32_t tmem, int k0, const float* __restrict__ bias, float us, int q,
-                                                 int part, int lane, uint32_t free_bar, uint32_t hold_bar) {
+                                                 int part, int lane, uint32_t free_bar, uint32_t hold_bar,
+                                                 unsigned long long* stamp = nullptr) {
   const int row = 32 * q + lane, kb = k0 + 64 * part;
   const uint32_t lane_base = tmem + ((uint32_t)(32 * q) << 16);
   const float us2 = us * kTwoLog2e;
@@ -1159,6 +1171,7 @@ __device__ __forceinline__ void epi128_tanh_half(uint8_t* smem, uint32_t tmem, i
   fence_tc_before();
   __syncwarp();
   if (lane == 0) mbar_arrive(free_bar);         // the accumulator region can take the next MMAs
+  if (stamp) stamp[0] = (unsigned long long)clock64();
   uint4 hh[8];
   uint32_t ll[32];
 #pragma unroll
@@ -1169,14 +1182,17 @@ __device__ __forceinline__ void epi128_tanh_half(uint8_t* smem, uint32_t tmem, i
     __half2 h[4], l[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float v0 = tanh_from_scaled(fmaf(__uint_as_float(raw[8 * g + 2 * j]), us2, bb[2 * j] * kTwoLog2e));
-      const float v1 = tanh_from_scaled(fmaf(__uint_as_float(raw[8 * g + 2 * j + 1]), us2, bb[2 * j + 1] * kTwoLog2e));
-      split_pair(v0, v1, h[j], l[j]);
+      const float s0 = tanh_scaled_4096(fmaf(__uint_as_float(raw[8 * g + 2 * j]), us2, bb[2 * j] * kTwoLog2e));
+      const float s1 = tanh_scaled_4096(fmaf(__uint_as_float(raw[8 * g + 2 * j + 1]), us2, bb[2 * j + 1] * kTwoLog2e));
+      h[j] = __floats2half2_rn(s0, s1);
+      const float2 hf = __half22float2(h[j]);
+      l[j] = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
       ll[4 * g + j] = *reinterpret_cast<uint32_t*>(&l[j]);
     }
     hh[g] = make_uint4(*reinterpret_cast<uint32_t*>(&h[0]), *reinterpret_cast<uint32_t*>(&h[1]), *reinterpret_cast<uint32_t*>(&h[2]),
                        *reinterpret_cast<uint32_t*>(&h[3]));
   }
+  if (stamp) stamp[1] = (unsigned long long)clock64();
   if (HOLD) mbar_wait(hold_bar, 0);
   uint8_t* hi = smem + OFF2_ACT;
 #pragma unroll
@@ -1300,24 +1316,31 @@ __global__ void __launch_bounds__(kThreads2, 1) policy_forward_m128_kernel(const
     const int row = 32 * q + lane;
     const uint32_t lane_base = tmem + ((uint32_t)(32 * q) << 16);
     uint8_t* hi = smem + OFF2_ACT;
-    {  // input row -> hi halves (shared memory) and lo halves (tensor memory) of 2^12 x; part p: columns 20 p .. 20 p + 19
-      const int gr = rowmap[row];
-      const float* xr = C.x + (size_t)(gr >= 0 ? gr : 0) * C.ldx;
-      float v[20];
+    {  // input tile -> hi halves (shared memory) and lo halves (tensor memory) of 2^12 x.  Coalesced: consecutive threads read
+       // consecutive floats of a row; the lo halves pass through the (still unused) activation tile as [128][80] halves, because
+       // only the thread that owns a TMEM lane (= row) can write it
+      __half* lo_stage = reinterpret_cast<__half*>(smem + OFF2_ACT);
+      const int d_in = C.d_in;
+      constexpr int kIter = TM2 * KX / (32 * kEpiWarps2);   // 20 elements per thread: all loads in flight before the first use
+      float xv[kIter];
 #pragma unroll
-      for (int j = 0; j < 20; ++j) {
-        const int c = 20 * part + j;
-        v[j] = (gr >= 0 && c < C.d_in) ? fminf(fmaxf(__ldg(xr + c), -ACT_CLAMP), ACT_CLAMP) : 0.0f;
+      for (int i = 0; i < kIter; ++i) {
+        const int e = et + i * 32 * kEpiWarps2, r = e / KX, c = e - r * KX;
+        const int gr = rowmap[r];
+        xv[i] = (gr >= 0 && c < d_in) ? __ldg(C.x + (size_t)gr * C.ldx + c) : 0.0f;
       }
+#pragma unroll
+      for (int i = 0; i < kIter; ++i) {
+        const int e = et + i * 32 * kEpiWarps2, r = e / KX, c = e - r * KX;
+        const float sv = fminf(fmaxf(xv[i], -ACT_CLAMP), ACT_CLAMP) * ACT_SCALE;
+        const __half h = __float2half_rn(sv);
+        *reinterpret_cast<__half*>(smem + OFF2_X + (uint32_t)((c >> 3) * (TM2 * 16) + r * 16 + (c & 7) * 2)) = h;
+        lo_stage[r * KX + c] = __float2half_rn(sv - __half2float(h));
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps2) : "memory");
       uint32_t lo_w[10];
 #pragma unroll
-      for (int j = 0; j < 10; ++j) {
-        __half2 h, l;
-        split_pair(v[2 * j], v[2 * j + 1], h, l);
-        const int c = 20 * part + 2 * j;
-        *reinterpret_cast<__half2*>(smem + OFF2_X + (uint32_t)((c >> 3) * (TM2 * 16) + row * 16 + (c & 7) * 2)) = h;
-        lo_w[j] = *reinterpret_cast<uint32_t*>(&l);
-      }
+      for (int j = 0; j < 10; ++j) lo_w[j] = *reinterpret_cast<const uint32_t*>(lo_stage + row * KX + 20 * part + 2 * j);
 #pragma unroll
       for (int j = 0; j < 5; ++j) tmem_st_32x32b_x2(lane_base + kXLoCol + 10 * part + 2 * j, lo_w[2 * j], lo_w[2 * j + 1]);
       warp_arrive_local(bar0 + 8 * (Q_ACT + 5), lane);
@@ -1338,48 +1361,62 @@ __global__ void __launch_bounds__(kThreads2, 1) policy_forward_m128_kernel(const
       mbar_wait(bar0 + 8 * (Q_ACC + 2), 0);
       if (prof && et == 0) prof[20] = (unsigned long long)clock64();
       fence_tc_after();
-      // this warp's columns of the block: pairs [pp_beg, pp_end) of the att_pad / 2 column pairs, split evenly over the 4 parts
-      const int n_pairs = C.att_pad >> 1, per = (n_pairs + 3) >> 2;
-      const int pp_beg = part * per, pp_end = min(n_pairs, pp_beg + per);
-      float v[20][2];                       // at most 80 / 4 = 20 pairs per part
-      float ss = 0.0f;
+      // this warp's columns of the block: [c_beg, c_end), a multiple of 8 per part (att_pad / 4 rounded up to 8: 32 or 40)
+      const int per = (((C.att_pad + 3) >> 2) + 7) & ~7;
+      const int c_beg = part * per, c_end = min((int)C.att_pad, c_beg + per);
+      const int klo = (C.att_lo + c_beg) >> 1;            // first column of the lo operand that belongs to this part
+      uint32_t racc[40], rlo[20];
 #pragma unroll
-      for (int u = 0; u < 20; ++u) {
-        const int pp = pp_beg + u;
-        v[u][0] = v[u][1] = 0.0f;
-        if (pp < pp_end) {                  // warp-uniform
-          uint32_t r0, r1, l0;
-          tmem_ld_32x32b_x2(lane_base + kAccCol + 2 * pp, r0, r1);
-          const int col = 2 * pp, k = C.att_lo + col;
-          // the lo pair of (k, k + 1) = ONE column (x1: a wider load would run past column 511 at the block's end)
-          asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(l0) : "r"(lane_base + kLoCol + (uint32_t)min(k >> 1, 255)));
-          tmem_ld_wait();
-          if (col < C.att_n) {
-            const float2 b = __ldg(reinterpret_cast<const float2*>(C.batt + col));
-            const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(hi + (uint32_t)((k >> 3) * (TM2 * 16) + row * 16 + (k & 7) * 2)));
-            const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&l0));
-            v[u][0] = fmaf(__uint_as_float(r0), us, b.x) + (hf.x + lf.x) * ACT_UNSCALE;
-            v[u][1] = fmaf(__uint_as_float(r1), us, b.y) + (hf.y + lf.y) * ACT_UNSCALE;
-            ss += v[u][0] * v[u][0] + v[u][1] * v[u][1];
-          }
+      for (int u = 0; u < 5; ++u) {
+        if (c_beg + 8 * u < c_end) {                       // warp-uniform
+          tmem_ld_32x32b_x8(lane_base + kAccCol + c_beg + 8 * u, *reinterpret_cast<uint32_t(*)[8]>(&racc[8 * u]));
+          // lo pairs of the same 8 columns = 4 TMEM columns (att_lo + att_pad <= 512, checked on the host: inside the lo region)
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(rlo[4 * u]), "=r"(rlo[4 * u + 1]), "=r"(rlo[4 * u + 2]), "=r"(rlo[4 * u + 3])
+                       : "r"(lane_base + kLoCol + (uint32_t)(klo + 4 * u)));
         }
       }
+      tmem_ld_wait();
       fence_tc_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar0 + 8 * (Q_FREE + 2));
+      float v[40];
+      float ss = 0.0f;
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int col = c_beg + 8 * u + 2 * j, k = C.att_lo + col;
+          float v0 = 0.0f, v1 = 0.0f;
+          if (col < c_end && col < C.att_n) {
+            const float2 b = __ldg(reinterpret_cast<const float2*>(C.batt + col));
+            const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(hi + (uint32_t)((k >> 3) * (TM2 * 16) + row * 16 + (k & 7) * 2)));
+            const uint32_t lw = rlo[4 * u + j];
+            const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw));
+            v0 = fmaf(__uint_as_float(racc[8 * u + 2 * j]), us, b.x) + (hf.x + lf.x) * ACT_UNSCALE;
+            v1 = fmaf(__uint_as_float(racc[8 * u + 2 * j + 1]), us, b.y) + (hf.y + lf.y) * ACT_UNSCALE;
+          }
+          v[8 * u + 2 * j] = v0;
+          v[8 * u + 2 * j + 1] = v1;
+          ss += v0 * v0 + v1 * v1;
+        }
+      }
       ssum[part][row] = ss;
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps2) : "memory");       // the sixteen epilogue warps
       const float inv = 1.0f / fmaxf(sqrtf(ssum[0][row] + ssum[1][row] + ssum[2][row] + ssum[3][row]), 1e-12f);   // F.normalize
 #pragma unroll
-      for (int u = 0; u < 20; ++u) {
-        const int pp = pp_beg + u, col = 2 * pp, k = C.att_lo + col;
-        if (pp < pp_end && col < C.att_n) {
-          __half2 h, l;
-          split_pair(v[u][0] * inv, v[u][1] * inv, h, l);
-          *reinterpret_cast<__half2*>(hi + (uint32_t)((k >> 3) * (TM2 * 16) + row * 16 + (k & 7) * 2)) = h;
-          // one 32-bit column of the lo operand = this pair (att_lo is even)
-          asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(lane_base + kLoCol + (k >> 1)), "r"(*reinterpret_cast<uint32_t*>(&l))
-                       : "memory");
+      for (int u = 0; u < 5; ++u) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int col = c_beg + 8 * u + 2 * j, k = C.att_lo + col;
+          if (col < c_end && col < C.att_n) {
+            __half2 h, l;
+            split_pair(v[8 * u + 2 * j] * inv, v[8 * u + 2 * j + 1] * inv, h, l);
+            *reinterpret_cast<__half2*>(hi + (uint32_t)((k >> 3) * (TM2 * 16) + row * 16 + (k & 7) * 2)) = h;
+            // one 32-bit column of the lo operand = this pair (att_lo is even)
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(lane_base + kLoCol + (k >> 1)), "r"(*reinterpret_cast<uint32_t*>(&l))
+                         : "memory");
+          }
         }
       }
       warp_arrive_local(bar0 + 8 * (Q_ACT + 2), lane);
@@ -1391,7 +1428,8 @@ __global__ void __launch_bounds__(kThreads2, 1) policy_forward_m128_kernel(const
       mbar_wait(bar0 + 8 * (Q_ACC + 3), 0);
       if (prof && et == 0) prof[22] = (unsigned long long)clock64();
       fence_tc_after();
-      epi128_tanh_half<true>(smem, tmem, 0, C.bs, us, q, part, lane, bar0 + 8 * (Q_FREE + 3), bar0 + 8 * (Q_ACC + 4));
+      epi128_tanh_half<true>(smem, tmem, 0, C.bs, us, q, part, lane, bar0 + 8 * (Q_FREE + 3), bar0 + 8 * (Q_ACC + 4),
+                             (prof && (et == 0 || et == 511)) ? prof + (et == 0 ? 27 : 30) : nullptr);
       warp_arrive_local(bar0 + 8 * (Q_ACT + 3), lane);
       if (prof && et == 0) prof[23] = (unsigned long long)clock64();
       fence_tc_after();
@@ -1399,41 +1437,49 @@ __global__ void __launch_bounds__(kThreads2, 1) policy_forward_m128_kernel(const
       warp_arrive_local(bar0 + 8 * (Q_ACT + 4), lane);
       if (prof && et == 0) prof[24] = (unsigned long long)clock64();
     }
-    if (part == 0) {  // head: logits or value (+ optional per-head argmax, env_base.py:373-382)
-      const float us = __ldg(C.us_wh);
-      mbar_wait(bar0 + 8 * (Q_ACC + 5), 0);
-      if (prof && et == 0) prof[25] = (unsigned long long)clock64();
-      fence_tc_after();
+    {  // head: logits or value (+ optional per-head argmax, env_base.py:373-382).  The four part-0 warps read the accumulator
+       // (thread = row, 32 columns) and stage the rows; all sixteen warps write them out, a row's columns on consecutive lanes
       float* lg = reinterpret_cast<float*>(smem + OFF2_X);       // [TM2][33]; the input tile is dead by now
-      uint32_t r[32];
-      tmem_ld_32x32b_x16(lane_base + kAccCol, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
-      tmem_ld_32x32b_x16(lane_base + kAccCol + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
-      tmem_ld_wait();
-      const int gr = rowmap[row];
+      if (part == 0) {
+        const float us = __ldg(C.us_wh);
+        mbar_wait(bar0 + 8 * (Q_ACC + 5), 0);
+        if (prof && et == 0) prof[25] = (unsigned long long)clock64();
+        fence_tc_after();
+        uint32_t r[32];
+        tmem_ld_32x32b_x16(lane_base + kAccCol, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+        tmem_ld_32x32b_x16(lane_base + kAccCol + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+        tmem_ld_wait();
 #pragma unroll
-      for (int col = 0; col < 32; ++col) {
-        if (col < C.n_out) {
-          const float x = fmaf(__uint_as_float(r[col]), us, __ldg(C.bh + col));
-          if (C.out && gr >= 0) C.out[(size_t)gr * C.ld_out + col] = x;
-          lg[row * 33 + col] = x;
+        for (int col = 0; col < 32; ++col) lg[row * 33 + col] = col < C.n_out ? fmaf(__uint_as_float(r[col]), us, __ldg(C.bh + col)) : 0.0f;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps2) : "memory");
+      const int ew = warp - 2;                                    // 0 .. 15: rows 8 ew .. 8 ew + 7
+      if (C.out && lane < C.n_out) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = 8 * ew + i, gr = rowmap[r];
+          if (gr >= 0) C.out[(size_t)gr * C.ld_out + lane] = lg[r * 33 + lane];
         }
       }
-      if (C.act_out && gr >= 0) {          // the thread holds its row's 32 columns: no exchange needed
-        const float* lr = lg + row * 33;
-        int4 a = make_int4(0, 0, 0, 0);
-        int o = 0;
+      if (C.act_out && lane < 8) {
+        const int r = 8 * ew + lane, gr = rowmap[r];
+        if (gr >= 0) {
+          const float* lr = lg + r * 33;
+          int4 a = make_int4(0, 0, 0, 0);
+          int o = 0;
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          if (h < C.n_heads) {
-            int best = 0;
-            float bv = lr[o];
-            for (int k = 1; k < C.head[h]; ++k)
-              if (lr[o + k] > bv) { bv = lr[o + k]; best = k; }      // first maximum, like torch.argmax
-            (h == 0 ? a.x : h == 1 ? a.y : h == 2 ? a.z : a.w) = best;
-            o += C.head[h];
+          for (int h = 0; h < 4; ++h) {
+            if (h < C.n_heads) {
+              int best = 0;
+              float bv = lr[o];
+              for (int k = 1; k < C.head[h]; ++k)
+                if (lr[o + k] > bv) { bv = lr[o + k]; best = k; }      // first maximum, like torch.argmax
+              (h == 0 ? a.x : h == 1 ? a.y : h == 2 ? a.z : a.w) = best;
+              o += C.head[h];
+            }
           }
+          reinterpret_cast<int4*>(C.act_out)[(size_t)gr * C.ld_act] = a;
         }
-        reinterpret_cast<int4*>(C.act_out)[(size_t)gr * C.ld_act] = a;
       }
     }
     if (prof && et == 0) prof[26] = (unsigned long long)clock64();
@@ -1586,6 +1632,10 @@ int hh_pf_tc_launch(const hh_policy_chain_ex* chains, int n_chains, int max_rows
       g.wait_free = (uint8_t)wait_free;
     };
     if (m128) {
+      if (s.att_n > 0 && s.att_lo + att_nn > KA) {
+        err = "hh_policy_forward_ex(precision = 2): attention block beyond the activation tile";
+        return -1;
+      }
       // one accumulator region: every segment waits for the drain of the previous one (accumulator-free barriers 0 .. 4:
       // after layer 1 half 0 / half 1, the attention block, the shared layer's half 0 / half 1)
       seg(s.img_w1, 0, 256, k1s, 1, 0, 0, 0, 1, 0xff, 0);

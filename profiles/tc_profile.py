@@ -59,4 +59,8 @@ for flags, label in modes:
             print(f"  {names[k]:18s} {a:9.0f} {c:9.0f}")
         print(f"  warp 1 waiting for weight stages (sum):     {sr[0, :, 15].median().item():9.0f} {sr[1, :, 15].median().item():9.0f}")
         print(f"  producer waiting for free slots (sum):      {sr[0, :, 28].median().item():9.0f} {sr[1, :, 28].median().item():9.0f}")
-        print(f"  warp 1 cycles in MMA issue / in commits:    {sr[0, :, 30].median().item():9.0f} {sr[0, :, 31].median().item():9.0f}")
+        if TM == 128:
+            print(f"  SH half 0, epilogue thread 0: drain done / math done: {rel[0, :, 27].median().item():9.0f} {rel[0, :, 28].median().item():9.0f}"
+                  f"   last epilogue thread: {rel[0, :, 30].median().item():9.0f} {rel[0, :, 31].median().item():9.0f}")
+        else:
+            print(f"  warp 1 cycles in MMA issue / in commits:    {sr[0, :, 30].median().item():9.0f} {sr[0, :, 31].median().item():9.0f}")
