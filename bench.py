@@ -472,10 +472,15 @@ def run_b200(args):
                         k1s = (fu.packed.W1[p_].shape[0] + 15) // 16
                         att_iss = 0
                         if fu.fight:
-                            lo_, n_, pad_ = fu.att[kk]
-                            att_iss = ((lo_ + n_ - (lo_ & ~7) + 15) // 16) * 16 * pad_
+                            from hhmarl_2d_b200.fused_forward import _att_image_geometry
+                            _, att_ks, att_nn = _att_image_geometry(fu.att[kk][0], fu.att[kk][1])
+                            att_iss = att_ks * 16 * att_nn
                         macs_issued += k1s * 16 * 512 + att_iss + 512 * 512 + 512 * 32
-                rows_pad = (n + 63) // 64 * 64
+                from hhmarl_2d_b200 import _native as _nat
+                tc_mode = int(_nat.lib().hh_policy_tc_mode())         # 2: 128-row tiles (default), 0: 64-row, 1: CTA pairs
+                tile_rows = 64 if tc_mode == 0 else 128
+                kname = {0: "policy_forward_tc_kernel", 1: "policy_forward_pair_kernel", 2: "policy_forward_m128_kernel"}[tc_mode]
+                rows_pad = (n + tile_rows - 1) // tile_rows * tile_rows
                 peak_tf, peak_src2 = 1590.0, "fallback (B200_PROFILING.md)"
                 try:
                     peak_tf = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
@@ -491,14 +496,20 @@ def run_b200(args):
                     pass
                 rollout["roofline"] = {
                     "bound": "tensor", "achieved": issued, "peak": peak_tf, "unit": "TFLOP/s", "frac": issued / peak_tf,
-                    "traffic": ptraffic, "tensor_pipe_active_pct_ncu": ptensor, "peak_source": peak_src2, "kernel": "hh::tc::policy_forward_tc_kernel", "kernel_us": kern_us,
+                    "traffic": ptraffic, "tensor_pipe_active_pct_ncu": ptensor, "peak_source": peak_src2, "kernel": "hh::tc::" + kname,
+                    "tile_rows": tile_rows, "kernel_us": kern_us,
                     "useful_tflops": 2 * macs_useful * n / (kern_us * 1e-6) / 1e12,
                     "useful_flop_per_launch": 2 * macs_useful * n, "issued_flop_per_launch": 3 * 2 * macs_issued * rows_pad,
                     "share_of_rollout_tick": kern_us * 1e-3 / rollout[tag]["ms_per_tick"],
                     "note": "fp32-equivalent forward = 3 kind::f16 MMAs per product on zero-padded tiles (K to 16, N to 256 / 104 / "
-                            "152 / 32): `achieved` counts the MMA work issued, `useful_tflops` the reference's own multiply-adds.  "
-                            "An M = 64 tile runs the tensor pipe at half the M = 128 rate (profiles/r2a_tcgen05_probe.txt), so 0.5 is the "
-                            "ceiling of `frac` for this tile shape; ncu: tensor pipe active 48 % of the cycles (profiles/r2q_policy_forward_ncu.md)"}
+                            "112 / 160 / 32): `achieved` counts the MMA work issued, `useful_tflops` the reference's own multiply-adds.  "
+                            + ("128-row tiles (M = 128 MMAs at the full tensor rate; A_hi in shared memory, A_lo in tensor memory); the "
+                               "layer chain of one tile is serial (MMA -> tanh epilogue -> next layer's operand) and one CTA per SM "
+                               "fits, so the tensor pipe idles during the exposed epilogues and the 256 tiles take two rounds on 148 "
+                               "SMs (0.86 occupancy of the second round): see DESIGN.md section 4 for the per-tile timeline"
+                               if tc_mode == 2 else
+                               "An M = 64 tile runs the tensor pipe at half the M = 128 rate (profiles/r2a_tcgen05_probe.txt), so 0.5 is "
+                               "the ceiling of `frac` for this tile shape")}
             del smp, env_r
         rollout["fragment_len"] = Tf
         if cpu_base is not None:   # N = 1, rank 0: the reference-style rollout worker on one host core, bounded sample

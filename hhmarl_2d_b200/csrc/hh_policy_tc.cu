@@ -75,6 +75,7 @@ struct Args {
   Chain c[8];
   unsigned long long* prof;   // optional clock64() stamps, 32 per CTA (hh_policy_tc_profile; null = off)
   int debug;                  // timing experiments only (results are garbage): 1 = no weight copies, 2 = no MMAs
+  uint32_t zero;              // always 0; a value the compiler cannot fold (orders the epilogue math after the accumulator release)
 };
 
 // barrier slots
@@ -303,6 +304,28 @@ __device__ __forceinline__ float tanh_scaled_4096(float a) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
   return fmaf(-2.0f * ACT_SCALE, r, ACT_SCALE);
+#endif
+}
+// Four at a time with ONE reciprocal: the conversions to fp16 share the 16-lane XU pipe with ex2 / rcp, which bounds the tanh
+// epilogues (3 XU operations per element); 1 / a_i = (1 / (a0 a1 a2 a3)) * (the other three) trades 0.75 of them for ~3 FMA-pipe
+// operations.  The exponent is clamped to 27 (tanh is 1.0f there already: identical results) so that the product stays finite.
+__device__ __forceinline__ void tanh_scaled_4096_x4(float& x0, float& x1, float& x2, float& x3) {
+#ifdef HH_TC_EXACT_TANH
+  x0 = tanh_scaled_4096(x0); x1 = tanh_scaled_4096(x1); x2 = tanh_scaled_4096(x2); x3 = tanh_scaled_4096(x3);
+#else
+  float e0, e1, e2, e3, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(x0, 27.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(x1, 27.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(fminf(x2, 27.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e3) : "f"(fminf(x3, 27.0f)));
+  const float a0 = e0 + 1.0f, a1 = e1 + 1.0f, a2 = e2 + 1.0f, a3 = e3 + 1.0f;
+  const float p01 = a0 * a1, p23 = a2 * a3;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p01 * p23));
+  const float r01 = r * p23, r23 = r * p01;      // 1 / (a0 a1), 1 / (a2 a3)
+  x0 = fmaf(-2.0f * ACT_SCALE, r01 * a1, ACT_SCALE);
+  x1 = fmaf(-2.0f * ACT_SCALE, r01 * a0, ACT_SCALE);
+  x2 = fmaf(-2.0f * ACT_SCALE, r23 * a3, ACT_SCALE);
+  x3 = fmaf(-2.0f * ACT_SCALE, r23 * a2, ACT_SCALE);
 #endif
 }
 __device__ __forceinline__ void split_pair(float v0, float v1, __half2& h, __half2& l) {
@@ -1114,7 +1137,9 @@ constexpr uint32_t OFF2_ACT = 0, OFF2_X = ACT2_BYTES, OFF2_RING = ACT2_BYTES + X
 constexpr uint32_t SMEM2_BYTES = OFF2_RING + NSTAGE * STAGE_BYTES;   // 217 088
 constexpr uint32_t LBO_A2 = TM2 * 16;
 constexpr int kEpiWarps2 = 16, kThreads2 = 64 + 32 * kEpiWarps2;     // 576
-constexpr uint32_t kAccCol = 0, kLoCol = 256, kXLoCol = 472;
+// x_lo aliases the lo halves of activation columns 0 .. 79: layer 1 writes its upper half (TMEM columns 384 ..) first, while the
+// MMAs of its lower half still read x_lo; the lower half's epilogue runs after all of layer 1's MMAs
+constexpr uint32_t kAccCol = 0, kLoCol = 256, kXLoCol = 256;
 constexpr int Q_FULL = 0, Q_EMPTY = NSTAGE, Q_ACC = 2 * NSTAGE, Q_ACT = Q_ACC + 6, Q_FREE = Q_ACT + 6, Q_COUNT = Q_FREE + 6;
 
 __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -1159,11 +1184,11 @@ __device__ __forceinline__ void warp_arrive_local(uint32_t bar, int lane) {
 // into the activation tile and lo into tensor memory at activation columns k0 + 64 part + [0, 64).
 template <bool HOLD>
 __device__ __forceinline__ void epi128_tanh_half(uint8_t* smem, uint32_t tmem, int k0, const float* __restrict__ bias, float us, int q,
-                                                 int part, int lane, uint32_t free_bar, uint32_t hold_bar,
+                                                 int part, int lane, uint32_t free_bar, uint32_t hold_bar, uint32_t zero_rt,
                                                  unsigned long long* stamp = nullptr) {
   const int row = 32 * q + lane, kb = k0 + 64 * part;
   const uint32_t lane_base = tmem + ((uint32_t)(32 * q) << 16);
-  const float us2 = us * kTwoLog2e;
+  float us2 = us * kTwoLog2e;
   uint32_t raw[64];
 #pragma unroll
   for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x16(lane_base + kAccCol + 64 * part + 16 * c, *reinterpret_cast<uint32_t(*)[16]>(&raw[16 * c]));
@@ -1171,6 +1196,12 @@ __device__ __forceinline__ void epi128_tanh_half(uint8_t* smem, uint32_t tmem, i
   fence_tc_before();
   __syncwarp();
   if (lane == 0) mbar_arrive(free_bar);         // the accumulator region can take the next MMAs
+  {  // Without a dependence ptxas hoists the tanh math between the four loads above (each has its own scoreboard), and the arrive
+     // -- the next segment's MMAs -- comes ~3 000 cycles late.  The scale picks up (clock & 0) read after the arrive.
+    uint32_t fence_clk;
+    asm volatile("mov.u32 %0, %%clock;" : "=r"(fence_clk)::"memory");
+    us2 = __uint_as_float(__float_as_uint(us2) | (fence_clk & zero_rt));
+  }
   if (stamp) stamp[0] = (unsigned long long)clock64();
   uint4 hh[8];
   uint32_t ll[32];
@@ -1180,10 +1211,14 @@ __device__ __forceinline__ void epi128_tanh_half(uint8_t* smem, uint32_t tmem, i
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + k)), b1 = __ldg(reinterpret_cast<const float4*>(bias + k + 4));
     const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
     __half2 h[4], l[4];
+    float sv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sv[j] = fmaf(__uint_as_float(raw[8 * g + j]), us2, bb[j] * kTwoLog2e);
+    tanh_scaled_4096_x4(sv[0], sv[1], sv[2], sv[3]);
+    tanh_scaled_4096_x4(sv[4], sv[5], sv[6], sv[7]);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float s0 = tanh_scaled_4096(fmaf(__uint_as_float(raw[8 * g + 2 * j]), us2, bb[2 * j] * kTwoLog2e));
-      const float s1 = tanh_scaled_4096(fmaf(__uint_as_float(raw[8 * g + 2 * j + 1]), us2, bb[2 * j + 1] * kTwoLog2e));
+      const float s0 = sv[2 * j], s1 = sv[2 * j + 1];
       h[j] = __floats2half2_rn(s0, s1);
       const float2 hf = __half22float2(h[j]);
       l[j] = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
@@ -1275,7 +1310,7 @@ __global__ void __launch_bounds__(kThreads2, 1) policy_forward_m128_kernel(const
         const uint32_t n = g.n, kps = g.kps, n_stage = g.ksteps / kps;
         if (g.wait_act != 0xff) mbar_wait_uniform(bar0 + 8 * (Q_ACT + g.wait_act), 0);
         if (g.wait_free != 0xff) mbar_wait_uniform(bar0 + 8 * (Q_FREE + g.wait_free), 0);
-        if (prof && lane == 0) prof[1 + 2 * s] = (unsigned long long)clock64();
+        if (prof && lane == 0 && s < 7) prof[1 + 2 * s] = (unsigned long long)clock64();
         fence_tc_after();
         const uint32_t idesc = instr_desc_f16(TM2, n);
         const uint32_t a_addr = smem_u32(smem + (g.a_src ? OFF2_ACT : OFF2_X)) + (uint32_t)(g.a_k0 >> 3) * (TM2 * 16);
@@ -1305,7 +1340,7 @@ __global__ void __launch_bounds__(kThreads2, 1) policy_forward_m128_kernel(const
           }
         }
         if (g.commit_acc != 0xff) umma_commit_elect(bar0 + 8 * (Q_ACC + g.commit_acc));
-        if (prof && lane == 0) prof[2 + 2 * s] = (unsigned long long)clock64();
+        if (prof && lane == 0 && s < 7) prof[2 + 2 * s] = (unsigned long long)clock64();
       }
       if (prof && lane == 0) prof[15] = (unsigned long long)stall;
     }
@@ -1347,11 +1382,11 @@ __global__ void __launch_bounds__(kThreads2, 1) policy_forward_m128_kernel(const
     }
     {  // H = tanh(x W1 + b1)
       const float us = __ldg(C.us_w1);
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < 2; ++h) {                    // processing order: columns 256 .. 511, then 0 .. 255 (see the segment table)
         mbar_wait(bar0 + 8 * (Q_ACC + h), 0);
         if (prof && et == 0) prof[16 + 2 * h] = (unsigned long long)clock64();
         fence_tc_after();
-        epi128_tanh_half<false>(smem, tmem, 256 * h, C.b1, us, q, part, lane, bar0 + 8 * (Q_FREE + h), 0u);
+        epi128_tanh_half<false>(smem, tmem, 256 * (1 - h), C.b1, us, q, part, lane, bar0 + 8 * (Q_FREE + h), 0u, args.zero);
         warp_arrive_local(bar0 + 8 * (Q_ACT + h), lane);
         if (prof && et == 0) prof[17 + 2 * h] = (unsigned long long)clock64();
       }
@@ -1384,11 +1419,12 @@ __global__ void __launch_bounds__(kThreads2, 1) policy_forward_m128_kernel(const
       float ss = 0.0f;
 #pragma unroll
       for (int u = 0; u < 5; ++u) {
+        const bool whole = c_beg + 8 * u + 8 <= c_end && c_beg + 8 * u + 8 <= C.att_n;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int col = c_beg + 8 * u + 2 * j, k = C.att_lo + col;
           float v0 = 0.0f, v1 = 0.0f;
-          if (col < c_end && col < C.att_n) {
+          if (whole || (col < c_end && col < C.att_n)) {
             const float2 b = __ldg(reinterpret_cast<const float2*>(C.batt + col));
             const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(hi + (uint32_t)((k >> 3) * (TM2 * 16) + row * 16 + (k & 7) * 2)));
             const uint32_t lw = rlo[4 * u + j];
@@ -1406,16 +1442,33 @@ __global__ void __launch_bounds__(kThreads2, 1) policy_forward_m128_kernel(const
       const float inv = 1.0f / fmaxf(sqrtf(ssum[0][row] + ssum[1][row] + ssum[2][row] + ssum[3][row]), 1e-12f);   // F.normalize
 #pragma unroll
       for (int u = 0; u < 5; ++u) {
+        const int col8 = c_beg + 8 * u;
+        if (col8 + 8 <= c_end && col8 + 8 <= C.att_n) {      // a whole group of eight columns (warp-uniform): one x4 store of lo
+          uint32_t lw[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int col = c_beg + 8 * u + 2 * j, k = C.att_lo + col;
-          if (col < c_end && col < C.att_n) {
+          for (int j = 0; j < 4; ++j) {
+            const int k = C.att_lo + col8 + 2 * j;
             __half2 h, l;
             split_pair(v[8 * u + 2 * j] * inv, v[8 * u + 2 * j + 1] * inv, h, l);
             *reinterpret_cast<__half2*>(hi + (uint32_t)((k >> 3) * (TM2 * 16) + row * 16 + (k & 7) * 2)) = h;
-            // one 32-bit column of the lo operand = this pair (att_lo is even)
-            asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(lane_base + kLoCol + (k >> 1)), "r"(*reinterpret_cast<uint32_t*>(&l))
-                         : "memory");
+            lw[j] = *reinterpret_cast<uint32_t*>(&l);
+          }
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(lane_base + kLoCol + (uint32_t)((C.att_lo + col8) >> 1)),
+                       "r"(lw[0]), "r"(lw[1]), "r"(lw[2]), "r"(lw[3])
+                       : "memory");
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int col = col8 + 2 * j, k = C.att_lo + col;
+            if (col < c_end && col < C.att_n) {
+              __half2 h, l;
+              split_pair(v[8 * u + 2 * j] * inv, v[8 * u + 2 * j + 1] * inv, h, l);
+              *reinterpret_cast<__half2*>(hi + (uint32_t)((k >> 3) * (TM2 * 16) + row * 16 + (k & 7) * 2)) = h;
+              // one 32-bit column of the lo operand = this pair (att_lo is even)
+              asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(lane_base + kLoCol + (k >> 1)),
+                           "r"(*reinterpret_cast<uint32_t*>(&l))
+                           : "memory");
+            }
           }
         }
       }
@@ -1428,12 +1481,12 @@ __global__ void __launch_bounds__(kThreads2, 1) policy_forward_m128_kernel(const
       mbar_wait(bar0 + 8 * (Q_ACC + 3), 0);
       if (prof && et == 0) prof[22] = (unsigned long long)clock64();
       fence_tc_after();
-      epi128_tanh_half<true>(smem, tmem, 0, C.bs, us, q, part, lane, bar0 + 8 * (Q_FREE + 3), bar0 + 8 * (Q_ACC + 4),
-                             (prof && (et == 0 || et == 511)) ? prof + (et == 0 ? 27 : 30) : nullptr);
+      epi128_tanh_half<true>(smem, tmem, 0, C.bs, us, q, part, lane, bar0 + 8 * (Q_FREE + 3), bar0 + 8 * (Q_ACC + 4), args.zero,
+                             (prof && et == 511) ? prof + 30 : nullptr);
       warp_arrive_local(bar0 + 8 * (Q_ACT + 3), lane);
       if (prof && et == 0) prof[23] = (unsigned long long)clock64();
       fence_tc_after();
-      epi128_tanh_half<false>(smem, tmem, 256, C.bs, us, q, part, lane, bar0 + 8 * (Q_FREE + 4), 0u);
+      epi128_tanh_half<false>(smem, tmem, 256, C.bs, us, q, part, lane, bar0 + 8 * (Q_FREE + 4), 0u, args.zero);
       warp_arrive_local(bar0 + 8 * (Q_ACT + 4), lane);
       if (prof && et == 0) prof[24] = (unsigned long long)clock64();
     }
@@ -1638,15 +1691,26 @@ int hh_pf_tc_launch(const hh_policy_chain_ex* chains, int n_chains, int max_rows
       }
       // one accumulator region: every segment waits for the drain of the previous one (accumulator-free barriers 0 .. 4:
       // after layer 1 half 0 / half 1, the attention block, the shared layer's half 0 / half 1)
-      seg(s.img_w1, 0, 256, k1s, 1, 0, 0, 0, 1, 0xff, 0);
-      seg(s.img_w1, (size_t)k1s * 256 * 64, 256, k1s, 1, 0, 0, 0, 1, 0xff, 1, 0);
+      // Layer 1 runs its upper half (columns 256 .. 511) first: the attention block lies there, so its MMAs start as soon as
+      // the lower half has left the accumulator and run under that half's tanh epilogue.
+      seg(s.img_w1, (size_t)k1s * 256 * 64, 256, k1s, 1, 0, 0, 0, 1, 0xff, 0);
+      seg(s.img_w1, 0, 256, k1s, 1, 0, 0, 0, 1, 0xff, 1, 0);
       int act_ready = 1, free_ready = 1;
       if (s.att_n > 0) {
         const int k0 = s.att_lo & ~15, ks = (s.att_lo + s.att_n - k0 + 15) / 16;
-        seg(s.img_att, 0, att_nn, ks, 1, 0, 1, k0, 1, 1, 2, 1);
+        // reads the first-processed half's activations (barrier 0) unless the block reaches below column 256
+        seg(s.img_att, 0, att_nn, ks, 1, 0, 1, k0, 1, k0 >= 256 ? 0 : 1, 2, 1);
         act_ready = 2; free_ready = 2;
       }
-      seg(s.img_ws, 0, 256, KA / 16, 1, 0, 1, 0, 1, act_ready, 3, free_ready);
+      if (s.att_n > 0 && s.att_lo >= 16) {
+        // The shared layer's K steps below the attention block do not read its output: they start as soon as the block has
+        // left the accumulator and run under the attention epilogue (residual, L2 normalisation, operand rewrite).
+        const int ks0 = s.att_lo / 16;
+        seg(s.img_ws, 0, 256, ks0, 1, 0, 1, 0, 1, 1, 0xff, 2);
+        seg(s.img_ws, (size_t)ks0 * 256 * 64, 256, KA / 16 - ks0, 1, 0, 1, 16 * ks0, 0, 2, 3);
+      } else {
+        seg(s.img_ws, 0, 256, KA / 16, 1, 0, 1, 0, 1, act_ready, 3, free_ready);
+      }
       seg(s.img_ws, (size_t)(KA / 16) * 256 * 64, 256, KA / 16, 1, 0, 1, 0, 1, 0xff, 4, 3);
       seg(s.img_wh, 0, 32, 16, 8, 0, 1, 0, 1, 3, 0xff, 4);
       seg(s.img_wh, (size_t)16 * 32 * 64, 32, 16, 8, 0, 1, 256, 0, 4, 5);
@@ -1672,6 +1736,7 @@ int hh_pf_tc_launch(const hh_policy_chain_ex* chains, int n_chains, int max_rows
   }
   a.prof = g_prof;
   a.debug = g_debug;
+  a.zero = 0;
   static bool opted_dev[64] = {};
   int dev = 0;
   cudaError_t ce = cudaGetDevice(&dev);

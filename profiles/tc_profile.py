@@ -31,6 +31,10 @@ names = {1: "seg0 L1h0 start", 2: "seg0 end", 3: "seg1 L1h1 start", 4: "seg1 end
          13: "seg6 HEADb start", 14: "seg6 end", 16: "epi L1h0 begin", 17: "epi L1h0 end", 18: "epi L1h1 begin", 19: "epi L1h1 end",
          20: "epi ATT begin", 21: "epi ATT end", 22: "epi SH begin", 23: "epi SHh0 end", 24: "epi SHh1 end", 25: "epi HEAD begin",
          26: "epi done", 29: "producer done"}
+if TM == 128:    # the 128-row form: layer 1's upper half first, the shared layer's first half split around the attention block
+    names.update({1: "seg0 L1 hi-half start", 3: "seg1 L1 lo-half start", 7: "seg3 SHh0a start", 9: "seg4 SHh0b start",
+                  11: "seg5 SHh1 start", 13: "seg6 HEADa start", 16: "epi L1 hi begin", 17: "epi L1 hi end", 18: "epi L1 lo begin",
+                  19: "epi L1 lo end"})
 L.hh_policy_tc_debug.argtypes = [ctypes.c_int32]
 modes = [(0, "normal")] + ([(1, "DEBUG no weight copies (timing only)"), (2, "DEBUG no MMAs (timing only)")] if len(sys.argv) > 2 else [])
 for flags, label in modes:
@@ -56,11 +60,10 @@ for flags, label in modes:
             if flags and not (7 <= k <= 10):
                 continue
             a, c = rel[0, :, k].median().item(), rel[1, :, k].median().item()
-            print(f"  {names[k]:18s} {a:9.0f} {c:9.0f}")
+            print(f"  {names[k]:22s} {a:9.0f} {c:9.0f}")
         print(f"  warp 1 waiting for weight stages (sum):     {sr[0, :, 15].median().item():9.0f} {sr[1, :, 15].median().item():9.0f}")
         print(f"  producer waiting for free slots (sum):      {sr[0, :, 28].median().item():9.0f} {sr[1, :, 28].median().item():9.0f}")
         if TM == 128:
-            print(f"  SH half 0, epilogue thread 0: drain done / math done: {rel[0, :, 27].median().item():9.0f} {rel[0, :, 28].median().item():9.0f}"
-                  f"   last epilogue thread: {rel[0, :, 30].median().item():9.0f} {rel[0, :, 31].median().item():9.0f}")
+            print(f"  SH half 0, last epilogue thread: drain done / math done: {rel[0, :, 30].median().item():9.0f} {rel[0, :, 31].median().item():9.0f}")
         else:
             print(f"  warp 1 cycles in MMA issue / in commits:    {sr[0, :, 30].median().item():9.0f} {sr[0, :, 31].median().item():9.0f}")
