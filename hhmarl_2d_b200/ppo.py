@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import torch
 import torch.distributed as dist
+from torch.nn.utils.stateless import _reparametrize_module
 
 from .sampler import multicategorical_logp_entropy_kl
 
@@ -34,7 +35,7 @@ class PPOLearner:
 
     def __init__(self, model1, model2, lr=1e-4, clip_param=0.25, kl_target=0.025, kl_coeff=0.2, vf_clip_param=10.0,
                  vf_loss_coeff=1.0, entropy_coeff=0.0, num_sgd_iter=30, sgd_minibatch_size=256, max_seq_len=20,
-                 seed=0):
+                 seed=0, use_cuda_graph=True):
         self.models = (model1, model2)
         self.splits = ((13, 9, 2, 2), (13, 9, 2))
         seen, params = set(), []
@@ -57,11 +58,26 @@ class PPOLearner:
                 p.grad = self.flat.grad[o:o + n].view_as(p)                  # autograd accumulates into the flat gradient
                 o += n
         self.grad_bytes = 4 * n_tot
+        # The loss is differentiated with respect to `flat` itself: each step re-binds the modules' parameter names to
+        # differentiable views flat.split(...) (one cat in the backward = the flat gradient).  `flat` is then the only leaf of
+        # the step's autograd graph, so no reference a caller may hold to a graph of the modules' own Parameters (a stray
+        # weight.clone(), a cached value output) can pin an AccumulateGrad node to another stream -- which breaks a capture.
+        self._sizes = [p.numel() for p in params]
+        index = {id(p): k for k, p in enumerate(params)}
+        self._names = [[(name, index[id(p)]) for name, p in m.named_parameters()] for m in self.models]
+        # On the GPU a minibatch step (gather, both policies' forward, loss, backward, Adam) is ~600 small kernels whose launch
+        # cost, not their run time, bounds the update: it is captured once per minibatch size into a CUDA graph and replayed
+        # (with more than one rank: forward / backward and optimiser as two graphs around the eager all-reduce).
+        self.use_graph = bool(use_cuda_graph) and dev.type == "cuda"
         try:
-            self.opt = torch.optim.Adam([self.flat], lr=lr, fused=dev.type == "cuda")
+            self.opt = torch.optim.Adam([self.flat], lr=lr, fused=dev.type == "cuda", capturable=self.use_graph)
         except (TypeError, RuntimeError):
             self.opt = torch.optim.Adam([self.flat], lr=lr)
+            self.use_graph = False
+        self._graphs, self._static, self._eager_runs, self._side = {}, None, {}, None
+        self.graph_warmup = 3                                                # eager minibatches of a size before its capture
         self.clip, self.kl_target, self.kl_coeff = clip_param, kl_target, [kl_coeff, kl_coeff]
+        self.kl_coeff_t = torch.tensor(self.kl_coeff, dtype=torch.float32, device=dev)   # what the loss reads (graph-safe)
         self.vf_clip, self.vf_coeff, self.ent_coeff = vf_clip_param, vf_loss_coeff, entropy_coeff
         self.num_sgd_iter, self.mb, self.L = num_sgd_iter, sgd_minibatch_size, max_seq_len
         self.gen = torch.Generator(device=dev)
@@ -103,13 +119,14 @@ class PPOLearner:
         var = (s[1] / s[2] - mean * mean).clamp_min(0.0)
         return mean, var.sqrt()
 
-    def _loss(self, i, flat, actions, old_logits, old_logp, adv, vtarg, seq_lens):
-        logits, vf = self.models[i].forward_flat(flat, seq_lens)
+    def _loss(self, i, views, flat, actions, old_logits, old_logp, adv, vtarg, seq_lens):
+        with _reparametrize_module(self.models[i], {name: views[k] for name, k in self._names[i]}):
+            logits, vf = self.models[i].forward_flat(flat, seq_lens)
         logp, ent, kl = multicategorical_logp_entropy_kl(logits, actions, self.splits[i], old_logits)
         ratio = torch.exp(logp - old_logp)
         surr = torch.min(adv * ratio, adv * torch.clamp(ratio, 1 - self.clip, 1 + self.clip))
         vf_loss = torch.clamp((vf - vtarg) ** 2, 0, self.vf_clip)
-        loss = (-surr + self.kl_coeff[i] * kl + self.vf_coeff * vf_loss - self.ent_coeff * ent).mean()
+        loss = (-surr + self.kl_coeff_t[i] * kl + self.vf_coeff * vf_loss - self.ent_coeff * ent).mean()
         return loss, kl.mean().detach(), vf_loss.mean().detach(), ent.mean().detach()
 
     def update(self, batch: dict, num_sgd_iter: int | None = None):
@@ -127,6 +144,8 @@ class PPOLearner:
                              logp=_seq_major(batch["logp"][:, :, i], L),
                              adv=(adv - mean) / std.clamp_min(1e-4), vtarg=_seq_major(batch["vtarg"][:, :, i], L)))
         dev = data[0]["flat"].device
+        if self.use_graph:
+            data = self._to_static(data)
         n_seq = data[0]["flat"].shape[0] // L
         seq_per_mb = max(1, min(n_seq, self.mb // L))     # a batch smaller than one minibatch is ONE (smaller) minibatch
         iters = self.num_sgd_iter if num_sgd_iter is None else num_sgd_iter
@@ -138,20 +157,7 @@ class PPOLearner:
             for s in range(0, n_seq, seq_per_mb):         # the last minibatch holds the remainder
                 sel = perm[s:s + seq_per_mb]
                 rows = (sel[:, None] * L + ar[None, :]).reshape(-1)
-                seq_lens = [L] * int(sel.shape[0])
-                total = 0.0
-                parts = []
-                for i in range(2):
-                    d = data[i]
-                    loss, kl, vfl, ent = self._loss(i, d["flat"][rows], d["actions"][rows], d["logits"][rows],
-                                                    d["logp"][rows], d["adv"][rows], d["vtarg"][rows], seq_lens)
-                    total = total + loss
-                    parts += [kl, vfl, ent]
-                self.flat.grad.zero_()
-                total.backward()
-                self._allreduce_grads()
-                self.opt.step()
-                acc += torch.stack([total.detach(), parts[0], parts[3], parts[1], parts[4], parts[2], parts[5]])
+                self._minibatch(data, rows, int(sel.shape[0]), acc)
                 n_mb += 1
         if self.world > 1 and n_mb:
             kl_sum = acc[1:3].clone()
@@ -165,9 +171,92 @@ class PPOLearner:
                     self.kl_coeff[i] *= 1.5
                 elif stats["kl"][i] < 0.5 * self.kl_target:
                     self.kl_coeff[i] *= 0.5
+            self.kl_coeff_t.copy_(torch.tensor(self.kl_coeff, dtype=torch.float32))
         stats["kl_coeff"] = list(self.kl_coeff)
         self.epoch += 1
         return stats
+
+    # ------------------------------------------------------------------ one minibatch: eager, or a CUDA-graph replay
+    def _fwd_bwd(self, data, rows, n_sel):
+        """Both policies' losses on the rows `rows`, gradient into the flat buffer.  Returns the 7 statistics as one tensor."""
+        seq_lens = [self.L] * n_sel
+        total, parts = 0.0, []
+        views = [v.view(p.shape) for v, p in zip(self.flat.split(self._sizes), self.params)]
+        for i in range(2):
+            d = data[i]
+            loss, kl, vfl, ent = self._loss(i, views, d["flat"][rows], d["actions"][rows], d["logits"][rows], d["logp"][rows],
+                                            d["adv"][rows], d["vtarg"][rows], seq_lens)
+            total = total + loss
+            parts += [kl, vfl, ent]
+        self.flat.grad.zero_()
+        total.backward()
+        return torch.stack([total.detach(), parts[0], parts[3], parts[1], parts[4], parts[2], parts[5]])
+
+    def _minibatch(self, data, rows, n_sel, acc):
+        if not self.use_graph:
+            st = self._fwd_bwd(data, rows, n_sel)
+            self._allreduce_grads()
+            self.opt.step()
+            acc += st
+            return
+        g = self._graphs.get(n_sel)
+        if g is None:
+            runs = self._eager_runs.get(n_sel, 0)
+            if runs < self.graph_warmup:       # real steps, on the stream the capture will use (what torch asks for before one)
+                if self._side is None:
+                    self._side = torch.cuda.Stream()
+                side = self._side
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    st = self._fwd_bwd(data, rows, n_sel)
+                    self._allreduce_grads()
+                    self.opt.step()
+                    acc += st
+                torch.cuda.current_stream().wait_stream(side)
+                self._eager_runs[n_sel] = runs + 1
+                return
+            g = self._capture(data, n_sel)
+            self._graphs[n_sel] = g
+        g["rows"].copy_(rows)
+        if self.world == 1:
+            g["g"].replay()
+        else:
+            g["g"].replay()
+            self._allreduce_grads()
+            g["g2"].replay()
+        acc += g["stats"]
+
+    def _capture(self, data, n_sel):
+        rows = torch.zeros(n_sel * self.L, dtype=torch.int64, device=self.flat.device)
+        g = {"rows": rows, "g": torch.cuda.CUDAGraph()}
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        for m in self.models:                  # drop the value head's cached output (it keeps the last eager step's graph alive)
+            if hasattr(m, "_val"):
+                m._val = None
+        torch.cuda.synchronize()
+        if self.world == 1:
+            with torch.cuda.graph(g["g"], stream=self._side):
+                g["stats"] = self._fwd_bwd(data, rows, n_sel)
+                self.opt.step()
+        else:
+            with torch.cuda.graph(g["g"], stream=self._side):
+                g["stats"] = self._fwd_bwd(data, rows, n_sel)
+            g["g2"] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g["g2"], pool=g["g"].pool(), stream=self._side):
+                self.opt.step()
+        return g
+
+    def _to_static(self, data):
+        """The graphs read the batch at fixed addresses: copy this update's batch into buffers that stay."""
+        shapes = [{k: (tuple(v.shape), v.dtype) for k, v in d.items()} for d in data]
+        if self._static is None or self._static[0] != shapes:
+            self._static = (shapes, [{k: torch.empty_like(v) for k, v in d.items()} for d in data])
+            self._graphs, self._eager_runs = {}, {}
+        for d, sd in zip(data, self._static[1]):
+            for k, v in d.items():
+                sd[k].copy_(v)
+        return self._static[1]
 
     # ------------------------------------------------------------------ training state (resume): what algo.save() keeps
     # beyond the policy weights -- optimiser moments, adaptive KL coefficients, epoch counter, shuffling RNG
@@ -180,5 +269,7 @@ class PPOLearner:
             self.flat.copy_(sd["flat"].to(self.flat.device))
         self.opt.load_state_dict(sd["opt"])
         self.kl_coeff = list(sd["kl_coeff"])
+        self.kl_coeff_t.copy_(torch.tensor(self.kl_coeff, dtype=torch.float32))
+        self._graphs, self._eager_runs = {}, {}        # the optimiser's state tensors were replaced: capture again
         self.epoch = int(sd["epoch"])
         self.gen.set_state(sd["gen"].cpu() if self.gen.device.type == "cpu" else sd["gen"])

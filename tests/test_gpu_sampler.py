@@ -132,7 +132,7 @@ def test_escape_mode_training_iterations(level, mode):
     m1.cuda(); m2.cuda()
     smp = VecSampler(env, TorchPolicy(m1, 1), TorchPolicy(m2, 2), fragment_len=20, use_cuda_graph=True)
     learner = PPOLearner(m1, m2, num_sgd_iter=2, sgd_minibatch_size=2560)
-    w0 = m1.inp2._model[0].weight.clone()
+    w0 = m1.inp2._model[0].weight.clone()     # (a live autograd graph of a parameter on the default stream: must not break the capture)
     for it in range(3):
         b = smp.collect()
         assert b["flat1"].shape[-1] == 7 + 30 + 29 and torch.isfinite(b["adv"]).all()
@@ -168,6 +168,36 @@ def test_learner_improves_the_level1_reward():
     first, last = np.mean(hist[:4]), np.mean(hist[-4:])
     print("level-1 fragment reward: first 4 iterations %.3f, last 4 %.3f" % (first, last), hist)
     assert last > first + 0.15, (first, last)
+
+
+def test_graph_replayed_minibatches_match_eager_minibatches():
+    """PPOLearner replays a captured CUDA graph per minibatch (after three eager minibatches of that size); the weights after two
+    updates must agree with a learner that runs every minibatch eagerly from the same initial weights on the same batches."""
+    import copy
+    from hhmarl_2d_b200 import VecLowLevelEnv, make_args, VecSampler, TorchPolicy, PPOLearner
+    from hhmarl_2d_b200 import models as M
+    torch.manual_seed(0)
+    env = VecLowLevelEnv(256, make_args(level=3), device=0, seed=4)
+    m1, m2 = M.build_policy_pair("fight")
+    m1.cuda(); m2.cuda()
+    e1, e2 = copy.deepcopy(m1), copy.deepcopy(m2)
+    e2.shared_layer = e1.shared_layer                         # deepcopy of each model alone would split the shared layer
+    smp = VecSampler(env, TorchPolicy(m1, 1), TorchPolicy(m2, 2), fragment_len=20, use_cuda_graph=False)
+    lg = PPOLearner(m1, m2, num_sgd_iter=2, sgd_minibatch_size=1024, seed=3, use_cuda_graph=True)
+    le = PPOLearner(e1, e2, num_sgd_iter=2, sgd_minibatch_size=1024, seed=3, use_cuda_graph=False)
+    assert lg.use_graph and not le.use_graph
+    assert torch.equal(lg.flat, le.flat)
+    for _ in range(2):
+        b = {k: v.clone() for k, v in smp.collect().items() if torch.is_tensor(v)}
+        sg, se = lg.update(b), le.update(b)                   # the sampler's weights are NOT refreshed: same batches for both
+        assert sg["minibatches"] == se["minibatches"] == 12   # 256 sequences, 51 per minibatch: 5 full + 1 remainder, twice
+    assert 51 in lg._graphs                                   # the full-size minibatch was captured and replayed
+    d = (lg.flat - le.flat).abs().max().item()
+    moved = (le.flat - torch.cat([p.detach().reshape(-1) for p in le.params])).abs().max().item()
+    assert moved == 0.0
+    assert d < 2e-5, d
+    for a, b_ in zip(sg["kl"] + sg["vf_loss"], se["kl"] + se["vf_loss"]):
+        assert abs(a - b_) <= 1e-4 * max(1.0, abs(b_)), (sg, se)
 
 
 def _nccl_worker(rank, world, port, out_dir):
