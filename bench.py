@@ -403,7 +403,8 @@ def run_b200(args):
         from hhmarl_2d_b200 import models as M
         rollout = {}
         Tf = 20
-        for tag, kw in (("fused_tc", dict(fused="tc")), ("fused_3xtf32", dict(fused="3xtf32")), ("fused_tf32", dict(fused="tf32")),
+        for tag, kw in (("fused_tc", dict(fused="tc")), ("fused_tc_one_group", dict(fused="tc", groups=1)),
+                        ("fused_3xtf32", dict(fused="3xtf32", groups=1)), ("fused_tf32", dict(fused="tf32", groups=1)),
                         ("fp32", dict(allow_tf32=False, fused=None)), ("tf32", dict(allow_tf32=True, fused=None)),
                         ("fp32_unpacked", dict(allow_tf32=False, packed=False, fused=None))):
             torch.manual_seed(rank)
@@ -524,7 +525,9 @@ def run_b200(args):
                 rollout["cpu_sampler_equivalent"] = {"error": repr(ex)}
         rollout["note"] = ("both policies' actor + central critic + Gumbel-max sampling + env step + GAE + action "
                            "write-back, one CUDA graph per 20-tick fragment; random-init weights.  'fused_tc' (the sampler's "
-                           "default): csrc/hh_policy_tc.cu, tcgen05 / TMEM forward, fp32-equivalent (fp16 hi/lo operand split); "
+                           "default): csrc/hh_policy_tc.cu, tcgen05 / TMEM forward, fp32-equivalent (fp16 hi/lo operand split), the "
+                           "batch advanced as 8 parts on their own streams inside the graph (a part steps while the other parts' "
+                           "forwards run; 'fused_tc_one_group' = the same kernels on one stream); "
                            "'fused_3xtf32' / 'fused_tf32': the mma.sync forward kernel csrc/hh_policy.cu (one launch "
                            "per tick, 3xTF32 = fp32-equivalent / plain TF32 tensor-core products); 'fp32' / 'tf32': packed "
                            "cuBLAS GEMMs (fused_forward.PackedPolicyPair); 'fp32_unpacked': per-layer forward of models.py")

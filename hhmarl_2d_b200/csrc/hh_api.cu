@@ -1058,6 +1058,29 @@ extern "C" int hh_step(hh_env* e, const int32_t* actions_dev, float* obs1, float
   return 0;
 }
 
+// arenas [first, first + count) only: the pointers address the WHOLE batch's arrays (arena 0 first).  Lets a caller keep two
+// halves of a batch in flight on two streams (the sampler's software pipeline: one half's policy forward runs while the other
+// half steps).  Levels 1-3, default step kernel; first must be a multiple of 32.
+extern "C" int hh_step_range(hh_env* e, int32_t first, int32_t count, const int32_t* actions_dev, float* obs1, float* obs2,
+                             float* rew, uint8_t* done, void* stream) {
+  if (!e) return fail(-1, "hh_step_range: null env");
+  if (!e->initialised) return fail(-4, "hh_step_range: call hh_reset first");
+  if (!actions_dev) return fail(-1, "hh_step_range: null actions");
+  if (e->cfg.level >= 4) return fail(-5, "hh_step_range: levels 1-3 only (levels 4/5: hh_step_begin / hh_step_finish)");
+  if (e->step_impl != 4) return fail(-5, "hh_step_range: needs the default step kernel (HH_STEP_IMPL=v4)");
+  if (first < 0 || count <= 0 || first % v4::kArenas != 0 || first + count > e->n)
+    return fail(-3, "hh_step_range: first must be a multiple of 32 and [first, first + count) inside the batch");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (e->cfg.level) {
+    case 1: launch_step_v4_range<1>(e, first, first + count, actions_dev, obs1, obs2, rew, done, st); break;
+    case 2: launch_step_v4_range<2>(e, first, first + count, actions_dev, obs1, obs2, rew, done, st); break;
+    default: launch_step_v4_range<3>(e, first, first + count, actions_dev, obs1, obs2, rew, done, st); break;
+  }
+  HH_CUDA(cudaGetLastError());
+  e->launches += 1;
+  return 0;
+}
+
 extern "C" int hh_step_begin(hh_env* e, const int32_t* actions_dev, float* opp_obs3_dev, float* opp_obs4_dev,
                              uint8_t* policy_set_dev, void* stream) {
   if (!e) return fail(-1, "hh_step_begin: null env");

@@ -1252,6 +1252,15 @@ __global__ void __launch_bounds__(kThreads2, 1) policy_forward_m128_kernel(const
   const int row0 = blockIdx.x * TM2;
   if (row0 >= cnt) return;              // CTA-uniform
   unsigned long long* prof = args.prof ? args.prof + 32 * (size_t)(blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
+  if (prof && tid == 0) {   // CTA entry: SM clock, SM id, wall clock (how the two rounds of tiles follow each other on an SM)
+    uint32_t smid;
+    unsigned long long gt;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    prof[27] = (unsigned long long)clock64();
+    prof[30] = smid;
+    prof[31] = gt;
+  }
   if (tid < TM2) {
     const int lr = row0 + tid;
     rowmap[tid] = lr < cnt ? (C.rows ? C.rows[beg + lr] : beg + lr) : -1;
@@ -1482,7 +1491,7 @@ __global__ void __launch_bounds__(kThreads2, 1) policy_forward_m128_kernel(const
       if (prof && et == 0) prof[22] = (unsigned long long)clock64();
       fence_tc_after();
       epi128_tanh_half<true>(smem, tmem, 0, C.bs, us, q, part, lane, bar0 + 8 * (Q_FREE + 3), bar0 + 8 * (Q_ACC + 4), args.zero,
-                             (prof && et == 511) ? prof + 30 : nullptr);
+                             nullptr);
       warp_arrive_local(bar0 + 8 * (Q_ACT + 3), lane);
       if (prof && et == 0) prof[23] = (unsigned long long)clock64();
       fence_tc_after();
@@ -1542,6 +1551,7 @@ __global__ void __launch_bounds__(kThreads2, 1) policy_forward_m128_kernel(const
   if (warp == 1) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
+    if (prof && lane == 0) prof[14] = (unsigned long long)clock64();      // CTA exit
   }
 }
 

@@ -123,6 +123,19 @@ class VecLowLevelEnv:
                                     b["rew"].data_ptr(), b["done"].data_ptr(), self._stream()), "hh_step")
         return b["obs1"], b["obs2"], b["rew"], b["done"]
 
+    def step_range(self, first, count, actions, out=None):
+        """step() for arenas [first, first + count) only (levels 1-3; `first` a multiple of 32).  `actions` and the output tensors
+        are the WHOLE batch's ([N, ...]); only the range's rows are read / written.  Two ranges may be in flight on two streams."""
+        b = out if out is not None else self._ensure_torch()
+        self._ensure_torch()
+        t = self._torch
+        if not (actions.is_cuda and actions.dtype == t.int32 and actions.is_contiguous()
+                and actions.numel() == self.n_arenas * 8):
+            raise ValueError("actions must be a contiguous int32 CUDA tensor of shape [N, 2, 4]")
+        nat.check(nat.lib().hh_step_range(self._h, int(first), int(count), actions.data_ptr(), b["obs1"].data_ptr(),
+                                          b["obs2"].data_ptr(), b["rew"].data_ptr(), b["done"].data_ptr(), self._stream()),
+                  "hh_step_range")
+
     # ------------------------------------------------------------------ levels 4/5: frozen-policy opponents
     def _ensure_opp_bufs(self):
         if getattr(self, "_opp_bufs", None) is None:

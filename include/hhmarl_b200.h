@@ -82,6 +82,11 @@ int32_t hh_obs_dim(const hh_env* env, int32_t agent_id /* 1 or 2 */);
 int hh_reset(hh_env* env, const uint8_t* mask_dev, float* obs1_dev, float* obs2_dev, void* stream);
 int hh_step(hh_env* env, const int32_t* actions_dev, float* obs1_dev, float* obs2_dev, float* rew_dev,
             uint8_t* done_dev, void* stream);
+/* The same for arenas [first, first + count) only (levels 1-3; `first` a multiple of 32).  All pointers address the whole batch's
+ * arrays.  Arenas are independent (each env of the reference is its own process, train_hetero.py:212), so two ranges may be in
+ * flight on two streams: the rollout sampler steps one half of the batch while the other half's policy forward runs. */
+int hh_step_range(hh_env* env, int32_t first, int32_t count, const int32_t* actions_dev, float* obs1_dev, float* obs2_dev,
+                  float* rew_dev, uint8_t* done_dev, void* stream);
 
 /* Levels 4/5 (frozen-policy opponents, env_base.py:349-398): the opponents' own observations are needed
  * mid-step, after the agents' fire decisions and before the tick, so the step is split around the

@@ -34,7 +34,7 @@ names = {1: "seg0 L1h0 start", 2: "seg0 end", 3: "seg1 L1h1 start", 4: "seg1 end
 if TM == 128:    # the 128-row form: layer 1's upper half first, the shared layer's first half split around the attention block
     names.update({1: "seg0 L1 hi-half start", 3: "seg1 L1 lo-half start", 7: "seg3 SHh0a start", 9: "seg4 SHh0b start",
                   11: "seg5 SHh1 start", 13: "seg6 HEADa start", 16: "epi L1 hi begin", 17: "epi L1 hi end", 18: "epi L1 lo begin",
-                  19: "epi L1 lo end"})
+                  19: "epi L1 lo end", 14: "CTA exit (TMEM freed)"})
 L.hh_policy_tc_debug.argtypes = [ctypes.c_int32]
 modes = [(0, "normal")] + ([(1, "DEBUG no weight copies (timing only)"), (2, "DEBUG no MMAs (timing only)")] if len(sys.argv) > 2 else [])
 for flags, label in modes:
@@ -64,6 +64,23 @@ for flags, label in modes:
         print(f"  warp 1 waiting for weight stages (sum):     {sr[0, :, 15].median().item():9.0f} {sr[1, :, 15].median().item():9.0f}")
         print(f"  producer waiting for free slots (sum):      {sr[0, :, 28].median().item():9.0f} {sr[1, :, 28].median().item():9.0f}")
         if TM == 128:
-            print(f"  SH half 0, last epilogue thread: drain done / math done: {rel[0, :, 30].median().item():9.0f} {rel[0, :, 31].median().item():9.0f}")
+            # how the rounds of tiles follow each other on an SM: entry / exit clocks per SM id (prof 27 / 14 / 30), wall clock (31)
+            allc = s.view(-1, 32)
+            smid, entry, start, done, exit_, gt = allc[:, 30], allc[:, 27], allc[:, 0], allc[:, 26], allc[:, 14], allc[:, 31]
+            print(f"  CTA entry -> set-up done (barriers, TMEM alloc, row map): {(start - entry).median().item():9.0f} cycles;"
+                  f"  output done -> exit: {(exit_ - done).median().item():9.0f}")
+            gaps, firsts, seconds = [], [], []
+            for sm in smid.unique().tolist():
+                idx = (smid == sm).nonzero().flatten()
+                if idx.numel() == 2:
+                    a, b = (idx[0], idx[1]) if entry[idx[0]] < entry[idx[1]] else (idx[1], idx[0])
+                    gaps.append((entry[b] - exit_[a]).item())
+                    firsts.append((exit_[a] - entry[a]).item())
+                    seconds.append((exit_[b] - entry[b]).item())
+            import statistics as st_
+            if gaps:
+                print(f"  SMs with two tiles: {len(gaps)}; first tile entry -> exit {st_.median(firsts):9.0f}, second {st_.median(seconds):9.0f}, "
+                      f"exit of the first -> entry of the second {st_.median(gaps):9.0f} cycles")
+            print(f"  wall clock, first CTA entry -> last CTA entry: {(gt.max() - gt.min()).item() / 1e3:9.1f} us")
         else:
             print(f"  warp 1 cycles in MMA issue / in commits:    {sr[0, :, 30].median().item():9.0f} {sr[0, :, 31].median().item():9.0f}")

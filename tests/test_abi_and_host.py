@@ -34,6 +34,7 @@ def test_create_validates_arguments_without_a_gpu():
     cfg = nat.HHConfig(level=1, map_size=0.3, horizon=150)
     assert L.hh_create(ctypes.byref(cfg), 0, 0, ctypes.byref(h)) == -1
     assert L.hh_step(None, None, None, None, None, None, None) == -1
+    assert L.hh_step_range(None, 0, 32, None, None, None, None, None, None) == -1
     assert L.hh_n_arenas(None) == 0 and L.hh_obs_dim(None, 1) == 0
 
 

@@ -170,6 +170,33 @@ def test_learner_improves_the_level1_reward():
     assert last > first + 0.15, (first, last)
 
 
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_groups_on_their_own_streams_collect_the_same_fragment(use_graph):
+    """VecSampler(groups=g) advances g equal parts of the batch on their own streams (hh_step_range; the kernels of the whole batch
+    pointed at each part's rows): every buffer of the fragment must equal the one-stream sampler's bit for bit, twice in a row."""
+    from hhmarl_2d_b200 import VecLowLevelEnv, make_args, VecSampler, TorchPolicy
+    from hhmarl_2d_b200 import models as M
+    torch.manual_seed(0)
+    m1, m2 = M.build_policy_pair("fight")
+    m1.cuda(); m2.cuda()
+    n, out = 1024, []
+    for groups in (1, 2, 8):
+        env = VecLowLevelEnv(n, make_args(level=3), device=0, seed=11, autoreset=True)
+        smp = VecSampler(env, TorchPolicy(m1, 1), TorchPolicy(m2, 2), fragment_len=20, use_cuda_graph=use_graph, groups=groups)
+        assert smp.groups == groups
+        frs = []
+        for _ in range(3 if use_graph else 2):           # (with a graph: warm-up / capture, then two replays)
+            frs.append({k: v.clone() for k, v in smp.collect().items()})
+        out.append(frs)
+    for other in out[1:]:
+        for fa, fb in zip(out[0], other):
+            for k in fa:
+                assert torch.equal(fa[k], fb[k]), k
+    assert VecSampler(VecLowLevelEnv(4096, make_args(level=3), device=0, seed=1), TorchPolicy(m1, 1), TorchPolicy(m2, 2)).groups == 4
+    with pytest.raises(ValueError):
+        VecSampler(VecLowLevelEnv(640, make_args(level=3), device=0, seed=1), TorchPolicy(m1, 1), TorchPolicy(m2, 2), groups=2)
+
+
 def test_graph_replayed_minibatches_match_eager_minibatches():
     """PPOLearner replays a captured CUDA graph per minibatch (after three eager minibatches of that size); the weights after two
     updates must agree with a learner that runs every minibatch eagerly from the same initial weights on the same batches."""
