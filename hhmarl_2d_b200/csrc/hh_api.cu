@@ -512,10 +512,26 @@ step_kernel_v4(StatePtrs S, Params P, const int32_t* __restrict__ actions, float
   v4::step_body<LEVEL, MODE>(*reinterpret_cast<v4::Smem*>(v4_smem), S, P, actions, obs1, obs2, rew_out, done_out,
                              blockIdx.x + block0);
 }
+// two sub-blocks per CTA (v4::step_body<.., DUAL = true>): blocks 2 b and 2 b + 1 of the plain launch
+template <int LEVEL, int MODE>
+__global__ void __launch_bounds__(2 * v4::kThreads, 1)
+step_kernel_v4_dual(StatePtrs S, Params P, const int32_t* __restrict__ actions, float* __restrict__ obs1,
+                    float* __restrict__ obs2, float* __restrict__ rew_out, uint8_t* __restrict__ done_out, int block0) {
+  extern __shared__ __align__(16) unsigned char v4_smem[];
+  const int sub = threadIdx.x / v4::kThreads;
+  const int block = 2 * (int)blockIdx.x + sub + block0;
+  if (block * v4::kArenas >= P.n_arenas) return;      // sub-block uniform (an odd number of blocks: the last CTA runs one)
+  v4::step_body<LEVEL, MODE, true>(*reinterpret_cast<v4::Smem*>(v4_smem + (size_t)sub * ((sizeof(v4::Smem) + 15) / 16 * 16)), S, P,
+                                   actions, obs1, obs2, rew_out, done_out, block);
+}
 template <int LEVEL, int MODE>
 static cudaError_t v4_opt_in_smem() {
-  return cudaFuncSetAttribute(step_kernel_v4<LEVEL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)sizeof(v4::Smem));
+  cudaError_t ce = cudaFuncSetAttribute(step_kernel_v4<LEVEL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)sizeof(v4::Smem));
+  if (ce == cudaSuccess)
+    ce = cudaFuncSetAttribute(step_kernel_v4_dual<LEVEL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)(2 * ((sizeof(v4::Smem) + 15) / 16 * 16)));
+  return ce;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -945,7 +961,7 @@ extern "C" int hh_create(const hh_config* cfg, int32_t n_arenas, int32_t device,
   }
   {
     const char* impl = getenv("HH_STEP_IMPL");
-    if (sizeof(v4::Smem) > 48 * 1024) {   // opt in to > 48 KB of dynamic shared memory (per device, idempotent)
+    if (2 * sizeof(v4::Smem) > 48 * 1024) {   // opt in to > 48 KB of dynamic shared memory (per device, idempotent; the dual form takes two)
       cudaError_t ce2 = v4_opt_in_smem<1, 0>();
       if (ce2 == cudaSuccess) ce2 = v4_opt_in_smem<1, 1>();
       if (ce2 == cudaSuccess) ce2 = v4_opt_in_smem<2, 0>();
@@ -1008,10 +1024,18 @@ extern "C" int hh_reset(hh_env* e, const uint8_t* mask_dev, float* obs1, float* 
 // arenas [first, end) of the v4 step (first a multiple of v4::kArenas); the whole batch is first = 0, end = n
 template <int LEVEL>
 static void launch_step_v4_range(hh_env* e, int first, int end, const int32_t* actions, float* obs1, float* obs2, float* rew,
-                                 uint8_t* done, cudaStream_t st) {
+                                 uint8_t* done, cudaStream_t st, bool dual = false) {
   Params P = e->P;
   P.n_arenas = end;
   const int block0 = first / v4::kArenas, vblocks = (end - first + v4::kArenas - 1) / v4::kArenas;
+  if (dual) {
+    const size_t sm2 = 2 * ((sizeof(v4::Smem) + 15) / 16 * 16);
+    if (e->cfg.agent_mode == 0)
+      step_kernel_v4_dual<LEVEL, 0><<<(vblocks + 1) / 2, 2 * v4::kThreads, sm2, st>>>(e->S, P, actions, obs1, obs2, rew, done, block0);
+    else
+      step_kernel_v4_dual<LEVEL, 1><<<(vblocks + 1) / 2, 2 * v4::kThreads, sm2, st>>>(e->S, P, actions, obs1, obs2, rew, done, block0);
+    return;
+  }
   if (e->cfg.agent_mode == 0)
     step_kernel_v4<LEVEL, 0><<<vblocks, v4::kThreads, sizeof(v4::Smem), st>>>(e->S, P, actions, obs1, obs2, rew, done, block0);
   else
@@ -1071,10 +1095,12 @@ extern "C" int hh_step_range(hh_env* e, int32_t first, int32_t count, const int3
   if (first < 0 || count <= 0 || first % v4::kArenas != 0 || first + count > e->n)
     return fail(-3, "hh_step_range: first must be a multiple of 32 and [first, first + count) inside the batch");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // ranges run next to other kernels (that is what they are for): two sub-blocks per CTA = half as many CTAs spread over the SMs
+  static const bool dual = [] { const char* v = getenv("HH_STEP_RANGE_DUAL"); return !v || atoi(v) != 0; }();
   switch (e->cfg.level) {
-    case 1: launch_step_v4_range<1>(e, first, first + count, actions_dev, obs1, obs2, rew, done, st); break;
-    case 2: launch_step_v4_range<2>(e, first, first + count, actions_dev, obs1, obs2, rew, done, st); break;
-    default: launch_step_v4_range<3>(e, first, first + count, actions_dev, obs1, obs2, rew, done, st); break;
+    case 1: launch_step_v4_range<1>(e, first, first + count, actions_dev, obs1, obs2, rew, done, st, dual); break;
+    case 2: launch_step_v4_range<2>(e, first, first + count, actions_dev, obs1, obs2, rew, done, st, dual); break;
+    default: launch_step_v4_range<3>(e, first, first + count, actions_dev, obs1, obs2, rew, done, st, dual); break;
   }
   HH_CUDA(cudaGetLastError());
   e->launches += 1;

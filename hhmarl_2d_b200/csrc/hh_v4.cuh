@@ -888,8 +888,18 @@ __device__ __forceinline__ void s10_store_rows(const Ctx& C, int t, int n_thread
     const int t = tid - (lo);                              \
     call;                                                  \
   }
-#define HH_BARRIER() __syncthreads()
-#define HH_TID_DECL const int tid = threadIdx.x;
+// DUAL (a template parameter of step_body): two 256-thread sub-blocks of kArenas arenas each share one 512-thread CTA -- the same
+// per-arena code, each sub-block with its own Smem and its own named barrier.  Halves the number of CTAs of a launch, which
+// matters when the launch shares the GPU with the policy forward's whole-SM CTAs (the sampler's grouped mode).
+#define HH_BARRIER()                                                                       \
+  do {                                                                                     \
+    if (DUAL) asm volatile("bar.sync %0, %1;" ::"r"(1 + hh_sub), "n"(8 * kArenas) : "memory"); \
+    else __syncthreads();                                                                  \
+  } while (0)
+#define HH_TID_DECL                                                    \
+  const int tid = DUAL ? (int)(threadIdx.x % (8 * kArenas)) : (int)threadIdx.x; \
+  const int hh_sub = DUAL ? (int)(threadIdx.x / (8 * kArenas)) : 0;    \
+  (void)hh_sub;
 #else   // host emulation (tests/emu): roles of a stage run one after the other, threads in emu_order
 #define HH_ROLE(lo, n, call)                               \
   for (int t_ = 0; t_ < (n); ++t_) {                       \
@@ -915,7 +925,7 @@ __device__ long long g_warp_arrive[512 * 8 * 16];   // [CTA][warp][barrier]: whe
     __syncthreads();                                                                                          \
   } while (0)
 #undef HH_TID_DECL
-#define HH_TID_DECL const int tid = threadIdx.x; int hh_bar = 0;
+#define HH_TID_DECL const int tid = threadIdx.x; int hh_bar = 0; (void)DUAL;
 #else
 #define HH_MARK(k)
 #endif
@@ -936,7 +946,7 @@ __device__ __forceinline__ void s2_warm(const Ctx& C, int t) {
 #define HH_WARM_S2
 #endif
 
-template <int LEVEL, int MODE>
+template <int LEVEL, int MODE, bool DUAL = false>
 __device__ __forceinline__ void step_body(Smem& S, const StatePtrs& G, const Params& P, const int32_t* __restrict__ actions,
                                           float* __restrict__ obs1, float* __restrict__ obs2,
                                           float* __restrict__ rew_out, uint8_t* __restrict__ done_out, int block) {
@@ -1034,6 +1044,7 @@ template <int MODE>
 __device__ __forceinline__ void reset_body(Smem& S, const StatePtrs& G, const Params& P, const uint8_t* __restrict__ mask,
                                            int first_time, float* __restrict__ obs1, float* __restrict__ obs2, int block) {
   constexpr int D1 = MODE == 0 ? OBS_AC1 : OBS_ESC_AC1, D2 = MODE == 0 ? OBS_AC2 : OBS_ESC_AC2;
+  constexpr bool DUAL = false;
   HH_TID_DECL
   const int arena0 = block * kArenas;
   const int n_valid_ = P.n_arenas - arena0;

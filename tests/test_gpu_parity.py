@@ -386,6 +386,38 @@ def test_pipelined_host_mode_matches_staged_host_mode():
         assert int(sa["steps"].max()) < 300        # episodes ended and were reset inside the launches
 
 
+def test_step_range_on_two_streams_matches_the_whole_batch_step():
+    """hh_step_range (two 256-thread sub-blocks per CTA by default): three ragged ranges of the batch stepped on three streams
+    reproduce hh_step of the whole batch bit for bit -- 300 ticks with auto-reset, both agent modes, a range that ends on an odd
+    number of 32-arena blocks and one that is a single partial block."""
+    import torch
+    for mode, n in (("fight", 2048 + 96 + 13), ("escape", 1024)):
+        a, b = _vec(n, 3, mode, 23), _vec(n, 3, mode, 23)
+        oa1, oa2 = a.reset()
+        ob1, ob2 = b.reset()
+        assert torch.equal(oa1, ob1) and torch.equal(oa2, ob2)
+        cuts = [0, 1024 + 32, 2048 + 96, n] if n > 2048 else [0, 512, 1024, n]
+        streams = [torch.cuda.Stream() for _ in range(3)]
+        g = torch.Generator(device="cuda").manual_seed(5)
+        for t in range(300):
+            act = torch.stack([torch.randint(0, 13, (n, 2), generator=g, device="cuda"), torch.randint(0, 9, (n, 2), generator=g, device="cuda"),
+                               torch.randint(0, 2, (n, 2), generator=g, device="cuda"), torch.randint(0, 2, (n, 2), generator=g, device="cuda")],
+                              dim=-1).to(torch.int32).contiguous()
+            x1, x2, xr, xd = a.step(act)
+            torch.cuda.synchronize()
+            for (lo, hi), st in zip(zip(cuts[:-1], cuts[1:]), streams):
+                if hi > lo:
+                    with torch.cuda.stream(st):
+                        b.step_range(lo, hi - lo, act)
+            torch.cuda.synchronize()
+            y = b._ensure_torch()
+            assert torch.equal(x1, y["obs1"]) and torch.equal(x2, y["obs2"]) and torch.equal(xr, y["rew"]) and torch.equal(xd, y["done"]), t
+        sa, sb = a.get_state(), b.get_state()
+        for k in sa:
+            assert np.array_equal(sa[k], sb[k]), k
+        assert int(sa["steps"].max()) < 300
+
+
 def test_send_poll_on_two_handles_matches_one_synchronous_env():
     """hh_step_host_begin / _end (send_actions / poll): two half-batch handles kept in flight together reproduce the
     synchronous full-batch env bit for bit (arena_base makes the halves the same arenas); misuse is an error."""
