@@ -431,13 +431,18 @@ def run_b200(args):
                 rollout["fragment_bytes"] = int(sum(v.numel() * v.element_size() for v in smp.buf.values()))
                 # (i) the same loop end to end: every fragment's batch is copied to pinned host memory inside the timed region
                 #     (what a host-side learner / RLlib's train batch would read); the sampler has no host INPUT
-                host = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in smp.buf.items()}
+                #     VecSampler(n_buffers=2).collect_host(): two buffer sets, fragment k travels D2H while k + 1 is sampled
+                env_h = VecLowLevelEnv(n, make_args(level=args.level), device=local, seed=1, arena_base=rank * n, autoreset=True)
+                smp_h = VecSampler(env_h, TorchPolicy(m1, 1), TorchPolicy(m2, 2), fragment_len=Tf, use_cuda_graph=True,
+                                   n_buffers=2, **kw)
+                for _ in range(6):
+                    smp_h.collect_host()
+                torch.cuda.synchronize()
                 barrier()
                 th0 = time.perf_counter()
                 for _ in range(R):
-                    bb = smp.collect()
-                    for k, v in bb.items():
-                        host[k].copy_(v, non_blocking=True)
+                    _, h_ev = smp_h.collect_host()
+                h_ev.synchronize()
                 torch.cuda.synchronize()
                 th1 = time.perf_counter()
                 et = torch.tensor([th1 - th0], dtype=torch.float64, device=dev)
@@ -445,8 +450,9 @@ def run_b200(args):
                     dist.all_reduce(et, op=dist.ReduceOp.MAX)
                 rollout["e2e"] = {"value": world * n * Tf * R / float(et.item()), "unit": UNIT, "h2d_bytes_per_step": 0,
                                   "d2h_bytes_per_step": rollout["fragment_bytes"] // Tf,
-                                  "api": "VecSampler.collect() + D2H of the whole fragment batch into pinned host memory"}
-                del host
+                                  "api": "VecSampler(n_buffers=2).collect_host(): every fragment's whole batch copied into pinned host "
+                                         "memory inside the timed region, the copy of fragment k under the sampling of fragment k + 1"}
+                del smp_h, env_h
                 # (ii) the dominant kernel alone: the tcgen05 policy forward on the recorded central observations of the
                 #      fragment (a different tick's rows every launch), CUDA events around R2 launches
                 fu, bufs = smp.packed, smp.buf

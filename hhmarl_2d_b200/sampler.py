@@ -91,7 +91,7 @@ class VecSampler:
 
     def __init__(self, env, policy1: TorchPolicy, policy2: TorchPolicy, fragment_len: int = 64,
                  gamma: float = 0.99, lam: float = 0.95, use_cuda_graph: bool = True, packed: bool = True,
-                 allow_tf32: bool = False, fused: str | None = "tc", groups: int | None = None):
+                 allow_tf32: bool = False, fused: str | None = "tc", groups: int | None = None, n_buffers: int = 1):
         """`fused`: "tc" (default: csrc/hh_policy_tc.cu, tcgen05 / TMEM forward, fp32-equivalent, one launch per tick),
         "3xtf32" / "tf32" (csrc/hh_policy.cu on mma.sync: fp32-equivalent / plain TF32 products) or None (cuBLAS:
         `packed` / per-layer torch forward).
@@ -100,7 +100,9 @@ class VecSampler:
         forward's rounds of row tiles interleave instead of ending with a partly filled round (8 192 arenas: 0.112 -> 0.100 ms
         per tick with 8 groups, profiles/r2zk_sampler_groups.txt).  Same per-arena results (tested bit for bit).
         None = 8 from 8 192 arenas, 4 from 4 096 (fused forward, levels 1-3, arenas a multiple of 128 x groups), else 1
-        (HH_SAMPLER_GROUPS overrides the default)."""
+        (HH_SAMPLER_GROUPS overrides the default).
+        `n_buffers`: 2 = two sets of rollout buffers used in turn (one CUDA graph each), so that collect_host() can copy
+        fragment k to the host while fragment k + 1 is sampled."""
         self.env, self.p1, self.p2, self.T = env, policy1, policy2, fragment_len
         self.allow_tf32 = allow_tf32
         self.packed = None
@@ -121,7 +123,9 @@ class VecSampler:
         dev = torch.device("cuda", env.device_index)
         self.dev = dev
         f32 = dict(dtype=torch.float32, device=dev)
-        self.buf = dict(
+        if n_buffers not in (1, 2):
+            raise ValueError("n_buffers must be 1 or 2")
+        self.bufs = [dict(
             flat1=torch.zeros((T, n, 7 + d1 + d2), **f32), flat2=torch.zeros((T, n, 7 + d1 + d2), **f32),
             actions=torch.zeros((T, n, 2, 4), dtype=torch.int32, device=dev),
             logp=torch.zeros((T, n, 2), **f32), vf=torch.zeros((T, n, 2), **f32),
@@ -129,7 +133,10 @@ class VecSampler:
             logits2=torch.zeros((T, n, sum(policy2.splits)), **f32),
             rew=torch.zeros((T, n, 2), **f32), done=torch.zeros((T, n), dtype=torch.uint8, device=dev),
             adv=torch.zeros((T, n, 2), **f32), vtarg=torch.zeros((T, n, 2), **f32),
-            last_vf=torch.zeros((n, 2), **f32))
+            last_vf=torch.zeros((n, 2), **f32)) for _ in range(n_buffers)]
+        self.buf = self.bufs[0]            # the set the next / last fragment uses
+        self._bi = 0
+        self._host, self._copy_stream, self._copy_done = None, None, [None] * n_buffers
         self.cur1 = torch.zeros((n, 7 + d1 + d2), **f32)   # [act_1_own(4) | act_2(3) | obs_1_own | obs_2], actions 0
         self.cur2 = torch.zeros((n, 7 + d1 + d2), **f32)   # [act_1_own(3) | act_2(4) | obs_1_own | obs_2]
         self.d1, self.d2 = d1, d2
@@ -151,7 +158,7 @@ class VecSampler:
         self.seed = int(getattr(env, "_cfg").seed) + 0x5A17
         self.scale = ACT_SCALE.to(dev)
         self.use_graph = use_cuda_graph
-        self._graph = None
+        self._graphs = [None] * n_buffers
         self._started = False
 
     # central_critic_observer, train_hetero.py:162-181
@@ -299,21 +306,47 @@ class VecSampler:
             torch.backends.cuda.matmul.allow_tf32 = prev_tf32
 
     def _collect(self):
+        i = self._bi
+        self.buf = self.bufs[i]
+        self._bi = (i + 1) % len(self.bufs)
+        if self._copy_done[i] is not None:       # collect_host(): this set's previous fragment is still on its way to the host
+            torch.cuda.current_stream(self.dev).wait_event(self._copy_done[i])
         if not self.use_graph:
             self._fragment()
             return self.buf
-        if self._graph is None:
+        if self._graphs[i] is None:
             s = torch.cuda.Stream(self.dev)
             s.wait_stream(torch.cuda.current_stream(self.dev))
             with torch.cuda.stream(s):
                 self._fragment()                 # warm-up (allocations, cuBLAS handles) outside capture
             torch.cuda.current_stream(self.dev).wait_stream(s)
-            self._graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph):
+            self._graphs[i] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graphs[i]):
                 self._fragment()
             return self.buf                       # the captured region ran once during capture-free warm-up
-        self._graph.replay()
+        self._graphs[i].replay()
         return self.buf
+
+    @torch.no_grad()
+    def collect_host(self):
+        """collect() + the copy of the whole fragment batch into pinned host memory (what a host-side learner or RLlib's train
+        batch reads).  Returns (host dict, event): the copy runs on its own stream and `event` completes when the dict holds this
+        fragment.  With n_buffers = 2 the next collect_host() samples into the other buffer set while this copy is in flight
+        (host buffers alternate likewise): read the dict after event.synchronize() and before the call after next."""
+        b = self.collect()
+        i = (self._bi - 1) % len(self.bufs)
+        if self._host is None:
+            self._host = [{k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in bb.items()} for bb in self.bufs]
+            self._copy_stream = torch.cuda.Stream(self.dev)
+        cs = self._copy_stream
+        cs.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(cs):
+            for k, v in b.items():
+                self._host[i][k].copy_(v, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        self._copy_done[i] = ev
+        return self._host[i], ev
 
     @property
     def env_steps_per_fragment(self):
