@@ -85,6 +85,12 @@ class VecHighLevelEnv:
         self.fused_policies = True   # the frozen low-level actors through csrc/hh_policy.cu (False: torch forward)
         self.policy_precision = 2    # 2: tcgen05 path (fp32-equivalent logits before the argmax), 0: 3xTF32 on mma.sync, 1: plain TF32
         self._fused = None
+        # use_cuda_graph: a commander step is ~70 launches with no host synchronisation; after `graph_warmup` eager steps it is
+        # captured once and replayed (commander actions pass through a buffer that stays).  Eager when a trace / tick hook /
+        # the torch policies are in use.
+        self.use_cuda_graph = True
+        self.graph_warmup = 2
+        self._graph, self._eager_steps, self._ca_static = None, 0, None
 
     def _stream(self):
         return self._torch.cuda.current_stream(self.device_index).cuda_stream
@@ -167,9 +173,27 @@ class VecHighLevelEnv:
     def step(self, commander_actions):
         """commander_actions: int32 CUDA tensor [N, 3] in {0: escape, 1: nearest opponent, 2: second nearest}.
         Returns (obs [N,3,34], rew [N,3], done [N] u8); `self.substeps` holds the sub-step counts."""
-        L, h, st = nat.lib(), self._h, self._stream()
         t = self._torch
         assert commander_actions.is_cuda and commander_actions.dtype == t.int32 and commander_actions.numel() == self.n_arenas * 3
+        if not (self.use_cuda_graph and self.fused_policies and self.trace is None and self.tick_hook is None):
+            return self._step(commander_actions)
+        if self._graph is None and self._eager_steps < self.graph_warmup:
+            self._eager_steps += 1
+            return self._step(commander_actions)
+        if self._ca_static is None:
+            self._ca_static = t.empty((self.n_arenas, 3), dtype=t.int32, device=self.dev)
+        self._ca_static.copy_(commander_actions.reshape(self.n_arenas, 3))
+        if self._graph is None:
+            t.cuda.synchronize(self.dev)
+            self._graph = t.cuda.CUDAGraph()
+            with t.cuda.graph(self._graph):           # records, does not run
+                self._step(self._ca_static)
+        self._graph.replay()
+        return self.obs, self.rew, self.done
+
+    def _step(self, commander_actions):
+        L, h, st = nat.lib(), self._h, self._stream()
+        t = self._torch
         lo, li, la = self.ll_obs.data_ptr(), self.ll_info.data_ptr(), self.ll_act.data_ptr()
         nat.check(L.hh_hier_begin(h, commander_actions.contiguous().data_ptr(), lo, li, st), "hh_hier_begin")
         self._build_rows()

@@ -117,6 +117,32 @@ def test_commander_sampler_fragment():
     assert torch.allclose(lsm, b["logp"], atol=1e-5)
 
 
+def test_graph_replayed_commander_steps_match_eager_steps():
+    """VecHighLevelEnv replays one captured CUDA graph per commander step (after two eager steps): observations, rewards, done
+    flags, sub-step counts and the eval-info counters must equal an eager env's, step by step, with episodes ending in between."""
+    from hhmarl_2d_b200.env_hier import VecHighLevelEnv, make_hier_args
+    n, T = 512, 12
+    torch.manual_seed(3)
+    ca = torch.randint(0, 3, (T, n, 3)).to(torch.int32).cuda()
+    envs = []
+    for use_graph in (False, True):
+        e = VecHighLevelEnv(n, make_hier_args(horizon=60, eval_info=True), device=0, seed=8, arena_base=70, autoreset=True)
+        e.use_cuda_graph = use_graph
+        envs.append(e)
+    assert torch.equal(envs[0].reset(), envs[1].reset())
+    n_done = 0
+    for t in range(T):
+        outs = []
+        for e in envs:
+            o, r, d = e.step(ca[t])
+            outs.append((o.clone(), r.clone(), d.clone(), e.substeps.clone(), e.info.clone()))
+        for a, b in zip(*outs):
+            assert torch.equal(a, b), t
+        n_done += int(outs[0][2].sum())
+    assert envs[1]._graph is not None and envs[0]._graph is None
+    assert n_done > 0
+
+
 def test_hier_full_size_properties():
     """BASELINE config 5 size (8 192 arenas, 3-vs-3): two runs agree bit for bit, observations stay in Box(0, 1),
     every arena makes between 1 and 16 sub-steps per commander step, a ragged slice of the arenas reproduces."""
