@@ -516,13 +516,14 @@ step_kernel_v4(StatePtrs S, Params P, const int32_t* __restrict__ actions, float
 template <int LEVEL, int MODE>
 __global__ void __launch_bounds__(2 * v4::kThreads, 1)
 step_kernel_v4_dual(StatePtrs S, Params P, const int32_t* __restrict__ actions, float* __restrict__ obs1,
-                    float* __restrict__ obs2, float* __restrict__ rew_out, uint8_t* __restrict__ done_out, int block0) {
+                    float* __restrict__ obs2, float* __restrict__ rew_out, uint8_t* __restrict__ done_out, int block0,
+                    float* cen1, float* cen2, int cen_ld) {
   extern __shared__ __align__(16) unsigned char v4_smem[];
   const int sub = threadIdx.x / v4::kThreads;
   const int block = 2 * (int)blockIdx.x + sub + block0;
   if (block * v4::kArenas >= P.n_arenas) return;      // sub-block uniform (an odd number of blocks: the last CTA runs one)
   v4::step_body<LEVEL, MODE, true>(*reinterpret_cast<v4::Smem*>(v4_smem + (size_t)sub * ((sizeof(v4::Smem) + 15) / 16 * 16)), S, P,
-                                   actions, obs1, obs2, rew_out, done_out, block);
+                                   actions, obs1, obs2, rew_out, done_out, block, cen1, cen2, cen_ld);
 }
 template <int LEVEL, int MODE>
 static cudaError_t v4_opt_in_smem() {
@@ -824,6 +825,54 @@ extern "C" int hh_gae(int32_t T, int32_t n_arenas, const float* rew_dev, const f
   return 0;
 }
 
+// The two ends of a rollout fragment in the sampler's central-critic layout (rows [7 action columns | own obs | other obs], D floats):
+//   prepare  : the critic sees ZERO actions while sampling -- clear the action columns of all T x N rows of both
+//              policies and seed tick 0 with the current central observation rows;
+//   writeback: CustomCallback.on_postprocess_trajectory (train_hetero.py:120-160) -- the critic's action columns get the real
+//              actions, scaled (a0 / 12, a1 / 8, a2, a3; train_hetero.py:143-146): flat1 = [own1 (4) | own2 (3)], flat2 = [own2 (3) | own1 (4)].
+__global__ void fragment_prepare_kernel(int T, int n, int D, float* __restrict__ flat1, float* __restrict__ flat2,
+                                        const float* __restrict__ cur1, const float* __restrict__ cur2) {
+  const size_t n0 = (size_t)n * D, nz = (size_t)(T - 1) * n * 7;
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n0 + nz; k += (size_t)gridDim.x * blockDim.x) {
+    if (k < n0) {
+      flat1[k] = cur1[k];
+      flat2[k] = cur2[k];
+    } else {
+      const size_t j = k - n0, row = n + j / 7;
+      flat1[row * D + j % 7] = 0.0f;
+      flat2[row * D + j % 7] = 0.0f;
+    }
+  }
+}
+__global__ void fragment_writeback_kernel(size_t rows, int D, const int32_t* __restrict__ actions, float* __restrict__ flat1,
+                                          float* __restrict__ flat2) {
+  for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (size_t)gridDim.x * blockDim.x) {
+    const int4 a1 = reinterpret_cast<const int4*>(actions)[2 * r], a2 = reinterpret_cast<const int4*>(actions)[2 * r + 1];
+    const float o1[4] = {(float)a1.x / 12.0f, (float)a1.y / 8.0f, (float)a1.z / 1.0f, (float)a1.w / 1.0f};
+    const float o2[3] = {(float)a2.x / 12.0f, (float)a2.y / 8.0f, (float)a2.z / 1.0f};
+    float* f1 = flat1 + r * D;
+    float* f2 = flat2 + r * D;
+    f1[0] = o1[0]; f1[1] = o1[1]; f1[2] = o1[2]; f1[3] = o1[3]; f1[4] = o2[0]; f1[5] = o2[1]; f1[6] = o2[2];
+    f2[0] = o2[0]; f2[1] = o2[1]; f2[2] = o2[2]; f2[3] = o1[0]; f2[4] = o1[1]; f2[5] = o1[2]; f2[6] = o1[3];
+  }
+}
+extern "C" int hh_fragment_prepare(int32_t T, int32_t n_arenas, int32_t D, float* flat1_dev, float* flat2_dev, const float* cur1_dev,
+                                   const float* cur2_dev, void* stream) {
+  if (T <= 0 || n_arenas <= 0 || D < 7 || !flat1_dev || !flat2_dev || !cur1_dev || !cur2_dev)
+    return fail(-1, "hh_fragment_prepare: bad argument");
+  fragment_prepare_kernel<<<592, 256, 0, static_cast<cudaStream_t>(stream)>>>(T, n_arenas, D, flat1_dev, flat2_dev, cur1_dev, cur2_dev);
+  HH_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int hh_fragment_writeback(int32_t T, int32_t n_arenas, int32_t D, const int32_t* actions_dev, float* flat1_dev,
+                                     float* flat2_dev, void* stream) {
+  if (T <= 0 || n_arenas <= 0 || D < 7 || !actions_dev || !flat1_dev || !flat2_dev)
+    return fail(-1, "hh_fragment_writeback: bad argument");
+  fragment_writeback_kernel<<<592, 256, 0, static_cast<cudaStream_t>(stream)>>>((size_t)T * n_arenas, D, actions_dev, flat1_dev, flat2_dev);
+  HH_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int hh_gae_agents(int32_t T, int32_t n_arenas, int32_t n_agents, const float* rew_dev, const float* vf_dev,
                              const float* last_vf_dev, const uint8_t* done_dev, float gamma, float lam, float* adv_dev,
                              float* vtarg_dev, void* stream) {
@@ -1024,16 +1073,19 @@ extern "C" int hh_reset(hh_env* e, const uint8_t* mask_dev, float* obs1, float* 
 // arenas [first, end) of the v4 step (first a multiple of v4::kArenas); the whole batch is first = 0, end = n
 template <int LEVEL>
 static void launch_step_v4_range(hh_env* e, int first, int end, const int32_t* actions, float* obs1, float* obs2, float* rew,
-                                 uint8_t* done, cudaStream_t st, bool dual = false) {
+                                 uint8_t* done, cudaStream_t st, bool dual = false, float* cen1 = nullptr, float* cen2 = nullptr,
+                                 int cen_ld = 0) {
   Params P = e->P;
   P.n_arenas = end;
   const int block0 = first / v4::kArenas, vblocks = (end - first + v4::kArenas - 1) / v4::kArenas;
   if (dual) {
     const size_t sm2 = 2 * ((sizeof(v4::Smem) + 15) / 16 * 16);
     if (e->cfg.agent_mode == 0)
-      step_kernel_v4_dual<LEVEL, 0><<<(vblocks + 1) / 2, 2 * v4::kThreads, sm2, st>>>(e->S, P, actions, obs1, obs2, rew, done, block0);
+      step_kernel_v4_dual<LEVEL, 0><<<(vblocks + 1) / 2, 2 * v4::kThreads, sm2, st>>>(e->S, P, actions, obs1, obs2, rew, done, block0,
+                                                                                      cen1, cen2, cen_ld);
     else
-      step_kernel_v4_dual<LEVEL, 1><<<(vblocks + 1) / 2, 2 * v4::kThreads, sm2, st>>>(e->S, P, actions, obs1, obs2, rew, done, block0);
+      step_kernel_v4_dual<LEVEL, 1><<<(vblocks + 1) / 2, 2 * v4::kThreads, sm2, st>>>(e->S, P, actions, obs1, obs2, rew, done, block0,
+                                                                                      cen1, cen2, cen_ld);
     return;
   }
   if (e->cfg.agent_mode == 0)
@@ -1085,8 +1137,22 @@ extern "C" int hh_step(hh_env* e, const int32_t* actions_dev, float* obs1, float
 // arenas [first, first + count) only: the pointers address the WHOLE batch's arrays (arena 0 first).  Lets a caller keep two
 // halves of a batch in flight on two streams (the sampler's software pipeline: one half's policy forward runs while the other
 // half steps).  Levels 1-3, default step kernel; first must be a multiple of 32.
+static int step_range_impl(hh_env* e, int32_t first, int32_t count, const int32_t* actions_dev, float* obs1, float* obs2,
+                           float* rew, uint8_t* done, float* cen1, float* cen2, int cen_ld, void* stream);
 extern "C" int hh_step_range(hh_env* e, int32_t first, int32_t count, const int32_t* actions_dev, float* obs1, float* obs2,
                              float* rew, uint8_t* done, void* stream) {
+  return step_range_impl(e, first, count, actions_dev, obs1, obs2, rew, done, nullptr, nullptr, 0, stream);
+}
+// ... and the observations ALSO (obs1 / obs2 may be NULL) as the next tick's central-critic rows of both policies:
+// central1[a][7 ..] = [obs1 | obs2], central2[a][7 ..] = [obs2 | obs1] (what hh_pack_central would write), row stride ld floats
+extern "C" int hh_step_range_central(hh_env* e, int32_t first, int32_t count, const int32_t* actions_dev, float* obs1, float* obs2,
+                                     float* rew, uint8_t* done, float* central1, float* central2, int32_t ld, void* stream) {
+  if (!central1 || !central2 || (e && ld < 7 + obs_dim(e->cfg, 1) + obs_dim(e->cfg, 2)))
+    return fail(-3, "hh_step_range_central: central1 / central2 with a row stride of at least 7 + d1 + d2 floats");
+  return step_range_impl(e, first, count, actions_dev, obs1, obs2, rew, done, central1, central2, ld, stream);
+}
+static int step_range_impl(hh_env* e, int32_t first, int32_t count, const int32_t* actions_dev, float* obs1, float* obs2,
+                           float* rew, uint8_t* done, float* cen1, float* cen2, int cen_ld, void* stream) {
   if (!e) return fail(-1, "hh_step_range: null env");
   if (!e->initialised) return fail(-4, "hh_step_range: call hh_reset first");
   if (!actions_dev) return fail(-1, "hh_step_range: null actions");
@@ -1096,11 +1162,12 @@ extern "C" int hh_step_range(hh_env* e, int32_t first, int32_t count, const int3
     return fail(-3, "hh_step_range: first must be a multiple of 32 and [first, first + count) inside the batch");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // ranges run next to other kernels (that is what they are for): two sub-blocks per CTA = half as many CTAs spread over the SMs
-  static const bool dual = [] { const char* v = getenv("HH_STEP_RANGE_DUAL"); return !v || atoi(v) != 0; }();
+  static const bool dual_env = [] { const char* v = getenv("HH_STEP_RANGE_DUAL"); return !v || atoi(v) != 0; }();
+  const bool dual = dual_env || cen1;      // the central rows are written by the dual form
   switch (e->cfg.level) {
-    case 1: launch_step_v4_range<1>(e, first, first + count, actions_dev, obs1, obs2, rew, done, st, dual); break;
-    case 2: launch_step_v4_range<2>(e, first, first + count, actions_dev, obs1, obs2, rew, done, st, dual); break;
-    default: launch_step_v4_range<3>(e, first, first + count, actions_dev, obs1, obs2, rew, done, st, dual); break;
+    case 1: launch_step_v4_range<1>(e, first, first + count, actions_dev, obs1, obs2, rew, done, st, dual, cen1, cen2, cen_ld); break;
+    case 2: launch_step_v4_range<2>(e, first, first + count, actions_dev, obs1, obs2, rew, done, st, dual, cen1, cen2, cen_ld); break;
+    default: launch_step_v4_range<3>(e, first, first + count, actions_dev, obs1, obs2, rew, done, st, dual, cen1, cen2, cen_ld); break;
   }
   HH_CUDA(cudaGetLastError());
   e->launches += 1;

@@ -77,6 +77,11 @@ struct Ctx {
   uint8_t* done_out;
   int arena0, n_valid;
   Geom g;
+  // optional second destination of the observations (DUAL launches only): the next tick's central-critic rows
+  // [7 action columns | own obs | other obs] of both policies (central_critic_observer, train_hetero.py:162-181), row stride cen_ld
+  float* cen1 = nullptr;
+  float* cen2 = nullptr;
+  int cen_ld = 0;
   // arenas beyond N shadow the last valid one (they compute, never store)
   __device__ __forceinline__ int arena_of(int al) const { return arena0 + (al < n_valid ? al : n_valid - 1); }
   __device__ __forceinline__ Rng rng(int al) const {
@@ -860,8 +865,20 @@ __device__ __forceinline__ void s10_store_unit(const Ctx& C, int t) {
 #else
 #define HH_NO_UNROLL
 #endif
+template <bool CENTRAL = false>
 __device__ __forceinline__ void s10_store_rows(const Ctx& C, int t, int n_threads, int d1, int d2) {
   const Smem& S = C.S;
+  if (CENTRAL && C.cen1) {
+    const int w = d1 + d2, nf = C.n_valid * w;
+    HH_NO_UNROLL
+    for (int k = t; k < nf; k += n_threads) {
+      const int a = k / w, c = k - a * w;
+      const float v = c < d1 ? S.obs1[a * d1 + c] : S.obs2[a * d2 + (c - d1)];
+      const size_t row = (size_t)(C.arena0 + a) * C.cen_ld + 7;
+      C.cen1[row + c] = v;                                   // [.. | obs1 | obs2]
+      C.cen2[row + (c < d1 ? d2 + c : c - d1)] = v;          // [.. | obs2 | obs1]
+    }
+  }
   if (C.obs1) {
     const int nf = C.n_valid * d1, n4 = nf >> 2;
     float* dst = C.obs1 + (size_t)C.arena0 * d1;
@@ -949,13 +966,14 @@ __device__ __forceinline__ void s2_warm(const Ctx& C, int t) {
 template <int LEVEL, int MODE, bool DUAL = false>
 __device__ __forceinline__ void step_body(Smem& S, const StatePtrs& G, const Params& P, const int32_t* __restrict__ actions,
                                           float* __restrict__ obs1, float* __restrict__ obs2,
-                                          float* __restrict__ rew_out, uint8_t* __restrict__ done_out, int block) {
+                                          float* __restrict__ rew_out, uint8_t* __restrict__ done_out, int block,
+                                          float* cen1 = nullptr, float* cen2 = nullptr, int cen_ld = 0) {
   constexpr int D1 = MODE == 0 ? OBS_AC1 : OBS_ESC_AC1, D2 = MODE == 0 ? OBS_AC2 : OBS_ESC_AC2;
   HH_TID_DECL
   const int arena0 = block * kArenas;
   const int n_valid_ = P.n_arenas - arena0;
   const Ctx C{S, G, P, actions, obs1, obs2, rew_out, done_out, arena0, n_valid_ < kArenas ? n_valid_ : kArenas,
-              P.geom};
+              P.geom, cen1, cen2, cen_ld};
   HH_MARK(0)
   HH_ROLE(0, A4, s0_load_unit(C, t))
   HH_ROLE(A4, A2, s0_load_actions(C, t))
@@ -996,7 +1014,7 @@ __device__ __forceinline__ void step_body(Smem& S, const StatePtrs& G, const Par
   HH_BARRIER();
   HH_MARK(9)
   HH_ROLE(0, A4, s10_store_unit(C, t))     // (storing the state during S9 instead was measured slower: r1o)
-  HH_ROLE(0, A8, s10_store_rows(C, t, A8, D1, D2))
+  HH_ROLE(0, A8, s10_store_rows<DUAL>(C, t, A8, D1, D2))
   HH_MARK(10)
 #if defined(HH_V4_PROFILE) && defined(__CUDACC__)
   if ((tid & 31) == 0 && block < 512) g_warp_arrive[(block * 8 + (tid >> 5)) * 16 + 15] = hh_bar;   // barriers passed

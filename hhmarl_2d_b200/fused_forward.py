@@ -322,13 +322,21 @@ class FusedPolicyPair:
         self._launch_tc([(0, flat1, out[0:2]), (1, flat2, out[2:4])], n_act)
         return out
 
-    def _launch_tc(self, jobs, n_act):
-        chains = (nat.HHPolicyChainEx * (2 * len(jobs)))()
+    def values(self, flat1, flat2, out):
+        """Only the two central critics (the bootstrap value at the end of a fragment): half the chains of forward().
+        `out` = (value1 [B], value2 [B]).  tcgen05 path only."""
+        assert self.precision == 2
+        self._launch_tc([(0, flat1, (None, out[0])), (1, flat2, (None, out[1]))], [None, None], kinds=(1,))
+        return out
+
+    def _launch_tc(self, jobs, n_act, kinds=(0, 1)):
+        nk = len(kinds)
+        chains = (nat.HHPolicyChainEx * (nk * len(jobs)))()
         for j, (p, x, o2) in enumerate(jobs):
             B = x.shape[0]
             assert x.dtype == torch.float32 and x.is_cuda and x.stride(1) == 1
-            for k in range(2):
-                c = chains[2 * j + k]
+            for i, k in enumerate(kinds):
+                c = chains[nk * j + i]
                 c.x, c.ldx, c.d_in, c.k1_pad = x.data_ptr(), x.stride(0), x.shape[1], self.k1_pad[p]
                 c.b1, c.bs, c.bh = self.b1[p][k].data_ptr(), self.bs.data_ptr(), self.bh[p][k].data_ptr()
                 c.img_w1, c.us_w1 = (t.data_ptr() for t in self.img[("w1", p, k)])

@@ -215,10 +215,10 @@ class VecSampler:
                                       int(self.env._cfg.arena_base) + lo, self.ctr[lo:hi].data_ptr(), 1, act[lo:hi].data_ptr(),
                                       b["logp"][t][lo:hi].data_ptr(), st), "hh_sample_actions")
         eb = self.env._ensure_torch()
-        self.env.step_range(lo, hi - lo, act, out=dict(obs1=eb["obs1"], obs2=eb["obs2"], rew=b["rew"][t], done=b["done"][t]))
         nxt1, nxt2 = (b["flat1"][t + 1], b["flat2"][t + 1]) if t + 1 < T else (self.cur1, self.cur2)
-        nat.check(L.hh_pack_central(hi - lo, self.d1, self.d2, eb["obs1"][lo:hi].data_ptr(), eb["obs2"][lo:hi].data_ptr(),
-                                    nxt1[lo:hi].data_ptr(), nxt2[lo:hi].data_ptr(), st), "hh_pack_central")
+        # the step kernel writes the next tick's central observation rows itself (hh_step_range_central): three launches per tick
+        self.env.step_range(lo, hi - lo, act, out=dict(obs1=eb["obs1"], obs2=eb["obs2"], rew=b["rew"][t], done=b["done"][t]),
+                            central=(nxt1, nxt2))
 
     def _tick(self, t):
         b = self.buf
@@ -259,13 +259,13 @@ class VecSampler:
 
     def _fragment(self):
         b = self.buf
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        D = 7 + self.d1 + self.d2
         if self.direct:
             # the critic sees ZERO actions while sampling: clear what the previous fragment's write-back
-            # left in the action columns, then seed tick 0 with the current central observation
-            b["flat1"][:, :, :7].zero_()
-            b["flat2"][:, :, :7].zero_()
-            b["flat1"][0].copy_(self.cur1)
-            b["flat2"][0].copy_(self.cur2)
+            # left in the action columns, then seed tick 0 with the current central observation (one launch)
+            nat.check(nat.lib().hh_fragment_prepare(self.T, self.env.n_arenas, D, b["flat1"].data_ptr(), b["flat2"].data_ptr(),
+                                                    self.cur1.data_ptr(), self.cur2.data_ptr(), st), "hh_fragment_prepare")
         if self.groups > 1:      # every half runs its own chain of T ticks on its own stream (fork / join around the loop)
             cur = torch.cuda.current_stream(self.dev)
             for (lo, hi), gs in zip(self._bounds, self._gstreams):
@@ -278,14 +278,20 @@ class VecSampler:
         else:
             for t in range(self.T):
                 self._tick(t)
-        _, v1, _, v2 = self._forward_both(self.cur1, self.cur2)
-        b["last_vf"][:, 0], b["last_vf"][:, 1] = v1, v2
-        st = torch.cuda.current_stream(self.dev).cuda_stream
+        if self.direct and getattr(self.packed, "precision", None) == 2:     # the bootstrap values: the two critics only
+            self.packed.values(self.cur1, self.cur2, out=(b["last_vf"][:, 0], b["last_vf"][:, 1]))
+        else:
+            _, v1, _, v2 = self._forward_both(self.cur1, self.cur2)
+            b["last_vf"][:, 0], b["last_vf"][:, 1] = v1, v2
         nat.check(nat.lib().hh_gae(self.T, self.env.n_arenas, b["rew"].data_ptr(), b["vf"].data_ptr(),
                                    b["last_vf"].data_ptr(), b["done"].data_ptr(), self.gamma, self.lam,
                                    b["adv"].data_ptr(), b["vtarg"].data_ptr(), st), "hh_gae")
         # CustomCallback.on_postprocess_trajectory (train_hetero.py:120-160): the critic's action columns get
         # the real actions, scaled; VF_PREDS / advantages above were computed with zeros
+        if self.native_glue:
+            nat.check(nat.lib().hh_fragment_writeback(self.T, self.env.n_arenas, D, b["actions"].data_ptr(), b["flat1"].data_ptr(),
+                                                      b["flat2"].data_ptr(), st), "hh_fragment_writeback")
+            return
         a = b["actions"].to(torch.float32)
         own1, own2 = a[:, :, 0, :] / self.scale, a[:, :, 1, :3] / self.scale[:3]
         b["flat1"][:, :, 0:4], b["flat1"][:, :, 4:7] = own1, own2

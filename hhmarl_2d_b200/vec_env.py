@@ -123,15 +123,28 @@ class VecLowLevelEnv:
                                     b["rew"].data_ptr(), b["done"].data_ptr(), self._stream()), "hh_step")
         return b["obs1"], b["obs2"], b["rew"], b["done"]
 
-    def step_range(self, first, count, actions, out=None):
+    def step_range(self, first, count, actions, out=None, central=None):
         """step() for arenas [first, first + count) only (levels 1-3; `first` a multiple of 32).  `actions` and the output tensors
-        are the WHOLE batch's ([N, ...]); only the range's rows are read / written.  Two ranges may be in flight on two streams."""
+        are the WHOLE batch's ([N, ...]); only the range's rows are read / written.  Two ranges may be in flight on two streams.
+        `central` = (flat1_next, flat2_next): the kernel also writes the new observations as the central-critic rows of both
+        policies ([N, 7 + d1 + d2] each, columns 7.. ; hh_step_range_central) -- no separate packing launch."""
         b = out if out is not None else self._ensure_torch()
         self._ensure_torch()
         t = self._torch
         if not (actions.is_cuda and actions.dtype == t.int32 and actions.is_contiguous()
                 and actions.numel() == self.n_arenas * 8):
             raise ValueError("actions must be a contiguous int32 CUDA tensor of shape [N, 2, 4]")
+        if central is not None:
+            c1, c2 = central
+            d1, d2 = self.obs_dim
+            if not (c1.is_cuda and c2.is_cuda and c1.dtype == t.float32 and c2.dtype == t.float32 and c1.shape == c2.shape
+                    and c1.shape[0] == self.n_arenas and c1.shape[1] >= 7 + d1 + d2 and c1.stride(1) == 1 and c2.stride(1) == 1
+                    and c1.stride(0) == c2.stride(0)):
+                raise ValueError("central must be two float32 CUDA tensors [N, >= 7 + d1 + d2] with the same row stride")
+            nat.check(nat.lib().hh_step_range_central(self._h, int(first), int(count), actions.data_ptr(), b["obs1"].data_ptr(),
+                                                      b["obs2"].data_ptr(), b["rew"].data_ptr(), b["done"].data_ptr(), c1.data_ptr(),
+                                                      c2.data_ptr(), int(c1.stride(0)), self._stream()), "hh_step_range_central")
+            return
         nat.check(nat.lib().hh_step_range(self._h, int(first), int(count), actions.data_ptr(), b["obs1"].data_ptr(),
                                           b["obs2"].data_ptr(), b["rew"].data_ptr(), b["done"].data_ptr(), self._stream()),
                   "hh_step_range")

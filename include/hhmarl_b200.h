@@ -87,6 +87,11 @@ int hh_step(hh_env* env, const int32_t* actions_dev, float* obs1_dev, float* obs
  * flight on two streams: the rollout sampler steps one half of the batch while the other half's policy forward runs. */
 int hh_step_range(hh_env* env, int32_t first, int32_t count, const int32_t* actions_dev, float* obs1_dev, float* obs2_dev,
                   float* rew_dev, uint8_t* done_dev, void* stream);
+/* hh_step_range that ALSO writes the new observations as the central-critic rows of both policies (central_critic_observer,
+ * train_hetero.py:162-181; what hh_pack_central does in a launch of its own): central1[a][7 ..] = [obs1 | obs2],
+ * central2[a][7 ..] = [obs2 | obs1], rows `ld` floats apart, the 7 action columns untouched.  obs1_dev / obs2_dev may be NULL. */
+int hh_step_range_central(hh_env* env, int32_t first, int32_t count, const int32_t* actions_dev, float* obs1_dev, float* obs2_dev,
+                          float* rew_dev, uint8_t* done_dev, float* central1_dev, float* central2_dev, int32_t ld, void* stream);
 
 /* Levels 4/5 (frozen-policy opponents, env_base.py:349-398): the opponents' own observations are needed
  * mid-step, after the agents' fire decisions and before the tick, so the step is split around the
@@ -138,6 +143,17 @@ int hh_gae(int32_t T, int32_t n_arenas, const float* rew_dev, const float* vf_de
 int hh_gae_agents(int32_t T, int32_t n_arenas, int32_t n_agents, const float* rew_dev, const float* vf_dev,
                   const float* last_vf_dev, const uint8_t* done_dev, float gamma, float lam, float* adv_dev,
                   float* vtarg_dev, void* stream);
+
+/* The two ends of a rollout fragment in the sampler's central-critic layout (rows [7 action columns | own obs | other obs] of D
+ * floats, flat f32[T][N][D] per policy):
+ * hh_fragment_prepare  : zero the action columns of all rows (the critic sees zero actions while sampling) and copy the current
+ *                        central observation rows cur1 / cur2 f32[N][D] into tick 0;
+ * hh_fragment_writeback: CustomCallback.on_postprocess_trajectory (train_hetero.py:120-160): the action columns get the taken
+ *                        actions int32[T][N][2][4], scaled a0 / 12, a1 / 8, a2, a3 (train_hetero.py:143-146). */
+int hh_fragment_prepare(int32_t T, int32_t n_arenas, int32_t D, float* flat1_dev, float* flat2_dev, const float* cur1_dev,
+                        const float* cur2_dev, void* stream);
+int hh_fragment_writeback(int32_t T, int32_t n_arenas, int32_t D, const int32_t* actions_dev, float* flat1_dev, float* flat2_dev,
+                          void* stream);
 
 /* Sampler glue (what RLlib's sampler does between the policy forward and env.step):
  * hh_sample_actions: TorchMultiCategorical.sample()/logp() of both policies in one launch.  logits1 f32[N][26]

@@ -398,6 +398,9 @@ def test_step_range_on_two_streams_matches_the_whole_batch_step():
         assert torch.equal(oa1, ob1) and torch.equal(oa2, ob2)
         cuts = [0, 1024 + 32, 2048 + 96, n] if n > 2048 else [0, 512, 1024, n]
         streams = [torch.cuda.Stream() for _ in range(3)]
+        d1, d2 = a.obs_dim
+        c1 = torch.full((n, 7 + d1 + d2), -1.0, device="cuda")
+        c2 = torch.full((n, 7 + d1 + d2), -1.0, device="cuda")
         g = torch.Generator(device="cuda").manual_seed(5)
         for t in range(300):
             act = torch.stack([torch.randint(0, 13, (n, 2), generator=g, device="cuda"), torch.randint(0, 9, (n, 2), generator=g, device="cuda"),
@@ -405,13 +408,17 @@ def test_step_range_on_two_streams_matches_the_whole_batch_step():
                               dim=-1).to(torch.int32).contiguous()
             x1, x2, xr, xd = a.step(act)
             torch.cuda.synchronize()
-            for (lo, hi), st in zip(zip(cuts[:-1], cuts[1:]), streams):
+            for j, ((lo, hi), st) in enumerate(zip(zip(cuts[:-1], cuts[1:]), streams)):
                 if hi > lo:
-                    with torch.cuda.stream(st):
-                        b.step_range(lo, hi - lo, act)
+                    with torch.cuda.stream(st):     # the middle range also writes the central-critic rows (hh_step_range_central)
+                        b.step_range(lo, hi - lo, act, central=(c1, c2) if j == 1 else None)
             torch.cuda.synchronize()
             y = b._ensure_torch()
             assert torch.equal(x1, y["obs1"]) and torch.equal(x2, y["obs2"]) and torch.equal(xr, y["rew"]) and torch.equal(xd, y["done"]), t
+            lo, hi = cuts[1], cuts[2]
+            assert torch.equal(c1[lo:hi, 7:], torch.cat([x1[lo:hi], x2[lo:hi]], dim=1)), t
+            assert torch.equal(c2[lo:hi, 7:], torch.cat([x2[lo:hi], x1[lo:hi]], dim=1)), t
+            assert (c1[:, :7] == -1).all() and (c1[:lo] == -1).all() and (c2[hi:] == -1).all()
         sa, sb = a.get_state(), b.get_state()
         for k in sa:
             assert np.array_equal(sa[k], sb[k]), k

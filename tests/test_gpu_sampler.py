@@ -192,6 +192,13 @@ def test_groups_on_their_own_streams_collect_the_same_fragment(use_graph):
         for fa, fb in zip(out[0], other):
             for k in fa:
                 assert torch.equal(fa[k], fb[k]), k
+    # hh_fragment_writeback = on_postprocess_trajectory (train_hetero.py:120-160): scaled actions in the critics' action columns
+    f = out[0][-1]
+    a = f["actions"].float()
+    sc = torch.tensor([12.0, 8.0, 1.0, 1.0], device="cuda")
+    own1, own2 = a[:, :, 0, :] / sc, a[:, :, 1, :3] / sc[:3]
+    assert torch.equal(f["flat1"][:, :, 0:4], own1) and torch.equal(f["flat1"][:, :, 4:7], own2)
+    assert torch.equal(f["flat2"][:, :, 0:3], own2) and torch.equal(f["flat2"][:, :, 3:7], own1)
     assert VecSampler(VecLowLevelEnv(4096, make_args(level=3), device=0, seed=1), TorchPolicy(m1, 1), TorchPolicy(m2, 2)).groups == 4
     with pytest.raises(ValueError):
         VecSampler(VecLowLevelEnv(640, make_args(level=3), device=0, seed=1), TorchPolicy(m1, 1), TorchPolicy(m2, 2), groups=2)
