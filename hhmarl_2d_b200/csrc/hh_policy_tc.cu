@@ -1365,21 +1365,32 @@ __global__ void __launch_bounds__(kThreads2, 1) policy_forward_m128_kernel(const
        // only the thread that owns a TMEM lane (= row) can write it
       __half* lo_stage = reinterpret_cast<__half*>(smem + OFF2_ACT);
       const int d_in = C.d_in;
-      constexpr int kIter = TM2 * KX / (32 * kEpiWarps2);   // 20 elements per thread: all loads in flight before the first use
-      float xv[kIter];
+      // thread = one column c of the tile and every sixth row (480 of the 512 threads): the column's predicate, global offset and
+      // shared-memory offset are loop constants, all 22 loads are in flight before the first use
+      constexpr int kRowsPerPass = 32 * kEpiWarps2 / KX;            // 6
+      constexpr int kIter = (TM2 + kRowsPerPass - 1) / kRowsPerPass; // 22
+      if (et < kRowsPerPass * KX) {
+        const int r0 = et / KX, c = et - r0 * KX;
+        const bool col_ok = c < d_in;
+        const float* xc = C.x + c;
+        float xv[kIter];
 #pragma unroll
-      for (int i = 0; i < kIter; ++i) {
-        const int e = et + i * 32 * kEpiWarps2, r = e / KX, c = e - r * KX;
-        const int gr = rowmap[r];
-        xv[i] = (gr >= 0 && c < d_in) ? __ldg(C.x + (size_t)gr * C.ldx + c) : 0.0f;
-      }
+        for (int i = 0; i < kIter; ++i) {
+          const int r = r0 + kRowsPerPass * i;
+          const int gr = r < TM2 ? rowmap[r] : -1;
+          xv[i] = (col_ok && gr >= 0) ? __ldg(xc + (size_t)gr * C.ldx) : 0.0f;
+        }
+        uint8_t* hi_c = smem + OFF2_X + (uint32_t)((c >> 3) * (TM2 * 16) + (c & 7) * 2);
 #pragma unroll
-      for (int i = 0; i < kIter; ++i) {
-        const int e = et + i * 32 * kEpiWarps2, r = e / KX, c = e - r * KX;
-        const float sv = fminf(fmaxf(xv[i], -ACT_CLAMP), ACT_CLAMP) * ACT_SCALE;
-        const __half h = __float2half_rn(sv);
-        *reinterpret_cast<__half*>(smem + OFF2_X + (uint32_t)((c >> 3) * (TM2 * 16) + r * 16 + (c & 7) * 2)) = h;
-        lo_stage[r * KX + c] = __float2half_rn(sv - __half2float(h));
+        for (int i = 0; i < kIter; ++i) {
+          const int r = r0 + kRowsPerPass * i;
+          if (r < TM2) {
+            const float sv = fminf(fmaxf(xv[i], -ACT_CLAMP), ACT_CLAMP) * ACT_SCALE;
+            const __half h = __float2half_rn(sv);
+            *reinterpret_cast<__half*>(hi_c + r * 16) = h;
+            lo_stage[r * KX + c] = __float2half_rn(sv - __half2float(h));
+          }
+        }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps2) : "memory");
       uint32_t lo_w[10];

@@ -223,6 +223,8 @@ class VecSampler:
     def _tick(self, t):
         b = self.buf
         if self.direct:
+            if int(self.env.level) <= 3:          # one group = the whole batch: forward, sample, step (+ central rows)
+                return self._tick_group(t, 0, self.env.n_arenas)
             return self._tick_direct(t)
         l1, v1, l2, v2 = self._forward_both(self.cur1, self.cur2)
         if self.native_glue:
