@@ -328,7 +328,7 @@ def run_b200(args):
                               f"{os.cpu_count()} logical CPUs) x {args.cpu_sample_steps} env-steps (L{args.level}, "
                               f"random actions, auto-reset), {dt:.1f} s wall"}
 
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if rank == 0 and not os.environ.get("HH_BENCH_NO_CLOCKS") else None
     env = VecLowLevelEnv(n, make_args(level=args.level), device=local, seed=0, arena_base=rank * n, autoreset=True)
     g = torch.Generator(device=dev)
     g.manual_seed(1234 + rank)
@@ -552,18 +552,25 @@ def run_b200(args):
         gh = torch.Generator(device=dev)
         gh.manual_seed(77 + rank)
         cmd = torch.randint(0, 3, (8, n, 3), device=dev, generator=gh).to(torch.int32)
-        for w in range(2):
+        tick_sum = torch.zeros((), dtype=torch.int64, device=dev)
+        for w in range(5):            # two eager steps, the capture of the step's CUDA graph, two replays
             henv.step(cmd[w])
+            tick_sum += henv.substeps.sum()      # (also loads the reduction kernel outside the timed region)
         barrier()
+        tick_sum.zero_()
         h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         h0.record()
-        ticks = 0
         HS = 5
+        hev = [torch.cuda.Event(enable_timing=True) for _ in range(HS + 1)]
+        hev[0].record()
         for k in range(HS):
-            henv.step(cmd[2 + k])
-            ticks += int(henv.substeps.sum().item())
+            henv.step(cmd[(5 + k) % 8])
+            tick_sum += henv.substeps.sum()
+            hev[k + 1].record()
         h1.record()
         barrier()
+        ticks = int(tick_sum.item())
+        hier_step_ms = [hev[k].elapsed_time(hev[k + 1]) for k in range(HS)]
         ht = torch.tensor([h0.elapsed_time(h1)], dtype=torch.float64, device=dev)
         tk = torch.tensor([float(ticks)], dtype=torch.float64, device=dev)
         if world > 1:
@@ -571,10 +578,10 @@ def run_b200(args):
             dist.all_reduce(tk)
         hier = {"commander_steps_per_s": world * n * HS / (float(ht.item()) * 1e-3),
                 "sim_ticks_per_s": float(tk.item()) / (float(ht.item()) * 1e-3), "commander_steps": HS,
-                "mean_substeps": float(tk.item()) / (world * n * HS), "arenas_per_gpu": n,
+                "mean_substeps": float(tk.item()) / (world * n * HS), "arenas_per_gpu": n, "step_ms": hier_step_ms,
                 "note": "HighLevelEnv 3-vs-3, 16 masked sub-steps x (2 staged env launches + 2 launches of csrc/hh_policy_tc.cu: the frozen "
                         "fight / escape actors of all six aircraft as gathered chains on tcgen05, fp32-equivalent, argmax in the epilogue; "
-                        "row lists built on the device, no host synchronisation inside a commander step)"}
+                        "row lists built on the device, no host synchronisation inside a commander step: replayed as one CUDA graph)"}
         from hhmarl_2d_b200.env_hier import CommanderSampler
         from hhmarl_2d_b200 import models as MM
         cs = CommanderSampler(henv, MM.CommanderGru().to(dev), fragment_len=4)

@@ -13,6 +13,7 @@ loads pickled RLlib models that are not in its repository).
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 
@@ -88,7 +89,7 @@ class VecHighLevelEnv:
         # use_cuda_graph: a commander step is ~70 launches with no host synchronisation; after `graph_warmup` eager steps it is
         # captured once and replayed (commander actions pass through a buffer that stays).  Eager when a trace / tick hook /
         # the torch policies are in use.
-        self.use_cuda_graph = True
+        self.use_cuda_graph = os.environ.get("HH_HIER_GRAPH", "1") != "0"
         self.graph_warmup = 2
         self._graph, self._eager_steps, self._ca_static = None, 0, None
 
