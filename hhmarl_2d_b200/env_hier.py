@@ -70,6 +70,8 @@ class VecHighLevelEnv:
         self.dev = dev
         n = self.n_arenas
         self.policies = lowlevel_policies if lowlevel_policies is not None else default_lowlevel_policies(0, dev)
+        for m in self.policies.values():       # supplied policies (checkpoint.load_highlevel_policies defaults to the CPU) move to
+            m.to(dev).eval()                   # the env's device: the fused forward hands their packed weights to the kernel
         self.obs = torch.empty((n, 3, OBS_HL), dtype=torch.float32, device=dev)
         self.rew = torch.empty((n, 3), dtype=torch.float32, device=dev)
         self.done = torch.empty((n,), dtype=torch.uint8, device=dev)
