@@ -1,4 +1,4 @@
-"""profiles/hier_only.py -- ms per commander step of VecHighLevelEnv at 8 192 arenas: eager launches against the CUDA-graph replay."""
+"""profiles/hier_only.py -- ms per commander step of VecHighLevelEnv at 8 192 arenas: eager launches against the CUDA-graph replay, one handle against groups of arenas on their own streams."""
 import os
 import sys
 
@@ -7,8 +7,8 @@ import torch  # noqa: E402
 from hhmarl_2d_b200.env_hier import VecHighLevelEnv  # noqa: E402
 
 n = 8192
-for use_graph in (False, True):
-    henv = VecHighLevelEnv(n, device=0, seed=2, autoreset=True)
+for use_graph, groups in ((False, 1), (True, 1), (True, 2), (True, 4), (True, 8)):
+    henv = VecHighLevelEnv(n, device=0, seed=2, autoreset=True, groups=groups)
     henv.use_cuda_graph = use_graph
     henv.reset()
     g = torch.Generator(device="cuda"); g.manual_seed(77)
@@ -22,4 +22,4 @@ for use_graph in (False, True):
         henv.step(cmd[4 + k])
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
-    print(f"use_cuda_graph={use_graph}: {ms:.3f} ms per commander step -> {n / ms / 1e3:.2f} M commander-steps/s")
+    print(f"use_cuda_graph={use_graph} groups={groups}: {ms:.3f} ms per commander step -> {n / ms / 1e3:.2f} M commander-steps/s")

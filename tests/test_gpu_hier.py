@@ -125,22 +125,30 @@ def test_graph_replayed_commander_steps_match_eager_steps():
     torch.manual_seed(3)
     ca = torch.randint(0, 3, (T, n, 3)).to(torch.int32).cuda()
     envs = []
-    for use_graph in (False, True):
-        e = VecHighLevelEnv(n, make_hier_args(horizon=60, eval_info=True), device=0, seed=8, arena_base=70, autoreset=True)
+    # one handle, eager | two groups of arenas on two streams inside the graph | three ragged groups, eager (phase by phase)
+    for use_graph, groups in ((False, 1), (True, 2), (False, 3), (True, 1)):
+        e = VecHighLevelEnv(n, make_hier_args(horizon=60, eval_info=True), device=0, seed=8, arena_base=70, autoreset=True,
+                            groups=groups)
+        assert e.groups == groups
         e.use_cuda_graph = use_graph
         envs.append(e)
-    assert torch.equal(envs[0].reset(), envs[1].reset())
+    first = envs[0].reset().clone()
+    for e in envs[1:]:
+        assert torch.equal(first, e.reset())
     n_done = 0
     for t in range(T):
         outs = []
         for e in envs:
             o, r, d = e.step(ca[t])
             outs.append((o.clone(), r.clone(), d.clone(), e.substeps.clone(), e.info.clone()))
-        for a, b in zip(*outs):
-            assert torch.equal(a, b), t
+        for other in outs[1:]:
+            for a, b in zip(outs[0], other):
+                assert torch.equal(a, b), t
         n_done += int(outs[0][2].sum())
-    assert envs[1]._graph is not None and envs[0]._graph is None
+    assert envs[1]._graph is not None and envs[3]._graph is not None and envs[0]._graph is None and envs[2]._graph is None
     assert n_done > 0
+    sa, sb = envs[0].get_state(), envs[1].get_state()
+    assert bytes(sa) == bytes(sb)
 
 
 def test_hier_full_size_properties():
