@@ -661,7 +661,7 @@ def run_b200(args):
         smp = VecSampler(envp, TorchPolicy(m1, 1), TorchPolicy(m2, 2), fragment_len=Tp, use_cuda_graph=True)
         learner = PPOLearner(m1, m2, num_sgd_iter=1, sgd_minibatch_size=8192)
         learner.time_allreduce = True
-        for _ in range(2):
+        for _ in range(3):           # (the remainder minibatch comes once per update: its graph is captured in the third)
             learner.update(smp.collect())
             smp.refresh_policy()
         IT = 3

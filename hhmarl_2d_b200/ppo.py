@@ -75,7 +75,7 @@ class PPOLearner:
             self.opt = torch.optim.Adam([self.flat], lr=lr)
             self.use_graph = False
         self._graphs, self._static, self._eager_runs, self._side = {}, None, {}, None
-        self.graph_warmup = 3                                                # eager minibatches of a size before its capture
+        self.graph_warmup = 2                                                # eager minibatches of a size before its capture
         self.clip, self.kl_target, self.kl_coeff = clip_param, kl_target, [kl_coeff, kl_coeff]
         self.kl_coeff_t = torch.tensor(self.kl_coeff, dtype=torch.float32, device=dev)   # what the loss reads (graph-safe)
         self.vf_clip, self.vf_coeff, self.ent_coeff = vf_clip_param, vf_loss_coeff, entropy_coeff

@@ -235,7 +235,7 @@ def test_collect_host_with_two_buffer_sets_delivers_every_fragment():
 
 
 def test_graph_replayed_minibatches_match_eager_minibatches():
-    """PPOLearner replays a captured CUDA graph per minibatch (after three eager minibatches of that size); the weights after two
+    """PPOLearner replays a captured CUDA graph per minibatch (after two eager minibatches of that size); the weights after two
     updates must agree with a learner that runs every minibatch eagerly from the same initial weights on the same batches."""
     import copy
     from hhmarl_2d_b200 import VecLowLevelEnv, make_args, VecSampler, TorchPolicy, PPOLearner
