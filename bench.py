@@ -416,12 +416,17 @@ def run_b200(args):
                 smp.collect()
             R = max(2, K // Tf)
             barrier()
+            r_sampler = ClockSampler(local) if (rank == 0 and tag == "fused_tc" and not os.environ.get("HH_BENCH_NO_CLOCKS")) else None
+            tr0 = time.perf_counter()
             r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             r0.record()
             for _ in range(R):
                 smp.collect()
             r1.record()
             barrier()
+            if r_sampler is not None:       # SM clock / throttle reasons DURING the rollout's timed region (the --leg rollout line's `clocks`)
+                rollout["clocks"] = r_sampler.summary(tr0, time.perf_counter())
+                rollout["launches_per_fragment"] = 4 + 3 * Tf * getattr(smp, "groups", 1)
             rt = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(rt, op=dist.ReduceOp.MAX)
@@ -846,7 +851,10 @@ def run_b200(args):
             r = rollout["fused_tc"]
             line.update(value=r["value"], ms_per_step=r["ms_per_tick"], config=workload_config(args, leg="rollout"),
                         dtype="f64 env + fp32-equivalent policy (fp16 hi/lo split on tcgen05)",
-                        e2e=rollout.get("e2e"), roofline=rollout.get("roofline"), gpu_launches=4 * rollout["fragment_len"] * max(2, K // 20))
+                        e2e=rollout.get("e2e"), roofline=rollout.get("roofline"),
+                        gpu_launches=int(rollout.get("launches_per_fragment", 4 * rollout["fragment_len"])) * max(2, K // 20))
+            if rollout.get("clocks"):
+                line["clocks"] = rollout["clocks"]
             if cpu_base is not None and isinstance(rollout.get("cpu_sampler_equivalent"), dict) and "value_per_worker" in rollout["cpu_sampler_equivalent"]:
                 c = rollout["cpu_sampler_equivalent"]
                 line["cpu_baseline"] = {"value": c["value_per_worker"], "unit": UNIT, "cores": 1, "kind": "port", "sample": c["sample"]}
