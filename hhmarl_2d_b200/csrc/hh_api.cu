@@ -718,6 +718,75 @@ __global__ void sample_actions_kernel(int n, const float* __restrict__ logits1, 
   logp[i] = lp;
 }
 
+// ------------------------------------------------------------------------------------------
+// The learner's MultiCategorical terms of one policy (RLlib TorchMultiCategorical.logp / entropy / kl, summed over the heads):
+// one thread per row.  Forward: logp of the taken actions, entropy, KL(old || new).  Backward: d / d logits from the three
+// upstream gradients; per head with p = softmax(z), q = softmax(z_old):
+//   d logp / d z_j = [j = a] - p_j,   d H / d z_j = -p_j (log p_j + H),   d KL / d z_j = p_j - q_j.
+// Replaces ~35 element-wise torch kernels per head and direction in PPOLearner's minibatch step.
+struct MultiCatShape { int n_heads, w[4], n_tot; };
+__device__ __forceinline__ void head_stats(const float* z, int w, float& mx, float& lse) {
+  mx = z[0];
+  for (int k = 1; k < w; ++k) mx = fmaxf(mx, z[k]);
+  float s = 0.0f;
+  for (int k = 0; k < w; ++k) s += expf(z[k] - mx);
+  lse = mx + logf(s);
+}
+__global__ void multicat_forward_kernel(int n, MultiCatShape sh, const float* __restrict__ logits, int ld, const float* __restrict__ old_logits,
+                                        int ld_old, const int32_t* __restrict__ actions, int ld_act, float* __restrict__ logp,
+                                        float* __restrict__ ent, float* __restrict__ kl) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* z = logits + (size_t)i * ld;
+  const float* zo = old_logits + (size_t)i * ld_old;
+  float lp = 0.0f, en = 0.0f, k_ = 0.0f;
+  int o = 0;
+  for (int h = 0; h < sh.n_heads; ++h) {
+    const int w = sh.w[h];
+    float mx, lse, mxo, lseo;
+    head_stats(z + o, w, mx, lse);
+    head_stats(zo + o, w, mxo, lseo);
+    const int a = actions[(size_t)i * ld_act + h];
+    lp += z[o + a] - lse;
+    for (int k = 0; k < w; ++k) {
+      const float l = z[o + k] - lse, lo = zo[o + k] - lseo;
+      en -= expf(l) * l;
+      k_ += expf(lo) * (lo - l);
+    }
+    o += w;
+  }
+  logp[i] = lp;
+  ent[i] = en;
+  kl[i] = k_;
+}
+__global__ void multicat_backward_kernel(int n, MultiCatShape sh, const float* __restrict__ logits, int ld, const float* __restrict__ old_logits,
+                                         int ld_old, const int32_t* __restrict__ actions, int ld_act, const float* __restrict__ g_logp,
+                                         const float* __restrict__ g_ent, const float* __restrict__ g_kl, float* __restrict__ g_logits) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* z = logits + (size_t)i * ld;
+  const float* zo = old_logits + (size_t)i * ld_old;
+  float* g = g_logits + (size_t)i * sh.n_tot;
+  const float gl = g_logp[i], ge = g_ent[i], gk = g_kl[i];
+  int o = 0;
+  for (int h = 0; h < sh.n_heads; ++h) {
+    const int w = sh.w[h];
+    float mx, lse, mxo, lseo;
+    head_stats(z + o, w, mx, lse);
+    head_stats(zo + o, w, mxo, lseo);
+    const int a = actions[(size_t)i * ld_act + h];
+    float H = 0.0f;
+    for (int k = 0; k < w; ++k) {
+      const float l = z[o + k] - lse;
+      H -= expf(l) * l;
+    }
+    for (int k = 0; k < w; ++k) {
+      const float l = z[o + k] - lse, p = expf(l), q = expf(zo[o + k] - lseo);
+      g[o + k] = gl * ((k == a ? 1.0f : 0.0f) - p) - ge * p * (l + H) + gk * (p - q);
+    }
+    o += w;
+  }
+}
 // central_critic_observer (train_hetero.py:162-181): flat_p = [act_own | act_other | obs_own | obs_other] with the
 // action columns zero at sampling time; writes the observation columns of both policies' inputs.
 __global__ void pack_central_kernel(int n, int d1, int d2, const float* __restrict__ obs1, const float* __restrict__ obs2,
@@ -882,6 +951,43 @@ extern "C" int hh_gae_agents(int32_t T, int32_t n_arenas, int32_t n_agents, cons
   gae_kernel<<<(n_pairs + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(T, n_pairs, n_agents, rew_dev, vf_dev,
                                                                                  last_vf_dev, done_dev, gamma, lam, adv_dev,
                                                                                  vtarg_dev);
+  HH_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int multicat_shape(int32_t n_heads, const int32_t* widths, MultiCatShape& sh) {
+  if (n_heads < 1 || n_heads > 4 || !widths) return -1;
+  sh.n_heads = n_heads;
+  sh.n_tot = 0;
+  for (int h = 0; h < 4; ++h) {
+    sh.w[h] = h < n_heads ? widths[h] : 0;
+    if (h < n_heads && (widths[h] < 1 || widths[h] > 64)) return -1;
+    sh.n_tot += sh.w[h];
+  }
+  return 0;
+}
+extern "C" int hh_multicat_forward(int32_t n_rows, int32_t n_heads, const int32_t* widths, const float* logits_dev, int32_t ld,
+                                   const float* old_logits_dev, int32_t ld_old, const int32_t* actions_dev, int32_t ld_act,
+                                   float* logp_dev, float* entropy_dev, float* kl_dev, void* stream) {
+  MultiCatShape sh;
+  if (n_rows <= 0 || multicat_shape(n_heads, widths, sh) || !logits_dev || !old_logits_dev || !actions_dev || !logp_dev || !entropy_dev ||
+      !kl_dev || ld < sh.n_tot || ld_old < sh.n_tot || ld_act < n_heads)
+    return fail(-1, "hh_multicat_forward: bad argument");
+  multicat_forward_kernel<<<(n_rows + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      n_rows, sh, logits_dev, ld, old_logits_dev, ld_old, actions_dev, ld_act, logp_dev, entropy_dev, kl_dev);
+  HH_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int hh_multicat_backward(int32_t n_rows, int32_t n_heads, const int32_t* widths, const float* logits_dev, int32_t ld,
+                                    const float* old_logits_dev, int32_t ld_old, const int32_t* actions_dev, int32_t ld_act,
+                                    const float* g_logp_dev, const float* g_entropy_dev, const float* g_kl_dev, float* g_logits_dev,
+                                    void* stream) {
+  MultiCatShape sh;
+  if (n_rows <= 0 || multicat_shape(n_heads, widths, sh) || !logits_dev || !old_logits_dev || !actions_dev || !g_logp_dev ||
+      !g_entropy_dev || !g_kl_dev || !g_logits_dev || ld < sh.n_tot || ld_old < sh.n_tot || ld_act < n_heads)
+    return fail(-1, "hh_multicat_backward: bad argument");
+  multicat_backward_kernel<<<(n_rows + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      n_rows, sh, logits_dev, ld, old_logits_dev, ld_old, actions_dev, ld_act, g_logp_dev, g_entropy_dev, g_kl_dev, g_logits_dev);
   HH_CUDA(cudaGetLastError());
   return 0;
 }

@@ -36,8 +36,46 @@ def multicategorical_sample(logits: torch.Tensor, splits, explore: bool = True):
     return torch.stack(acts, dim=1), logp
 
 
+class _FusedMultiCat(torch.autograd.Function):
+    """The three MultiCategorical terms of one policy as ONE forward and ONE backward kernel (hh_multicat_forward / _backward)
+    instead of ~35 element-wise torch kernels per head and direction.  CUDA float32 only."""
+
+    @staticmethod
+    def forward(ctx, logits, old_logits, actions, splits):
+        import ctypes
+        n = logits.shape[0]
+        logits = logits.contiguous()
+        w = (ctypes.c_int32 * len(splits))(*[int(v) for v in splits])
+        out = torch.empty((3, n), dtype=torch.float32, device=logits.device)
+        st = torch.cuda.current_stream(logits.device).cuda_stream
+        nat.check(nat.lib().hh_multicat_forward(n, len(splits), w, logits.data_ptr(), logits.stride(0), old_logits.data_ptr(),
+                                                old_logits.stride(0), actions.data_ptr(), actions.stride(0), out[0].data_ptr(),
+                                                out[1].data_ptr(), out[2].data_ptr(), st), "hh_multicat_forward")
+        ctx.save_for_backward(logits, old_logits, actions)
+        ctx.splits = tuple(int(v) for v in splits)
+        return out[0], out[1], out[2]
+
+    @staticmethod
+    def backward(ctx, g_logp, g_ent, g_kl):
+        import ctypes
+        logits, old_logits, actions = ctx.saved_tensors
+        n = logits.shape[0]
+        w = (ctypes.c_int32 * len(ctx.splits))(*ctx.splits)
+        g = torch.stack([g_logp, g_ent, g_kl]).contiguous()     # (also materialises expanded / zero gradients)
+        gz = torch.empty((n, sum(ctx.splits)), dtype=torch.float32, device=logits.device)
+        st = torch.cuda.current_stream(logits.device).cuda_stream
+        nat.check(nat.lib().hh_multicat_backward(n, len(ctx.splits), w, logits.data_ptr(), logits.stride(0), old_logits.data_ptr(),
+                                                 old_logits.stride(0), actions.data_ptr(), actions.stride(0), g[0].data_ptr(),
+                                                 g[1].data_ptr(), g[2].data_ptr(), gz.data_ptr(), st), "hh_multicat_backward")
+        return gz, None, None, None
+
+
 def multicategorical_logp_entropy_kl(logits, actions, splits, old_logits=None):
     """log-prob of `actions`, entropy and (optionally) KL(old || new), summed over the heads."""
+    if (logits.is_cuda and old_logits is not None and logits.dtype == torch.float32 and old_logits.dtype == torch.float32
+            and actions.dtype == torch.int32 and old_logits.stride(-1) == 1 and actions.stride(-1) == 1
+            and logits.shape[1] == sum(splits) and len(splits) <= 4):
+        return _FusedMultiCat.apply(logits, old_logits, actions, tuple(splits))
     logp = ent = kl = 0.0
     o = 0
     for h, n in enumerate(splits):

@@ -144,6 +144,17 @@ int hh_gae_agents(int32_t T, int32_t n_arenas, int32_t n_agents, const float* re
                   const float* last_vf_dev, const uint8_t* done_dev, float gamma, float lam, float* adv_dev,
                   float* vtarg_dev, void* stream);
 
+/* The learner's MultiCategorical terms of one policy (RLlib TorchMultiCategorical.logp / entropy / kl, summed over the MultiDiscrete
+ * heads of widths[n_heads], e.g. {13, 9, 2, 2}): forward writes logp of the taken actions int32[N][ld_act], the entropy and
+ * KL(old || new) per row; backward writes d / d logits f32[N][sum(widths)] (contiguous) from the three upstream gradients.
+ * `widths` is a HOST array.  Used by PPOLearner's loss (hhmarl_2d_b200/sampler.py: multicategorical_logp_entropy_kl). */
+int hh_multicat_forward(int32_t n_rows, int32_t n_heads, const int32_t* widths, const float* logits_dev, int32_t ld,
+                        const float* old_logits_dev, int32_t ld_old, const int32_t* actions_dev, int32_t ld_act, float* logp_dev,
+                        float* entropy_dev, float* kl_dev, void* stream);
+int hh_multicat_backward(int32_t n_rows, int32_t n_heads, const int32_t* widths, const float* logits_dev, int32_t ld,
+                         const float* old_logits_dev, int32_t ld_old, const int32_t* actions_dev, int32_t ld_act,
+                         const float* g_logp_dev, const float* g_entropy_dev, const float* g_kl_dev, float* g_logits_dev, void* stream);
+
 /* The two ends of a rollout fragment in the sampler's central-critic layout (rows [7 action columns | own obs | other obs] of D
  * floats, flat f32[T][N][D] per policy):
  * hh_fragment_prepare  : zero the action columns of all rows (the critic sees zero actions while sampling) and copy the current

@@ -234,6 +234,28 @@ def test_collect_host_with_two_buffer_sets_delivers_every_fragment():
     assert all(v.is_pinned() for v in hh.values())
 
 
+def test_fused_multicategorical_terms_match_torch():
+    """hh_multicat_forward / _backward (the learner's logp / entropy / KL of a MultiDiscrete policy in one kernel each) against the
+    per-head torch expression: values and the gradient with respect to the logits, both policies' head layouts, strided inputs."""
+    from hhmarl_2d_b200.sampler import multicategorical_logp_entropy_kl as f
+    torch.manual_seed(0)
+    for splits in ((13, 9, 2, 2), (13, 9, 2)):
+        n, w = 3000, sum(splits)
+        z = (3 * torch.randn(n, w, device="cuda")).requires_grad_()
+        zo = (3 * torch.randn(n, w + 5, device="cuda"))[:, :w]                     # row stride != width
+        act = torch.stack([torch.randint(0, k, (n,), device="cuda") for k in splits] + [torch.zeros(n, device="cuda", dtype=torch.long)] * (4 - len(splits)),
+                          dim=1).to(torch.int32)[:, :len(splits)]                    # int32, row stride 4
+        cw = torch.randn(3, n, device="cuda")
+        lp, en, kl = f(z, act, splits, zo)                                          # fused (CUDA, int32 actions, old logits given)
+        (gz,) = torch.autograd.grad((cw[0] * lp + cw[1] * en + cw[2] * kl).sum(), z)
+        z2 = z.detach().clone().requires_grad_()
+        lp2, en2, kl2 = f(z2, act.long(), splits, zo)                               # int64 actions -> the per-head torch path
+        (gz2,) = torch.autograd.grad((cw[0] * lp2 + cw[1] * en2 + cw[2] * kl2).sum(), z2)
+        for a, b, name in ((lp, lp2, "logp"), (en, en2, "entropy"), (kl, kl2, "kl"), (gz, gz2, "grad")):
+            err = (a - b).abs().max().item()
+            assert err <= 2e-5 * max(1.0, b.abs().max().item()), (splits, name, err)
+
+
 def test_graph_replayed_minibatches_match_eager_minibatches():
     """PPOLearner replays a captured CUDA graph per minibatch (after two eager minibatches of that size); the weights after two
     updates must agree with a learner that runs every minibatch eagerly from the same initial weights on the same batches."""
