@@ -15,9 +15,20 @@ from __future__ import annotations
 
 import torch
 import torch.distributed as dist
-from torch.nn.utils.stateless import _reparametrize_module
+from torch.func import functional_call
 
 from .sampler import multicategorical_logp_entropy_kl
+
+
+class _FlatForward(torch.nn.Module):
+    """forward_flat of a policy model as a Module.forward, so that torch.func.functional_call can re-bind its parameters."""
+
+    def __init__(self, model):
+        super().__init__()
+        self.m = model
+
+    def forward(self, flat, seq_lens):
+        return self.m.forward_flat(flat, seq_lens)
 
 
 def _seq_major(x, L):
@@ -64,7 +75,8 @@ class PPOLearner:
         # weight.clone(), a cached value output) can pin an AccumulateGrad node to another stream -- which breaks a capture.
         self._sizes = [p.numel() for p in params]
         index = {id(p): k for k, p in enumerate(params)}
-        self._names = [[(name, index[id(p)]) for name, p in m.named_parameters()] for m in self.models]
+        self._names = [[("m." + name, index[id(p)]) for name, p in m.named_parameters()] for m in self.models]
+        self._wrapped = [_FlatForward(m) for m in self.models]
         # On the GPU a minibatch step (gather, both policies' forward, loss, backward, Adam) is ~600 small kernels whose launch
         # cost, not their run time, bounds the update: it is captured once per minibatch size into a CUDA graph and replayed
         # (with more than one rank: forward / backward and optimiser as two graphs around the eager all-reduce).
@@ -120,8 +132,7 @@ class PPOLearner:
         return mean, var.sqrt()
 
     def _loss(self, i, views, flat, actions, old_logits, old_logp, adv, vtarg, seq_lens):
-        with _reparametrize_module(self.models[i], {name: views[k] for name, k in self._names[i]}):
-            logits, vf = self.models[i].forward_flat(flat, seq_lens)
+        logits, vf = functional_call(self._wrapped[i], {name: views[k] for name, k in self._names[i]}, (flat, seq_lens))
         logp, ent, kl = multicategorical_logp_entropy_kl(logits, actions, self.splits[i], old_logits)
         ratio = torch.exp(logp - old_logp)
         surr = torch.min(adv * ratio, adv * torch.clamp(ratio, 1 - self.clip, 1 + self.clip))
