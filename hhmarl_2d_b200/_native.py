@@ -149,6 +149,9 @@ def bind(L: ctypes.CDLL, partial: bool = False) -> ctypes.CDLL:
     L.hh_multicat_forward.restype = ctypes.c_int
     L.hh_multicat_backward.argtypes = [I32, I32, VP, VP, I32, VP, I32, VP, I32, VP, VP, VP, VP, VP]
     L.hh_multicat_backward.restype = ctypes.c_int
+    F32 = ctypes.c_float
+    L.hh_ppo_loss.argtypes = [I32, VP, VP, VP, VP, VP, VP, VP, VP, F32, F32, F32, F32, VP, VP, VP]
+    L.hh_ppo_loss.restype = ctypes.c_int
     L.hh_fragment_prepare.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, VP, VP, VP, VP, VP]
     L.hh_fragment_prepare.restype = ctypes.c_int
     L.hh_fragment_writeback.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, VP, VP, VP, VP]
@@ -227,7 +230,7 @@ def bind(L: ctypes.CDLL, partial: bool = False) -> ctypes.CDLL:
     return real
 
 
-EXPORTS = ["hh_create", "hh_destroy", "hh_n_arenas", "hh_obs_dim", "hh_reset", "hh_step", "hh_step_range", "hh_step_range_central", "hh_fragment_prepare", "hh_fragment_writeback", "hh_multicat_forward", "hh_multicat_backward", "hh_step_begin", "hh_step_finish", "hh_reset_host",
+EXPORTS = ["hh_create", "hh_destroy", "hh_n_arenas", "hh_obs_dim", "hh_reset", "hh_step", "hh_step_range", "hh_step_range_central", "hh_fragment_prepare", "hh_fragment_writeback", "hh_multicat_forward", "hh_multicat_backward", "hh_ppo_loss", "hh_step_begin", "hh_step_finish", "hh_reset_host",
            "hh_step_host", "hh_step_host_begin", "hh_step_host_end", "hh_host_buffers", "hh_set_host_mode", "hh_get_state", "hh_set_state", "hh_launch_count", "hh_gae", "hh_gae_agents", "hh_sample_actions", "hh_pack_central", "hh_debug_geodesic", "hh_last_error", "hh_version", "hh_policy_forward", "hh_policy_forward_ex", "hh_policy_pack", "hh_policy_image_bytes", "hh_policy_tc_pair", "hh_policy_tc_mode", "hh_policy_rows_by_key", "hh_policy_last_error",
            "hh_hier_create", "hh_hier_destroy", "hh_hier_reset", "hh_hier_begin", "hh_hier_agents", "hh_hier_tick",
            "hh_hier_end", "hh_hier_policy_rows", "hh_hier_eval_info", "hh_hier_get_state", "hh_hier_set_state", "hh_hier_launch_count", "hh_hier_last_error"]

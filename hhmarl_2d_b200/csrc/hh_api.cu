@@ -955,6 +955,61 @@ extern "C" int hh_gae_agents(int32_t T, int32_t n_arenas, int32_t n_agents, cons
   return 0;
 }
 
+// PPO's per-policy loss (RLlib 2.4 ppo_torch_policy.loss) from the per-row terms, one thread per row:
+//   ratio = exp(logp - old_logp), surr = min(adv ratio, adv clamp(ratio, 1 - c, 1 + c)), vfl = clamp((vf - vtarg)^2, 0, vf_clip),
+//   loss_i = -surr + kl_coeff kl + vf_coeff vfl - ent_coeff ent;
+// sums[0..3] += loss_i, kl_i, vfl_i, ent_i (the caller divides by n), deriv[4][n] = d (mean loss) / d {logp, ent, kl, vf}_i.
+__global__ void ppo_loss_kernel(int n, const float* __restrict__ logp, const float* __restrict__ ent, const float* __restrict__ kl,
+                                const float* __restrict__ vf, const float* __restrict__ old_logp, const float* __restrict__ adv,
+                                const float* __restrict__ vtarg, const float* __restrict__ kl_coeff, float clip, float vf_clip,
+                                float vf_coeff, float ent_coeff, float* __restrict__ sums, float* __restrict__ deriv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  if (i < n) {
+    const float klc = kl_coeff[0], inv_n = 1.0f / (float)n;
+    const float ratio = expf(logp[i] - old_logp[i]), a = adv[i];
+    const float rc = fminf(fmaxf(ratio, 1.0f - clip), 1.0f + clip);
+    const float s1 = a * ratio, s2 = a * rc;
+    const float surr = fminf(s1, s2);
+    // d surr / d ratio: torch.min splits a tie evenly between its arguments, clamp passes the gradient on [1 - c, 1 + c]
+    const float in_range = (ratio >= 1.0f - clip && ratio <= 1.0f + clip) ? 1.0f : 0.0f;
+    const float ds = s1 < s2 ? a : (s1 > s2 ? a * in_range : 0.5f * a + 0.5f * a * in_range);
+    const float d = vf[i] - vtarg[i], sq = d * d;
+    const float vfl = fminf(fmaxf(sq, 0.0f), vf_clip);
+    const float dv = (sq >= 0.0f && sq <= vf_clip) ? 2.0f * d : 0.0f;
+    v[0] = -surr + klc * kl[i] + vf_coeff * vfl - ent_coeff * ent[i];
+    v[1] = kl[i];
+    v[2] = vfl;
+    v[3] = ent[i];
+    deriv[i] = -ds * ratio * inv_n;
+    deriv[(size_t)n + i] = -ent_coeff * inv_n;
+    deriv[2 * (size_t)n + i] = klc * inv_n;
+    deriv[3 * (size_t)n + i] = vf_coeff * dv * inv_n;
+  }
+  __shared__ float red[4][4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float x = v[k];
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) atomicAdd(sums + threadIdx.x, red[threadIdx.x][0] + red[threadIdx.x][1] + red[threadIdx.x][2] + red[threadIdx.x][3]);
+}
+extern "C" int hh_ppo_loss(int32_t n_rows, const float* logp_dev, const float* entropy_dev, const float* kl_dev, const float* vf_dev,
+                           const float* old_logp_dev, const float* adv_dev, const float* vtarg_dev, const float* kl_coeff_dev,
+                           float clip, float vf_clip, float vf_coeff, float ent_coeff, float* sums_dev, float* deriv_dev, void* stream) {
+  if (n_rows <= 0 || !logp_dev || !entropy_dev || !kl_dev || !vf_dev || !old_logp_dev || !adv_dev || !vtarg_dev || !kl_coeff_dev ||
+      !sums_dev || !deriv_dev)
+    return fail(-1, "hh_ppo_loss: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  HH_CUDA(cudaMemsetAsync(sums_dev, 0, 4 * sizeof(float), st));
+  ppo_loss_kernel<<<(n_rows + 127) / 128, 128, 0, st>>>(n_rows, logp_dev, entropy_dev, kl_dev, vf_dev, old_logp_dev, adv_dev, vtarg_dev,
+                                                        kl_coeff_dev, clip, vf_clip, vf_coeff, ent_coeff, sums_dev, deriv_dev);
+  HH_CUDA(cudaGetLastError());
+  return 0;
+}
+
 static int multicat_shape(int32_t n_heads, const int32_t* widths, MultiCatShape& sh) {
   if (n_heads < 1 || n_heads > 4 || !widths) return -1;
   sh.n_heads = n_heads;

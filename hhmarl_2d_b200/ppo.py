@@ -31,6 +31,30 @@ class _FlatForward(torch.nn.Module):
         return self.m.forward_flat(flat, seq_lens)
 
 
+class _FusedPPOLoss(torch.autograd.Function):
+    """One policy's PPO loss from its per-row terms as ONE kernel (hh_ppo_loss): returns [mean loss, mean kl, mean value loss,
+    mean entropy]; the backward is one multiply of the stored per-row derivatives.  CUDA float32 only."""
+
+    @staticmethod
+    def forward(ctx, logp, ent, kl, vf, old_logp, adv, vtarg, kl_coeff, clip, vf_clip, vf_coeff, ent_coeff):
+        from . import _native as nat
+        n = logp.shape[0]
+        args = [t.contiguous() for t in (logp, ent, kl, vf, old_logp, adv, vtarg)]
+        sums = torch.empty(4, dtype=torch.float32, device=logp.device)
+        deriv = torch.empty((4, n), dtype=torch.float32, device=logp.device)
+        st = torch.cuda.current_stream(logp.device).cuda_stream
+        nat.check(nat.lib().hh_ppo_loss(n, *[t.data_ptr() for t in args], kl_coeff.data_ptr(), float(clip), float(vf_clip),
+                                        float(vf_coeff), float(ent_coeff), sums.data_ptr(), deriv.data_ptr(), st), "hh_ppo_loss")
+        ctx.save_for_backward(deriv)
+        return sums / n
+
+    @staticmethod
+    def backward(ctx, g):
+        (deriv,) = ctx.saved_tensors
+        d = deriv * g[0]                     # only the loss (element 0) is differentiated; the other three are statistics
+        return d[0], d[1], d[2], d[3], None, None, None, None, None, None, None, None
+
+
 def _seq_major(x, L):
     """[T, N, ...] -> [(T/L)*N*L, ...] ordered (chunk, arena, time): rows of one sequence are contiguous."""
     T, N = x.shape[0], x.shape[1]
@@ -134,6 +158,10 @@ class PPOLearner:
     def _loss(self, i, views, flat, actions, old_logits, old_logp, adv, vtarg, seq_lens):
         logits, vf = functional_call(self._wrapped[i], {name: views[k] for name, k in self._names[i]}, (flat, seq_lens))
         logp, ent, kl = multicategorical_logp_entropy_kl(logits, actions, self.splits[i], old_logits)
+        if logp.is_cuda and logp.dtype == torch.float32:
+            out = _FusedPPOLoss.apply(logp, ent, kl, vf, old_logp, adv, vtarg, self.kl_coeff_t[i:i + 1], self.clip, self.vf_clip,
+                                      self.vf_coeff, self.ent_coeff)
+            return out[0], out[1].detach(), out[2].detach(), out[3].detach()
         ratio = torch.exp(logp - old_logp)
         surr = torch.min(adv * ratio, adv * torch.clamp(ratio, 1 - self.clip, 1 + self.clip))
         vf_loss = torch.clamp((vf - vtarg) ** 2, 0, self.vf_clip)

@@ -155,6 +155,15 @@ int hh_multicat_backward(int32_t n_rows, int32_t n_heads, const int32_t* widths,
                          const float* old_logits_dev, int32_t ld_old, const int32_t* actions_dev, int32_t ld_act,
                          const float* g_logp_dev, const float* g_entropy_dev, const float* g_kl_dev, float* g_logits_dev, void* stream);
 
+/* PPO's loss of one policy from its per-row terms (RLlib 2.4 ppo_torch_policy.loss): clipped surrogate of
+ * ratio = exp(logp - old_logp) with advantages adv, kl_coeff (a DEVICE scalar: it adapts between updates) x kl, vf_coeff x the
+ * value loss clamp((vf - vtarg)^2, 0, vf_clip), -ent_coeff x entropy.  sums[4] = sum over the rows of {loss, kl, value loss,
+ * entropy}; deriv f32[4][N] = d (mean loss) / d {logp, entropy, kl, vf} per row (what PPOLearner's backward multiplies by the
+ * upstream gradient). */
+int hh_ppo_loss(int32_t n_rows, const float* logp_dev, const float* entropy_dev, const float* kl_dev, const float* vf_dev,
+                const float* old_logp_dev, const float* adv_dev, const float* vtarg_dev, const float* kl_coeff_dev, float clip,
+                float vf_clip, float vf_coeff, float ent_coeff, float* sums_dev, float* deriv_dev, void* stream);
+
 /* The two ends of a rollout fragment in the sampler's central-critic layout (rows [7 action columns | own obs | other obs] of D
  * floats, flat f32[T][N][D] per policy):
  * hh_fragment_prepare  : zero the action columns of all rows (the critic sees zero actions while sampling) and copy the current

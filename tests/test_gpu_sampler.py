@@ -256,6 +256,37 @@ def test_fused_multicategorical_terms_match_torch():
             assert err <= 2e-5 * max(1.0, b.abs().max().item()), (splits, name, err)
 
 
+def test_fused_ppo_loss_matches_the_torch_expression():
+    """hh_ppo_loss (clipped surrogate + KL + clamped value loss + entropy bonus of one policy in one kernel) against the torch
+    expression PPOLearner uses on the CPU: the four means and the gradients with respect to logp / entropy / kl / vf, with ratios
+    inside and outside the clip range, both advantage signs, value errors beyond vf_clip and a non-zero entropy coefficient."""
+    from hhmarl_2d_b200.ppo import _FusedPPOLoss
+    torch.manual_seed(1)
+    n, clip, vf_clip, vf_coeff, ent_coeff = 5000, 0.25, 10.0, 1.0, 0.01
+    klc = torch.tensor([0.3], device="cuda")
+    old_logp, adv = torch.randn(n, device="cuda"), torch.randn(n, device="cuda")
+    vtarg = 3 * torch.randn(n, device="cuda")
+    base = [old_logp + 0.4 * torch.randn(n, device="cuda"), torch.rand(n, device="cuda"), torch.rand(n, device="cuda"),
+            vtarg + 4 * torch.randn(n, device="cuda")]
+    outs = []
+    for fused in (True, False):
+        logp, ent, kl, vf = (t.clone().requires_grad_() for t in base)
+        if fused:
+            o = _FusedPPOLoss.apply(logp, ent, kl, vf, old_logp, adv, vtarg, klc, clip, vf_clip, vf_coeff, ent_coeff)
+        else:
+            ratio = torch.exp(logp - old_logp)
+            surr = torch.min(adv * ratio, adv * torch.clamp(ratio, 1 - clip, 1 + clip))
+            vfl = torch.clamp((vf - vtarg) ** 2, 0, vf_clip)
+            o = torch.stack([(-surr + klc[0] * kl + vf_coeff * vfl - ent_coeff * ent).mean(), kl.mean(), vfl.mean(), ent.mean()])
+        g = torch.autograd.grad(o[0] * 1.7, (logp, ent, kl, vf))
+        outs.append((o.detach(), g))
+    (of, gf), (ot, gt) = outs
+    assert (of - ot).abs().max().item() <= 1e-5 * max(1.0, ot.abs().max().item()), (of, ot)
+    for a, b, name in zip(gf, gt, ("logp", "entropy", "kl", "vf")):
+        assert (a - b).abs().max().item() <= 1e-6 * max(1.0, b.abs().max().item()) + 1e-9, name
+    assert ((torch.exp(base[0] - old_logp) - 1).abs() > clip).float().mean().item() > 0.2      # the clip branches are exercised
+
+
 def test_graph_replayed_minibatches_match_eager_minibatches():
     """PPOLearner replays a captured CUDA graph per minibatch (after two eager minibatches of that size); the weights after two
     updates must agree with a learner that runs every minibatch eagerly from the same initial weights on the same batches."""
