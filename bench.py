@@ -696,6 +696,27 @@ def run_b200(args):
                "note": "level-5 self-play rollout (frozen stand-in opponents) + PPOLearner.update (both policies, flat "
                        "parameter / gradient buffers, fused Adam), one all-reduce of the flat gradient per minibatch; "
                        "num_sgd_iter 1 here to bound the bench (train_hetero.py uses the RLlib default 30)"}
+        try:      # the same update with the learner's GEMMs as TF32 tensor-core products (PPOLearner(matmul_tf32=True); not the default)
+            m1t, m2t = M.build_policy_pair("fight")
+            m1t.to(dev); m2t.to(dev)
+            lt = PPOLearner(m1t, m2t, num_sgd_iter=1, sgd_minibatch_size=8192, matmul_tf32=True)
+            bt = smp.collect()
+            for _ in range(3):
+                lt.update(bt)
+            barrier()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record()
+            for _ in range(IT):
+                lt.update(bt)
+            q1.record()
+            barrier()
+            qt = torch.tensor([q0.elapsed_time(q1) / IT], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(qt, op=dist.ReduceOp.MAX)
+            ppo["learner_ms_per_update_matmul_tf32"] = float(qt.item())
+            del lt
+        except Exception as ex:  # noqa: BLE001
+            ppo["learner_ms_per_update_matmul_tf32"] = repr(ex)
         del smp, envp, learner
     except Exception as ex:  # noqa: BLE001
         ppo = {"error": repr(ex)}

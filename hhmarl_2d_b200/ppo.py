@@ -70,7 +70,7 @@ class PPOLearner:
 
     def __init__(self, model1, model2, lr=1e-4, clip_param=0.25, kl_target=0.025, kl_coeff=0.2, vf_clip_param=10.0,
                  vf_loss_coeff=1.0, entropy_coeff=0.0, num_sgd_iter=30, sgd_minibatch_size=256, max_seq_len=20,
-                 seed=0, use_cuda_graph=True):
+                 seed=0, use_cuda_graph=True, matmul_tf32=False):
         self.models = (model1, model2)
         self.splits = ((13, 9, 2, 2), (13, 9, 2))
         seen, params = set(), []
@@ -104,6 +104,9 @@ class PPOLearner:
         # On the GPU a minibatch step (gather, both policies' forward, loss, backward, Adam) is ~600 small kernels whose launch
         # cost, not their run time, bounds the update: it is captured once per minibatch size into a CUDA graph and replayed
         # (with more than one rank: forward / backward and optimiser as two graphs around the eager all-reduce).
+        # matmul_tf32: run the learner's GEMMs (half of its GPU time as SIMT fp32 SGEMMs) as TF32 tensor-core products.  Off by
+        # default -- RLlib's torch learner multiplies in fp32 (torch.backends.cuda.matmul.allow_tf32 is False by default).
+        self.matmul_tf32 = bool(matmul_tf32)
         self.use_graph = bool(use_cuda_graph) and dev.type == "cuda"
         try:
             self.opt = torch.optim.Adam([self.flat], lr=lr, fused=dev.type == "cuda", capturable=self.use_graph)
@@ -218,6 +221,16 @@ class PPOLearner:
     # ------------------------------------------------------------------ one minibatch: eager, or a CUDA-graph replay
     def _fwd_bwd(self, data, rows, n_sel):
         """Both policies' losses on the rows `rows`, gradient into the flat buffer.  Returns the 7 statistics as one tensor."""
+        if self.flat.is_cuda:
+            prev = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = self.matmul_tf32
+            try:
+                return self._fwd_bwd_impl(data, rows, n_sel)
+            finally:
+                torch.backends.cuda.matmul.allow_tf32 = prev
+        return self._fwd_bwd_impl(data, rows, n_sel)
+
+    def _fwd_bwd_impl(self, data, rows, n_sel):
         seq_lens = [self.L] * n_sel
         total, parts = 0.0, []
         views = [v.view(p.shape) for v, p in zip(self.flat.split(self._sizes), self.params)]
