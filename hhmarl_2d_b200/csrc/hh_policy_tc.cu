@@ -1129,7 +1129,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) policy_
 // DRAINS it into registers (64 values per thread: thread = row, 16 epilogue warps = 4 lane quadrants x 4 column parts) and frees
 // it at once, so the next half's MMAs run under the tanh / split / store work; the shared layer's first half is held in
 // registers until the second half's MMAs have read the tile it overwrites.  The input tile's lo halves sit in TMEM columns
-// [472, 512) (the tail of the lo region, rewritten only by layer 1's LAST epilogue).  Weight images are those of the 64-row form.
+// [256, 296) (the head of the lo region, rewritten only by layer 1's LAST epilogue: layer 1 computes its upper half first).
+// Schedule (segment table in hh_pf_tc_launch): L1 upper half, L1 lower half, attention (MMAs under the lower half's epilogue),
+// shared layer half 0 below the attention block (under the attention epilogue), half 0 from the block on, half 1, head on the
+// first / second 256 columns.  Weight images are those of the 64-row form (the attention image starts on a K = 16 step).
 constexpr int TM2 = 128;
 constexpr uint32_t ACT2_BYTES = TM2 * KA * 2;              // 131 072: hi halves only
 constexpr uint32_t X2_BYTES = TM2 * KX * 2;                // 20 480
